@@ -1,0 +1,237 @@
+/*
+ * mre_b200.h -- C ABI of libmre_b200.so: the B200 (sm_100a) link-prediction scorer + filtered ranker,
+ * Bernoulli negative sampler and TransE margin-loss step.
+ *
+ * This is the drop-in boundary for the reference's hot path.  The reference's own native boundary is
+ * OpenKE's Base.so (all paths below are relative to /root/reference):
+ *   OpenKE/openke/base/Setting.h:17-145   setInPath / setBern / setWorkThreads / get*Total
+ *   OpenKE/openke/base/Reader.h:53-257    importTrainFiles / importTestFiles
+ *   OpenKE/openke/base/Base.cpp:161-197   sampling(h,t,r,y,B,negRate,negRelRate,mode,filter,p,val_loss)
+ *   OpenKE/openke/base/Test.h:22-390      initTest / getHeadBatch / getTailBatch / testHead / testTail /
+ *                                         test_link_prediction / getTestLink{MRR,MR,Hit10,Hit3,Hit1}
+ * That cut hands a host float[E] score vector per query to testHead/testTail, which is exactly what
+ * forces the query x entity score matrix through host memory.  This ABI re-cuts the same path one level
+ * up: the caller hands (h, r, t, side) query ids and the embedding tables, and gets integer rank counts
+ * back; scores never leave the SM.  Every entry point names the reference interface it replaces.
+ *
+ * Conventions
+ *   - plain C, no torch types; opaque handles; every function returns MRE_OK (0) or a negative code and
+ *     records a message retrievable with mre_last_error() (thread-local).
+ *   - "device" pointers are CUDA device pointers owned by the caller (e.g. torch storages); `stream` is
+ *     a cudaStream_t passed as void* (NULL = legacy default stream).  Functions taking device pointers
+ *     are asynchronous on `stream` unless stated otherwise.
+ *   - ids are int64 (the reference's INT = long, Setting.h:3); scores float32 (REAL = float, :4).
+ *   - side: 0 = head query (?, r, t) -- candidates replace the head (Test.h:65-127, mode "head_batch");
+ *           1 = tail query (h, r, ?) -- candidates replace the tail (Test.h:130-192, mode "tail_batch").
+ *   - score orientation: LOWER IS BETTER for every scorer, exactly as Model.predict returns
+ *     (TransE.py:88-94 distance; DistMult.py:70-72 and ComplEx.py:60-61 negate the similarity).
+ *   - there is NO CPU fallback: every compute entry point fails with MRE_ERR_CUDA without a B200.
+ */
+#ifndef MRE_B200_H
+#define MRE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MRE_ABI_VERSION 1
+
+/* error codes */
+#define MRE_OK               0
+#define MRE_ERR_INVALID     -1   /* bad argument */
+#define MRE_ERR_CUDA        -2   /* CUDA runtime error / no device */
+#define MRE_ERR_NOMEM       -3
+#define MRE_ERR_IO          -4   /* benchmark file missing / malformed */
+#define MRE_ERR_UNSUPPORTED -5
+
+/* scorers */
+#define MRE_TRANSE   0   /* OpenKE/openke/module/model/TransE.py:46-60, module/NegativeSampling.py:142-157 */
+#define MRE_DISTMULT 1   /* OpenKE/openke/module/model/DistMult.py:34-44 */
+#define MRE_COMPLEX  2   /* OpenKE/openke/module/model/ComplEx.py:20-27 */
+
+/* filter sources */
+#define MRE_FILTER_NONE  0   /* raw ranks only */
+#define MRE_FILTER_INDEX 1   /* train+valid+test membership from the index == _find, Corrupt.h:166-177 */
+#define MRE_FILTER_CSR   2   /* caller-supplied per-query known-true lists (paper path: e1rel_e2, utils/gen_mode_candidates.py:30-34) */
+
+/* rank conventions (the reference has three) */
+#define MRE_RANK_STRICT      0   /* 1 + #(s_j <  s_true)                 Test.h:80-112 */
+#define MRE_RANK_TIES_HALF   1   /* 1 + #(s_j <  s_true) + #(s_j == s_true)/2   main.py:245-250 */
+#define MRE_RANK_PESSIMISTIC 2   /* 1 + #(s_j <= s_true), upper end of module/zsl_module.py:705-706's unpinned argsort */
+
+/* index totals */
+#define MRE_TOTAL_ENTITY   0   /* getEntityTotal   Setting.h:107-110 */
+#define MRE_TOTAL_RELATION 1   /* getRelationTotal */
+#define MRE_TOTAL_TRAIN    2   /* getTrainTotal (after de-duplication, Reader.h:92-105) */
+#define MRE_TOTAL_VALID    3   /* getValidTotal */
+#define MRE_TOTAL_TEST     4   /* getTestTotal */
+#define MRE_TOTAL_TRIPLE   5   /* getTripleTotal = test + raw train + valid */
+
+#define MRE_SPLIT_TRAIN 0      /* de-duplicated, sorted (h,r,t)  == trainList, Reader.h:107 */
+#define MRE_SPLIT_VALID 1      /* sorted (r,h,t), Reader.h:228 */
+#define MRE_SPLIT_TEST  2      /* sorted (r,h,t), Reader.h:227 -- the order Tester iterates */
+
+typedef struct mre_index mre_index;   /* knowledge-graph index (Reader.h tables), host + device copies */
+typedef struct mre_ctx   mre_ctx;     /* per-device workspace: scratch buffers, pinned staging, SM count */
+
+/* ---------------------------------------------------------------------------------------------- misc */
+const char *mre_last_error(void);
+int         mre_abi_version(void);
+/* 0 when a CUDA device with compute capability 10.x is visible, MRE_ERR_CUDA otherwise */
+int         mre_device_ok(int device);
+
+/* --------------------------------------------------------------------------------------------- index */
+/*
+ * Build the index from id triples given as (h, t, r) column arrays in host memory (the column order of
+ * OpenKE's *2id.txt files, OpenKE/README.md:126-141).  Restates importTrainFiles (Reader.h:53-160:
+ * de-dup, (h,r,t) and (t,r,h) orders, tph/hpt) and importTestFiles (Reader.h:167-257: the all-splits
+ * membership list, test/valid sorted by (r,h,t)).  Host-only; no device needed.
+ */
+int mre_index_create(int64_t E, int64_t R,
+                     const int64_t *train_h, const int64_t *train_t, const int64_t *train_r, int64_t n_train,
+                     const int64_t *valid_h, const int64_t *valid_t, const int64_t *valid_r, int64_t n_valid,
+                     const int64_t *test_h, const int64_t *test_t, const int64_t *test_r, int64_t n_test,
+                     mre_index **out);
+/* Same, reading entity2id.txt / relation2id.txt / {train,valid,test}2id.txt under `in_path`
+ * (setInPath + importTrainFiles + importTestFiles, Setting.h:17-27, Reader.h:53-257).
+ * valid2id.txt / test2id.txt may be absent (training-only use). */
+int mre_index_create_from_dir(const char *in_path, mre_index **out);
+void mre_index_destroy(mre_index *ix);
+/* upload the filter / sampler tables to `device` (idempotent) */
+int mre_index_to_device(mre_index *ix, int device);
+int64_t mre_index_total(const mre_index *ix, int which);
+int mre_index_get_split(const mre_index *ix, int split, int64_t *h, int64_t *t, int64_t *r);
+/* left_mean = tph, right_mean = hpt per relation (Reader.h:142-159) */
+int mre_index_get_means(const mre_index *ix, float *tph, float *hpt);
+/* 1 when (h,r,t) is in train+valid+test: _find, Corrupt.h:166-177 (host) */
+int mre_index_find(const mre_index *ix, int64_t h, int64_t t, int64_t r);
+
+/* ----------------------------------------------------------------------------------------- workspace */
+int  mre_ctx_create(int device, mre_ctx **out);
+void mre_ctx_destroy(mre_ctx *ctx);
+int  mre_ctx_sm_count(const mre_ctx *ctx);
+/* number of kernels this library has launched through `ctx` since creation (bench.py gpu_launches) */
+int64_t mre_ctx_launch_count(const mre_ctx *ctx);
+
+/* ------------------------------------------------------------------------------------------- ranking */
+/*
+ * One ranking job: Q queries, each ranked against a candidate set, fused score + compare + count.
+ * Replaces, per query, Model.predict (TransE.py:88-94 / DistMult.py:70-72 / ComplEx.py:60-61) +
+ * getHeadBatch/getTailBatch (Test.h:36-53) + testHead/testTail (Test.h:65-192); with candidate groups
+ * it replaces main.evaluate's per-triple candidate loop (main.py:230-250).
+ */
+typedef struct mre_rank_job {
+    /* embedding tables, device, row-major [rows, D], row stride = D floats */
+    const float *ent;        /* [E, D]   ent_embeddings / ent_re_embeddings */
+    const float *rel;        /* [R, D]   rel_embeddings / rel_re_embeddings */
+    const float *ent_im;     /* [E, D]   ComplEx only (ent_im_embeddings) */
+    const float *rel_im;     /* [R, D]   ComplEx only */
+    int64_t E, R, D;
+    int32_t scorer;          /* MRE_TRANSE | MRE_DISTMULT | MRE_COMPLEX */
+    int32_t p_norm;          /* TransE: 1 or 2 (TransE.py:10,59) */
+    int32_t normalize;       /* TransE norm_flag (TransE.py:47-50): L2-normalise h, r, t rows first */
+    int32_t filter;          /* MRE_FILTER_* */
+    /* queries, device int64 [Q]; q_side NULL => every query uses `side` */
+    const int64_t *q_h, *q_t, *q_r;
+    const uint8_t *q_side;
+    int32_t side;
+    int32_t n_groups;        /* 0 => one group: every query ranks against all E entities */
+    int64_t Q;
+    /* candidate groups (n_groups > 0): queries must be ordered by group.
+     * group_qptr / group_cptr are HOST int64 [n_groups+1] prefix arrays; cand_idx is a DEVICE int64 array
+     * of entity ids, each group's slice sorted ascending without duplicates. */
+    const int64_t *group_qptr;
+    const int64_t *group_cptr;
+    const int64_t *cand_idx;
+    /* MRE_FILTER_CSR: device int64 prefix [Q+1] and entity ids; entries outside the query's candidate
+     * group are ignored; the true entity is always excluded from the filtered counts. */
+    const int64_t *filt_ptr;
+    const int64_t *filt_idx;
+    /* output, device int32 [4][Q]: raw_lt, raw_eq, filt_lt, filt_eq
+     *   raw_lt  = #{j in S_q : s_j <  s_true}          raw_eq  = #{j in S_q : s_j == s_true}
+     *   filt_*  = the same over S_q minus known-true entities minus the true entity itself
+     * OpenKE's l_s / l_filter_s (Test.h:80-87) are raw_lt / filt_lt. */
+    int32_t *counts;
+} mre_rank_job;
+
+/* asynchronous on `stream`; `ix` may be NULL unless filter == MRE_FILTER_INDEX */
+int mre_rank(mre_ctx *ctx, const mre_index *ix, const mre_rank_job *job, void *stream);
+
+/*
+ * End-to-end variant for callers holding HOST query arrays (the reference's loaders yield numpy arrays,
+ * Tester.py:62-68): q_h/q_t/q_r/q_side and counts in `job` are HOST pointers (cand_idx, filt_*, tables
+ * stay device).  Copies queries in through pinned staging, ranks, copies counts back, synchronises.
+ */
+int mre_rank_host(mre_ctx *ctx, const mre_index *ix, const mre_rank_job *job, void *stream);
+
+/*
+ * Materialised 1-vs-all scores for ONE query (Model.predict's float32[E] vector), for drop-in callers that
+ * still want the score vector and for tests.  scores_out: device float32 [E].
+ */
+int mre_predict(mre_ctx *ctx, const mre_rank_job *job, int64_t query, float *scores_out, void *stream);
+
+/*
+ * Metric sums from counts (test_link_prediction, Test.h:232-277, without the printf table; the paper's
+ * main.py:263-272 and zsl_module.py:707-745 summaries).  counts: device int32 [4][Q]; q_side as in the job.
+ * sums_out: device int64 [2][8] per side s: {n, sum_rank, hits@1, hits@3, hits@5, hits@10, 0, 0} for the
+ * FILTERED rank and rr_out: device double [2] sum of 1/rank, reduced in a fixed order (deterministic).
+ * raw != 0 => use the raw counts instead of the filtered ones.  hist (nullable): device int64 [hist_len],
+ * hist[k] += #queries with rank k (k clipped to hist_len-1): the integer form combined across GPUs by allreduce.
+ */
+int mre_metrics(mre_ctx *ctx, const int32_t *counts, const uint8_t *q_side, int32_t side, int64_t Q,
+                int32_t rank_mode, int32_t raw, int64_t *sums_out, double *rr_out,
+                int64_t *hist, int64_t hist_len, void *stream);
+
+/* ------------------------------------------------------------------------------------------ sampling */
+/*
+ * One training batch of B positives + B*neg Bernoulli-corrupted negatives, layout [B pos | neg blocks of B]
+ * (row b's k-th negative at b + (k+1)*B): sampling / getBatch, Base.cpp:78-197, with corrupt_head /
+ * corrupt_tail (Corrupt.h:7-83) and the tph/hpt rule (Base.cpp:101-122).  The reference's per-thread LCG
+ * (Random.h:11-29) is replaced by counter-based Philox4x32-10:
+ *   key = (seed_lo, seed_hi); ctr = (row b, slot, step_lo, (step_hi & 0xffff) | stream_id << 16)
+ *   slot 0: positive index = (x1:x0) % trainTotal;  slot k+1: keep_head = float(x0 % 1000) < prob_r, draw word (x2:x1)
+ * mode: 0 normal (Bernoulli), -1 always corrupt head ("head_batch"), 1 always corrupt tail (Base.cpp:125-137).
+ * Outputs are device arrays of length B*(1+neg): int64 h, t, r and float32 y (+1 / -1).
+ */
+int mre_sample(mre_ctx *ctx, const mre_index *ix, uint64_t seed, uint64_t step, uint32_t stream_id,
+               int64_t B, int64_t neg, int32_t mode, int32_t bern,
+               int64_t *h, int64_t *t, int64_t *r, float *y, void *stream);
+/* same with HOST output arrays (what TrainDataLoader hands out); synchronous */
+int mre_sample_host(mre_ctx *ctx, const mre_index *ix, uint64_t seed, uint64_t step, uint32_t stream_id,
+                    int64_t B, int64_t neg, int32_t mode, int32_t bern,
+                    int64_t *h, int64_t *t, int64_t *r, float *y, void *stream);
+
+/* ------------------------------------------------------------------------------------------ training */
+/*
+ * Fused TransE margin-loss step, forward + backward, on one sampled batch (n = B*(1+neg) triples):
+ *   score = || h^ + r^ - t^ ||_p  (TransE.py:46-74), p = score[:B], n[b,k] = score[B + k*B + b]
+ *   (strategy/NegativeSampling.py:13-21), loss = mean max(p - n, -margin) + margin (MarginLoss.py:24-28).
+ * Accumulates dLoss/d(ent) into grad_ent [E,D] and dLoss/d(rel) into grad_rel [R,D] (caller zeroes them),
+ * writes the scalar loss to loss_out[0] and, if scores_out != NULL, the n scores.  All pointers device.
+ */
+int mre_transe_margin_step(mre_ctx *ctx, const float *ent, const float *rel, int64_t E, int64_t R, int64_t D,
+                           const int64_t *h, const int64_t *t, const int64_t *r, int64_t B, int64_t neg,
+                           float margin, int32_t p_norm, int32_t normalize,
+                           float *grad_ent, float *grad_rel, float *loss_out, float *scores_out, void *stream);
+/* w -= lr * g (torch.optim.SGD as Trainer.py:73-78 configures it), then g = 0; device arrays of n floats */
+int mre_sgd_update(mre_ctx *ctx, float *w, float *g, int64_t n, float lr, void *stream);
+
+/* ------------------------------------------------------------------------------------------- probes */
+/* FP32 FADD issue-rate microbenchmark: returns lane-ops per second in *lane_ops_per_s (the TransE roofline
+ * denominator) and the SM clock-independent instruction count used. Synchronous. */
+int mre_probe_fp32_peak(mre_ctx *ctx, double *lane_ops_per_s);
+/* TF32 tcgen05 dense MMA microbenchmark: flops per second (the DistMult/ComplEx roofline denominator) */
+int mre_probe_tf32_peak(mre_ctx *ctx, double *flops_per_s);
+/* Per-launch device timing of the dominant kernel (the fused score+rank kernel of mre_rank / mre_rank_host, or the
+ * train-step kernel): while enabled, every such launch is bracketed by a CUDA event pair recorded on the launching
+ * stream.  mre_ctx_timing_read synchronises, returns the summed duration and the number of launches since the
+ * last read, and resets both (bench.py's roofline leg). */
+int mre_ctx_timing(mre_ctx *ctx, int32_t enable);
+int mre_ctx_timing_read(mre_ctx *ctx, double *total_ms, int64_t *n_launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MRE_B200_H */

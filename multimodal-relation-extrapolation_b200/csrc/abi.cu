@@ -1,0 +1,224 @@
+// extern "C" entry points of libmre_b200.so that dispatch to the kernels (see include/mre_b200.h), the
+// host-buffer (end-to-end) variants, per-launch timing and the FP32 issue-rate probe.
+#include <algorithm>
+
+#include "common.h"
+
+int mre_ctx::time_begin(cudaStream_t st) {
+    if (!timing) return MRE_OK;
+    if (ev_used + 2 > ev_pool.size()) {
+        for (int i = 0; i < 2; i++) {
+            cudaEvent_t e;
+            MRE_CUDA(cudaEventCreate(&e));
+            ev_pool.push_back(e);
+        }
+    }
+    MRE_CUDA(cudaEventRecord(ev_pool[ev_used], st));
+    return MRE_OK;
+}
+int mre_ctx::time_end(cudaStream_t st) {
+    if (!timing) return MRE_OK;
+    MRE_CUDA(cudaEventRecord(ev_pool[ev_used + 1], st));
+    ev_used += 2;
+    return MRE_OK;
+}
+
+namespace mre {
+
+static int check_job(const mre_rank_job *job) {
+    MRE_CHECK_ARG(job != nullptr, "job is NULL");
+    MRE_CHECK_ARG(job->E > 0 && job->R > 0 && job->D > 0, "E, R, D must be positive");
+    MRE_CHECK_ARG(job->Q >= 0, "Q must be non-negative");
+    MRE_CHECK_ARG(job->E < (1LL << 31) && job->Q < (1LL << 31), "E and Q must fit int32 counts");
+    MRE_CHECK_ARG(job->ent && job->rel, "ent / rel table is NULL");
+    MRE_CHECK_ARG(job->scorer >= MRE_TRANSE && job->scorer <= MRE_COMPLEX, "unknown scorer %d", job->scorer);
+    MRE_CHECK_ARG(job->scorer != MRE_COMPLEX || (job->ent_im && job->rel_im), "ComplEx needs ent_im and rel_im");
+    MRE_CHECK_ARG(job->filter >= MRE_FILTER_NONE && job->filter <= MRE_FILTER_CSR, "unknown filter %d", job->filter);
+    MRE_CHECK_ARG(job->side == 0 || job->side == 1, "side must be 0 or 1");
+    MRE_CHECK_ARG(job->Q == 0 || (job->q_h && job->q_t && job->q_r), "query arrays are NULL");
+    MRE_CHECK_ARG(job->Q == 0 || job->counts, "counts is NULL");
+    return MRE_OK;
+}
+
+static int dispatch_rank(mre_ctx *ctx, const mre_index *ix, const mre_rank_job *job, cudaStream_t st) {
+    if (job->scorer == MRE_TRANSE) return rank_transe(ctx, ix, job, st);
+    return rank_bilinear(ctx, ix, job, st);
+}
+
+// -------------------------------------------------------------------------------- FP32 FADD issue-rate probe
+constexpr int PROBE_ACC = 8;
+__global__ void __launch_bounds__(256) fadd_probe_kernel(float *out, int iters, float c) {
+    float a[PROBE_ACC];
+#pragma unroll
+    for (int i = 0; i < PROBE_ACC; i++) a[i] = (float)(threadIdx.x + i);
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+#pragma unroll
+            for (int i = 0; i < PROBE_ACC; i++) asm volatile("add.f32 %0, %0, %1;" : "+f"(a[i]) : "f"(c));
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < PROBE_ACC; i++) s += a[i];
+    if (s == 12345.678f) out[0] = s;  // never true in practice; keeps the chain live
+}
+
+int probe_fp32_peak(mre_ctx *ctx, double *lane_ops_per_s) {
+    MRE_CHECK_ARG(lane_ops_per_s != nullptr, "NULL output");
+    MRE_TRY(ctx->misc.reserve(256));
+    const int iters = 4096, blocks = ctx->sm_count * 8, threads = 256;
+    double best = 0;
+    for (int rep = 0; rep < 5; rep++) {
+        MRE_CUDA(cudaEventRecord(ctx->ev0, 0));
+        fadd_probe_kernel<<<blocks, threads>>>(ctx->misc.as<float>(), iters, 1e-7f);
+        MRE_CUDA(cudaEventRecord(ctx->ev1, 0));
+        MRE_CUDA(cudaEventSynchronize(ctx->ev1));
+        float ms = 0;
+        MRE_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        double ops = (double)blocks * threads * iters * 8.0 * PROBE_ACC;
+        if (rep > 0) best = std::max(best, ops / (ms * 1e-3));
+    }
+    ctx->launches += 5;
+    *lane_ops_per_s = best;
+    return MRE_OK;
+}
+
+}  // namespace mre
+
+using namespace mre;
+
+extern "C" {
+
+int mre_rank(mre_ctx *ctx, const mre_index *ix, const mre_rank_job *job, void *stream) {
+    MRE_CHECK_ARG(ctx != nullptr, "ctx is NULL");
+    MRE_TRY(check_job(job));
+    MRE_CUDA(cudaSetDevice(ctx->device));
+    return dispatch_rank(ctx, ix, job, (cudaStream_t)stream);
+}
+
+int mre_rank_host(mre_ctx *ctx, const mre_index *ix, const mre_rank_job *job, void *stream) {
+    MRE_CHECK_ARG(ctx != nullptr, "ctx is NULL");
+    MRE_TRY(check_job(job));
+    MRE_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t Q = job->Q;
+    if (Q == 0) return MRE_OK;
+    // device staging: [h | t | r] int64, counts int32 [4][Q], side bytes
+    const size_t ids = (size_t)Q * sizeof(int64_t);
+    const size_t cnt = (size_t)4 * Q * sizeof(int32_t);
+    MRE_TRY(ctx->stage_dev.reserve(3 * ids + cnt + (size_t)Q));
+    char *base = ctx->stage_dev.as<char>();
+    int64_t *d_h = (int64_t *)base, *d_t = d_h + Q, *d_r = d_t + Q;
+    int32_t *d_counts = (int32_t *)(base + 3 * ids);
+    uint8_t *d_side = (uint8_t *)(base + 3 * ids + cnt);
+    MRE_CUDA(cudaMemcpyAsync(d_h, job->q_h, ids, cudaMemcpyHostToDevice, st));
+    MRE_CUDA(cudaMemcpyAsync(d_t, job->q_t, ids, cudaMemcpyHostToDevice, st));
+    MRE_CUDA(cudaMemcpyAsync(d_r, job->q_r, ids, cudaMemcpyHostToDevice, st));
+    if (job->q_side) MRE_CUDA(cudaMemcpyAsync(d_side, job->q_side, (size_t)Q, cudaMemcpyHostToDevice, st));
+    mre_rank_job dev = *job;
+    dev.q_h = d_h; dev.q_t = d_t; dev.q_r = d_r;
+    dev.q_side = job->q_side ? d_side : nullptr;
+    dev.counts = d_counts;
+    MRE_TRY(dispatch_rank(ctx, ix, &dev, st));
+    MRE_CUDA(cudaMemcpyAsync(job->counts, d_counts, cnt, cudaMemcpyDeviceToHost, st));
+    MRE_CUDA(cudaStreamSynchronize(st));
+    return MRE_OK;
+}
+
+int mre_predict(mre_ctx *ctx, const mre_rank_job *job, int64_t query, float *scores_out, void *stream) {
+    MRE_CHECK_ARG(ctx != nullptr && scores_out != nullptr, "NULL argument");
+    mre_rank_job j = *job;
+    int32_t dummy = 0;
+    if (!j.counts) j.counts = &dummy;  // unused by predict; keeps check_job happy
+    MRE_TRY(check_job(&j));
+    MRE_CHECK_ARG(query >= 0 && query < job->Q, "query %lld out of range", (long long)query);
+    MRE_CUDA(cudaSetDevice(ctx->device));
+    if (job->scorer == MRE_TRANSE) return predict_transe(ctx, job, query, scores_out, (cudaStream_t)stream);
+    return predict_bilinear(ctx, job, query, scores_out, (cudaStream_t)stream);
+}
+
+int mre_metrics(mre_ctx *ctx, const int32_t *counts, const uint8_t *q_side, int32_t side, int64_t Q, int32_t rank_mode,
+                int32_t raw, int64_t *sums_out, double *rr_out, int64_t *hist, int64_t hist_len, void *stream) {
+    MRE_CHECK_ARG(ctx != nullptr, "ctx is NULL");
+    MRE_CUDA(cudaSetDevice(ctx->device));
+    return metrics(ctx, counts, q_side, side, Q, rank_mode, raw, sums_out, rr_out, hist, hist_len, (cudaStream_t)stream);
+}
+
+int mre_sample(mre_ctx *ctx, const mre_index *ix, uint64_t seed, uint64_t step, uint32_t stream_id, int64_t B, int64_t neg,
+               int32_t mode, int32_t bern, int64_t *h, int64_t *t, int64_t *r, float *y, void *stream) {
+    MRE_CHECK_ARG(ctx != nullptr, "ctx is NULL");
+    MRE_CUDA(cudaSetDevice(ctx->device));
+    return sample(ctx, ix, seed, step, stream_id, B, neg, mode, bern, h, t, r, y, (cudaStream_t)stream);
+}
+
+int mre_sample_host(mre_ctx *ctx, const mre_index *ix, uint64_t seed, uint64_t step, uint32_t stream_id, int64_t B,
+                    int64_t neg, int32_t mode, int32_t bern, int64_t *h, int64_t *t, int64_t *r, float *y, void *stream) {
+    MRE_CHECK_ARG(ctx != nullptr, "ctx is NULL");
+    MRE_CHECK_ARG(B > 0 && neg >= 0, "B must be positive and neg non-negative");
+    MRE_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t n = (size_t)B * (size_t)(1 + neg);
+    MRE_TRY(ctx->stage_dev.reserve(n * (3 * sizeof(int64_t) + sizeof(float))));
+    int64_t *dh = ctx->stage_dev.as<int64_t>(), *dt = dh + n, *dr = dt + n;
+    float *dy = (float *)(dr + n);
+    MRE_TRY(sample(ctx, ix, seed, step, stream_id, B, neg, mode, bern, dh, dt, dr, dy, st));
+    MRE_CUDA(cudaMemcpyAsync(h, dh, n * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    MRE_CUDA(cudaMemcpyAsync(t, dt, n * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    MRE_CUDA(cudaMemcpyAsync(r, dr, n * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    MRE_CUDA(cudaMemcpyAsync(y, dy, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+    MRE_CUDA(cudaStreamSynchronize(st));
+    return MRE_OK;
+}
+
+int mre_transe_margin_step(mre_ctx *ctx, const float *ent, const float *rel, int64_t E, int64_t R, int64_t D, const int64_t *h,
+                           const int64_t *t, const int64_t *r, int64_t B, int64_t neg, float margin, int32_t p_norm,
+                           int32_t normalize, float *grad_ent, float *grad_rel, float *loss_out, float *scores_out,
+                           void *stream) {
+    MRE_CHECK_ARG(ctx != nullptr, "ctx is NULL");
+    MRE_CUDA(cudaSetDevice(ctx->device));
+    return transe_margin_step(ctx, ent, rel, E, R, D, h, t, r, B, neg, margin, p_norm, normalize, grad_ent, grad_rel, loss_out,
+                              scores_out, (cudaStream_t)stream);
+}
+
+int mre_sgd_update(mre_ctx *ctx, float *w, float *g, int64_t n, float lr, void *stream) {
+    MRE_CHECK_ARG(ctx != nullptr, "ctx is NULL");
+    MRE_CUDA(cudaSetDevice(ctx->device));
+    return sgd_update(ctx, w, g, n, lr, (cudaStream_t)stream);
+}
+
+int mre_probe_fp32_peak(mre_ctx *ctx, double *lane_ops_per_s) {
+    MRE_CHECK_ARG(ctx != nullptr, "ctx is NULL");
+    MRE_CUDA(cudaSetDevice(ctx->device));
+    return probe_fp32_peak(ctx, lane_ops_per_s);
+}
+
+int mre_probe_tf32_peak(mre_ctx *ctx, double *flops_per_s) {
+    MRE_CHECK_ARG(ctx != nullptr, "ctx is NULL");
+    MRE_CUDA(cudaSetDevice(ctx->device));
+    return probe_tf32_peak(ctx, flops_per_s);
+}
+
+int mre_ctx_timing(mre_ctx *ctx, int32_t enable) {
+    MRE_CHECK_ARG(ctx != nullptr, "ctx is NULL");
+    ctx->timing = enable != 0;
+    return MRE_OK;
+}
+
+int mre_ctx_timing_read(mre_ctx *ctx, double *total_ms, int64_t *n_launches) {
+    MRE_CHECK_ARG(ctx && total_ms && n_launches, "NULL argument");
+    MRE_CUDA(cudaSetDevice(ctx->device));
+    double total = 0;
+    for (size_t i = 0; i + 1 < ctx->ev_used; i += 2) {
+        MRE_CUDA(cudaEventSynchronize(ctx->ev_pool[i + 1]));
+        float ms = 0;
+        MRE_CUDA(cudaEventElapsedTime(&ms, ctx->ev_pool[i], ctx->ev_pool[i + 1]));
+        total += ms;
+    }
+    *total_ms = total;
+    *n_launches = (int64_t)(ctx->ev_used / 2);
+    ctx->ev_used = 0;
+    return MRE_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,74 @@
+// Device-side helpers shared by the kernels: mbarrier / bulk-copy (TMA unit) PTX wrappers, searches, Philox.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mre {
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+// TMA-unit bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP).
+// src and dst 16-byte aligned, bytes a multiple of 16.
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
+// first index in [lo, hi) with a[i] >= key
+__device__ __forceinline__ int64_t lower_bound_i64(const int64_t *__restrict__ a, int64_t lo, int64_t hi, int64_t key) {
+    while (lo < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        if (__ldg(a + mid) < key) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+__device__ __forceinline__ bool contains_i64(const int64_t *__restrict__ a, int64_t lo, int64_t hi, int64_t key) {
+    int64_t p = lower_bound_i64(a, lo, hi, key);
+    return p < hi && __ldg(a + p) == key;
+}
+
+// Philox4x32-10 (Salmon et al., SC'11); same constants and round order as oracle/kge_oracle.c:orc_philox4x32_10.
+struct Philox4 {
+    uint32_t x[4];
+};
+__host__ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                                          uint32_t k1) {
+#pragma unroll
+    for (int round = 0; round < 10; round++) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    Philox4 o;
+    o.x[0] = c0; o.x[1] = c1; o.x[2] = c2; o.x[3] = c3;
+    return o;
+}
+
+}  // namespace mre

@@ -1,0 +1,74 @@
+// Rank -> metric sums.
+//
+// Reference path replaced (paths relative to /root/reference):
+//   OpenKE/openke/base/Test.h:102-112,166-177  per-query Hits@10/3/1, rank and reciprocal-rank accumulation
+//   OpenKE/openke/base/Test.h:232-277          test_link_prediction: divide by testTotal, average head and tail
+//   main.py:263-272, module/zsl_module.py:707-745  the paper's Hits@1/3/10 and Hits@10/5/1 + MRR summaries
+// The reference accumulates in float32 globals (Test.h:13-20), which loses integer exactness past 2^24; here every
+// sum is an int64 and the reciprocal-rank sum is a float64 reduced in a FIXED order by a single CTA, so the result
+// is deterministic.  The optional rank histogram is the all-integer form that is summed across GPUs.
+#include "common.h"
+
+namespace mre {
+
+constexpr int MET_THREADS = 1024;
+
+__global__ void __launch_bounds__(MET_THREADS) metrics_kernel(const int32_t *__restrict__ counts, const uint8_t *__restrict__ q_side,
+                                                              int side, int64_t Q, int rank_mode, int raw,
+                                                              int64_t *__restrict__ sums_out, double *__restrict__ rr_out,
+                                                              unsigned long long *__restrict__ hist, int64_t hist_len) {
+    __shared__ long long s_int[MET_THREADS];
+    __shared__ double s_rr[MET_THREADS];
+    const int32_t *lt = counts + (raw ? 0 : 2) * Q;
+    const int32_t *eq = counts + (raw ? 1 : 3) * Q;
+    long long acc[2][6] = {{0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0}};
+    double rr[2] = {0.0, 0.0};
+    for (int64_t q = threadIdx.x; q < Q; q += MET_THREADS) {
+        const int s = q_side ? (int)q_side[q] : side;
+        long long a = max(lt[q], 0), e = max(eq[q], 0);
+        long long rank = a + 1;
+        if (rank_mode == MRE_RANK_TIES_HALF) rank += e / 2;
+        else if (rank_mode == MRE_RANK_PESSIMISTIC) rank += e;
+        acc[s][0] += 1;
+        acc[s][1] += rank;
+        acc[s][2] += rank <= 1;
+        acc[s][3] += rank <= 3;
+        acc[s][4] += rank <= 5;
+        acc[s][5] += rank <= 10;
+        rr[s] += 1.0 / (double)rank;
+        if (hist) atomicAdd(hist + min((long long)hist_len - 1, rank), 1ull);
+    }
+    for (int s = 0; s < 2; s++) {
+        for (int k = 0; k < 7; k++) {
+            if (k < 6) s_int[threadIdx.x] = acc[s][k]; else s_rr[threadIdx.x] = rr[s];
+            __syncthreads();
+            for (int w = MET_THREADS / 2; w > 0; w >>= 1) {
+                if (threadIdx.x < w) {
+                    if (k < 6) s_int[threadIdx.x] += s_int[threadIdx.x + w];
+                    else s_rr[threadIdx.x] += s_rr[threadIdx.x + w];
+                }
+                __syncthreads();
+            }
+            if (threadIdx.x == 0) {
+                if (k < 6) sums_out[s * 8 + k] = s_int[0]; else rr_out[s] = s_rr[0];
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) { sums_out[s * 8 + 6] = 0; sums_out[s * 8 + 7] = 0; }
+    }
+}
+
+int metrics(mre_ctx *ctx, const int32_t *counts, const uint8_t *q_side, int32_t side, int64_t Q, int32_t rank_mode,
+            int32_t raw, int64_t *sums_out, double *rr_out, int64_t *hist, int64_t hist_len, cudaStream_t st) {
+    MRE_CHECK_ARG(counts && sums_out && rr_out, "NULL argument");
+    MRE_CHECK_ARG(rank_mode >= MRE_RANK_STRICT && rank_mode <= MRE_RANK_PESSIMISTIC, "unknown rank_mode %d", rank_mode);
+    MRE_CHECK_ARG(hist == nullptr || hist_len >= 2, "hist_len must be >= 2");
+    MRE_CHECK_ARG(side == 0 || side == 1, "side must be 0 or 1");
+    metrics_kernel<<<1, MET_THREADS, 0, st>>>(counts, q_side, side, Q, rank_mode, raw, sums_out, rr_out,
+                                              reinterpret_cast<unsigned long long *>(hist), hist_len);
+    ctx->launches += 1;
+    MRE_CUDA(cudaGetLastError());
+    return MRE_OK;
+}
+
+}  // namespace mre

@@ -1,0 +1,97 @@
+// Counter-based Philox Bernoulli negative sampler.
+//
+// Reference path replaced (paths relative to /root/reference):
+//   OpenKE/openke/base/Base.cpp:78-159   getBatch: positive draw, tph/hpt Bernoulli choice, batch layout
+//   OpenKE/openke/base/Base.cpp:161-197  sampling: pthread fan-out over row slices
+//   OpenKE/openke/base/Corrupt.h:7-83    corrupt_head / corrupt_tail: exact-uniform draw outside the true set
+//   OpenKE/openke/base/Random.h:11-29    per-thread LCG  (replaced by Philox4x32-10, see include/mre_b200.h)
+// The reference walks rows sequentially per pthread because its LCG is a serial stream.  A counter-based
+// generator makes every output slot independent: one GPU thread per slot (positive or negative), addressed as
+// (row b, slot k), so writes are coalesced along b exactly in the reference's [B pos | neg blocks of B] layout.
+// The filtered draw keeps the reference's order-statistic skip (no rejection loop => no divergence tail, and
+// never a train triple), with the (entity, relation) run located by two lower_bounds on a packed key column.
+#include <algorithm>
+
+#include "common.h"
+#include "device_utils.cuh"
+
+namespace mre {
+
+struct SamplerTables {
+    const int64_t *tr_h, *tr_r, *tr_t;  // trainList columns
+    const int64_t *hr_key;              // h*R + r, sorted; payload tr_t
+    const int64_t *tr_key, *tr_val;     // t*R + r, sorted; payload heads
+    const float *bern_prob;
+    int64_t n_train, E, R;
+};
+
+// tmp-th entity NOT in the sorted run vals[ll..rr] (Corrupt.h:25-43 / 64-82)
+__device__ __forceinline__ int64_t skip_draw(const int64_t *__restrict__ vals, int64_t ll, int64_t rr, int64_t E, uint64_t word,
+                                             int64_t fallback) {
+    const int64_t k = rr - ll + 1;
+    if (E - k <= 0) return fallback;  // every entity completes a train triple: the reference would divide by zero
+    const int64_t tmp = (int64_t)(word % (uint64_t)(E - k));
+    if (tmp < __ldg(vals + ll)) return tmp;
+    if (tmp > __ldg(vals + rr) - k) return tmp + k;
+    int64_t lo = ll, hi = rr + 1;
+    while (lo + 1 < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        if (__ldg(vals + mid) - (mid - ll) - 1 < tmp) lo = mid; else hi = mid;
+    }
+    return tmp + (lo - ll) + 1;
+}
+
+__global__ void __launch_bounds__(256) sample_kernel(const SamplerTables T, uint32_t k0, uint32_t k1, uint32_t c2, uint32_t c3,
+                                                     int64_t B, int64_t neg, int mode, int bern, int64_t *__restrict__ bh,
+                                                     int64_t *__restrict__ bt, int64_t *__restrict__ br, float *__restrict__ by) {
+    const int64_t n = B * (1 + neg);
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t k = idx / B, b = idx - k * B;
+        Philox4 x = philox4x32_10((uint32_t)b, 0u, c2, c3, k0, k1);
+        const int64_t i = (int64_t)((((uint64_t)x.x[1] << 32) | x.x[0]) % (uint64_t)T.n_train);
+        int64_t h = __ldg(T.tr_h + i), r = __ldg(T.tr_r + i), t = __ldg(T.tr_t + i);
+        float y = 1.f;
+        if (k > 0) {
+            x = philox4x32_10((uint32_t)b, (uint32_t)k, c2, c3, k0, k1);
+            const uint64_t word = ((uint64_t)x.x[2] << 32) | x.x[1];
+            const float prob = bern ? __ldg(T.bern_prob + r) : 500.0f;
+            const bool keep_head = mode == 0 ? ((float)(x.x[0] % 1000u) < prob) : (mode != -1);
+            if (keep_head) {
+                const int64_t key = h * T.R + r;
+                const int64_t ll = lower_bound_i64(T.hr_key, 0, T.n_train, key);
+                const int64_t rr = lower_bound_i64(T.hr_key, ll, T.n_train, key + 1) - 1;
+                t = skip_draw(T.tr_t, ll, rr, T.E, word, t);
+            } else {
+                const int64_t key = t * T.R + r;
+                const int64_t ll = lower_bound_i64(T.tr_key, 0, T.n_train, key);
+                const int64_t rr = lower_bound_i64(T.tr_key, ll, T.n_train, key + 1) - 1;
+                h = skip_draw(T.tr_val, ll, rr, T.E, word, h);
+            }
+            y = -1.f;
+        }
+        bh[idx] = h; bt[idx] = t; br[idx] = r; by[idx] = y;
+    }
+}
+
+int sample(mre_ctx *ctx, const mre_index *ix, uint64_t seed, uint64_t step, uint32_t stream_id, int64_t B, int64_t neg,
+           int32_t mode, int32_t bern, int64_t *h, int64_t *t, int64_t *r, float *y, cudaStream_t st) {
+    MRE_CHECK_ARG(ix != nullptr, "index is NULL");
+    MRE_CHECK_ARG(ix->device == ctx->device, "index is not on device %d (call mre_index_to_device)", ctx->device);
+    MRE_CHECK_ARG(B > 0 && neg >= 0, "B must be positive and neg non-negative");
+    MRE_CHECK_ARG(B <= 0xffffffffLL && neg < 0xffffffffLL, "B and neg must fit the 32-bit Philox counter words");
+    MRE_CHECK_ARG(stream_id < 65536u, "stream_id must be < 65536");
+    MRE_CHECK_ARG(mode >= -1 && mode <= 1, "mode must be -1, 0 or 1");
+    MRE_CHECK_ARG(ix->n_train > 0, "the index holds no train triples");
+    MRE_CHECK_ARG(h && t && r && y, "NULL output");
+    SamplerTables T{ix->d_tr_h, ix->d_tr_r, ix->d_tr_t, ix->d_tr_hr_key, ix->d_tr_tr_key, ix->d_tr_tr_val, ix->d_bern_prob,
+                    ix->n_train, ix->E, ix->R};
+    const uint32_t c2 = (uint32_t)step, c3 = ((uint32_t)(step >> 32) & 0xffffu) | (stream_id << 16);
+    const int64_t n = B * (1 + neg);
+    const int grid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)ctx->sm_count * 8);
+    sample_kernel<<<grid, 256, 0, st>>>(T, (uint32_t)seed, (uint32_t)(seed >> 32), c2, c3, B, neg, mode, bern, h, t, r, y);
+    ctx->launches += 1;
+    MRE_CUDA(cudaGetLastError());
+    return MRE_OK;
+}
+
+}  // namespace mre

@@ -1,0 +1,458 @@
+// TransE L1/L2 fused score + rank for sm_100a.
+//
+// Reference path replaced (paths relative to /root/reference):
+//   OpenKE/openke/module/model/TransE.py:46-60   _calc: optional F.normalize, h + (r - t) | (h + r) - t, ||.||_p
+//   OpenKE/openke/module/model/TransE.py:88-94   predict -> host float32[E] per query
+//   module/NegativeSampling.py:142-157,294-305   the paper's scorer/evaluate (p = 1, no normalisation)
+//   OpenKE/openke/base/Test.h:65-192             testHead / testTail: E-long compare loop + _find per hit
+//   main.py:245-250                              candidate-list rank with ties//2
+//
+// Design.  The query x entity score matrix is never written.  A pre-pass turns every query into one FP32
+// vector  v_q  such that |v_q[d] - e_j[d]| is bit-identical to the reference's element (tail: v = h + r;
+// head: v = -(r - t), because e + (r - t) == -(v - e) exactly), and computes s_true with the SAME sequential-d
+// accumulation the tile kernel uses, so `s_j < s_true` is decided on identical bits for every j.
+// The main kernel is persistent: each CTA walks 128-query x 128-entity work items; a rotating producer warp streams
+// 128-byte row chunks of both operands into a 3-stage shared-memory ring with TMA-unit bulk copies
+// (cp.async.bulk + mbarrier complete_tx; entity rows may be gathered through a candidate list), the eight
+// warps hold an 8x8 register micro-tile per thread and read the ring with conflict-free 128-bit LDS.  The
+// epilogue compares the 64 accumulators against the per-query thresholds, reduces the counts with warp
+// shuffles and adds them to the per-query counters.  After its tiles a CTA runs the known-true correction
+// (rank_common.cuh) with warp ballot/popc.  The kernel is bound by the FP32 pipe: 2 lane-ops per (q, e, d).
+#include <math.h>
+
+#include <vector>
+
+#include "common.h"
+#include "rank_common.cuh"
+
+namespace mre {
+
+constexpr int CHUNK = 32;            // floats of D per pipeline stage (128 B per row)
+constexpr int ROW_STRIDE = 36;       // smem row stride in floats: 144 B => 8 consecutive rows hit 8 distinct 16-B bank groups
+constexpr int STAGES = 3;
+constexpr int CONSUMER_WARPS = 8;
+constexpr int RANK_THREADS = CONSUMER_WARPS * 32;
+constexpr int STAGE_FLOATS = (TILE_Q + TILE_E) * ROW_STRIDE;
+constexpr size_t RANK_SMEM = (size_t)STAGES * STAGE_FLOATS * sizeof(float) + 2 * STAGES * sizeof(uint64_t);
+
+// ------------------------------------------------------------------------------------------ scalar scorer
+// The one definition of a TransE accumulator: sequential over d, acc = acc + |v - e| (p = 1) or fma(u, u, acc) (p = 2).
+template <int P>
+__device__ __forceinline__ float transe_acc(const float *__restrict__ v, const float *__restrict__ e, int64_t D) {
+    float acc = 0.f;
+    for (int64_t d = 0; d < D; d += 4) {
+        float4 a = *reinterpret_cast<const float4 *>(v + d);
+        float4 b = *reinterpret_cast<const float4 *>(e + d);
+        float u0 = a.x - b.x, u1 = a.y - b.y, u2 = a.z - b.z, u3 = a.w - b.w;
+        if (P == 1) {
+            acc = acc + fabsf(u0); acc = acc + fabsf(u1); acc = acc + fabsf(u2); acc = acc + fabsf(u3);
+        } else {
+            acc = fmaf(u0, u0, acc); acc = fmaf(u1, u1, acc); acc = fmaf(u2, u2, acc); acc = fmaf(u3, u3, acc);
+        }
+    }
+    return acc;
+}
+
+// ------------------------------------------------------------------------------------------ pre-pass kernels
+// F.normalize(x, 2, -1) = x / max(||x||_2, 1e-12) (TransE.py:47-50), written into a table whose rows are padded
+// with zeros to Dp (a multiple of 4).  One thread per row, sequential fma: bit-identical to oracle/kge_oracle.c.
+__global__ void normalize_rows_kernel(const float *__restrict__ x, int64_t n, int64_t D, int64_t Dp, int normalize,
+                                      float *__restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float *row = x + i * D;
+    float nrm = 1.f;
+    if (normalize) {
+        float ss = 0.f;
+        for (int64_t d = 0; d < D; d++) ss = fmaf(row[d], row[d], ss);
+        nrm = __fsqrt_rn(ss);
+        if (nrm < 1e-12f) nrm = 1e-12f;
+    }
+    float *o = out + i * Dp;
+    for (int64_t d = 0; d < D; d++) o[d] = normalize ? __fdiv_rn(row[d], nrm) : row[d];
+    for (int64_t d = D; d < Dp; d++) o[d] = 0.f;
+}
+
+// v_q = h + r (tail query) or -(r - t) (head query); grid-stride over Q * D elements
+__global__ void transe_qvec_kernel(const float *__restrict__ ent, const float *__restrict__ rel, int64_t D,
+                                   const int64_t *__restrict__ q_h, const int64_t *__restrict__ q_t,
+                                   const int64_t *__restrict__ q_r, const uint8_t *__restrict__ q_side, int side,
+                                   int64_t Q, float *__restrict__ qvec) {
+    int64_t total = Q * D;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t q = i / D, d = i - q * D;
+        int s = q_side ? (int)q_side[q] : side;
+        float rv = rel[q_r[q] * D + d];
+        float v;
+        if (s) v = ent[q_h[q] * D + d] + rv;
+        else v = -(rv - ent[q_t[q] * D + d]);
+        qvec[i] = v;
+    }
+}
+
+// thresholds from the true entity's accumulator.  p = 1: score = acc.  p = 2: score = sqrt(acc) and the reference
+// compares the square roots, so lo = min{x : sqrt(x) >= s_true}, hi = min{x : sqrt(x) > s_true} (sqrt is monotone),
+// which lets the tile kernel compare raw accumulators and still agree with sqrtf(acc_j) < sqrtf(acc_true) exactly.
+template <int P>
+__global__ void transe_threshold_kernel(const float *__restrict__ ent, int64_t D, const int64_t *__restrict__ q_h,
+                                        const int64_t *__restrict__ q_t, const uint8_t *__restrict__ q_side, int side,
+                                        int64_t Q, const float *__restrict__ qvec, float2 *__restrict__ thr) {
+    int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= Q) return;
+    int s = q_side ? (int)q_side[q] : side;
+    int64_t truth = s ? q_t[q] : q_h[q];
+    float acc = transe_acc<P>(qvec + q * D, ent + truth * D, D);
+    float lo = acc, hi = acc;
+    if (acc >= 0.f && acc < INFINITY) {
+        if (P == 1) {
+            hi = __int_as_float(__float_as_int(acc) + 1);
+        } else {
+            float st = __fsqrt_rn(acc);
+            float x = acc;
+            while (x > 0.f) {
+                float y = __int_as_float(__float_as_int(x) - 1);
+                if (__fsqrt_rn(y) >= st) x = y; else break;
+            }
+            lo = x;
+            x = acc;
+            for (;;) {
+                float y = __int_as_float(__float_as_int(x) + 1);
+                if (y < INFINITY && __fsqrt_rn(y) <= st) x = y; else { hi = y; break; }
+            }
+        }
+    }
+    thr[q] = make_float2(lo, hi);
+}
+
+// Model.predict for one query: the materialised float32[E] score vector (tests / drop-in callers only)
+template <int P>
+__global__ void transe_predict_kernel(const float *__restrict__ ent, int64_t E, int64_t D, const float *__restrict__ qv,
+                                      float *__restrict__ out) {
+    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= E) return;
+    float acc = transe_acc<P>(qv, ent + j * D, D);
+    out[j] = P == 1 ? acc : __fsqrt_rn(acc);
+}
+
+__global__ void init_counts_kernel(int32_t *counts, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) counts[i] = 0;
+}
+
+// ------------------------------------------------------------------------------------------ main kernel
+template <int P>
+__device__ __forceinline__ float upd(float acc, float q, float e) {
+    float u = q - e;
+    return P == 1 ? acc + fabsf(u) : fmaf(u, u, acc);
+}
+
+// One pipeline chunk = CHUNK floats of every row of one work item's two operands.  Issued by a whole warp:
+// lane l copies rows l, l+32, l+64, l+96 of the query tile and of the candidate tile.
+__device__ __forceinline__ void issue_chunk(const RankParams &p, int64_t flat, int n_chunks, uint32_t ring_u32, uint32_t full0,
+                                            uint32_t empty0, int lane) {
+    const int64_t item = blockIdx.x + (flat / n_chunks) * (int64_t)gridDim.x;
+    if (item >= p.total_items) return;
+    const int c = (int)(flat % n_chunks);
+    int g, qt, et;
+    decode_item(p, item, g, qt, et);
+    const GroupDesc &gd = p.groups[g];
+    const int64_t qbase = gd.q0 + (int64_t)qt * TILE_Q;
+    const int nq = (int)min((int64_t)TILE_Q, gd.q0 + gd.nq - qbase);
+    const int64_t cbase = (int64_t)et * TILE_E;
+    const int ne = (int)min((int64_t)TILE_E, gd.nc - cbase);
+    const int stage = (int)(flat % STAGES);
+    const uint32_t full = full0 + 8 * stage;
+    mbar_wait(empty0 + 8 * stage, (uint32_t)((flat / STAGES) & 1) ^ 1u);
+    const int d0 = c * CHUNK;
+    const uint32_t bytes = (uint32_t)min((int64_t)CHUNK, p.D - d0) * 4u;
+    if (lane == 0) mbar_arrive_expect_tx(full, (uint32_t)(nq + ne) * bytes);
+    __syncwarp();
+    const uint32_t sq = ring_u32 + (uint32_t)stage * (STAGE_FLOATS * 4);
+    const uint32_t se = sq + TILE_Q * ROW_STRIDE * 4;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int row = lane + 32 * k;
+        if (row < nq) bulk_g2s(sq + row * ROW_STRIDE * 4, p.qvec + (qbase + row) * p.D + d0, bytes, full);
+        if (row < ne) {
+            const int64_t cidx = cbase + row;
+            const int64_t ent_id = p.all_entities ? cidx : __ldg(p.cand_idx + gd.c0 + cidx);
+            bulk_g2s(se + row * ROW_STRIDE * 4, p.ent + ent_id * p.D + d0, bytes, full);
+        }
+    }
+}
+
+template <int P, bool NEED_EQ>
+__global__ void __launch_bounds__(RANK_THREADS, 2) transe_rank_kernel(const RankParams p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float *ring = reinterpret_cast<float *>(smem_raw);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t)STAGES * STAGE_FLOATS * sizeof(float));
+    const uint32_t ring_u32 = smem_u32(ring);
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; s++) {
+            mbar_init(full0 + 8 * s, 1);
+            mbar_init(empty0 + 8 * s, CONSUMER_WARPS);
+        }
+        fence_barrier_init();
+    }
+    __syncthreads();
+
+    const int n_chunks = (int)((p.D + CHUNK - 1) / CHUNK);
+    // The producer role rotates over the warps: chunk f is issued by warp f % 8, STAGES-1 chunks ahead of its use,
+    // so no warp is set aside (256 threads x 128 registers x 2 CTAs fill the register file exactly).
+    if (warp < STAGES - 1) issue_chunk(p, warp, n_chunks, ring_u32, full0, empty0, lane);
+
+    const int te = threadIdx.x & 15, tq = threadIdx.x >> 4;  // entity rows te + 16 j, query rows tq + 16 i
+    int64_t it = 0;
+    for (int64_t item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+        int g, qt, et;
+        decode_item(p, item, g, qt, et);
+        const GroupDesc gd = p.groups[g];
+        const int64_t qbase = gd.q0 + (int64_t)qt * TILE_Q;
+        const int nq = (int)min((int64_t)TILE_Q, gd.q0 + gd.nq - qbase);
+        const int ne = (int)min((int64_t)TILE_E, gd.nc - (int64_t)et * TILE_E);
+
+        float acc[8][8];
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+#pragma unroll
+            for (int j = 0; j < 8; j++) acc[i][j] = 0.f;
+
+        for (int c = 0; c < n_chunks; c++, it++) {
+            if (warp == (int)((it + STAGES - 1) % CONSUMER_WARPS))
+                issue_chunk(p, it + STAGES - 1, n_chunks, ring_u32, full0, empty0, lane);
+            const int stage = (int)(it % STAGES);
+            mbar_wait(full0 + 8 * stage, (uint32_t)((it / STAGES) & 1));
+            const float *sQ = ring + (size_t)stage * STAGE_FLOATS + tq * ROW_STRIDE;
+            const float *sE = ring + (size_t)stage * STAGE_FLOATS + TILE_Q * ROW_STRIDE + te * ROW_STRIDE;
+            const int nk4 = (int)min((int64_t)CHUNK, p.D - (int64_t)c * CHUNK) >> 2;
+#pragma unroll 2
+            for (int k4 = 0; k4 < nk4; k4++) {
+                float4 ev[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) ev[j] = *reinterpret_cast<const float4 *>(sE + j * 16 * ROW_STRIDE + k4 * 4);
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const float4 qv = *reinterpret_cast<const float4 *>(sQ + i * 16 * ROW_STRIDE + k4 * 4);
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        float a = acc[i][j];
+                        a = upd<P>(a, qv.x, ev[j].x);
+                        a = upd<P>(a, qv.y, ev[j].y);
+                        a = upd<P>(a, qv.z, ev[j].z);
+                        a = upd<P>(a, qv.w, ev[j].w);
+                        acc[i][j] = a;
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty0 + 8 * stage);
+        }
+
+    // ---- epilogue: compare against the per-query thresholds, count, reduce over the 16 lanes sharing a query row
+        bool ev_ok[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) ev_ok[j] = (te + 16 * j) < ne;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int ql = tq + 16 * i;
+            const bool q_ok = ql < nq;
+            float2 th = make_float2(-INFINITY, -INFINITY);
+            if (q_ok) th = __ldg(p.thr + qbase + ql);
+            int n_lt = 0, n_eq = 0;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const float s = acc[i][j];
+                const bool lt = ev_ok[j] && s < th.x;
+                n_lt += lt ? 1 : 0;
+                if (NEED_EQ) n_eq += (ev_ok[j] && !lt && s < th.y) ? 1 : 0;
+            }
+#pragma unroll
+            for (int m = 1; m < 16; m <<= 1) {
+                n_lt += __shfl_xor_sync(0xffffffffu, n_lt, m);
+                if (NEED_EQ) n_eq += __shfl_xor_sync(0xffffffffu, n_eq, m);
+            }
+            if (q_ok && te == 0) {
+                const int64_t q = qbase + ql;
+                if (n_lt) {
+                    atomicAdd(p.counts + q, n_lt);
+                    atomicAdd(p.counts + 2 * p.Q + q, n_lt);
+                }
+                if (NEED_EQ && n_eq) {
+                    atomicAdd(p.counts + p.Q + q, n_eq);
+                    atomicAdd(p.counts + 3 * p.Q + q, n_eq);
+                }
+            }
+        }
+    }
+
+    // ==================================== known-true correction (warp per query) ====================================
+    if (p.filter != MRE_FILTER_NONE || NEED_EQ) {
+        const int64_t n_warps = (int64_t)gridDim.x * CONSUMER_WARPS;
+        for (int64_t q = (int64_t)blockIdx.x * CONSUMER_WARPS + warp; q < p.Q; q += n_warps) {
+            correct_query<NEED_EQ>(p, q, lane, [&](int64_t qq, int64_t x) {
+                return transe_acc<P>(p.qvec + qq * p.D, p.ent + x * p.D, p.D);
+            });
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ host side
+static int build_groups(mre_ctx *ctx, const mre_rank_job *job, int tile_q, int tile_e, std::vector<GroupDesc> &groups,
+                        int64_t *total_items) {
+    groups.clear();
+    int64_t items = 0;
+    if (job->n_groups <= 0) {
+        GroupDesc g{};
+        g.q0 = 0; g.nq = job->Q; g.c0 = 0; g.nc = job->E; g.item0 = 0;
+        g.n_qt = (int32_t)((job->Q + tile_q - 1) / tile_q);
+        g.n_et = (int32_t)((job->E + tile_e - 1) / tile_e);
+        items = (int64_t)g.n_qt * g.n_et;
+        groups.push_back(g);
+    } else {
+        MRE_CHECK_ARG(job->group_qptr && job->group_cptr && job->cand_idx, "candidate groups need group_qptr, group_cptr, cand_idx");
+        MRE_CHECK_ARG(job->group_qptr[0] == 0 && job->group_qptr[job->n_groups] == job->Q, "group_qptr must span [0, Q]");
+        for (int i = 0; i < job->n_groups; i++) {
+            GroupDesc g{};
+            g.q0 = job->group_qptr[i]; g.nq = job->group_qptr[i + 1] - g.q0;
+            g.c0 = job->group_cptr[i]; g.nc = job->group_cptr[i + 1] - g.c0;
+            MRE_CHECK_ARG(g.nq >= 0 && g.nc >= 0, "group %d has a negative size", i);
+            if (g.nq == 0 || g.nc == 0) continue;
+            g.item0 = items;
+            g.n_qt = (int32_t)((g.nq + tile_q - 1) / tile_q);
+            g.n_et = (int32_t)((g.nc + tile_e - 1) / tile_e);
+            items += (int64_t)g.n_qt * g.n_et;
+            groups.push_back(g);
+        }
+        if (groups.empty()) {  // nothing to count; keep one empty descriptor so lookups stay in range
+            GroupDesc g{};
+            groups.push_back(g);
+        }
+    }
+    *total_items = items;
+    (void)ctx;
+    return MRE_OK;
+}
+
+int fill_rank_params(mre_ctx *ctx, const mre_index *ix, const mre_rank_job *job, int tile_q, int tile_e, cudaStream_t st,
+                     RankParams &p) {
+    std::vector<GroupDesc> groups;
+    int64_t items = 0;
+    MRE_TRY(build_groups(ctx, job, tile_q, tile_e, groups, &items));
+    MRE_TRY(ctx->tiles.reserve(groups.size() * sizeof(GroupDesc)));
+    MRE_CUDA(cudaMemcpyAsync(ctx->tiles.p, groups.data(), groups.size() * sizeof(GroupDesc), cudaMemcpyHostToDevice, st));
+    // the descriptor vector dies with this frame; the copy above is from pageable memory and therefore staged
+    // synchronously by the runtime before cudaMemcpyAsync returns
+    p.E = job->E; p.R = job->R;
+    p.q_h = job->q_h; p.q_t = job->q_t; p.q_r = job->q_r; p.q_side = job->q_side; p.side = job->side; p.Q = job->Q;
+    p.groups = ctx->tiles.as<GroupDesc>();
+    p.n_groups = (int32_t)groups.size();
+    p.all_entities = job->n_groups <= 0 ? 1 : 0;
+    p.cand_idx = job->cand_idx;
+    p.total_items = items;
+    p.filter = job->filter;
+    p.hr_key = p.hr_val = p.tr_key = p.tr_val = nullptr;
+    p.n_all = 0;
+    if (job->filter == MRE_FILTER_INDEX) {
+        MRE_CHECK_ARG(ix != nullptr, "MRE_FILTER_INDEX needs an index");
+        MRE_CHECK_ARG(ix->device == ctx->device, "index is not on device %d (call mre_index_to_device)", ctx->device);
+        MRE_CHECK_ARG(ix->E == job->E && ix->R == job->R, "index E/R (%lld/%lld) differ from the job's (%lld/%lld)",
+                      (long long)ix->E, (long long)ix->R, (long long)job->E, (long long)job->R);
+        p.hr_key = ix->d_all_hr_key; p.hr_val = ix->d_all_hr_val; p.tr_key = ix->d_all_tr_key; p.tr_val = ix->d_all_tr_val;
+        p.n_all = ix->n_all;
+    } else if (job->filter == MRE_FILTER_CSR) {
+        MRE_CHECK_ARG(job->filt_ptr && job->filt_idx, "MRE_FILTER_CSR needs filt_ptr and filt_idx");
+    }
+    p.filt_ptr = job->filt_ptr; p.filt_idx = job->filt_idx;
+    p.counts = job->counts;
+    return MRE_OK;
+}
+
+static inline int grid_for(int64_t n, int block) { return (int)std::min<int64_t>((n + block - 1) / block, 148 * 32); }
+
+template <int P>
+static int transe_prepass(mre_ctx *ctx, const mre_rank_job *job, cudaStream_t st, const float **ent_out, int64_t *Dp_out) {
+    const int64_t D = job->D, Dp = (D + 3) & ~(int64_t)3;
+    const float *ent = job->ent, *rel = job->rel;
+    if (job->normalize || Dp != D) {
+        MRE_TRY(ctx->ent_n.reserve((size_t)job->E * Dp * sizeof(float)));
+        MRE_TRY(ctx->rel_n.reserve((size_t)job->R * Dp * sizeof(float)));
+        normalize_rows_kernel<<<(unsigned)((job->E + 127) / 128), 128, 0, st>>>(job->ent, job->E, D, Dp, job->normalize, ctx->ent_n.as<float>());
+        normalize_rows_kernel<<<(unsigned)((job->R + 127) / 128), 128, 0, st>>>(job->rel, job->R, D, Dp, job->normalize, ctx->rel_n.as<float>());
+        ctx->launches += 2;
+        ent = ctx->ent_n.as<float>();
+        rel = ctx->rel_n.as<float>();
+    }
+    if (job->Q > 0) {
+        MRE_TRY(ctx->qvec.reserve((size_t)job->Q * Dp * sizeof(float)));
+        MRE_TRY(ctx->thr.reserve((size_t)job->Q * sizeof(float2)));
+        transe_qvec_kernel<<<grid_for(job->Q * Dp, 256), 256, 0, st>>>(ent, rel, Dp, job->q_h, job->q_t, job->q_r, job->q_side,
+                                                                       job->side, job->Q, ctx->qvec.as<float>());
+        transe_threshold_kernel<P><<<(unsigned)((job->Q + 127) / 128), 128, 0, st>>>(
+            ent, Dp, job->q_h, job->q_t, job->q_side, job->side, job->Q, ctx->qvec.as<float>(), ctx->thr.as<float2>());
+        ctx->launches += 2;
+    }
+    *ent_out = ent;
+    *Dp_out = Dp;
+    MRE_CUDA(cudaGetLastError());
+    return MRE_OK;
+}
+
+template <int P, bool NEED_EQ>
+static int launch_rank(mre_ctx *ctx, const RankParams &p, cudaStream_t st) {
+    auto kern = transe_rank_kernel<P, NEED_EQ>;
+    static bool configured = false;
+    if (!configured) {
+        MRE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RANK_SMEM));
+        configured = true;
+    }
+    int64_t want = std::max<int64_t>(p.total_items, (p.Q + CONSUMER_WARPS - 1) / CONSUMER_WARPS);
+    int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)ctx->sm_count * 2));
+    kern<<<grid, RANK_THREADS, RANK_SMEM, st>>>(p);
+    ctx->launches += 1;
+    MRE_CUDA(cudaGetLastError());
+    return MRE_OK;
+}
+
+int rank_transe(mre_ctx *ctx, const mre_index *ix, const mre_rank_job *job, cudaStream_t st) {
+    MRE_CHECK_ARG(job->p_norm == 1 || job->p_norm == 2, "p_norm must be 1 or 2");
+    const float *ent = nullptr;
+    int64_t Dp = 0;
+    if (job->p_norm == 1) MRE_TRY(transe_prepass<1>(ctx, job, st, &ent, &Dp));
+    else MRE_TRY(transe_prepass<2>(ctx, job, st, &ent, &Dp));
+    RankParams p{};
+    MRE_TRY(fill_rank_params(ctx, ix, job, TILE_Q, TILE_E, st, p));
+    p.ent = ent;
+    p.D = Dp;
+    p.qvec = ctx->qvec.as<float>();
+    p.thr = ctx->thr.as<float2>();
+    if (job->Q == 0) return MRE_OK;
+    init_counts_kernel<<<grid_for(4 * job->Q, 256), 256, 0, st>>>(job->counts, 4 * job->Q);
+    ctx->launches += 1;
+    MRE_TRY(ctx->time_begin(st));
+    // the tie count is always on: one extra compare per score, in the epilogue only
+    if (job->p_norm == 1) MRE_TRY((launch_rank<1, true>(ctx, p, st)));
+    else MRE_TRY((launch_rank<2, true>(ctx, p, st)));
+    MRE_TRY(ctx->time_end(st));
+    return MRE_OK;
+}
+
+int predict_transe(mre_ctx *ctx, const mre_rank_job *job, int64_t query, float *scores_out, cudaStream_t st) {
+    mre_rank_job one = *job;
+    one.q_h = job->q_h + query; one.q_t = job->q_t + query; one.q_r = job->q_r + query;
+    one.q_side = job->q_side ? job->q_side + query : nullptr;
+    one.Q = 1;
+    const float *ent = nullptr;
+    int64_t Dp = 0;
+    if (job->p_norm == 1) MRE_TRY(transe_prepass<1>(ctx, &one, st, &ent, &Dp));
+    else MRE_TRY(transe_prepass<2>(ctx, &one, st, &ent, &Dp));
+    unsigned grid = (unsigned)((job->E + 127) / 128);
+    if (job->p_norm == 1) transe_predict_kernel<1><<<grid, 128, 0, st>>>(ent, job->E, Dp, ctx->qvec.as<float>(), scores_out);
+    else transe_predict_kernel<2><<<grid, 128, 0, st>>>(ent, job->E, Dp, ctx->qvec.as<float>(), scores_out);
+    ctx->launches += 1;
+    MRE_CUDA(cudaGetLastError());
+    return MRE_OK;
+}
+
+}  // namespace mre

@@ -1,0 +1,333 @@
+"""Host-side objects over the C ABI: the knowledge-graph index, the per-device workspace and the rank /
+sample / train-step calls on torch CUDA tensors.  torch supplies device memory and streams only; every
+computation below happens inside libmre_b200.so.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+
+def _i64(a):
+    return np.ascontiguousarray(a, dtype=np.int64)
+
+
+def _ptr(t):
+    """device/host pointer of a contiguous torch tensor or numpy array (None -> NULL)"""
+    if t is None:
+        return None
+    if isinstance(t, np.ndarray):
+        assert t.flags["C_CONTIGUOUS"]
+        return t.ctypes.data
+    assert t.is_contiguous()
+    return t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+class KGIndex:
+    """Reader.h's tables (OpenKE/openke/base/Reader.h:53-257) built by mre_index_create*."""
+
+    def __init__(self, handle):
+        self._h = C.c_void_p(handle)
+        self.device = None
+        lib = L.lib()
+        self.ent_tot = lib.mre_index_total(self._h, L.TOTAL_ENTITY)
+        self.rel_tot = lib.mre_index_total(self._h, L.TOTAL_RELATION)
+        self.train_tot = lib.mre_index_total(self._h, L.TOTAL_TRAIN)
+        self.valid_tot = lib.mre_index_total(self._h, L.TOTAL_VALID)
+        self.test_tot = lib.mre_index_total(self._h, L.TOTAL_TEST)
+        self.triple_tot = lib.mre_index_total(self._h, L.TOTAL_TRIPLE)
+
+    @classmethod
+    def from_arrays(cls, E, R, train, valid=None, test=None):
+        """train / valid / test: (h, t, r) column arrays (OpenKE's file column order)."""
+        empty = (np.zeros(0, np.int64),) * 3
+        cols = []
+        keep = []
+        for split in (train, valid or empty, test or empty):
+            h, t, r = (_i64(x) for x in split)
+            assert len(h) == len(t) == len(r)
+            keep += [h, t, r]
+            cols += [h.ctypes.data, t.ctypes.data, r.ctypes.data, len(h)]
+        out = C.c_void_p()
+        L.check(L.lib().mre_index_create(int(E), int(R), *cols, C.byref(out)))
+        return cls(out.value)
+
+    @classmethod
+    def from_dir(cls, in_path):
+        """setInPath + importTrainFiles + importTestFiles (Setting.h:17-27, Reader.h:53-257)."""
+        out = C.c_void_p()
+        L.check(L.lib().mre_index_create_from_dir(str(in_path).encode(), C.byref(out)))
+        return cls(out.value)
+
+    def __del__(self):
+        try:
+            if self._h:
+                L.lib().mre_index_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def to_device(self, device=0):
+        L.check(L.lib().mre_index_to_device(self._h, int(device)))
+        self.device = int(device)
+        return self
+
+    def _split(self, which, n):
+        h, t, r = (np.empty(n, np.int64) for _ in range(3))
+        L.check(L.lib().mre_index_get_split(self._h, which, h.ctypes.data, t.ctypes.data, r.ctypes.data))
+        return h, t, r
+
+    def train_triples(self):
+        """de-duplicated train list, (h,r,t) order == trainList"""
+        return self._split(L.SPLIT_TRAIN, self.train_tot)
+
+    def valid_triples(self):
+        return self._split(L.SPLIT_VALID, self.valid_tot)
+
+    def test_triples(self):
+        """test list in the order Tester iterates it: sorted (r,h,t) (Reader.h:227)"""
+        return self._split(L.SPLIT_TEST, self.test_tot)
+
+    def means(self):
+        tph, hpt = np.empty(self.rel_tot, np.float32), np.empty(self.rel_tot, np.float32)
+        L.check(L.lib().mre_index_get_means(self._h, tph.ctypes.data, hpt.ctypes.data))
+        return tph, hpt
+
+    def find(self, h, t, r):
+        return bool(L.lib().mre_index_find(self._h, int(h), int(t), int(r)))
+
+
+class Context:
+    """mre_ctx: scratch buffers and launch accounting for one device."""
+
+    def __init__(self, device=0):
+        out = C.c_void_p()
+        L.check(L.lib().mre_ctx_create(int(device), C.byref(out)))
+        self._h = out
+        self.device = int(device)
+
+    def __del__(self):
+        try:
+            if self._h:
+                L.lib().mre_ctx_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    @property
+    def sm_count(self):
+        return L.lib().mre_ctx_sm_count(self._h)
+
+    @property
+    def launches(self):
+        return L.lib().mre_ctx_launch_count(self._h)
+
+    def timing(self, enable):
+        L.check(L.lib().mre_ctx_timing(self._h, 1 if enable else 0))
+
+    def timing_read(self):
+        ms, n = C.c_double(), C.c_int64()
+        L.check(L.lib().mre_ctx_timing_read(self._h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    def probe_fp32_peak(self):
+        v = C.c_double()
+        L.check(L.lib().mre_probe_fp32_peak(self._h, C.byref(v)))
+        return v.value
+
+    def probe_tf32_peak(self):
+        v = C.c_double()
+        L.check(L.lib().mre_probe_tf32_peak(self._h, C.byref(v)))
+        return v.value
+
+
+SCORERS = {"transe": L.TRANSE, "distmult": L.DISTMULT, "complex": L.COMPLEX}
+RANK_MODES = {"strict": L.RANK_STRICT, "ties_half": L.RANK_TIES_HALF, "pessimistic": L.RANK_PESSIMISTIC}
+
+
+class CandidateGroups:
+    """Candidate lists shared by runs of queries (rel2candidates, utils/gen_rel2candidates.py:23-27).
+    qptr / cptr: host int64 prefix arrays [G+1]; cand: device int64, each slice sorted and unique."""
+
+    def __init__(self, qptr, cptr, cand):
+        self.qptr = _i64(qptr)
+        self.cptr = _i64(cptr)
+        self.cand = cand
+        assert len(self.qptr) == len(self.cptr)
+
+    @classmethod
+    def from_lists(cls, query_counts, cand_lists, device):
+        qptr = np.concatenate([[0], np.cumsum(query_counts)])
+        uniq = [np.unique(_i64(c)) for c in cand_lists]
+        cptr = np.concatenate([[0], np.cumsum([len(u) for u in uniq])])
+        flat = np.concatenate(uniq) if uniq else np.zeros(0, np.int64)
+        return cls(qptr, cptr, torch.from_numpy(flat).to(device))
+
+
+class Ranker:
+    """Fused score + filtered-rank engine for one device (mre_rank / mre_rank_host / mre_metrics)."""
+
+    def __init__(self, ctx=None, device=0):
+        self.ctx = ctx or Context(device)
+        self.device = torch.device("cuda", self.ctx.device)
+
+    def _job(self, scorer, tables, Q, side, p_norm, normalize, index, filt, groups, filt_csr):
+        job = L.RankJob()
+        if scorer == "complex":
+            ent, ent_im, rel, rel_im = tables
+            job.ent_im, job.rel_im = _ptr(ent_im), _ptr(rel_im)
+            assert ent_im.shape == ent.shape and rel_im.shape == rel.shape
+        else:
+            ent, rel = tables
+        for t in tables:
+            assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous(), "tables must be contiguous float32 CUDA tensors"
+        job.ent, job.rel = _ptr(ent), _ptr(rel)
+        job.E, job.D = ent.shape
+        job.R = rel.shape[0]
+        assert rel.shape[1] == ent.shape[1]
+        job.scorer = SCORERS[scorer]
+        job.p_norm, job.normalize = int(p_norm), int(bool(normalize))
+        if filt is None:
+            filt = "csr" if filt_csr is not None else ("index" if index is not None else "none")
+        job.filter = {"none": L.FILTER_NONE, "index": L.FILTER_INDEX, "csr": L.FILTER_CSR}[filt]
+        job.Q = int(Q)
+        keep = []
+        if isinstance(side, (int, np.integer)):
+            job.side = int(side)
+        else:
+            job.side = 0
+            keep.append(side)
+            job.q_side = _ptr(side)
+        if groups is not None:
+            job.n_groups = len(groups.qptr) - 1
+            job.group_qptr, job.group_cptr = groups.qptr.ctypes.data, groups.cptr.ctypes.data
+            job.cand_idx = _ptr(groups.cand)
+        if filt_csr is not None:
+            job.filt_ptr, job.filt_idx = _ptr(filt_csr[0]), _ptr(filt_csr[1])
+        return job, keep
+
+    def rank(self, scorer, tables, q_h, q_t, q_r, side, *, p_norm=1, normalize=False, index=None, filter=None,
+             groups=None, filt_csr=None, out=None):
+        """Device queries -> device int32 counts [4, Q] = (raw_lt, raw_eq, filt_lt, filt_eq).  Asynchronous."""
+        Q = q_h.numel()
+        job, keep = self._job(scorer, tables, Q, side, p_norm, normalize, index, filter, groups, filt_csr)
+        for t in (q_h, q_t, q_r):
+            assert t.is_cuda and t.dtype == torch.int64 and t.is_contiguous() and t.numel() == Q
+        if not isinstance(side, (int, np.integer)):
+            assert side.is_cuda and side.dtype == torch.uint8 and side.numel() == Q
+        job.q_h, job.q_t, job.q_r = _ptr(q_h), _ptr(q_t), _ptr(q_r)
+        counts = out if out is not None else torch.empty((4, Q), dtype=torch.int32, device=self.device)
+        job.counts = _ptr(counts)
+        L.check(L.lib().mre_rank(self.ctx._h, index._h if index is not None else None, C.byref(job), _stream()))
+        return counts
+
+    def rank_host(self, scorer, tables, q_h, q_t, q_r, side, *, p_norm=1, normalize=False, index=None, filter=None,
+                  groups=None, filt_csr=None, out=None):
+        """Host (numpy / pinned torch CPU) queries -> host int32 counts [4, Q]; copies included; synchronous."""
+        Q = len(q_h)
+        job, keep = self._job(scorer, tables, Q, side, p_norm, normalize, index, filter, groups, filt_csr)
+        arrs = []
+        for a in (q_h, q_t, q_r):
+            a = a if isinstance(a, torch.Tensor) else _i64(a)
+            assert (a.dtype == torch.int64) if isinstance(a, torch.Tensor) else True
+            arrs.append(a)
+        job.q_h, job.q_t, job.q_r = (_ptr(a) for a in arrs)
+        if not isinstance(side, (int, np.integer)):
+            side = side if isinstance(side, torch.Tensor) else np.ascontiguousarray(side, dtype=np.uint8)
+            job.q_side = _ptr(side)
+        counts = out if out is not None else np.empty((4, Q), np.int32)
+        job.counts = _ptr(counts)
+        L.check(L.lib().mre_rank_host(self.ctx._h, index._h if index is not None else None, C.byref(job), _stream()))
+        return counts
+
+    def predict(self, scorer, tables, q_h, q_t, q_r, side, query=0, *, p_norm=1, normalize=False):
+        """Model.predict's float32[E] vector for one query (device tensor)."""
+        Q = q_h.numel()
+        job, keep = self._job(scorer, tables, Q, side, p_norm, normalize, None, "none", None, None)
+        job.q_h, job.q_t, job.q_r = _ptr(q_h), _ptr(q_t), _ptr(q_r)
+        out = torch.empty(job.E, dtype=torch.float32, device=self.device)
+        L.check(L.lib().mre_predict(self.ctx._h, C.byref(job), int(query), _ptr(out), _stream()))
+        return out
+
+    def metrics(self, counts, side, rank_mode="strict", raw=False, hist_len=0):
+        """counts [4, Q] (device) -> dict of per-side integer sums + float64 reciprocal-rank sums (+ histogram)."""
+        Q = counts.shape[1]
+        sums = torch.zeros((2, 8), dtype=torch.int64, device=self.device)
+        rr = torch.zeros(2, dtype=torch.float64, device=self.device)
+        hist = torch.zeros(hist_len, dtype=torch.int64, device=self.device) if hist_len else None
+        if isinstance(side, (int, np.integer)):
+            side_ptr, side_val = None, int(side)
+        else:
+            side_ptr, side_val = _ptr(side), 0
+        L.check(L.lib().mre_metrics(self.ctx._h, _ptr(counts), side_ptr, side_val, Q, RANK_MODES[rank_mode], int(raw),
+                                    _ptr(sums), _ptr(rr), _ptr(hist), int(hist_len), _stream()))
+        return {"sums": sums, "rr": rr, "hist": hist}
+
+
+def summarize(sums, rr):
+    """per-side integer sums + rr sums (host numpy) -> dict of means per side: mrr, mr, hits@1/3/5/10"""
+    out = []
+    for s in range(2):
+        n = int(sums[s][0])
+        if n == 0:
+            out.append(None)
+            continue
+        out.append({"n": n, "mr": float(sums[s][1]) / n, "mrr": float(rr[s]) / n, "hits1": float(sums[s][2]) / n,
+                    "hits3": float(sums[s][3]) / n, "hits5": float(sums[s][4]) / n, "hits10": float(sums[s][5]) / n})
+    return out
+
+
+class Sampler:
+    """mre_sample: Philox Bernoulli negative sampler (Base.cpp:78-197)."""
+
+    def __init__(self, index, ctx=None, seed=0, stream_id=0):
+        self.index = index
+        self.ctx = ctx or Context(index.device if index.device is not None else 0)
+        if index.device is None:
+            index.to_device(self.ctx.device)
+        self.seed, self.stream_id = int(seed), int(stream_id)
+        self.device = torch.device("cuda", self.ctx.device)
+
+    def sample(self, step, B, neg, mode=0, bern=1):
+        n = B * (1 + neg)
+        h, t, r = (torch.empty(n, dtype=torch.int64, device=self.device) for _ in range(3))
+        y = torch.empty(n, dtype=torch.float32, device=self.device)
+        L.check(L.lib().mre_sample(self.ctx._h, self.index._h, self.seed, int(step), self.stream_id, B, neg, mode, bern,
+                                   _ptr(h), _ptr(t), _ptr(r), _ptr(y), _stream()))
+        return h, t, r, y
+
+    def sample_host(self, step, B, neg, mode=0, bern=1, out=None):
+        n = B * (1 + neg)
+        if out is None:
+            out = (np.empty(n, np.int64), np.empty(n, np.int64), np.empty(n, np.int64), np.empty(n, np.float32))
+        h, t, r, y = out
+        L.check(L.lib().mre_sample_host(self.ctx._h, self.index._h, self.seed, int(step), self.stream_id, B, neg, mode, bern,
+                                        _ptr(h), _ptr(t), _ptr(r), _ptr(y), _stream()))
+        return h, t, r, y
+
+
+def transe_margin_step(ctx, ent, rel, h, t, r, B, neg, margin, p_norm=1, normalize=True, grad_ent=None, grad_rel=None,
+                       want_scores=False):
+    """mre_transe_margin_step on device tensors -> (loss[1], grad_ent, grad_rel, scores|None)."""
+    E, D = ent.shape
+    R = rel.shape[0]
+    if grad_ent is None:
+        grad_ent = torch.zeros_like(ent)
+    if grad_rel is None:
+        grad_rel = torch.zeros_like(rel)
+    loss = torch.zeros(1, dtype=torch.float32, device=ent.device)
+    scores = torch.empty(B * (1 + neg), dtype=torch.float32, device=ent.device) if want_scores else None
+    L.check(L.lib().mre_transe_margin_step(ctx._h, _ptr(ent), _ptr(rel), E, R, D, _ptr(h), _ptr(t), _ptr(r), B, neg,
+                                           float(margin), int(p_norm), int(bool(normalize)), _ptr(grad_ent), _ptr(grad_rel),
+                                           _ptr(loss), _ptr(scores), _stream()))
+    return loss, grad_ent, grad_rel, scores
+
+
+def sgd_update(ctx, w, g, lr):
+    L.check(L.lib().mre_sgd_update(ctx._h, _ptr(w), _ptr(g), w.numel(), float(lr), _stream()))
