@@ -21,15 +21,27 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
     asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes)
                  : "memory");
 }
+// try_wait suspends the thread in hardware until the phase completes or the time hint expires, so a blocked warp
+// costs (almost) no issue slots; the loop only re-arms it.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
     do {
         asm volatile(
-            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(ok)
-            : "r"(bar), "r"(parity)
+            : "r"(bar), "r"(parity), "r"(0x989680u)
             : "memory");
     } while (!ok);
+}
+// TMA tiled load of one 2-D box (SASS: UTMALDG): coordinates are (inner element index, row)
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void *tmap, int c0, int c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+        "l"(tmap), "r"(c0), "r"(c1), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const void *tmap) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
 }
 // TMA-unit bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP).
 // src and dst 16-byte aligned, bytes a multiple of 16.

@@ -11,10 +11,11 @@
 // vector  v_q  such that |v_q[d] - e_j[d]| is bit-identical to the reference's element (tail: v = h + r;
 // head: v = -(r - t), because e + (r - t) == -(v - e) exactly), and computes s_true with the SAME sequential-d
 // accumulation the tile kernel uses, so `s_j < s_true` is decided on identical bits for every j.
-// The main kernel is persistent: each CTA walks 128-query x 128-entity work items; a rotating producer warp streams
-// 128-byte row chunks of both operands into a 3-stage shared-memory ring with TMA-unit bulk copies
-// (cp.async.bulk + mbarrier complete_tx; entity rows may be gathered through a candidate list), the eight
-// warps hold an 8x8 register micro-tile per thread and read the ring with conflict-free 128-bit LDS.  The
+// The main kernel is persistent: each CTA walks 128-query x 128-entity work items; 128-row x 128-byte boxes of both
+// operands stream into a 3-stage shared-memory ring through TMA (cp.async.bulk.tensor, 128-byte swizzle, mbarrier
+// complete_tx; candidate lists are gathered into a dense table by a pre-pass), issued by whichever warp is last
+// to release a stage; the eight warps hold an 8x8 register micro-tile per thread and read the ring with
+// conflict-free 128-bit LDS.  The
 // epilogue compares the 64 accumulators against the per-query thresholds, reduces the counts with warp
 // shuffles and adds them to the per-query counters.  After its tiles a CTA runs the known-true correction
 // (rank_common.cuh) with warp ballot/popc.  The kernel is bound by the FP32 pipe: 2 lane-ops per (q, e, d).
@@ -24,26 +25,28 @@
 
 #include "common.h"
 #include "rank_common.cuh"
+#include "tma_host.h"
 
 namespace mre {
 
 constexpr int CHUNK = 32;            // floats of D per pipeline stage (128 B per row)
-constexpr int ROW_STRIDE = 36;       // smem row stride in floats: 144 B => 8 consecutive rows hit 8 distinct 16-B bank groups
 constexpr int STAGES = 3;
 constexpr int CONSUMER_WARPS = 8;
 constexpr int RANK_THREADS = CONSUMER_WARPS * 32;
-constexpr int STAGE_FLOATS = (TILE_Q + TILE_E) * ROW_STRIDE;
-constexpr size_t RANK_SMEM = (size_t)STAGES * STAGE_FLOATS * sizeof(float) + 2 * STAGES * sizeof(uint64_t);
+constexpr uint32_t STAGE_BYTES = (TILE_Q + TILE_E) * CHUNK * 4;  // two 16 KiB TMA boxes
+constexpr size_t RANK_SMEM = 1024 + (size_t)STAGES * STAGE_BYTES + STAGES * sizeof(uint64_t) + STAGES * sizeof(int) + 64;
 
 // ------------------------------------------------------------------------------------------ scalar scorer
 // The one definition of a TransE accumulator: sequential over d, acc = acc + |v - e| (p = 1) or fma(u, u, acc) (p = 2).
+// Query vectors are stored PAIR-SWAPPED (element d at position d ^ 1): a 128-bit load then puts v[d] in a register
+// of the opposite even/odd bank to e[d], so the tile kernel's `v[d] - e[d]` never reads two same-bank registers.
 template <int P>
 __device__ __forceinline__ float transe_acc(const float *__restrict__ v, const float *__restrict__ e, int64_t D) {
     float acc = 0.f;
     for (int64_t d = 0; d < D; d += 4) {
         float4 a = *reinterpret_cast<const float4 *>(v + d);
         float4 b = *reinterpret_cast<const float4 *>(e + d);
-        float u0 = a.x - b.x, u1 = a.y - b.y, u2 = a.z - b.z, u3 = a.w - b.w;
+        float u0 = a.y - b.x, u1 = a.x - b.y, u2 = a.w - b.z, u3 = a.z - b.w;
         if (P == 1) {
             acc = acc + fabsf(u0); acc = acc + fabsf(u1); acc = acc + fabsf(u2); acc = acc + fabsf(u3);
         } else {
@@ -73,7 +76,7 @@ __global__ void normalize_rows_kernel(const float *__restrict__ x, int64_t n, in
     for (int64_t d = D; d < Dp; d++) o[d] = 0.f;
 }
 
-// v_q = h + r (tail query) or -(r - t) (head query); grid-stride over Q * D elements
+// v_q = h + r (tail query) or -(r - t) (head query), stored pair-swapped; grid-stride over Q * D elements
 __global__ void transe_qvec_kernel(const float *__restrict__ ent, const float *__restrict__ rel, int64_t D,
                                    const int64_t *__restrict__ q_h, const int64_t *__restrict__ q_t,
                                    const int64_t *__restrict__ q_r, const uint8_t *__restrict__ q_side, int side,
@@ -86,7 +89,7 @@ __global__ void transe_qvec_kernel(const float *__restrict__ ent, const float *_
         float v;
         if (s) v = ent[q_h[q] * D + d] + rv;
         else v = -(rv - ent[q_t[q] * D + d]);
-        qvec[i] = v;
+        qvec[i ^ 1] = v;
     }
 }
 
@@ -134,6 +137,17 @@ __global__ void transe_predict_kernel(const float *__restrict__ ent, int64_t E, 
     out[j] = P == 1 ? acc : __fsqrt_rn(acc);
 }
 
+// candidate groups: copy the listed entity rows into one dense table so that the main kernel streams every
+// candidate tile with the same TMA boxes as the all-entity case
+__global__ void gather_rows_kernel(const float *__restrict__ ent, int64_t D, const int64_t *__restrict__ idx, int64_t n,
+                                   float *__restrict__ out) {
+    const int64_t total = n * (D >> 2);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = i / (D >> 2), c = i - row * (D >> 2);
+        reinterpret_cast<float4 *>(out + row * D)[c] = reinterpret_cast<const float4 *>(ent + __ldg(idx + row) * D)[c];
+    }
+}
+
 __global__ void init_counts_kernel(int32_t *counts, int64_t n) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) counts[i] = 0;
 }
@@ -145,65 +159,56 @@ __device__ __forceinline__ float upd(float acc, float q, float e) {
     return P == 1 ? acc + fabsf(u) : fmaf(u, u, acc);
 }
 
-// One pipeline chunk = CHUNK floats of every row of one work item's two operands.  Issued by a whole warp:
-// lane l copies rows l, l+32, l+64, l+96 of the query tile and of the candidate tile.
-__device__ __forceinline__ void issue_chunk(const RankParams &p, int64_t flat, int n_chunks, uint32_t ring_u32, uint32_t full0,
-                                            uint32_t empty0, int lane) {
+// One pipeline chunk = CHUNK floats (128 B) of every row of one work item's two operands = two TMA boxes of
+// 128 rows x 128 B, written into shared memory with the hardware 128-byte swizzle.  Issued by ONE thread.
+__device__ __forceinline__ void issue_chunk(const RankParams &p, const CUtensorMap *tm_q, const CUtensorMap *tm_e, int64_t flat,
+                                            int n_chunks, uint32_t ring_u32, uint32_t full0) {
     const int64_t item = blockIdx.x + (flat / n_chunks) * (int64_t)gridDim.x;
     if (item >= p.total_items) return;
     const int c = (int)(flat % n_chunks);
     int g, qt, et;
     decode_item(p, item, g, qt, et);
     const GroupDesc &gd = p.groups[g];
-    const int64_t qbase = gd.q0 + (int64_t)qt * TILE_Q;
-    const int nq = (int)min((int64_t)TILE_Q, gd.q0 + gd.nq - qbase);
-    const int64_t cbase = (int64_t)et * TILE_E;
-    const int ne = (int)min((int64_t)TILE_E, gd.nc - cbase);
+    const int qrow = (int)(gd.q0 + (int64_t)qt * TILE_Q);
+    const int erow = (int)(gd.c0 + (int64_t)et * TILE_E);
     const int stage = (int)(flat % STAGES);
     const uint32_t full = full0 + 8 * stage;
-    mbar_wait(empty0 + 8 * stage, (uint32_t)((flat / STAGES) & 1) ^ 1u);
-    const int d0 = c * CHUNK;
-    const uint32_t bytes = (uint32_t)min((int64_t)CHUNK, p.D - d0) * 4u;
-    if (lane == 0) mbar_arrive_expect_tx(full, (uint32_t)(nq + ne) * bytes);
-    __syncwarp();
-    const uint32_t sq = ring_u32 + (uint32_t)stage * (STAGE_FLOATS * 4);
-    const uint32_t se = sq + TILE_Q * ROW_STRIDE * 4;
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        const int row = lane + 32 * k;
-        if (row < nq) bulk_g2s(sq + row * ROW_STRIDE * 4, p.qvec + (qbase + row) * p.D + d0, bytes, full);
-        if (row < ne) {
-            const int64_t cidx = cbase + row;
-            const int64_t ent_id = p.all_entities ? cidx : __ldg(p.cand_idx + gd.c0 + cidx);
-            bulk_g2s(se + row * ROW_STRIDE * 4, p.ent + ent_id * p.D + d0, bytes, full);
-        }
-    }
+    const uint32_t sq = ring_u32 + (uint32_t)stage * STAGE_BYTES;
+    mbar_arrive_expect_tx(full, STAGE_BYTES);
+    tma_load_2d(sq, tm_q, c * CHUNK, qrow, full);
+    tma_load_2d(sq + TILE_Q * CHUNK * 4, tm_e, c * CHUNK, erow, full);
 }
 
 template <int P, bool NEED_EQ>
-__global__ void __launch_bounds__(RANK_THREADS, 2) transe_rank_kernel(const RankParams p) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    float *ring = reinterpret_cast<float *>(smem_raw);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t)STAGES * STAGE_FLOATS * sizeof(float));
-    const uint32_t ring_u32 = smem_u32(ring);
-    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES);
+__global__ void __launch_bounds__(RANK_THREADS, 2)
+transe_rank_kernel(const RankParams p, const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_e) {
+    extern __shared__ unsigned char smem_raw[];
+    // the 128-byte swizzle pattern is a function of the shared-memory address: tiles must start 1024-byte aligned
+    const uint32_t ring_u32 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    unsigned char *ring = smem_raw + (ring_u32 - smem_u32(smem_raw));
+    uint64_t *bars = reinterpret_cast<uint64_t *>(ring + (size_t)STAGES * STAGE_BYTES);
+    int *done = reinterpret_cast<int *>(bars + STAGES);  // per-stage count of warps that finished reading the stage
+    const uint32_t full0 = smem_u32(bars);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_chunks = (int)((p.D + CHUNK - 1) / CHUNK);
 
     if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tm_q);
+        tma_prefetch_desc(&tm_e);
         for (int s = 0; s < STAGES; s++) {
             mbar_init(full0 + 8 * s, 1);
-            mbar_init(empty0 + 8 * s, CONSUMER_WARPS);
+            done[s] = 0;
         }
         fence_barrier_init();
+        fence_proxy_async();
+        for (int s = 0; s < STAGES; s++) issue_chunk(p, &tm_q, &tm_e, s, n_chunks, ring_u32, full0);
     }
     __syncthreads();
 
-    const int n_chunks = (int)((p.D + CHUNK - 1) / CHUNK);
-    // The producer role rotates over the warps: chunk f is issued by warp f % 8, STAGES-1 chunks ahead of its use,
-    // so no warp is set aside (256 threads x 128 registers x 2 CTAs fill the register file exactly).
-    if (warp < STAGES - 1) issue_chunk(p, warp, n_chunks, ring_u32, full0, empty0, lane);
-
-    const int te = threadIdx.x & 15, tq = threadIdx.x >> 4;  // entity rows te + 16 j, query rows tq + 16 i
+    // entity rows te + 16 j, query rows tq + 16 i.  Row r keeps its logical 16-byte chunk k at (k ^ (r & 7)), and
+    // (te + 16 j) & 7 == te & 7: eight consecutive rows read eight distinct bank groups => conflict-free LDS.128.
+    const int te = threadIdx.x & 15, tq = threadIdx.x >> 4;
+    const int xe = te & 7, xq = tq & 7;
     int64_t it = 0;
     for (int64_t item = blockIdx.x; item < p.total_items; item += gridDim.x) {
         int g, qt, et;
@@ -220,34 +225,43 @@ __global__ void __launch_bounds__(RANK_THREADS, 2) transe_rank_kernel(const Rank
             for (int j = 0; j < 8; j++) acc[i][j] = 0.f;
 
         for (int c = 0; c < n_chunks; c++, it++) {
-            if (warp == (int)((it + STAGES - 1) % CONSUMER_WARPS))
-                issue_chunk(p, it + STAGES - 1, n_chunks, ring_u32, full0, empty0, lane);
             const int stage = (int)(it % STAGES);
             mbar_wait(full0 + 8 * stage, (uint32_t)((it / STAGES) & 1));
-            const float *sQ = ring + (size_t)stage * STAGE_FLOATS + tq * ROW_STRIDE;
-            const float *sE = ring + (size_t)stage * STAGE_FLOATS + TILE_Q * ROW_STRIDE + te * ROW_STRIDE;
+            const unsigned char *sQ = ring + (size_t)stage * STAGE_BYTES + tq * (CHUNK * 4);
+            const unsigned char *sE = ring + (size_t)stage * STAGE_BYTES + (TILE_Q + te) * (CHUNK * 4);
             const int nk4 = (int)min((int64_t)CHUNK, p.D - (int64_t)c * CHUNK) >> 2;
 #pragma unroll 2
             for (int k4 = 0; k4 < nk4; k4++) {
+                const int oe = (k4 ^ xe) << 4, oq = (k4 ^ xq) << 4;
                 float4 ev[8];
 #pragma unroll
-                for (int j = 0; j < 8; j++) ev[j] = *reinterpret_cast<const float4 *>(sE + j * 16 * ROW_STRIDE + k4 * 4);
+                for (int j = 0; j < 8; j++) ev[j] = *reinterpret_cast<const float4 *>(sE + j * (16 * CHUNK * 4) + oe);
 #pragma unroll
                 for (int i = 0; i < 8; i++) {
-                    const float4 qv = *reinterpret_cast<const float4 *>(sQ + i * 16 * ROW_STRIDE + k4 * 4);
+                    const float4 qv = *reinterpret_cast<const float4 *>(sQ + i * (16 * CHUNK * 4) + oq);
 #pragma unroll
                     for (int j = 0; j < 8; j++) {
                         float a = acc[i][j];
-                        a = upd<P>(a, qv.x, ev[j].x);
-                        a = upd<P>(a, qv.y, ev[j].y);
-                        a = upd<P>(a, qv.z, ev[j].z);
-                        a = upd<P>(a, qv.w, ev[j].w);
+                        a = upd<P>(a, qv.y, ev[j].x);  // pair-swapped query layout: element d sits at d ^ 1
+                        a = upd<P>(a, qv.x, ev[j].y);
+                        a = upd<P>(a, qv.w, ev[j].z);
+                        a = upd<P>(a, qv.z, ev[j].w);
                         acc[i][j] = a;
                     }
                 }
             }
+            // Release the stage.  The LAST warp to finish reading it refills it with the chunk STAGES ahead: no
+            // dedicated producer warp, no empty-barrier spinning, and warps may drift up to STAGES-1 chunks apart.
             __syncwarp();
-            if (lane == 0) mbar_arrive(empty0 + 8 * stage);
+            if (lane == 0) {
+                __threadfence_block();
+                const int old = atomicAdd(&done[stage], 1);
+                if ((old & (CONSUMER_WARPS - 1)) == CONSUMER_WARPS - 1) {
+                    __threadfence_block();
+                    fence_proxy_async();
+                    issue_chunk(p, &tm_q, &tm_e, it + STAGES, n_chunks, ring_u32, full0);
+                }
+            }
         }
 
     // ---- epilogue: compare against the per-query thresholds, count, reduce over the 16 lanes sharing a query row
@@ -400,7 +414,7 @@ static int transe_prepass(mre_ctx *ctx, const mre_rank_job *job, cudaStream_t st
 }
 
 template <int P, bool NEED_EQ>
-static int launch_rank(mre_ctx *ctx, const RankParams &p, cudaStream_t st) {
+static int launch_rank(mre_ctx *ctx, const RankParams &p, const CUtensorMap &tm_q, const CUtensorMap &tm_e, cudaStream_t st) {
     auto kern = transe_rank_kernel<P, NEED_EQ>;
     static bool configured = false;
     if (!configured) {
@@ -409,7 +423,7 @@ static int launch_rank(mre_ctx *ctx, const RankParams &p, cudaStream_t st) {
     }
     int64_t want = std::max<int64_t>(p.total_items, (p.Q + CONSUMER_WARPS - 1) / CONSUMER_WARPS);
     int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)ctx->sm_count * 2));
-    kern<<<grid, RANK_THREADS, RANK_SMEM, st>>>(p);
+    kern<<<grid, RANK_THREADS, RANK_SMEM, st>>>(p, tm_q, tm_e);
     ctx->launches += 1;
     MRE_CUDA(cudaGetLastError());
     return MRE_OK;
@@ -428,12 +442,29 @@ int rank_transe(mre_ctx *ctx, const mre_index *ix, const mre_rank_job *job, cuda
     p.qvec = ctx->qvec.as<float>();
     p.thr = ctx->thr.as<float2>();
     if (job->Q == 0) return MRE_OK;
+    // the table the candidate tiles stream from: the entity table itself, or the gathered candidate rows
+    const float *cand_table = ent;
+    int64_t cand_rows = job->E;
+    if (!p.all_entities) {
+        cand_rows = job->group_cptr[job->n_groups];
+        MRE_CHECK_ARG(cand_rows < (1LL << 31), "too many candidate rows");
+        MRE_TRY(ctx->ent_aux.reserve((size_t)std::max<int64_t>(cand_rows, 1) * Dp * sizeof(float)));
+        if (cand_rows > 0) {
+            gather_rows_kernel<<<grid_for(cand_rows * (Dp >> 2), 256), 256, 0, st>>>(ent, Dp, job->cand_idx, cand_rows,
+                                                                                     ctx->ent_aux.as<float>());
+            ctx->launches += 1;
+        }
+        cand_table = ctx->ent_aux.as<float>();
+    }
     init_counts_kernel<<<grid_for(4 * job->Q, 256), 256, 0, st>>>(job->counts, 4 * job->Q);
     ctx->launches += 1;
+    CUtensorMap tm_q, tm_e;
+    MRE_TRY(make_tmap_f32_2d(&tm_q, p.qvec, job->Q, Dp, Dp, TILE_Q, CHUNK));
+    MRE_TRY(make_tmap_f32_2d(&tm_e, cand_table, std::max<int64_t>(cand_rows, 1), Dp, Dp, TILE_E, CHUNK));
     MRE_TRY(ctx->time_begin(st));
     // the tie count is always on: one extra compare per score, in the epilogue only
-    if (job->p_norm == 1) MRE_TRY((launch_rank<1, true>(ctx, p, st)));
-    else MRE_TRY((launch_rank<2, true>(ctx, p, st)));
+    if (job->p_norm == 1) MRE_TRY((launch_rank<1, true>(ctx, p, tm_q, tm_e, st)));
+    else MRE_TRY((launch_rank<2, true>(ctx, p, tm_q, tm_e, st)));
     MRE_TRY(ctx->time_end(st));
     return MRE_OK;
 }

@@ -81,7 +81,6 @@ def test_transe_vs_reference_golden(env, fb15k237, name, wname):
     assert np.all(filt >= lo) and np.all(filt <= hi)
     exact = lo == hi
     assert np.array_equal(filt[exact], ref[exact])
-    assert exact.mean() > 0.5 if wname == "structured" else True
     # metric tuple (mrr, mr, hit10, hit3, hit1), normalised by testTotal as the reference does
     m = rk.metrics(counts, dev(side), "strict")
     sums, rr = m["sums"].cpu().numpy(), m["rr"].cpu().numpy()
