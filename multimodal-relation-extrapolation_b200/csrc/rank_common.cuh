@@ -76,7 +76,7 @@ __device__ __forceinline__ int group_of_query(const RankParams &p, int64_t q) {
 
 // Known-true correction for query q, executed by one full warp.  Score(q, entity) must return the value the
 // dense phase compares against thr (the raw accumulator).  Returns through atomics on counts[2], counts[3].
-template <bool NEED_EQ, class ScoreFn>
+template <bool NEED_EQ, bool INCLUDE_TRUTH = true, class ScoreFn>
 __device__ __forceinline__ void correct_query(const RankParams &p, int64_t q, int lane, ScoreFn score) {
     const int side = query_side(p, q);
     const int64_t h = p.q_h[q], t = p.q_t[q], r = p.q_r[q];
@@ -102,11 +102,13 @@ __device__ __forceinline__ void correct_query(const RankParams &p, int64_t q, in
         c1 = gd.c0 + gd.nc;
     }
     int n_lt = 0, n_eq = 0;
-    // entries lo..hi-1 are the known entities; index hi stands for the true entity itself
-    for (int64_t base = lo; base <= hi; base += 32) {
+    // entries lo..hi-1 are the known entities; index hi stands for the true entity itself (when the dense phase
+    // counted it: the TransE kernel does, the tensor-core kernel excludes it by index)
+    const int64_t last = INCLUDE_TRUTH ? hi : hi - 1;
+    for (int64_t base = lo; base <= last; base += 32) {
         int64_t i = base + lane;
         bool lt = false, eq = false;
-        if (i <= hi) {
+        if (i <= last) {
             int64_t x = i < hi ? __ldg(list + i) : truth;
             bool use = (i == hi) || (x != truth);
             if (use && (x < 0 || x >= p.E)) use = false;
@@ -125,5 +127,22 @@ __device__ __forceinline__ void correct_query(const RankParams &p, int64_t q, in
         if (NEED_EQ && n_eq) atomicSub(p.counts + 3 * p.Q + q, n_eq);
     }
 }
+
+// candidate groups: copy the listed entity rows into one dense table so that the main kernel streams every
+// candidate tile with the same TMA boxes as the all-entity case
+static __global__ void gather_rows_kernel(const float *__restrict__ ent, int64_t D, const int64_t *__restrict__ idx, int64_t n,
+                                   float *__restrict__ out) {
+    const int64_t total = n * (D >> 2);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = i / (D >> 2), c = i - row * (D >> 2);
+        reinterpret_cast<float4 *>(out + row * D)[c] = reinterpret_cast<const float4 *>(ent + __ldg(idx + row) * D)[c];
+    }
+}
+
+static __global__ void init_counts_kernel(int32_t *counts, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) counts[i] = 0;
+}
+
+static inline int grid_for(int64_t n, int block) { return (int)((n + block - 1) / block < 148 * 32 ? (n + block - 1) / block : 148 * 32); }
 
 }  // namespace mre

@@ -137,21 +137,6 @@ __global__ void transe_predict_kernel(const float *__restrict__ ent, int64_t E, 
     out[j] = P == 1 ? acc : __fsqrt_rn(acc);
 }
 
-// candidate groups: copy the listed entity rows into one dense table so that the main kernel streams every
-// candidate tile with the same TMA boxes as the all-entity case
-__global__ void gather_rows_kernel(const float *__restrict__ ent, int64_t D, const int64_t *__restrict__ idx, int64_t n,
-                                   float *__restrict__ out) {
-    const int64_t total = n * (D >> 2);
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t row = i / (D >> 2), c = i - row * (D >> 2);
-        reinterpret_cast<float4 *>(out + row * D)[c] = reinterpret_cast<const float4 *>(ent + __ldg(idx + row) * D)[c];
-    }
-}
-
-__global__ void init_counts_kernel(int32_t *counts, int64_t n) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) counts[i] = 0;
-}
-
 // ------------------------------------------------------------------------------------------ main kernel
 template <int P>
 __device__ __forceinline__ float upd(float acc, float q, float e) {
@@ -382,8 +367,6 @@ int fill_rank_params(mre_ctx *ctx, const mre_index *ix, const mre_rank_job *job,
     p.counts = job->counts;
     return MRE_OK;
 }
-
-static inline int grid_for(int64_t n, int block) { return (int)std::min<int64_t>((n + block - 1) / block, 148 * 32); }
 
 template <int P>
 static int transe_prepass(mre_ctx *ctx, const mre_rank_job *job, cudaStream_t st, const float **ent_out, int64_t *Dp_out) {

@@ -1,0 +1,150 @@
+"""GPU parity of the tcgen05 DistMult / ComplEx contraction + rank path (mre_rank with scorer distmult|complex).
+
+The tensor-core path computes 3xTF32 split products, but every column closer to s_true than a rigorous error guard is
+re-scored with the sequential FP32 scorer, so the COUNTS must equal the FP32 oracle's BIT FOR BIT (DistMult, whose
+oracle uses the same association) -- and sit inside the reference's (torch) tie band of SURVEY Appendix F, exactly equal
+where the band is empty, with MRR / Hits within 1e-4."""
+import numpy as np
+import pytest
+import torch
+
+import golden_util as gu
+import helpers
+from oracle import kge_oracle as ko
+
+pytestmark = pytest.mark.gpu
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+@pytest.fixture(scope="module")
+def env(mre, fb15k237):
+    eng = mre.engine
+    ix = eng.KGIndex.from_arrays(fb15k237.E, fb15k237.R, fb15k237.train, fb15k237.valid, fb15k237.test).to_device(0)
+    return eng, ix, eng.Ranker(device=0)
+
+
+def tables_for(kind, wname, E, R, D):
+    ent, rel, ent_im, rel_im = gu.WEIGHT_SETS[wname](gu.SEED, [(E, D), (R, D), (E, D), (R, D)])
+    return (ent, ent_im, rel, rel_im) if kind == "complex" else (ent, rel)
+
+
+@pytest.mark.parametrize("wname", list(gu.WEIGHT_SETS))
+@pytest.mark.parametrize("kind", ["distmult", "complex"])
+def test_bilinear_vs_reference_golden(env, fb15k237, kind, wname):
+    eng, ix, rk = env
+    g = gu.load("golden_fb15k237.npz")
+    E, R, D = fb15k237.E, fb15k237.R, int(g["D"])
+    tabs = tables_for(kind, wname, E, R, D)
+    th, tt, tr = fb15k237.oracle.test_triples()
+    qidx = g["qidx"]
+    q_h, q_t, q_r = np.repeat(th[qidx], 2), np.repeat(tt[qidx], 2), np.repeat(tr[qidx], 2)
+    side = np.tile(np.array([0, 1], np.uint8), len(qidx))
+    counts = rk.rank(kind, tuple(dev(t) for t in tabs), dev(q_h), dev(q_t), dev(q_r), dev(side), index=ix)
+    c = counts.cpu().numpy()
+    key = f"{wname}_{kind}"
+    filt = c[2].reshape(-1, 2)
+    # this arithmetic is not bit-matched to torch's: the interval is the 3x band (the reference's own FP32 summation error
+    # reaches ~0.5 band on the structured tables, see DESIGN.md "parity"); at least 99% must also sit inside the 1x band
+    lo, hi, ref = g[key + "_lo3"], g[key + "_hi3"], g[key + "_filt"]
+    assert np.all(filt >= lo) and np.all(filt <= hi), (np.abs(filt - ref).max(), (filt < lo).sum(), (filt > hi).sum())
+    exact = lo == hi
+    assert np.array_equal(filt[exact], ref[exact])
+    inside1 = (filt >= g[key + "_lo"]) & (filt <= g[key + "_hi"])
+    assert inside1.mean() >= 0.99
+    m = rk.metrics(counts, dev(side), "strict")
+    sums, rr = m["sums"].cpu().numpy(), m["rr"].cpu().numpy()
+    T = float(fb15k237.oracle.test_total)
+    mine = np.array([(rr[0] + rr[1]) / 2 / T, (sums[0][5] + sums[1][5]) / 2 / T, (sums[0][3] + sums[1][3]) / 2 / T,
+                     (sums[0][2] + sums[1][2]) / 2 / T])
+    assert np.allclose(mine, g[key + "_tuple"].astype(np.float64)[[0, 2, 3, 4]], atol=1e-4)
+    # Model.predict on the probe entities
+    for k in (0, len(qidx) - 1):
+        for s in (0, 1):
+            sc = rk.predict(kind, tuple(dev(t) for t in tabs), dev(q_h), dev(q_t), dev(q_r), dev(side), query=2 * k + s).cpu().numpy()
+            refp = g[key + "_probe_scores"][k, s]
+            assert np.allclose(sc[g["probe"]], refp, rtol=1e-4, atol=1e-5 * np.abs(refp).mean())
+
+
+def test_distmult_counts_bit_exact_vs_oracle(env, fb15k237):
+    eng, ix, rk = env
+    E, R, D = fb15k237.E, fb15k237.R, 200
+    th, tt, tr = fb15k237.oracle.test_triples()
+    sel = np.linspace(0, len(th) - 1, 120).astype(np.int64)
+    q_h, q_t, q_r = np.repeat(th[sel], 2), np.repeat(tt[sel], 2), np.repeat(tr[sel], 2)
+    side = np.tile(np.array([0, 1], np.uint8), len(sel))
+    for wname in gu.WEIGHT_SETS:
+        ent, rel = tables_for("distmult", wname, E, R, D)
+        raw_o, filt_o = helpers.oracle_counts(fb15k237, lambda s, h, t, r: ko.distmult_scores(ent, rel, s, h, t, r), q_h, q_t, q_r, side)
+        c = rk.rank("distmult", (dev(ent), dev(rel)), dev(q_h), dev(q_t), dev(q_r), dev(side), index=ix).cpu().numpy()
+        assert np.array_equal(c[0], raw_o)
+        assert np.array_equal(c[2], filt_o)
+
+
+@pytest.mark.parametrize("kind", ["distmult", "complex"])
+@pytest.mark.parametrize("E,D,Q", [(1, 8, 1), (255, 8, 3), (257, 36, 130), (700, 6, 257), (3000, 200, 129), (513, 132, 64)])
+def test_bilinear_ragged_shapes_vs_oracle(mre, kind, E, D, Q):
+    """tile edges (E vs 256, Q vs 128), partial K blocks, K not a multiple of 8 / 4; counts inside the oracle's tie band"""
+    eng = mre.engine
+    rng = np.random.default_rng(E * 1000 + D)
+    R = 5
+    ds = helpers.synthetic_graph(3, E, R, 4 * E, E // 2 + 1, Q)
+    ix = eng.KGIndex.from_arrays(E, R, ds.train, ds.valid, ds.test).to_device(0)
+    rk = eng.Ranker(device=0)
+    tabs = [rng.standard_normal(s).astype(np.float32) for s in ([(E, D), (R, D)] if kind == "distmult" else [(E, D), (E, D), (R, D), (R, D)])]
+    th, tt, tr = ds.oracle.test_triples()
+    side = (np.arange(Q) % 2).astype(np.uint8)
+    c = rk.rank(kind, tuple(dev(t) for t in tabs), dev(th), dev(tt), dev(tr), dev(side), index=ix).cpu().numpy()
+    all_h = np.concatenate([ds.train[0], ds.valid[0], ds.test[0]]); all_t = np.concatenate([ds.train[1], ds.valid[1], ds.test[1]])
+    all_r = np.concatenate([ds.train[2], ds.valid[2], ds.test[2]])
+    tails_of, heads_of = gu.group_lists(all_h, all_r, all_t), gu.group_lists(all_t, all_r, all_h)
+    n_exact = 0
+    for q in range(Q):
+        h, t, r, s = int(th[q]), int(tt[q]), int(tr[q]), int(side[q])
+        sc = ko.distmult_scores(tabs[0], tabs[1], s, h, t, r) if kind == "distmult" else ko.complex_scores(*tabs, s, h, t, r)
+        truth = h if s == 0 else t
+        known = heads_of[(t, r)] if s == 0 else tails_of[(h, r)]
+        band = gu.TIE_BAND * max(abs(float(sc[truth])), float(np.abs(sc).mean()))
+        lo, hi = gu.band_counts(sc, truth, known, band)
+        assert lo <= c[2][q] <= hi, (q, lo, c[2][q], hi)
+        raw_lo = int((np.delete(sc, truth) < sc[truth] - band).sum()); raw_hi = int((np.delete(sc, truth) <= sc[truth] + band).sum())
+        assert raw_lo <= c[0][q] <= raw_hi
+        n_exact += lo == hi
+        if kind == "distmult":      # same association as the oracle => the counts are the oracle's, bit for bit
+            assert (int(c[0][q]), int(c[2][q])) == ds.oracle.rank_from_scores(sc, s, h, t, r)
+    assert n_exact >= Q // 2
+
+
+def test_distmult_predict_bit_exact_vs_oracle(mre, fb15k237):
+    eng = mre.engine
+    rk = eng.Ranker(device=0)
+    E, R, D = fb15k237.E, fb15k237.R, 200
+    ent, rel = gu.xavier_tables(11, [(E, D), (R, D)])
+    q_h, q_t, q_r, side = np.array([5, 77]), np.array([900, 12000]), np.array([3, 200]), np.array([0, 1], np.uint8)
+    for q in range(2):
+        sc = rk.predict("distmult", (dev(ent), dev(rel)), dev(q_h), dev(q_t), dev(q_r), dev(side), query=q).cpu().numpy()
+        assert np.array_equal(sc, ko.distmult_scores(ent, rel, int(side[q]), int(q_h[q]), int(q_t[q]), int(q_r[q])))
+
+
+def test_bilinear_candidate_groups(mre):
+    """candidate lists + CSR filter on the tensor-core path: counts over S minus known minus truth, inside the band"""
+    eng = mre.engine
+    rng = np.random.default_rng(5)
+    E, R, D = 2000, 6, 64
+    ent, rel = rng.standard_normal((E, D)).astype(np.float32), rng.standard_normal((R, D)).astype(np.float32)
+    n_per = [150, 1, 300]
+    cands = [np.sort(rng.choice(E, n, replace=False)) for n in (700, 300, 257)]
+    h = rng.integers(0, E, sum(n_per)); t = rng.integers(0, E, sum(n_per)); r = np.repeat(np.arange(3), n_per)
+    lists = [np.unique(np.concatenate([[tt], rng.integers(0, E, 5)])) for tt in t]
+    fptr = np.concatenate([[0], np.cumsum([len(x) for x in lists])]).astype(np.int64)
+    groups = eng.CandidateGroups.from_lists(n_per, cands, "cuda")
+    rk = eng.Ranker(device=0)
+    c = rk.rank("distmult", (dev(ent), dev(rel)), dev(h), dev(t), dev(r), 1, groups=groups,
+                filt_csr=(dev(fptr), dev(np.concatenate(lists)))).cpu().numpy()
+    for q in range(len(h)):
+        sc = ko.distmult_scores(ent, rel, 1, int(h[q]), int(t[q]), int(r[q]))
+        S = np.setdiff1d(cands[int(r[q])], lists[q])
+        band = gu.TIE_BAND * max(abs(float(sc[t[q]])), float(np.abs(sc).mean()))
+        assert (sc[S] < sc[t[q]] - band).sum() <= c[2][q] <= (sc[S] <= sc[t[q]] + band).sum()
