@@ -215,6 +215,18 @@ int mre_transe_margin_step(mre_ctx *ctx, const float *ent, const float *rel, int
                            const int64_t *h, const int64_t *t, const int64_t *r, int64_t B, int64_t neg,
                            float margin, int32_t p_norm, int32_t normalize,
                            float *grad_ent, float *grad_rel, float *loss_out, float *scores_out, void *stream);
+/*
+ * The same step in two halves, for callers that put their own loss between them (Model.forward, TransE.py:62-74,
+ * DistMult.py:46-57, ComplEx.py:29-40; head_batch / tail_batch callers expand their index arrays to length n first):
+ * mre_score_triples writes the raw model score of n explicit triples (TransE: the distance; DistMult / ComplEx: the
+ * similarity, which predict() negates); mre_transe_backward scatters dLoss/d(ent), dLoss/d(rel) given dLoss/dscore.
+ */
+int mre_score_triples(mre_ctx *ctx, int32_t scorer, const float *ent, const float *ent_im, const float *rel, const float *rel_im,
+                      int64_t D, const int64_t *h, const int64_t *t, const int64_t *r, int64_t n, int32_t p_norm,
+                      int32_t normalize, float *score_out, void *stream);
+int mre_transe_backward(mre_ctx *ctx, const float *ent, const float *rel, int64_t D, const int64_t *h, const int64_t *t,
+                        const int64_t *r, int64_t n, int32_t p_norm, int32_t normalize, const float *score, const float *dscore,
+                        float *grad_ent, float *grad_rel, void *stream);
 /* w -= lr * g (torch.optim.SGD as Trainer.py:73-78 configures it), then g = 0; device arrays of n floats */
 int mre_sgd_update(mre_ctx *ctx, float *w, float *g, int64_t n, float lr, void *stream);
 

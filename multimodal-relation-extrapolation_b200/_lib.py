@@ -111,6 +111,8 @@ def lib():
     L.mre_sample_host.argtypes = samp
     L.mre_transe_margin_step.argtypes = [vp, vp, vp, i64, i64, i64, vp, vp, vp, i64, i64, f32, i32, i32, vp, vp, vp, vp, vp]
     L.mre_sgd_update.argtypes = [vp, vp, vp, i64, f32, vp]
+    L.mre_score_triples.argtypes = [vp, i32, vp, vp, vp, vp, i64, vp, vp, vp, i64, i32, i32, vp, vp]
+    L.mre_transe_backward.argtypes = [vp, vp, vp, i64, vp, vp, vp, i64, i32, i32, vp, vp, vp, vp, vp]
     L.mre_probe_fp32_peak.argtypes = [vp, P(C.c_double)]
     L.mre_probe_tf32_peak.argtypes = [vp, P(C.c_double)]
     L.mre_ctx_timing.argtypes = [vp, i32]

@@ -181,6 +181,22 @@ int mre_transe_margin_step(mre_ctx *ctx, const float *ent, const float *rel, int
                               scores_out, (cudaStream_t)stream);
 }
 
+int mre_score_triples(mre_ctx *ctx, int32_t scorer, const float *ent, const float *ent_im, const float *rel, const float *rel_im,
+                      int64_t D, const int64_t *h, const int64_t *t, const int64_t *r, int64_t n, int32_t p_norm, int32_t normalize,
+                      float *score_out, void *stream) {
+    MRE_CHECK_ARG(ctx != nullptr, "ctx is NULL");
+    MRE_CUDA(cudaSetDevice(ctx->device));
+    return score_triples(ctx, scorer, ent, ent_im, rel, rel_im, D, h, t, r, n, p_norm, normalize, score_out, (cudaStream_t)stream);
+}
+
+int mre_transe_backward(mre_ctx *ctx, const float *ent, const float *rel, int64_t D, const int64_t *h, const int64_t *t,
+                        const int64_t *r, int64_t n, int32_t p_norm, int32_t normalize, const float *score, const float *dscore,
+                        float *grad_ent, float *grad_rel, void *stream) {
+    MRE_CHECK_ARG(ctx != nullptr, "ctx is NULL");
+    MRE_CUDA(cudaSetDevice(ctx->device));
+    return transe_backward(ctx, ent, rel, D, h, t, r, n, p_norm, normalize, score, dscore, grad_ent, grad_rel, (cudaStream_t)stream);
+}
+
 int mre_sgd_update(mre_ctx *ctx, float *w, float *g, int64_t n, float lr, void *stream) {
     MRE_CHECK_ARG(ctx != nullptr, "ctx is NULL");
     MRE_CUDA(cudaSetDevice(ctx->device));

@@ -126,6 +126,12 @@ int transe_margin_step(mre_ctx *ctx, const float *ent, const float *rel, int64_t
                        int32_t p_norm, int32_t normalize, float *grad_ent, float *grad_rel, float *loss_out,
                        float *scores_out, cudaStream_t st);
 int sgd_update(mre_ctx *ctx, float *w, float *g, int64_t n, float lr, cudaStream_t st);
+int score_triples(mre_ctx *ctx, int scorer, const float *ent, const float *ent_im, const float *rel, const float *rel_im, int64_t D,
+                  const int64_t *h, const int64_t *t, const int64_t *r, int64_t n, int32_t p_norm, int32_t normalize, float *score,
+                  cudaStream_t st);
+int transe_backward(mre_ctx *ctx, const float *ent, const float *rel, int64_t D, const int64_t *h, const int64_t *t, const int64_t *r,
+                    int64_t n, int32_t p_norm, int32_t normalize, const float *score, const float *dscore, float *grad_ent,
+                    float *grad_rel, cudaStream_t st);
 int probe_fp32_peak(mre_ctx *ctx, double *lane_ops_per_s);
 int probe_tf32_peak(mre_ctx *ctx, double *flops_per_s);
 }  // namespace mre

