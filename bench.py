@@ -245,7 +245,7 @@ def run_reference(args, w):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    per_step = 128
+    per_step = 512
     rng = np.random.default_rng(0)
     with stdout_to_stderr():
         run, n_test, kind = reference_eval_setup(w, threads)
@@ -297,8 +297,7 @@ def main():
     mre_b200.build()
     eng = mre_b200.engine
     torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dctx = mre_b200.dist.DistContext() if world > 1 else None
     ctx = eng.Context(local)
     rk = eng.Ranker(ctx)
     dev = torch.device("cuda", local)
@@ -411,9 +410,8 @@ def main():
         e2e_s = e2e_timed(step_e2e, args.steps, args.warmup)
     # metric tuple of this rank's shard, combined across ranks by one integer all-reduce
     sums, rr = out["sums"].clone(), out["rr"].clone()
-    if world > 1:
-        dist.all_reduce(sums)
-        dist.all_reduce(rr)
+    if dctx is not None:
+        sums, rr = dctx.all_reduce_metrics(sums, rr)
     summ = eng.summarize(sums.cpu().numpy(), rr.cpu().numpy())
 
     value = world * Q * args.steps / (ms * 1e-3)
