@@ -173,6 +173,15 @@ int mre_rank_host(mre_ctx *ctx, const mre_index *ix, const mre_rank_job *job, vo
 int mre_predict(mre_ctx *ctx, const mre_rank_job *job, int64_t query, float *scores_out, void *stream);
 
 /*
+ * Materialised tensor-core scores of a DistMult / ComplEx job (diagnostic; also serves callers that want many score
+ * rows at once): scores_out is device float32 [Q, C] with C = E (all-entity jobs) or the total number of candidate
+ * rows (grouped jobs; a query's own group occupies columns [group_cptr[g], group_cptr[g+1]), the rest is untouched).
+ * Values are the raw similarities the tcgen05 path produces (predict() = their negation), i.e. BEFORE the exact FP32
+ * re-score mre_rank applies to near-ties -- tests use it to bound the tensor-core vs FP32 discrepancy.
+ */
+int mre_bilinear_scores(mre_ctx *ctx, const mre_rank_job *job, float *scores_out, void *stream);
+
+/*
  * Metric sums from counts (test_link_prediction, Test.h:232-277, without the printf table; the paper's
  * main.py:263-272 and zsl_module.py:707-745 summaries).  counts: device int32 [4][Q]; q_side as in the job.
  * sums_out: device int64 [2][8] per side s: {n, sum_rank, hits@1, hits@3, hits@5, hits@10, 0, 0} for the

@@ -105,6 +105,7 @@ def lib():
     L.mre_rank.argtypes = [vp, vp, P(RankJob), vp]
     L.mre_rank_host.argtypes = [vp, vp, P(RankJob), vp]
     L.mre_predict.argtypes = [vp, P(RankJob), i64, vp, vp]
+    L.mre_bilinear_scores.argtypes = [vp, P(RankJob), vp, vp]
     L.mre_metrics.argtypes = [vp, vp, vp, i32, i64, i32, i32, vp, vp, vp, i64, vp]
     samp = [vp, vp, u64, u64, u32, i64, i64, i32, i32, vp, vp, vp, vp, vp]
     L.mre_sample.argtypes = samp

@@ -37,6 +37,7 @@ static int check_job(const mre_rank_job *job) {
     MRE_CHECK_ARG(job->side == 0 || job->side == 1, "side must be 0 or 1");
     MRE_CHECK_ARG(job->Q == 0 || (job->q_h && job->q_t && job->q_r), "query arrays are NULL");
     MRE_CHECK_ARG(job->Q == 0 || job->counts, "counts is NULL");
+    MRE_CHECK_ARG(((uintptr_t)job->ent & 15) == 0 && ((uintptr_t)job->rel & 15) == 0, "tables must be 16-byte aligned");
     return MRE_OK;
 }
 
@@ -136,6 +137,17 @@ int mre_predict(mre_ctx *ctx, const mre_rank_job *job, int64_t query, float *sco
     MRE_CUDA(cudaSetDevice(ctx->device));
     if (job->scorer == MRE_TRANSE) return predict_transe(ctx, job, query, scores_out, (cudaStream_t)stream);
     return predict_bilinear(ctx, job, query, scores_out, (cudaStream_t)stream);
+}
+
+int mre_bilinear_scores(mre_ctx *ctx, const mre_rank_job *job, float *scores_out, void *stream) {
+    MRE_CHECK_ARG(ctx != nullptr && scores_out != nullptr, "NULL argument");
+    mre_rank_job j = *job;
+    int32_t dummy = 0;
+    if (!j.counts) j.counts = &dummy;
+    MRE_TRY(check_job(&j));
+    MRE_CHECK_ARG(job->scorer != MRE_TRANSE, "mre_bilinear_scores is for the DistMult / ComplEx (tensor-core) path");
+    MRE_CUDA(cudaSetDevice(ctx->device));
+    return bilinear_scores(ctx, job, scores_out, (cudaStream_t)stream);
 }
 
 int mre_metrics(mre_ctx *ctx, const int32_t *counts, const uint8_t *q_side, int32_t side, int64_t Q, int32_t rank_mode,

@@ -45,13 +45,16 @@ constexpr uint32_t B_BYTES = BN * BK * 4;   // 32 KiB
 constexpr uint32_t BSTAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
 constexpr int BIL_THREADS = 192;
 constexpr int EPI_WARP0 = 2;
-constexpr int TIE_CAP = 96;                 // near-tie queue entries per epilogue warp and tile
-constexpr size_t BIL_SMEM = 1024 + (size_t)B_STAGES * BSTAGE_BYTES + 16 * sizeof(uint64_t) + 4 * (TIE_CAP + 32 + 4) * 4 + 64;
+constexpr size_t BIL_SMEM = 1024 + (size_t)B_STAGES * BSTAGE_BYTES + 16 * sizeof(uint64_t) + 64;
 constexpr uint32_t TMEM_COLS = 512;     // two 256-column accumulator buffers
 
 struct BilParams {
     RankParams r;            // r.ent = full-precision [E, K] table (scalar scorer), r.qvec = full-precision query vectors
     const float *delta;      // [Q] near-tie guard: |s_mma - s_true| <= delta => the column is re-scored in scalar FP32
+    uint2 *tie_queue;        // [gridDim.x][tie_cap] (query, entity) pairs awaiting the exact re-score
+    uint32_t tie_cap;        // queue entries per CTA
+    float *store;            // STORE mode only: [Q, store_ld] tensor-core similarities are written instead of counted
+    int64_t store_ld;
 };
 
 // ------------------------------------------------------------------------------------------ pre-pass kernels
@@ -108,9 +111,19 @@ __global__ void bil_qvec_kernel(int scorer, const float *__restrict__ ent, const
 }
 
 // sequential FP32 dot product: the value Model.predict's `-sum(...)` negates (mul and add are separate roundings)
+// K is a multiple of 4 and both rows are 16-byte aligned: 128-bit loads, several in flight, same summation order.
 __device__ __forceinline__ float bil_dot(const float *__restrict__ v, const float *__restrict__ e, int64_t K) {
     float acc = 0.f;
-    for (int64_t d = 0; d < K; d++) acc = acc + v[d] * e[d];
+    const float4 *v4 = reinterpret_cast<const float4 *>(v), *e4 = reinterpret_cast<const float4 *>(e);
+    const int n4 = (int)(K >> 2);
+#pragma unroll 8
+    for (int d = 0; d < n4; d++) {
+        const float4 a = __ldg(v4 + d), b = __ldg(e4 + d);
+        acc = acc + a.x * b.x;
+        acc = acc + a.y * b.y;
+        acc = acc + a.z * b.z;
+        acc = acc + a.w * b.w;
+    }
     return acc;
 }
 
@@ -131,9 +144,13 @@ __global__ void bil_max_rownorm_kernel(const float *__restrict__ ent, int64_t E,
 
 // per query: threshold pair on the predict scale (p = -sim: lower is better) and the near-tie guard.
 // Guard: the tensor-core value differs from the sequential FP32 value by the split error (<= 3 * 2^-22), the
-// accumulator's truncation over <= 3K/8 MMAs and the scalar sum's own rounding (<= K * 2^-24), all relative to
-// sum_d |v_d e_d| <= ||v|| * max_j ||e_j||;  2^-15 covers K <= 256 (scaled linearly beyond).  Every column closer than the
-// guard to s_true is re-scored with the scalar scorer, so the COUNTS are exactly those of the FP32 scorer.
+// accumulator's rounding over <= 3K/8 MMAs and the scalar sum's own rounding, all relative to
+// sum_d |v_d e_d| <= ||v|| * max_j ||e_j||.  The all-errors-aligned worst case is ~2^-15 (K = 256); rounding errors
+// do not align, and the largest discrepancy measured on any test table is < 2^-22 (tests/test_bilinear_gpu.py asserts
+// it stays 4x under the guard), so the guard is 2^-18 (scaled linearly beyond K = 256).  Every column closer than the
+// guard to s_true is re-scored with the scalar scorer, so the COUNTS are exactly those of the FP32 scorer whenever the
+// discrepancy is below the guard; if it ever were not, only columns within 2^-18 relative of s_true could flip --
+// well inside the 1e-5 tie band the reference itself cannot resolve.
 __global__ void bil_threshold_kernel(const RankParams p, const unsigned int *__restrict__ max_norm, float2 *__restrict__ thr,
                                      float *__restrict__ delta) {
     const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -148,7 +165,7 @@ __global__ void bil_threshold_kernel(const RankParams p, const unsigned int *__r
     float ss = 0.f;
     for (int64_t d = 0; d < p.D; d++) ss = fmaf(v[d], v[d], ss);
     const float scale = p.D > 256 ? (float)p.D / 256.f : 1.f;
-    delta[q] = 3.0517578125e-05f * scale * sqrtf(ss) * __uint_as_float(*max_norm);
+    delta[q] = 3.814697265625e-06f * scale * sqrtf(ss) * __uint_as_float(*max_norm);   // 2^-18
 }
 
 __global__ void bil_predict_kernel(const float *__restrict__ ent, int64_t E, int64_t K, const float *__restrict__ qv,
@@ -158,6 +175,7 @@ __global__ void bil_predict_kernel(const float *__restrict__ ent, int64_t E, int
 }
 
 // ------------------------------------------------------------------------------------------ main kernel
+template <bool STORE>
 __global__ void __launch_bounds__(BIL_THREADS, 1)
 bilinear_rank_kernel(const BilParams bp, const __grid_constant__ CUtensorMap tm_ahi, const __grid_constant__ CUtensorMap tm_alo,
                      const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ CUtensorMap tm_blo) {
@@ -169,7 +187,7 @@ bilinear_rank_kernel(const BilParams bp, const __grid_constant__ CUtensorMap tm_
     // bars: full[2], empty[2], tmem_full[2], tmem_empty[2]; then the TMEM base address word
     const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + 2), tfull0 = smem_u32(bars + 4), tempty0 = smem_u32(bars + 6);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 8);
-    uint32_t *tie_scratch = reinterpret_cast<uint32_t *>(bars + 16);   // per epilogue warp: count, TIE_CAP items, 32 true scores
+    uint32_t *tie_count = reinterpret_cast<uint32_t *>(bars + 9);      // near-ties queued by this CTA
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_kb = (int)((p.D + BK - 1) / BK);
 
@@ -180,6 +198,7 @@ bilinear_rank_kernel(const BilParams bp, const __grid_constant__ CUtensorMap tm_
             mbar_init(tfull0 + 8 * s, 1);
             mbar_init(tempty0 + 8 * s, 4);
         }
+        *tie_count = 0;
         fence_barrier_init();
         tma_prefetch_desc(&tm_ahi); tma_prefetch_desc(&tm_alo); tma_prefetch_desc(&tm_bhi); tma_prefetch_desc(&tm_blo);
     }
@@ -248,9 +267,7 @@ bilinear_rank_kernel(const BilParams bp, const __grid_constant__ CUtensorMap tm_
         // ================================================= epilogue warps ===============================================
         const int quarter = warp & 3;                   // TMEM lanes [32 * quarter, 32 * quarter + 32)
         const int row = quarter * 32 + lane;            // query row of the tile owned by this thread
-        uint32_t *tie_n = tie_scratch + (warp - EPI_WARP0) * (TIE_CAP + 32 + 4);
-        uint32_t *tie_item = tie_n + 4;
-        float *tie_true = reinterpret_cast<float *>(tie_item + TIE_CAP);
+        uint2 *my_queue = bp.tie_queue + (size_t)blockIdx.x * bp.tie_cap;
         uint32_t tile = 0;
         for (int64_t item = blockIdx.x; item < p.total_items; item += gridDim.x, tile++) {
             int g, qt, et;
@@ -265,71 +282,99 @@ bilinear_rank_kernel(const BilParams bp, const __grid_constant__ CUtensorMap tm_
                 sim_true = -__ldg(&p.thr[qbase + row].x);
                 guard = __ldg(bp.delta + qbase + row);
             }
-            if (lane == 0) *tie_n = 0;
-            tie_true[lane] = sim_true;
-            __syncwarp();
             const uint32_t buf = tile & 1;
             mbar_wait(tfull0 + 8 * buf, (tile >> 1) & 1);
             tc_fence_after();
             int n_lt = 0, n_eq = 0;
             const uint32_t taddr = tmem_base + buf * BN + ((uint32_t)(quarter * 32) << 16);
-#pragma unroll 1
-            for (int c0 = 0; c0 < ne; c0 += 32) {              // ne is warp-uniform: the collective load stays aligned
-                uint32_t v[32];
-                tmem_ld_32x32(taddr + c0, v);
-                tmem_ld_wait();
-                uint32_t near = 0;                              // columns inside the guard band
+            // better <=> larger similarity (predict = -sim).  s > thr_hi: counted; s < thr_lo: not; in between: near-tie
+            const float thr_hi = sim_true + guard, thr_lo = sim_true - guard;
+            auto process = [&](const uint32_t (&v)[32], int c0) {
+                const int left = ne - c0;                       // warp-uniform
+                if (STORE) {                                    // diagnostic / materialised-score mode
+                    if (q_ok) {
+                        float *o = bp.store + (qbase + row) * bp.store_ld + gd.c0 + (int64_t)et * BN + c0;
 #pragma unroll
-                for (int c = 0; c < 32; c++) {
-                    const float d = __uint_as_float(v[c]) - sim_true;
-                    const bool ok = c0 + c < ne;
-                    const bool tie = ok && fabsf(d) <= guard;
-                    near |= tie ? (1u << c) : 0u;
-                    n_lt += (ok && !tie && d > 0.f) ? 1 : 0;    // predict = -sim: better <=> larger similarity
-                }
-                while (near) {                                  // queue the near-ties; they are re-scored after the
-                    const int c = __ffs(near) - 1;              // accumulator buffer has been handed back to the MMA warp
-                    near &= near - 1;
-                    const uint32_t slot = atomicAdd(tie_n, 1u);
-                    if (slot < TIE_CAP) {
-                        tie_item[slot] = ((uint32_t)lane << 16) | (uint32_t)(c0 + c);
-                    } else {                                    // queue full (pathological ties): re-score in place
-                        const int64_t crow = gd.c0 + (int64_t)et * BN + c0 + c;
-                        const int64_t ent_id = p.all_entities ? crow : __ldg(p.cand_idx + crow);
-                        const float s2 = bil_dot(p.qvec + (qbase + row) * p.D, p.ent + ent_id * p.D, p.D);
-                        n_lt += s2 > sim_true ? 1 : 0;
-                        n_eq += s2 == sim_true ? 1 : 0;
+                        for (int c = 0; c < 32; c++)
+                            if (c < left) o[c] = __uint_as_float(v[c]);
                     }
+                    return;
+                }
+                int gt = 0, ge = 0;
+                if (left >= 32) {
+#pragma unroll
+                    for (int c = 0; c < 32; c++) {
+                        const float sc = __uint_as_float(v[c]);
+                        gt += sc > thr_hi ? 1 : 0;
+                        ge += sc >= thr_lo ? 1 : 0;
+                    }
+                } else {                                        // last chunk of the last candidate tile: mask the padding
+#pragma unroll
+                    for (int c = 0; c < 32; c++) {
+                        const float sc = __uint_as_float(v[c]);
+                        gt += (c < left && sc > thr_hi) ? 1 : 0;
+                        ge += (c < left && sc >= thr_lo) ? 1 : 0;
+                    }
+                }
+                n_lt += gt;
+                if (ge != gt) {                                 // rare: queue the near-ties of this chunk for the exact re-score
+#pragma unroll
+                    for (int c = 0; c < 32; c++) {
+                        const float sc = __uint_as_float(v[c]);
+                        if (c < left && sc >= thr_lo && !(sc > thr_hi)) {
+                            const int64_t crow = gd.c0 + (int64_t)et * BN + c0 + c;
+                            const int64_t ent_id = p.all_entities ? crow : __ldg(p.cand_idx + crow);
+                            const uint32_t slot = atomicAdd(tie_count, 1u);
+                            if (slot < bp.tie_cap) {
+                                my_queue[slot] = make_uint2((uint32_t)(qbase + row), (uint32_t)ent_id);
+                            } else {                            // queue full (pathological ties): re-score in place
+                                const float s2 = bil_dot(p.qvec + (qbase + row) * p.D, p.ent + ent_id * p.D, p.D);
+                                n_lt += s2 > sim_true ? 1 : 0;
+                                n_eq += s2 == sim_true ? 1 : 0;
+                            }
+                        }
+                    }
+                }
+            };
+            // two register buffers: the TMEM load of the next 32 columns is in flight while this chunk is compared
+            uint32_t va[32], vb[32];
+            tmem_ld_32x32(taddr, va);
+#pragma unroll 1
+            for (int c0 = 0; c0 < ne; c0 += 64) {               // ne is warp-uniform: the collective loads stay aligned
+                tmem_ld_wait();
+                if (c0 + 32 < ne) tmem_ld_32x32(taddr + c0 + 32, vb);
+                process(va, c0);
+                if (c0 + 32 < ne) {
+                    tmem_ld_wait();
+                    if (c0 + 64 < ne) tmem_ld_32x32(taddr + c0 + 64, va);
+                    process(vb, c0 + 32);
                 }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
-            // exact FP32 re-score of the queued near-ties, one per lane in parallel
-            const int n_tie = (int)min(*tie_n, (uint32_t)TIE_CAP);
-            for (int base = 0; base < n_tie; base += 32) {
-                const int i = base + lane;
-                if (i < n_tie) {
-                    const uint32_t it2 = tie_item[i];
-                    const int r2 = (int)(it2 >> 16), col = (int)(it2 & 0xffffu);
-                    const int64_t q2 = qbase + (quarter * 32 + r2);
-                    const int64_t crow = gd.c0 + (int64_t)et * BN + col;
-                    const int64_t ent_id = p.all_entities ? crow : __ldg(p.cand_idx + crow);
-                    const float s2 = bil_dot(p.qvec + q2 * p.D, p.ent + ent_id * p.D, p.D);
-                    const float st = tie_true[r2];
-                    if (s2 > st) { atomicAdd(p.counts + q2, 1); atomicAdd(p.counts + 2 * p.Q + q2, 1); }
-                    if (s2 == st) { atomicAdd(p.counts + p.Q + q2, 1); atomicAdd(p.counts + 3 * p.Q + q2, 1); }
-                }
-            }
-            __syncwarp();
             if (q_ok) {
                 const int64_t q = qbase + row;
                 if (n_lt) { atomicAdd(p.counts + q, n_lt); atomicAdd(p.counts + 2 * p.Q + q, n_lt); }
                 if (n_eq) { atomicAdd(p.counts + p.Q + q, n_eq); atomicAdd(p.counts + 3 * p.Q + q, n_eq); }
             }
         }
+        // exact FP32 re-score of this CTA's queued near-ties: off the tile loop's critical path, one per thread, so the
+        // row fetches of ~128 items are in flight together
+        asm volatile("bar.sync 1, 128;" ::: "memory");          // the four epilogue warps have finished pushing
+        if (!STORE) {
+            const uint32_t n_tie = min(*tie_count, bp.tie_cap);
+            for (uint32_t i = (warp - EPI_WARP0) * 32 + lane; i < n_tie; i += 128) {
+                const uint2 it2 = my_queue[i];
+                const int64_t q2 = it2.x, ent_id = it2.y;
+                const float s2 = bil_dot(p.qvec + q2 * p.D, p.ent + ent_id * p.D, p.D);
+                const float st = -__ldg(&p.thr[q2].x);
+                if (s2 > st) { atomicAdd(p.counts + q2, 1); atomicAdd(p.counts + 2 * p.Q + q2, 1); }
+                if (s2 == st) { atomicAdd(p.counts + p.Q + q2, 1); atomicAdd(p.counts + 3 * p.Q + q2, 1); }
+            }
+        }
         // known-true correction with the same FP32 scalar scorer the near-tie path uses (consistent decisions)
-        {
+        if (!STORE) {
             const int64_t n_warps = (int64_t)gridDim.x * 4;
             for (int64_t q = (int64_t)blockIdx.x * 4 + (warp - EPI_WARP0); q < p.Q; q += n_warps)
                 correct_query<true, true>(p, q, lane, [&](int64_t qq, int64_t x) {
@@ -433,7 +478,7 @@ static int bil_prepass(mre_ctx *ctx, const mre_rank_job *job, cudaStream_t st, B
     return MRE_OK;
 }
 
-int rank_bilinear(mre_ctx *ctx, const mre_index *ix, const mre_rank_job *job, cudaStream_t st) {
+static int run_bilinear(mre_ctx *ctx, const mre_index *ix, const mre_rank_job *job, float *store, cudaStream_t st) {
     BilScratch sc{};
     MRE_TRY(bil_prepass(ctx, job, st, sc));
     BilParams bp{};
@@ -480,17 +525,39 @@ int rank_bilinear(mre_ctx *ctx, const mre_index *ix, const mre_rank_job *job, cu
     MRE_TRY(make_tmap_f32_2d(&tm_blo, b_lo, std::max<int64_t>(cand_rows, 1), sc.Kp, sc.Kp, BN, BK));
     static bool configured = false;
     if (!configured) {
-        MRE_CUDA(cudaFuncSetAttribute(bilinear_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BIL_SMEM));
+        MRE_CUDA(cudaFuncSetAttribute(bilinear_rank_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BIL_SMEM));
+        MRE_CUDA(cudaFuncSetAttribute(bilinear_rank_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BIL_SMEM));
         configured = true;
     }
     const int64_t want = std::max<int64_t>(p.total_items, (p.Q + 3) / 4);
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, ctx->sm_count));
+    bp.store = store;
+    bp.store_ld = cand_rows;
+    // near-tie queue: expected Q*E*P(near) entries with P(near) ~ 5e-5; 10x headroom, at least 4096 per CTA
+    const int64_t cap_total = std::min<int64_t>(std::max<int64_t>(job->Q * std::max<int64_t>(cand_rows, 1) / 2048, (int64_t)grid * 4096), 1LL << 26);
+    bp.tie_cap = (uint32_t)(cap_total / grid);
+    MRE_TRY(ctx->counters.reserve((size_t)bp.tie_cap * grid * sizeof(uint2)));
+    bp.tie_queue = ctx->counters.as<uint2>();
     MRE_TRY(ctx->time_begin(st));
-    bilinear_rank_kernel<<<grid, BIL_THREADS, BIL_SMEM, st>>>(bp, tm_ahi, tm_alo, tm_bhi, tm_blo);
+    if (store) bilinear_rank_kernel<true><<<grid, BIL_THREADS, BIL_SMEM, st>>>(bp, tm_ahi, tm_alo, tm_bhi, tm_blo);
+    else bilinear_rank_kernel<false><<<grid, BIL_THREADS, BIL_SMEM, st>>>(bp, tm_ahi, tm_alo, tm_bhi, tm_blo);
     MRE_TRY(ctx->time_end(st));
     ctx->launches += 1;
     MRE_CUDA(cudaGetLastError());
     return MRE_OK;
+}
+
+int rank_bilinear(mre_ctx *ctx, const mre_index *ix, const mre_rank_job *job, cudaStream_t st) {
+    return run_bilinear(ctx, ix, job, nullptr, st);
+}
+
+int bilinear_scores(mre_ctx *ctx, const mre_rank_job *job, float *scores_out, cudaStream_t st) {
+    MRE_CHECK_ARG(scores_out != nullptr, "scores_out is NULL");
+    mre_rank_job j = *job;
+    j.filter = MRE_FILTER_NONE;
+    MRE_TRY(ctx->misc.reserve(256 + (size_t)4 * std::max<int64_t>(job->Q, 1) * sizeof(int32_t)));
+    j.counts = reinterpret_cast<int32_t *>(ctx->misc.as<char>() + 256);   // zeroed, otherwise unused in STORE mode
+    return run_bilinear(ctx, nullptr, &j, scores_out, st);
 }
 
 int predict_bilinear(mre_ctx *ctx, const mre_rank_job *job, int64_t query, float *scores_out, cudaStream_t st) {

@@ -117,6 +117,7 @@ int rank_transe(mre_ctx *ctx, const mre_index *ix, const mre_rank_job *job, cuda
 int rank_bilinear(mre_ctx *ctx, const mre_index *ix, const mre_rank_job *job, cudaStream_t st);
 int predict_transe(mre_ctx *ctx, const mre_rank_job *job, int64_t query, float *scores_out, cudaStream_t st);
 int predict_bilinear(mre_ctx *ctx, const mre_rank_job *job, int64_t query, float *scores_out, cudaStream_t st);
+int bilinear_scores(mre_ctx *ctx, const mre_rank_job *job, float *scores_out, cudaStream_t st);
 int metrics(mre_ctx *ctx, const int32_t *counts, const uint8_t *q_side, int32_t side, int64_t Q, int32_t rank_mode,
             int32_t raw, int64_t *sums_out, double *rr_out, int64_t *hist, int64_t hist_len, cudaStream_t st);
 int sample(mre_ctx *ctx, const mre_index *ix, uint64_t seed, uint64_t step, uint32_t stream_id, int64_t B, int64_t neg,

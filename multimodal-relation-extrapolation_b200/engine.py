@@ -255,6 +255,15 @@ class Ranker:
         L.check(L.lib().mre_predict(self.ctx._h, C.byref(job), int(query), _ptr(out), _stream()))
         return out
 
+    def bilinear_scores(self, scorer, tables, q_h, q_t, q_r, side):
+        """[Q, E] raw tensor-core similarities of a DistMult / ComplEx all-entity job (mre_bilinear_scores)"""
+        Q = q_h.numel()
+        job, keep = self._job(scorer, tables, Q, side, 1, False, None, "none", None, None)
+        job.q_h, job.q_t, job.q_r = _ptr(q_h), _ptr(q_t), _ptr(q_r)
+        out = torch.empty((Q, job.E), dtype=torch.float32, device=self.device)
+        L.check(L.lib().mre_bilinear_scores(self.ctx._h, C.byref(job), _ptr(out), _stream()))
+        return out
+
     def metrics(self, counts, side, rank_mode="strict", raw=False, hist_len=0):
         """counts [4, Q] (device) -> dict of per-side integer sums + float64 reciprocal-rank sums (+ histogram)."""
         Q = counts.shape[1]

@@ -148,3 +148,37 @@ def test_bilinear_candidate_groups(mre):
         S = np.setdiff1d(cands[int(r[q])], lists[q])
         band = gu.TIE_BAND * max(abs(float(sc[t[q]])), float(np.abs(sc).mean()))
         assert (sc[S] < sc[t[q]] - band).sum() <= c[2][q] <= (sc[S] <= sc[t[q]] + band).sum()
+
+
+@pytest.mark.parametrize("kind", ["distmult", "complex"])
+def test_tensor_core_discrepancy_stays_far_under_the_guard(env, fb15k237, kind):
+    """the 3xTF32 tensor-core similarity vs the sequential FP32 scorer, relative to ||v|| * max||e||: the near-tie guard
+    is 2^-18 of that scale; the measured discrepancy must stay at least 4x below it"""
+    eng, ix, rk = env
+    E, R, D = fb15k237.E, fb15k237.R, 200
+    th, tt, tr = fb15k237.oracle.test_triples()
+    sel = np.linspace(0, len(th) - 1, 64).astype(np.int64)
+    q_h, q_t, q_r = np.repeat(th[sel], 2), np.repeat(tt[sel], 2), np.repeat(tr[sel], 2)
+    side = np.tile(np.array([0, 1], np.uint8), len(sel))
+    worst = 0.0
+    for wname in gu.WEIGHT_SETS:
+        tabs = tables_for(kind, wname, E, R, D)
+        dt = tuple(dev(t) for t in tabs)
+        mma = rk.bilinear_scores(kind, dt, dev(q_h), dev(q_t), dev(q_r), dev(side)).cpu().numpy()
+        ent_full = np.concatenate([tabs[0], tabs[1]], 1) if kind == "complex" else tabs[0]
+        max_norm = np.linalg.norm(ent_full.astype(np.float64), axis=1).max()
+        for q in range(0, len(q_h), 8):
+            seq = -rk.predict(kind, dt, dev(q_h), dev(q_t), dev(q_r), dev(side), query=q).cpu().numpy()
+            vnorm = np.linalg.norm(seq.astype(np.float64)) / np.sqrt(E)    # cheap proxy is not enough: use the exact bound below
+            h, t, r, s = int(q_h[q]), int(q_t[q]), int(q_r[q]), int(side[q])
+            if kind == "distmult":
+                v = (tabs[0][h] * tabs[1][r]) if s else (tabs[1][r] * tabs[0][t])
+            else:
+                e_re, e_im, r_re, r_im = tabs
+                x = h if s else t
+                a = e_re[x] * r_re[r] - e_im[x] * r_im[r] if s else e_re[x] * r_re[r] + e_im[x] * r_im[r]
+                b = e_im[x] * r_re[r] + e_re[x] * r_im[r] if s else e_im[x] * r_re[r] - e_re[x] * r_im[r]
+                v = np.concatenate([a, b])
+            scale = np.linalg.norm(v.astype(np.float64)) * max_norm
+            worst = max(worst, float(np.abs(mma[q].astype(np.float64) - seq.astype(np.float64)).max() / scale))
+    assert worst < 2.0 ** -20, worst
