@@ -43,9 +43,11 @@ constexpr size_t RANK_SMEM = 1024 + (size_t)STAGES * STAGE_BYTES + STAGES * size
 template <int P>
 __device__ __forceinline__ float transe_acc(const float *__restrict__ v, const float *__restrict__ e, int64_t D) {
     float acc = 0.f;
-    for (int64_t d = 0; d < D; d += 4) {
-        float4 a = *reinterpret_cast<const float4 *>(v + d);
-        float4 b = *reinterpret_cast<const float4 *>(e + d);
+    const int n = (int)D;
+#pragma unroll 8
+    for (int d = 0; d < n; d += 4) {   // unrolled: the row fetches of 8 steps are in flight together (latency-bound callers)
+        float4 a = __ldg(reinterpret_cast<const float4 *>(v + d));
+        float4 b = __ldg(reinterpret_cast<const float4 *>(e + d));
         float u0 = a.y - b.x, u1 = a.x - b.y, u2 = a.w - b.z, u3 = a.z - b.w;
         if (P == 1) {
             acc = acc + fabsf(u0); acc = acc + fabsf(u1); acc = acc + fabsf(u2); acc = acc + fabsf(u3);
