@@ -149,6 +149,9 @@ typedef struct mre_rank_job {
      * group are ignored; the true entity is always excluded from the filtered counts. */
     const int64_t *filt_ptr;
     const int64_t *filt_idx;
+    /* optional upper bound on the number of (query, known entity) pairs of this job (MRE_FILTER_CSR: filt_ptr[Q]);
+     * 0 = unknown, the library then reads the exact count back with one small stream synchronisation */
+    int64_t filt_nnz;
     /* output, device int32 [4][Q]: raw_lt, raw_eq, filt_lt, filt_eq
      *   raw_lt  = #{j in S_q : s_j <  s_true}          raw_eq  = #{j in S_q : s_j == s_true}
      *   filt_*  = the same over S_q minus known-true entities minus the true entity itself

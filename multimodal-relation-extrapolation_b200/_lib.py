@@ -11,10 +11,10 @@ import sys
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 BUILD_DIR = os.path.join(_HERE, "build")
-LIB_PATH = os.path.join(BUILD_DIR, "libmre_b200.so")
+LIB_PATH = os.environ.get("MRE_B200_LIB") or os.path.join(BUILD_DIR, "libmre_b200.so")   # override: A/B timing of two builds
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include", "mre_b200.h")
 
-SOURCES = ["index.cpp", "tma_host.cpp", "abi.cu", "transe_rank.cu", "metrics.cu", "sampler.cu", "train_step.cu", "bilinear_rank.cu"]
+SOURCES = ["index.cpp", "tma_host.cpp", "abi.cu", "transe_rank.cu", "metrics.cu", "sampler.cu", "train_step.cu", "bilinear_rank.cu", "tile_filter.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
               "-Xcompiler", "-fPIC,-O2", "-shared"]
 
@@ -40,7 +40,7 @@ class RankJob(C.Structure):
         ("q_h", C.c_void_p), ("q_t", C.c_void_p), ("q_r", C.c_void_p), ("q_side", C.c_void_p),
         ("side", C.c_int32), ("n_groups", C.c_int32), ("Q", C.c_int64),
         ("group_qptr", C.c_void_p), ("group_cptr", C.c_void_p), ("cand_idx", C.c_void_p),
-        ("filt_ptr", C.c_void_p), ("filt_idx", C.c_void_p),
+        ("filt_ptr", C.c_void_p), ("filt_idx", C.c_void_p), ("filt_nnz", C.c_int64),
         ("counts", C.c_void_p),
     ]
 
@@ -55,7 +55,7 @@ def sources_newer_than_lib():
 
 def build(verbose=False, force=False):
     """Compile csrc/ into build/libmre_b200.so for sm_100a with nvcc (cross-compiles without a GPU)."""
-    if not force and not sources_newer_than_lib():
+    if os.environ.get("MRE_B200_LIB") or (not force and not sources_newer_than_lib()):
         return LIB_PATH
     os.makedirs(BUILD_DIR, exist_ok=True)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

@@ -100,6 +100,7 @@ struct mre_ctx {
     mre::DevBuf tiles;               // tile descriptors
     mre::DevBuf counters;            // raw/corr counters, work counters
     mre::DevBuf misc;                // loss partials etc.
+    mre::DevBuf misc2;               // known-true pair list of the tile filter
     mre::DevBuf stage_dev;           // device staging for *_host entry points
     mre::PinnedBuf stage_pin;        // pinned host staging
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;

@@ -46,6 +46,8 @@ struct RankParams {
     const int64_t *hr_key, *hr_val, *tr_key, *tr_val;
     int64_t n_all;
     const int64_t *filt_ptr, *filt_idx;
+    // known-true pairs per work item (tile_filter.cu): pairs[ptr[item] .. ptr[item+1]) = (row << 16 | col)
+    const uint32_t *tf_ptr, *tf_pairs;
     // outputs [4][Q]
     int32_t *counts;
 };

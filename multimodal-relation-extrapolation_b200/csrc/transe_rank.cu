@@ -16,15 +16,16 @@
 // complete_tx; candidate lists are gathered into a dense table by a pre-pass), issued by whichever warp is last
 // to release a stage; the eight warps hold an 8x8 register micro-tile per thread and read the ring with
 // conflict-free 128-bit LDS.  The
-// epilogue compares the 64 accumulators against the per-query thresholds, reduces the counts with warp
-// shuffles and adds them to the per-query counters.  After its tiles a CTA runs the known-true correction
-// (rank_common.cuh) with warp ballot/popc.  The kernel is bound by the FP32 pipe: 2 lane-ops per (q, e, d).
+// epilogue compares the 64 accumulators against the per-query thresholds, masks the known-true slots routed to this
+// tile by tile_filter.cu (raw and filtered counts come from the SAME registers), reduces the counts with warp
+// shuffles and adds them to the per-query counters.  The kernel is bound by the FP32 pipe: 2 lane-ops per (q, e, d).
 #include <math.h>
 
 #include <vector>
 
 #include "common.h"
 #include "rank_common.cuh"
+#include "rank_host.h"
 #include "tma_host.h"
 
 namespace mre {
@@ -34,7 +35,7 @@ constexpr int STAGES = 3;
 constexpr int CONSUMER_WARPS = 8;
 constexpr int RANK_THREADS = CONSUMER_WARPS * 32;
 constexpr uint32_t STAGE_BYTES = (TILE_Q + TILE_E) * CHUNK * 4;  // two 16 KiB TMA boxes
-constexpr size_t RANK_SMEM = 1024 + (size_t)STAGES * STAGE_BYTES + STAGES * sizeof(uint64_t) + STAGES * sizeof(int) + 64;
+constexpr size_t RANK_SMEM = 1024 + (size_t)STAGES * STAGE_BYTES + STAGES * sizeof(uint64_t) + 4 * sizeof(int) + CONSUMER_WARPS * 32 * sizeof(unsigned long long) + 64;
 
 // ------------------------------------------------------------------------------------------ scalar scorer
 // The one definition of a TransE accumulator: sequential over d, acc = acc + |v - e| (p = 1) or fma(u, u, acc) (p = 2).
@@ -175,6 +176,8 @@ transe_rank_kernel(const RankParams p, const __grid_constant__ CUtensorMap tm_q,
     unsigned char *ring = smem_raw + (ring_u32 - smem_u32(smem_raw));
     uint64_t *bars = reinterpret_cast<uint64_t *>(ring + (size_t)STAGES * STAGE_BYTES);
     int *done = reinterpret_cast<int *>(bars + STAGES);  // per-stage count of warps that finished reading the stage
+    // per-warp known-true masks: bit (i * 8 + j) of lane l's word marks accumulator (i, j) of that thread
+    unsigned long long *wmask = reinterpret_cast<unsigned long long *>(done + 4) + (threadIdx.x >> 5) * 32;
     const uint32_t full0 = smem_u32(bars);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_chunks = (int)((p.D + CHUNK - 1) / CHUNK);
@@ -204,6 +207,9 @@ transe_rank_kernel(const RankParams p, const __grid_constant__ CUtensorMap tm_q,
         const int64_t qbase = gd.q0 + (int64_t)qt * TILE_Q;
         const int nq = (int)min((int64_t)TILE_Q, gd.q0 + gd.nq - qbase);
         const int ne = (int)min((int64_t)TILE_E, gd.nc - (int64_t)et * TILE_E);
+        // this item's known-true pairs; the first 32 are fetched now so the epilogue does not wait on them
+        const uint32_t pf0 = __ldg(p.tf_ptr + item), pf1 = __ldg(p.tf_ptr + item + 1);
+        const uint32_t pair0 = pf0 + lane < pf1 ? __ldg(p.tf_pairs + pf0 + lane) : 0xffffffffu;
 
         float acc[8][8];
 #pragma unroll
@@ -251,7 +257,24 @@ transe_rank_kernel(const RankParams p, const __grid_constant__ CUtensorMap tm_q,
             }
         }
 
-    // ---- epilogue: compare against the per-query thresholds, count, reduce over the 16 lanes sharing a query row
+        // ---- known-true mask of this warp's 32 threads: every pair routed to this item by tile_filter.cu
+        unsigned long long known = 0ull;
+        if (pf1 > pf0) {
+            wmask[lane] = 0ull;
+            __syncwarp();
+            for (uint32_t k = pf0 + lane; k < pf1; k += 32) {
+                const uint32_t pr = k < pf0 + 32 ? pair0 : __ldg(p.tf_pairs + k);
+                const int row = (int)(pr >> 16), col = (int)(pr & 0xffffu);
+                const int otq = row & 15;                    // owner thread: tq = row % 16, te = col % 16
+                if ((otq >> 1) == warp)
+                    atomicOr(&wmask[((otq & 1) << 4) | (col & 15)], 1ull << (((row >> 4) << 3) | (col >> 4)));
+            }
+            __syncwarp();
+            known = wmask[lane];
+        }
+        // ---- epilogue: compare against the per-query thresholds, count raw and known hits, reduce over the 16 lanes
+        // sharing a query row (four 8-bit counters packed in one word: each is at most 128 after the reduction)
+        const bool any_known = __any_sync(0xffffffffu, known != 0ull);   // warp-uniform: most warps of most tiles hold none
         bool ev_ok[8];
 #pragma unroll
         for (int j = 0; j < 8; j++) ev_ok[j] = (te + 16 * j) < ne;
@@ -261,40 +284,35 @@ transe_rank_kernel(const RankParams p, const __grid_constant__ CUtensorMap tm_q,
             const bool q_ok = ql < nq;
             float2 th = make_float2(-INFINITY, -INFINITY);
             if (q_ok) th = __ldg(p.thr + qbase + ql);
-            int n_lt = 0, n_eq = 0;
+            uint32_t packed = 0;
+            if (any_known) {
 #pragma unroll
-            for (int j = 0; j < 8; j++) {
-                const float s = acc[i][j];
-                const bool lt = ev_ok[j] && s < th.x;
-                n_lt += lt ? 1 : 0;
-                if (NEED_EQ) n_eq += (ev_ok[j] && !lt && s < th.y) ? 1 : 0;
+                for (int j = 0; j < 8; j++) {
+                    const float s = acc[i][j];
+                    const bool lt = ev_ok[j] && s < th.x;
+                    const bool eq = NEED_EQ && ev_ok[j] && !lt && s < th.y;
+                    const bool kn = (known >> (i * 8 + j)) & 1ull;
+                    packed += (lt ? 1u : 0u) + (eq ? 0x100u : 0u) + ((lt && kn) ? 0x10000u : 0u) + ((eq && kn) ? 0x1000000u : 0u);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const float s = acc[i][j];
+                    const bool lt = ev_ok[j] && s < th.x;
+                    const bool eq = NEED_EQ && ev_ok[j] && !lt && s < th.y;
+                    packed += (lt ? 1u : 0u) + (eq ? 0x100u : 0u);
+                }
             }
 #pragma unroll
-            for (int m = 1; m < 16; m <<= 1) {
-                n_lt += __shfl_xor_sync(0xffffffffu, n_lt, m);
-                if (NEED_EQ) n_eq += __shfl_xor_sync(0xffffffffu, n_eq, m);
-            }
-            if (q_ok && te == 0) {
+            for (int m = 1; m < 16; m <<= 1) packed += __shfl_xor_sync(0xffffffffu, packed, m);
+            if (q_ok && te == 0 && packed) {
                 const int64_t q = qbase + ql;
-                if (n_lt) {
-                    atomicAdd(p.counts + q, n_lt);
-                    atomicAdd(p.counts + 2 * p.Q + q, n_lt);
-                }
-                if (NEED_EQ && n_eq) {
-                    atomicAdd(p.counts + p.Q + q, n_eq);
-                    atomicAdd(p.counts + 3 * p.Q + q, n_eq);
-                }
+                const int n_lt = packed & 0xff, n_eq = (packed >> 8) & 0xff, k_lt = (packed >> 16) & 0xff, k_eq = packed >> 24;
+                if (n_lt) atomicAdd(p.counts + q, n_lt);
+                if (n_eq) atomicAdd(p.counts + p.Q + q, n_eq);
+                if (n_lt - k_lt) atomicAdd(p.counts + 2 * p.Q + q, n_lt - k_lt);
+                if (n_eq - k_eq) atomicAdd(p.counts + 3 * p.Q + q, n_eq - k_eq);
             }
-        }
-    }
-
-    // ==================================== known-true correction (warp per query) ====================================
-    if (p.filter != MRE_FILTER_NONE || NEED_EQ) {
-        const int64_t n_warps = (int64_t)gridDim.x * CONSUMER_WARPS;
-        for (int64_t q = (int64_t)blockIdx.x * CONSUMER_WARPS + warp; q < p.Q; q += n_warps) {
-            correct_query<NEED_EQ>(p, q, lane, [&](int64_t qq, int64_t x) {
-                return transe_acc<P>(p.qvec + qq * p.D, p.ent + x * p.D, p.D);
-            });
         }
     }
 }
@@ -406,8 +424,7 @@ static int launch_rank(mre_ctx *ctx, const RankParams &p, const CUtensorMap &tm_
         MRE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RANK_SMEM));
         configured = true;
     }
-    int64_t want = std::max<int64_t>(p.total_items, (p.Q + CONSUMER_WARPS - 1) / CONSUMER_WARPS);
-    int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)ctx->sm_count * 2));
+    int grid = (int)std::max<int64_t>(1, std::min<int64_t>(p.total_items, (int64_t)ctx->sm_count * 2));
     kern<<<grid, RANK_THREADS, RANK_SMEM, st>>>(p, tm_q, tm_e);
     ctx->launches += 1;
     MRE_CUDA(cudaGetLastError());
@@ -443,6 +460,7 @@ int rank_transe(mre_ctx *ctx, const mre_index *ix, const mre_rank_job *job, cuda
     }
     init_counts_kernel<<<grid_for(4 * job->Q, 256), 256, 0, st>>>(job->counts, 4 * job->Q);
     ctx->launches += 1;
+    MRE_TRY(build_tile_filter(ctx, job, p, TILE_Q, TILE_E, st));
     CUtensorMap tm_q, tm_e;
     MRE_TRY(make_tmap_f32_2d(&tm_q, p.qvec, job->Q, Dp, Dp, TILE_Q, CHUNK));
     MRE_TRY(make_tmap_f32_2d(&tm_e, cand_table, std::max<int64_t>(cand_rows, 1), Dp, Dp, TILE_E, CHUNK));
