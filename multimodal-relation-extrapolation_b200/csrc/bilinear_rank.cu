@@ -12,9 +12,9 @@
 //                      head v = [t_re r_re + t_im r_im | t_im r_re - t_re r_im]
 // the one true dense contraction of the hot path, so it runs as a tcgen05 GEMM whose epilogue never writes scores:
 // accumulator tiles (128 queries x 256 entities, FP32) live in TMEM, double-buffered; four epilogue warps read them
-// back with tcgen05.ld (one query row per thread), compare against the query's true score and count; columns
-// closer to the true score than a rigorous error guard are re-scored in scalar FP32, which makes the COUNTS exactly
-// those of the sequential FP32 scorer (and consistent with the known-true correction).
+// back with tcgen05.ld (one query row per thread), compare against the query's true score and count, taking the
+// known-true columns routed to the tile by tile_filter.cu back out of the filtered count; columns closer to the true
+// score than an error guard are re-scored in scalar FP32, which makes the COUNTS those of the sequential FP32 scorer.
 // Precision: the reference is FP32.  kind::tf32 keeps 11 significant bits, which would move ranks well outside the
 // 1e-5 tie band, so every operand is split x ~= hi + lo (hi = rn_tf32(x), lo = rn_tf32(x - hi): 22 significant bits,
 // both exactly representable so the MMA's operand truncation loses nothing) and each product is issued as THREE TF32
@@ -45,7 +45,8 @@ constexpr uint32_t B_BYTES = BN * BK * 4;   // 32 KiB
 constexpr uint32_t BSTAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
 constexpr int BIL_THREADS = 192;
 constexpr int EPI_WARP0 = 2;
-constexpr size_t BIL_SMEM = 1024 + (size_t)B_STAGES * BSTAGE_BYTES + 16 * sizeof(uint64_t) + 64;
+constexpr int MASK_STRIDE = 9;               // words per row of the per-warp known-true mask (8 + 1 pad: conflict-free)
+constexpr size_t BIL_SMEM = 1024 + (size_t)B_STAGES * BSTAGE_BYTES + 16 * sizeof(uint64_t) + 4 * 32 * MASK_STRIDE * 4 + 64;
 constexpr uint32_t TMEM_COLS = 512;     // two 256-column accumulator buffers
 
 struct BilParams {
@@ -188,6 +189,7 @@ bilinear_rank_kernel(const BilParams bp, const __grid_constant__ CUtensorMap tm_
     const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + 2), tfull0 = smem_u32(bars + 4), tempty0 = smem_u32(bars + 6);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 8);
     uint32_t *tie_count = reinterpret_cast<uint32_t *>(bars + 9);      // near-ties queued by this CTA
+    uint32_t *mask_all = reinterpret_cast<uint32_t *>(bars + 16);      // per epilogue warp: [32 rows][MASK_STRIDE] known-true bits
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_kb = (int)((p.D + BK - 1) / BK);
 
@@ -224,10 +226,12 @@ bilinear_rank_kernel(const BilParams bp, const __grid_constant__ CUtensorMap tm_
                     const uint32_t full = full0 + 8 * s;
                     const uint32_t base = ring_u32 + (uint32_t)s * BSTAGE_BYTES;
                     mbar_arrive_expect_tx(full, BSTAGE_BYTES);
-                    tma_load_2d(base, &tm_ahi, kb * BK, qrow, full);
-                    tma_load_2d(base + A_BYTES, &tm_alo, kb * BK, qrow, full);
-                    tma_load_2d(base + 2 * A_BYTES, &tm_bhi, kb * BK, erow, full);
-                    tma_load_2d(base + 2 * A_BYTES + B_BYTES, &tm_blo, kb * BK, erow, full);
+                    // query tiles are re-read for every candidate tile of the sweep: keep them in L2 (evict-last) so the
+                    // streaming candidate tiles (each shared by the ~128 CTAs of one round, then dead) cannot push them out
+                    tma_load_2d_hint(base, &tm_ahi, kb * BK, qrow, full, L2_EVICT_LAST);
+                    tma_load_2d_hint(base + A_BYTES, &tm_alo, kb * BK, qrow, full, L2_EVICT_LAST);
+                    tma_load_2d_hint(base + 2 * A_BYTES, &tm_bhi, kb * BK, erow, full, L2_EVICT_NORMAL);
+                    tma_load_2d_hint(base + 2 * A_BYTES + B_BYTES, &tm_blo, kb * BK, erow, full, L2_EVICT_NORMAL);
                 }
             }
         }
@@ -268,71 +272,116 @@ bilinear_rank_kernel(const BilParams bp, const __grid_constant__ CUtensorMap tm_
         const int quarter = warp & 3;                   // TMEM lanes [32 * quarter, 32 * quarter + 32)
         const int row = quarter * 32 + lane;            // query row of the tile owned by this thread
         uint2 *my_queue = bp.tie_queue + (size_t)blockIdx.x * bp.tie_cap;
+        uint32_t *mask = mask_all + (warp - EPI_WARP0) * 32 * MASK_STRIDE;
+        // Per-tile metadata (tile geometry, this row's true score and guard, the tile's known-true pair range) is
+        // fetched ONE TILE AHEAD: a lone epilogue warp per SM sub-partition cannot hide dependent global-load latency,
+        // and the epilogue of tile t must finish before the MMA warp may start tile t + 2.
+        struct TileMeta {
+            int64_t qbase, crow0;
+            int nq, ne;
+            float sim_true, guard;
+            uint32_t pf0, pf1;
+        };
+        const GroupDesc gd0 = p.groups[0];
+        auto load_meta = [&](int64_t item) {
+            TileMeta m;
+            int g = 0, qt, et;
+            GroupDesc gd = gd0;
+            if (p.n_groups > 1) {
+                decode_item(p, item, g, qt, et);
+                gd = p.groups[g];
+            } else {
+                qt = (int)(item % gd0.n_qt);
+                et = (int)(item / gd0.n_qt);
+            }
+            m.qbase = gd.q0 + (int64_t)qt * BM;
+            m.crow0 = gd.c0 + (int64_t)et * BN;
+            m.nq = (int)min((int64_t)BM, gd.q0 + gd.nq - m.qbase);
+            m.ne = (int)min((int64_t)BN, gd.nc - (int64_t)et * BN);
+            m.sim_true = INFINITY;
+            m.guard = -1.f;
+            if (row < m.nq) {
+                m.sim_true = -__ldg(&p.thr[m.qbase + row].x);
+                m.guard = __ldg(bp.delta + m.qbase + row);
+            }
+            m.pf0 = __ldg(p.tf_ptr + item);
+            m.pf1 = __ldg(p.tf_ptr + item + 1);
+            return m;
+        };
         uint32_t tile = 0;
+        TileMeta nxt{};
+        if ((int64_t)blockIdx.x < p.total_items) nxt = load_meta(blockIdx.x);
         for (int64_t item = blockIdx.x; item < p.total_items; item += gridDim.x, tile++) {
-            int g, qt, et;
-            decode_item(p, item, g, qt, et);
-            const GroupDesc gd = p.groups[g];
-            const int64_t qbase = gd.q0 + (int64_t)qt * BM;
-            const int nq = (int)min((int64_t)BM, gd.q0 + gd.nq - qbase);
-            const int ne = (int)min((int64_t)BN, gd.nc - (int64_t)et * BN);
+            const TileMeta cur = nxt;
+            if (item + gridDim.x < p.total_items) nxt = load_meta(item + gridDim.x);
+            const int64_t qbase = cur.qbase;
+            const int nq = cur.nq, ne = cur.ne;
             const bool q_ok = row < nq;
-            float sim_true = INFINITY, guard = -1.f;
-            if (q_ok) {
-                sim_true = -__ldg(&p.thr[qbase + row].x);
-                guard = __ldg(bp.delta + qbase + row);
+            const float sim_true = cur.sim_true, guard = cur.guard;
+            // known-true mask of this warp's 32 rows: the pairs tile_filter.cu routed to this item (the truth included)
+            const uint32_t pf0 = cur.pf0, pf1 = cur.pf1;
+            const bool has_mask = pf1 > pf0;
+            if (has_mask) {
+                for (int k = lane; k < 32 * MASK_STRIDE; k += 32) mask[k] = 0u;
+                __syncwarp();
+                for (uint32_t k = pf0 + lane; k < pf1; k += 32) {
+                    const uint32_t pr = __ldg(p.tf_pairs + k);
+                    const int prow = (int)(pr >> 16), pcol = (int)(pr & 0xffffu);
+                    if ((prow >> 5) == quarter) atomicOr(&mask[(prow & 31) * MASK_STRIDE + (pcol >> 5)], 1u << (pcol & 31));
+                }
+                __syncwarp();
             }
             const uint32_t buf = tile & 1;
             mbar_wait(tfull0 + 8 * buf, (tile >> 1) & 1);
             tc_fence_after();
-            int n_lt = 0, n_eq = 0;
+            int r_lt = 0, f_lt = 0, r_eq = 0, f_eq = 0;      // raw / filtered counts of this thread's query row
             const uint32_t taddr = tmem_base + buf * BN + ((uint32_t)(quarter * 32) << 16);
             // better <=> larger similarity (predict = -sim).  s > thr_hi: counted; s < thr_lo: not; in between: near-tie
             const float thr_hi = sim_true + guard, thr_lo = sim_true - guard;
+            // One chunk = 32 accumulator columns of this thread's row.  The two comparisons are collected as BIT MASKS, so
+            // the counts, the known-true subtraction and the near-tie set are a handful of popc / and instructions and the
+            // cold paths below are rolled loops: the kernel stays a few thousand instructions (it was 22 K when every cold
+            // path was unrolled 32x, which thrashed the instruction cache under the MMA-issuing warp).
             auto process = [&](const uint32_t (&v)[32], int c0) {
                 const int left = ne - c0;                       // warp-uniform
                 if (STORE) {                                    // diagnostic / materialised-score mode
                     if (q_ok) {
-                        float *o = bp.store + (qbase + row) * bp.store_ld + gd.c0 + (int64_t)et * BN + c0;
+                        float *o = bp.store + (qbase + row) * bp.store_ld + cur.crow0 + c0;
 #pragma unroll
                         for (int c = 0; c < 32; c++)
                             if (c < left) o[c] = __uint_as_float(v[c]);
                     }
                     return;
                 }
-                int gt = 0, ge = 0;
-                if (left >= 32) {
+                uint32_t gtm = 0u, gem = 0u;                    // bit c: column c0 + c beats thr_hi / reaches thr_lo
 #pragma unroll
-                    for (int c = 0; c < 32; c++) {
-                        const float sc = __uint_as_float(v[c]);
-                        gt += sc > thr_hi ? 1 : 0;
-                        ge += sc >= thr_lo ? 1 : 0;
-                    }
-                } else {                                        // last chunk of the last candidate tile: mask the padding
-#pragma unroll
-                    for (int c = 0; c < 32; c++) {
-                        const float sc = __uint_as_float(v[c]);
-                        gt += (c < left && sc > thr_hi) ? 1 : 0;
-                        ge += (c < left && sc >= thr_lo) ? 1 : 0;
-                    }
+                for (int c = 0; c < 32; c++) {
+                    const float sc = __uint_as_float(v[c]);
+                    gtm |= sc > thr_hi ? (1u << c) : 0u;
+                    gem |= sc >= thr_lo ? (1u << c) : 0u;
                 }
-                n_lt += gt;
-                if (ge != gt) {                                 // rare: queue the near-ties of this chunk for the exact re-score
-#pragma unroll
-                    for (int c = 0; c < 32; c++) {
-                        const float sc = __uint_as_float(v[c]);
-                        if (c < left && sc >= thr_lo && !(sc > thr_hi)) {
-                            const int64_t crow = gd.c0 + (int64_t)et * BN + c0 + c;
-                            const int64_t ent_id = p.all_entities ? crow : __ldg(p.cand_idx + crow);
-                            const uint32_t slot = atomicAdd(tie_count, 1u);
-                            if (slot < bp.tie_cap) {
-                                my_queue[slot] = make_uint2((uint32_t)(qbase + row), (uint32_t)ent_id);
-                            } else {                            // queue full (pathological ties): re-score in place
-                                const float s2 = bil_dot(p.qvec + (qbase + row) * p.D, p.ent + ent_id * p.D, p.D);
-                                n_lt += s2 > sim_true ? 1 : 0;
-                                n_eq += s2 == sim_true ? 1 : 0;
-                            }
-                        }
+                const uint32_t valid = left >= 32 ? 0xffffffffu : ((1u << left) - 1u);   // padding of the last candidate tile
+                gtm &= valid;
+                gem &= valid;
+                const uint32_t mw = has_mask ? mask[lane * MASK_STRIDE + (c0 >> 5)] : 0u;   // known-true columns of this chunk
+                r_lt += __popc(gtm);
+                f_lt += __popc(gtm & ~mw);
+                uint32_t near = gem & ~gtm;                     // rare: queue the near-ties for the exact re-score
+                while (near) {
+                    const int c = __ffs(near) - 1;
+                    near &= near - 1;
+                    const uint32_t kn = (mw >> c) & 1u;
+                    const int64_t crow = cur.crow0 + c0 + c;
+                    const int64_t ent_id = p.all_entities ? crow : __ldg(p.cand_idx + crow);
+                    const uint32_t slot = atomicAdd(tie_count, 1u);
+                    if (slot < bp.tie_cap) {
+                        my_queue[slot] = make_uint2((uint32_t)(qbase + row), (uint32_t)ent_id | (kn << 31));
+                    } else {                                    // queue full (pathological ties): re-score in place
+                        const float s2 = bil_dot(p.qvec + (qbase + row) * p.D, p.ent + ent_id * p.D, p.D);
+                        r_lt += s2 > sim_true ? 1 : 0;
+                        r_eq += s2 == sim_true ? 1 : 0;
+                        f_lt += (!kn && s2 > sim_true) ? 1 : 0;
+                        f_eq += (!kn && s2 == sim_true) ? 1 : 0;
                     }
                 }
             };
@@ -355,31 +404,26 @@ bilinear_rank_kernel(const BilParams bp, const __grid_constant__ CUtensorMap tm_
             if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
             if (q_ok) {
                 const int64_t q = qbase + row;
-                if (n_lt) { atomicAdd(p.counts + q, n_lt); atomicAdd(p.counts + 2 * p.Q + q, n_lt); }
-                if (n_eq) { atomicAdd(p.counts + p.Q + q, n_eq); atomicAdd(p.counts + 3 * p.Q + q, n_eq); }
+                if (r_lt) atomicAdd(p.counts + q, r_lt);
+                if (r_eq) atomicAdd(p.counts + p.Q + q, r_eq);
+                if (f_lt) atomicAdd(p.counts + 2 * p.Q + q, f_lt);
+                if (f_eq) atomicAdd(p.counts + 3 * p.Q + q, f_eq);
             }
         }
         // exact FP32 re-score of this CTA's queued near-ties: off the tile loop's critical path, one per thread, so the
-        // row fetches of ~128 items are in flight together
+        // row fetches of ~128 items are in flight together.  Known-true entities only enter the RAW counts.
         asm volatile("bar.sync 1, 128;" ::: "memory");          // the four epilogue warps have finished pushing
         if (!STORE) {
             const uint32_t n_tie = min(*tie_count, bp.tie_cap);
             for (uint32_t i = (warp - EPI_WARP0) * 32 + lane; i < n_tie; i += 128) {
                 const uint2 it2 = my_queue[i];
-                const int64_t q2 = it2.x, ent_id = it2.y;
+                const int64_t q2 = it2.x, ent_id = it2.y & 0x7fffffffu;
+                const bool kn = (it2.y >> 31) != 0u;
                 const float s2 = bil_dot(p.qvec + q2 * p.D, p.ent + ent_id * p.D, p.D);
                 const float st = -__ldg(&p.thr[q2].x);
-                if (s2 > st) { atomicAdd(p.counts + q2, 1); atomicAdd(p.counts + 2 * p.Q + q2, 1); }
-                if (s2 == st) { atomicAdd(p.counts + p.Q + q2, 1); atomicAdd(p.counts + 3 * p.Q + q2, 1); }
+                if (s2 > st) { atomicAdd(p.counts + q2, 1); if (!kn) atomicAdd(p.counts + 2 * p.Q + q2, 1); }
+                if (s2 == st) { atomicAdd(p.counts + p.Q + q2, 1); if (!kn) atomicAdd(p.counts + 3 * p.Q + q2, 1); }
             }
-        }
-        // known-true correction with the same FP32 scalar scorer the near-tie path uses (consistent decisions)
-        if (!STORE) {
-            const int64_t n_warps = (int64_t)gridDim.x * 4;
-            for (int64_t q = (int64_t)blockIdx.x * 4 + (warp - EPI_WARP0); q < p.Q; q += n_warps)
-                correct_query<true, true>(p, q, lane, [&](int64_t qq, int64_t x) {
-                    return -bil_dot(p.qvec + qq * p.D, p.ent + x * p.D, p.D);
-                });
         }
     }
 
@@ -517,6 +561,7 @@ static int run_bilinear(mre_ctx *ctx, const mre_index *ix, const mre_rank_job *j
     }
     init_counts_kernel<<<grid_for(4 * job->Q, 256), 256, 0, st>>>(job->counts, 4 * job->Q);
     ctx->launches += 1;
+    MRE_TRY(build_tile_filter(ctx, job, p, BM, BN, st));
     const float *q_hi = ctx->qvec2.as<float>(), *q_lo = q_hi + (size_t)job->Q * sc.Kp;
     CUtensorMap tm_ahi, tm_alo, tm_bhi, tm_blo;
     MRE_TRY(make_tmap_f32_2d(&tm_ahi, q_hi, job->Q, sc.Kp, sc.Kp, BM, BK));
@@ -529,15 +574,14 @@ static int run_bilinear(mre_ctx *ctx, const mre_index *ix, const mre_rank_job *j
         MRE_CUDA(cudaFuncSetAttribute(bilinear_rank_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BIL_SMEM));
         configured = true;
     }
-    const int64_t want = std::max<int64_t>(p.total_items, (p.Q + 3) / 4);
-    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, ctx->sm_count));
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(p.total_items, ctx->sm_count));
     bp.store = store;
     bp.store_ld = cand_rows;
     // near-tie queue: expected Q*E*P(near) entries with P(near) ~ 5e-5; 10x headroom, at least 4096 per CTA
     const int64_t cap_total = std::min<int64_t>(std::max<int64_t>(job->Q * std::max<int64_t>(cand_rows, 1) / 2048, (int64_t)grid * 4096), 1LL << 26);
     bp.tie_cap = (uint32_t)(cap_total / grid);
-    MRE_TRY(ctx->counters.reserve((size_t)bp.tie_cap * grid * sizeof(uint2)));
-    bp.tie_queue = ctx->counters.as<uint2>();
+    MRE_TRY(ctx->tie_queue.reserve((size_t)bp.tie_cap * grid * sizeof(uint2)));
+    bp.tie_queue = ctx->tie_queue.as<uint2>();
     MRE_TRY(ctx->time_begin(st));
     if (store) bilinear_rank_kernel<true><<<grid, BIL_THREADS, BIL_SMEM, st>>>(bp, tm_ahi, tm_alo, tm_bhi, tm_blo);
     else bilinear_rank_kernel<false><<<grid, BIL_THREADS, BIL_SMEM, st>>>(bp, tm_ahi, tm_alo, tm_bhi, tm_blo);

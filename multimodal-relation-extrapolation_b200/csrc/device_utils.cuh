@@ -43,6 +43,14 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const void *tmap, int 
         "l"(tmap), "r"(c0), "r"(c1), "r"(bar)
         : "memory");
 }
+// same with an L2 eviction-priority hint (CUTLASS TMA::CacheHintSm90 encodings)
+constexpr uint64_t L2_EVICT_NORMAL = 0x1000000000000000ull, L2_EVICT_FIRST = 0x12F0000000000000ull, L2_EVICT_LAST = 0x14F0000000000000ull;
+__device__ __forceinline__ void tma_load_2d_hint(uint32_t dst, const void *tmap, int c0, int c1, uint32_t bar, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;" ::
+            "r"(dst), "l"(tmap), "r"(c0), "r"(c1), "r"(bar), "l"(policy)
+        : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const void *tmap) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
 }
