@@ -105,6 +105,20 @@ int64_t mre_index_total(const mre_index *ix, int which);
 int mre_index_get_split(const mre_index *ix, int split, int64_t *h, int64_t *t, int64_t *r);
 /* left_mean = tph, right_mean = hpt per relation (Reader.h:142-159) */
 int mre_index_get_means(const mre_index *ix, float *tph, float *hpt);
+/*
+ * Type constraints: importTypeFiles, Reader.h:267-317 (type_constrain.txt: per relation the admissible head ids, then the
+ * admissible tail ids).  mre_index_create_from_dir loads the file when it is present; these entry points load it from
+ * another path or install lists held in memory (prefix arrays [R+1] + ids; sorted and de-duplicated on the way in, as
+ * the reference sorts them and its merge pointer counts a repeated id once, Test.h:89-90).  side 0 = head lists, 1 = tail.
+ * A type-constrained rank (Test.h:88-98,153-163) is mre_rank with one candidate group per relation over these lists.
+ */
+int mre_index_load_type_constrain(mre_index *ix, const char *path);
+int mre_index_set_type_constrain(mre_index *ix, const int64_t *head_ptr, const int64_t *head_idx,
+                                 const int64_t *tail_ptr, const int64_t *tail_idx);
+/* number of ids over all relations of `side`, or -1 when no constraints are loaded */
+int64_t mre_index_type_total(const mre_index *ix, int side);
+/* ptr: int64 [R+1], idx: int64 [mre_index_type_total] (may be NULL to fetch the prefix only) */
+int mre_index_get_type_constrain(const mre_index *ix, int side, int64_t *ptr, int64_t *idx);
 /* 1 when (h,r,t) is in train+valid+test: _find, Corrupt.h:166-177 (host) */
 int mre_index_find(const mre_index *ix, int64_t h, int64_t t, int64_t r);
 
@@ -214,6 +228,27 @@ int mre_sample(mre_ctx *ctx, const mre_index *ix, uint64_t seed, uint64_t step, 
 int mre_sample_host(mre_ctx *ctx, const mre_index *ix, uint64_t seed, uint64_t step, uint32_t stream_id,
                     int64_t B, int64_t neg, int32_t mode, int32_t bern,
                     int64_t *h, int64_t *t, int64_t *r, float *y, void *stream);
+
+/*
+ * The paper's subgraph sampler: NegativeSampling.neg_sample_fn + __normal_batch + __corrupt_head / __corrupt_tail
+ * (module/NegativeSampling.py:114-140, 321-375).  Edges and node_list hold LOCAL node ids of one sampled subgraph;
+ * local_to_global[local] is the entity id the train triples use.  Per edge, neg_ent decision draws split the negatives
+ * into nh head-corruptions (slots 1..nh) and neg_ent - nh tail-corruptions (slots nh+1..neg_ent), each with probability
+ * 0.5, or hpt/(hpt+tph) of the edge's relation when bern != 0 (the reference's bern branch reads tables it never fills,
+ * :95-99,324).  A replacement is drawn uniformly from node_list; when filter != 0 (filter_flag) it is redrawn while its
+ * global id completes a TRAIN triple with the kept entity and the relation (h_of_tr / t_of_hr, :360,373).
+ *   key = (seed_lo, seed_hi); ctr = (edge b, slot | attempt << 16, step_lo, (step_hi & 0xffff) | stream_id << 16)
+ *   attempt 0, slot j (1..neg_ent): decision j of the edge = (x0 >> 8) * 2^-24 < prob
+ *   attempt a >= 1, slot k:         position (x1:x0) % n_nodes in node_list; at most 64 attempts, then the first
+ *                                   admissible node scanning on from the last position; none => the edge's own id is kept
+ * Outputs: device int32 arrays of length n_edges * (1 + neg_ent) in the reference's transposed layout (slot k of edge b at
+ * k * n_edges + b; slot 0 = the edge itself): expand_edge_index[0], expand_edge_index[1], expand_edge_type (:138-140).
+ */
+int mre_sample_subgraph(mre_ctx *ctx, const mre_index *ix, uint64_t seed, uint64_t step, uint32_t stream_id,
+                        const int64_t *edge_h, const int64_t *edge_t, const int64_t *edge_r, int64_t n_edges,
+                        const int64_t *node_list, int64_t n_nodes, const int64_t *local_to_global, int64_t n_local,
+                        int64_t neg_ent, int32_t bern, int32_t filter,
+                        int32_t *out_h, int32_t *out_t, int32_t *out_r, void *stream);
 
 /* ------------------------------------------------------------------------------------------ training */
 /*

@@ -96,6 +96,11 @@ def lib():
     L.mre_index_get_split.argtypes = [vp, i32, vp, vp, vp]
     L.mre_index_get_means.argtypes = [vp, vp, vp]
     L.mre_index_find.argtypes = [vp, i64, i64, i64]
+    L.mre_index_load_type_constrain.argtypes = [vp, C.c_char_p]
+    L.mre_index_set_type_constrain.argtypes = [vp, vp, vp, vp, vp]
+    L.mre_index_type_total.argtypes = [vp, i32]
+    L.mre_index_type_total.restype = i64
+    L.mre_index_get_type_constrain.argtypes = [vp, i32, vp, vp]
     L.mre_ctx_create.argtypes = [i32, P(vp)]
     L.mre_ctx_destroy.argtypes = [vp]
     L.mre_ctx_destroy.restype = None
@@ -110,6 +115,7 @@ def lib():
     samp = [vp, vp, u64, u64, u32, i64, i64, i32, i32, vp, vp, vp, vp, vp]
     L.mre_sample.argtypes = samp
     L.mre_sample_host.argtypes = samp
+    L.mre_sample_subgraph.argtypes = [vp, vp, u64, u64, u32, vp, vp, vp, i64, vp, i64, vp, i64, i64, i32, i32, vp, vp, vp, vp]
     L.mre_transe_margin_step.argtypes = [vp, vp, vp, i64, i64, i64, vp, vp, vp, i64, i64, f32, i32, i32, vp, vp, vp, vp, vp]
     L.mre_sgd_update.argtypes = [vp, vp, vp, i64, f32, vp]
     L.mre_score_triples.argtypes = [vp, i32, vp, vp, vp, vp, i64, vp, vp, vp, i64, i32, i32, vp, vp]

@@ -183,6 +183,16 @@ int mre_sample_host(mre_ctx *ctx, const mre_index *ix, uint64_t seed, uint64_t s
     return MRE_OK;
 }
 
+int mre_sample_subgraph(mre_ctx *ctx, const mre_index *ix, uint64_t seed, uint64_t step, uint32_t stream_id, const int64_t *edge_h,
+                        const int64_t *edge_t, const int64_t *edge_r, int64_t n_edges, const int64_t *node_list, int64_t n_nodes,
+                        const int64_t *local_to_global, int64_t n_local, int64_t neg_ent, int32_t bern, int32_t filter,
+                        int32_t *out_h, int32_t *out_t, int32_t *out_r, void *stream) {
+    MRE_CHECK_ARG(ctx != nullptr, "ctx is NULL");
+    MRE_CUDA(cudaSetDevice(ctx->device));
+    return sample_subgraph(ctx, ix, seed, step, stream_id, edge_h, edge_t, edge_r, n_edges, node_list, n_nodes, local_to_global,
+                           n_local, neg_ent, bern, filter, out_h, out_t, out_r, (cudaStream_t)stream);
+}
+
 int mre_transe_margin_step(mre_ctx *ctx, const float *ent, const float *rel, int64_t E, int64_t R, int64_t D, const int64_t *h,
                            const int64_t *t, const int64_t *r, int64_t B, int64_t neg, float margin, int32_t p_norm,
                            int32_t normalize, float *grad_ent, float *grad_rel, float *loss_out, float *scores_out,

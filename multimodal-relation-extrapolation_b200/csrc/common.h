@@ -74,6 +74,10 @@ struct mre_index {
     std::vector<mre::Triple> all_head;    // test + raw train + valid, sorted (h,r,t), duplicates kept (== tripleList)
     std::vector<mre::Triple> test, valid; // sorted (r,h,t)
     int64_t n_train_raw = 0;
+    // ---- host, type constraints (Reader.h:267-317): per relation the sorted, de-duplicated head / tail candidate lists
+    bool has_type = false;
+    std::vector<int64_t> type_ptr[2];     // [side][R + 1], side 0 = head lists, 1 = tail lists
+    std::vector<int64_t> type_idx[2];
     // ---- device (uploaded by mre_index_to_device)
     int device = -1;
     // filter tables over all splits, de-duplicated
@@ -124,6 +128,10 @@ int metrics(mre_ctx *ctx, const int32_t *counts, const uint8_t *q_side, int32_t 
             int32_t raw, int64_t *sums_out, double *rr_out, int64_t *hist, int64_t hist_len, cudaStream_t st);
 int sample(mre_ctx *ctx, const mre_index *ix, uint64_t seed, uint64_t step, uint32_t stream_id, int64_t B, int64_t neg,
            int32_t mode, int32_t bern, int64_t *h, int64_t *t, int64_t *r, float *y, cudaStream_t st);
+int sample_subgraph(mre_ctx *ctx, const mre_index *ix, uint64_t seed, uint64_t step, uint32_t stream_id, const int64_t *edge_h,
+                    const int64_t *edge_t, const int64_t *edge_r, int64_t n_edges, const int64_t *node_list, int64_t n_nodes,
+                    const int64_t *local_to_global, int64_t n_local, int64_t neg, int32_t bern, int32_t filter, int32_t *out_h,
+                    int32_t *out_t, int32_t *out_r, cudaStream_t st);
 int transe_margin_step(mre_ctx *ctx, const float *ent, const float *rel, int64_t E, int64_t R, int64_t D,
                        const int64_t *h, const int64_t *t, const int64_t *r, int64_t B, int64_t neg, float margin,
                        int32_t p_norm, int32_t normalize, float *grad_ent, float *grad_rel, float *loss_out,

@@ -207,6 +207,81 @@ static int read_triples(const std::string &path, bool optional, int64_t E, int64
     return MRE_OK;
 }
 
+// type_constrain.txt (Reader.h:267-317; written by benchmarks/*/n-n.py): a count line, then per relation two rows
+// "rel n id*n" -- the admissible heads, then the admissible tails.  Lists are kept sorted and de-duplicated: the reference
+// sorts them (:299,:307) and its merge pointer (Test.h:89-90) lets a repeated id count once.
+static int read_type_constrain(const std::string &path, mre_index *ix) {
+    FILE *f = fopen(path.c_str(), "rb");
+    if (!f) {
+        set_error("cannot open %s", path.c_str());
+        return MRE_ERR_IO;
+    }
+    fseek(f, 0, SEEK_END);
+    long sz = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    std::string buf((size_t)sz + 1, '\0');
+    size_t got = fread(&buf[0], 1, (size_t)sz, f);
+    fclose(f);
+    buf[got] = '\0';
+    const char *p = buf.c_str();
+    char *end = nullptr;
+    auto next = [&](long long *v) {
+        *v = strtoll(p, &end, 10);
+        if (end == p) return false;
+        p = end;
+        return true;
+    };
+    long long n_rel = 0;
+    if (!next(&n_rel) || n_rel < 0) {
+        set_error("%s: missing count line", path.c_str());
+        return MRE_ERR_IO;
+    }
+    std::vector<std::vector<int64_t>> lists[2];
+    lists[0].resize((size_t)ix->R);
+    lists[1].resize((size_t)ix->R);
+    for (long long i = 0; i < n_rel; i++) {
+        for (int side = 0; side < 2; side++) {
+            long long rel = 0, tot = 0;
+            if (!next(&rel) || !next(&tot) || tot < 0) {
+                set_error("%s: truncated at relation row %lld", path.c_str(), 2 * i + side);
+                return MRE_ERR_IO;
+            }
+            if (rel < 0 || rel >= ix->R) {
+                set_error("%s: relation %lld out of range for R=%lld", path.c_str(), rel, (long long)ix->R);
+                return MRE_ERR_INVALID;
+            }
+            std::vector<int64_t> &dst = lists[side][(size_t)rel];
+            dst.clear();
+            dst.reserve((size_t)tot);
+            for (long long j = 0; j < tot; j++) {
+                long long e = 0;
+                if (!next(&e)) {
+                    set_error("%s: relation %lld: list shorter than its count %lld", path.c_str(), rel, tot);
+                    return MRE_ERR_IO;
+                }
+                if (e < 0 || e >= ix->E) {
+                    set_error("%s: relation %lld: entity %lld out of range for E=%lld", path.c_str(), rel, e, (long long)ix->E);
+                    return MRE_ERR_INVALID;
+                }
+                dst.push_back(e);
+            }
+        }
+    }
+    for (int side = 0; side < 2; side++) {
+        ix->type_ptr[side].assign((size_t)ix->R + 1, 0);
+        ix->type_idx[side].clear();
+        for (int64_t r = 0; r < ix->R; r++) {
+            std::vector<int64_t> &l = lists[side][(size_t)r];
+            std::sort(l.begin(), l.end());
+            l.erase(std::unique(l.begin(), l.end()), l.end());
+            ix->type_idx[side].insert(ix->type_idx[side].end(), l.begin(), l.end());
+            ix->type_ptr[side][(size_t)r + 1] = (int64_t)ix->type_idx[side].size();
+        }
+    }
+    ix->has_type = true;
+    return MRE_OK;
+}
+
 template <class T>
 static int upload(const std::vector<T> &v, T **dst) {
     size_t bytes = std::max<size_t>(v.size(), 1) * sizeof(T);
@@ -280,6 +355,13 @@ int mre_index_create_from_dir(const char *in_path, mre_index **out) {
     if (rc == MRE_OK) rc = read_triples(dir + "valid2id.txt", true, E, R, va);
     if (rc == MRE_OK) rc = read_triples(dir + "test2id.txt", true, E, R, te);
     if (rc == MRE_OK) rc = build(ix, tr, va, te);
+    if (rc == MRE_OK) {   // importTypeFiles (Reader.h:267-317); the file is optional here, the reference crashes without it
+        FILE *f = fopen((dir + "type_constrain.txt").c_str(), "r");
+        if (f) {
+            fclose(f);
+            rc = read_type_constrain(dir + "type_constrain.txt", ix);
+        }
+    }
     if (rc != MRE_OK) {
         delete ix;
         return rc;
@@ -369,6 +451,53 @@ int mre_index_get_means(const mre_index *ix, float *tph, float *hpt) {
     MRE_CHECK_ARG(ix && tph && hpt, "NULL argument");
     memcpy(tph, ix->left_mean.data(), ix->left_mean.size() * sizeof(float));
     memcpy(hpt, ix->right_mean.data(), ix->right_mean.size() * sizeof(float));
+    return MRE_OK;
+}
+
+int mre_index_load_type_constrain(mre_index *ix, const char *path) {
+    MRE_CHECK_ARG(ix && path, "NULL argument");
+    return read_type_constrain(path, ix);
+}
+
+int mre_index_set_type_constrain(mre_index *ix, const int64_t *head_ptr, const int64_t *head_idx, const int64_t *tail_ptr,
+                                 const int64_t *tail_idx) {
+    MRE_CHECK_ARG(ix && head_ptr && tail_ptr, "NULL argument");
+    const int64_t *ptrs[2] = {head_ptr, tail_ptr}, *idxs[2] = {head_idx, tail_idx};
+    std::vector<int64_t> new_ptr[2], new_idx[2];
+    for (int side = 0; side < 2; side++) {
+        MRE_CHECK_ARG(ptrs[side][0] == 0, "type-constraint prefix must start at 0");
+        new_ptr[side].assign((size_t)ix->R + 1, 0);
+        for (int64_t r = 0; r < ix->R; r++) {
+            const int64_t lo = ptrs[side][r], hi = ptrs[side][r + 1];
+            MRE_CHECK_ARG(hi >= lo, "type-constraint prefix decreases at relation %lld", (long long)r);
+            MRE_CHECK_ARG(hi == lo || idxs[side], "type-constraint ids are NULL");
+            std::vector<int64_t> l(idxs[side] + lo, idxs[side] + hi);
+            for (int64_t e : l) MRE_CHECK_ARG(e >= 0 && e < ix->E, "type-constraint entity %lld out of range", (long long)e);
+            std::sort(l.begin(), l.end());
+            l.erase(std::unique(l.begin(), l.end()), l.end());
+            new_idx[side].insert(new_idx[side].end(), l.begin(), l.end());
+            new_ptr[side][(size_t)r + 1] = (int64_t)new_idx[side].size();
+        }
+    }
+    for (int side = 0; side < 2; side++) {
+        ix->type_ptr[side].swap(new_ptr[side]);
+        ix->type_idx[side].swap(new_idx[side]);
+    }
+    ix->has_type = true;
+    return MRE_OK;
+}
+
+int64_t mre_index_type_total(const mre_index *ix, int side) {
+    if (!ix || !ix->has_type || side < 0 || side > 1) return -1;
+    return (int64_t)ix->type_idx[side].size();
+}
+
+int mre_index_get_type_constrain(const mre_index *ix, int side, int64_t *ptr, int64_t *idx) {
+    MRE_CHECK_ARG(ix && ptr, "NULL argument");
+    MRE_CHECK_ARG(side == 0 || side == 1, "side must be 0 or 1");
+    MRE_CHECK_ARG(ix->has_type, "the index holds no type constraints (type_constrain.txt was not loaded)");
+    memcpy(ptr, ix->type_ptr[side].data(), ix->type_ptr[side].size() * sizeof(int64_t));
+    if (idx && !ix->type_idx[side].empty()) memcpy(idx, ix->type_idx[side].data(), ix->type_idx[side].size() * sizeof(int64_t));
     return MRE_OK;
 }
 

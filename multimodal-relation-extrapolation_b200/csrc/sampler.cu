@@ -94,4 +94,96 @@ int sample(mre_ctx *ctx, const mre_index *ix, uint64_t seed, uint64_t step, uint
     return MRE_OK;
 }
 
+// ------------------------------------------------------------------------------------ subgraph sampler (paper side)
+// module/NegativeSampling.py:114-140 (neg_sample_fn), :321-375 (__normal_batch, __corrupt_head, __corrupt_tail): per edge
+// of a sampled subgraph, neg_ent corruptions drawn from the subgraph's node list (LOCAL ids), split into head- and
+// tail-corruptions by neg_ent Bernoulli(prob) draws, heads filling slots 1..nh and tails slots nh+1..neg_ent; a drawn
+// node is discarded when its GLOBAL id completes a train triple with the kept (entity, relation).  The reference does this
+// with random.sample + np.in1d in a Python loop per edge and retries until enough survive; here one thread owns one
+// output slot, re-derives the edge's head/tail split from the same neg_ent decision words, and runs a bounded rejection
+// loop on its own Philox sub-stream (attempt number in the counter), then a deterministic scan of the node list, so the
+// kernel always terminates (the reference spins forever when every node is a known answer).
+constexpr int SUB_MAX_ATTEMPTS = 64;
+
+__device__ __forceinline__ bool sub_known(const SamplerTables &T, const int64_t *__restrict__ keys, const int64_t *__restrict__ vals,
+                                          int64_t fixed_global, int64_t r, int64_t cand_global) {
+    if (fixed_global < 0 || fixed_global >= T.E || cand_global < 0) return false;
+    const int64_t key = fixed_global * T.R + r;
+    const int64_t ll = lower_bound_i64(keys, 0, T.n_train, key);
+    const int64_t rr = lower_bound_i64(keys, ll, T.n_train, key + 1);
+    return contains_i64(vals, ll, rr, cand_global);
+}
+
+__global__ void __launch_bounds__(256) subgraph_sample_kernel(const SamplerTables T, uint32_t k0, uint32_t k1, uint32_t c2, uint32_t c3,
+                                                              const int64_t *__restrict__ eh, const int64_t *__restrict__ et,
+                                                              const int64_t *__restrict__ er, int64_t n_edges,
+                                                              const int64_t *__restrict__ nodes, int64_t n_nodes,
+                                                              const int64_t *__restrict__ l2g, int64_t n_local, int64_t neg, int bern,
+                                                              int filter, int32_t *__restrict__ oh, int32_t *__restrict__ ot,
+                                                              int32_t *__restrict__ orel) {
+    const int64_t n = n_edges * (1 + neg);
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t k = idx / n_edges, b = idx - k * n_edges;
+        int64_t h = __ldg(eh + b), t = __ldg(et + b);
+        const int64_t r = __ldg(er + b);
+        if (k > 0 && n_nodes > 0) {
+            // head/tail split of this edge: neg decision words, uniform [0,1) from the top 24 bits
+            float prob = 0.5f;
+            if (bern && r >= 0 && r < T.R) prob = __ldg(T.bern_prob + r) * 1e-3f;
+            int nh = 0;
+            for (int64_t j = 1; j <= neg; j++) {
+                const Philox4 x = philox4x32_10((uint32_t)b, (uint32_t)j, c2, c3, k0, k1);
+                nh += ((float)(x.x[0] >> 8) * 5.9604644775390625e-8f < prob) ? 1 : 0;
+            }
+            const bool corrupt_head = k <= nh;
+            const int64_t fixed_local = corrupt_head ? t : h;
+            const int64_t fixed_global = (fixed_local >= 0 && fixed_local < n_local) ? __ldg(l2g + fixed_local) : -1;
+            const int64_t *keys = corrupt_head ? T.tr_key : T.hr_key;
+            const int64_t *vals = corrupt_head ? T.tr_val : T.tr_t;
+            int64_t pick = -1, pos = 0;
+            for (int a = 0; a < SUB_MAX_ATTEMPTS && pick < 0; a++) {
+                const Philox4 x = philox4x32_10((uint32_t)b, (uint32_t)k | ((uint32_t)(a + 1) << 16), c2, c3, k0, k1);
+                pos = (int64_t)((((uint64_t)x.x[1] << 32) | x.x[0]) % (uint64_t)n_nodes);
+                const int64_t cand = __ldg(nodes + pos);
+                const int64_t cg = (cand >= 0 && cand < n_local) ? __ldg(l2g + cand) : -1;
+                if (!filter || !sub_known(T, keys, vals, fixed_global, r, cg)) pick = cand;
+            }
+            for (int64_t step = 1; step <= n_nodes && pick < 0; step++) {   // rare: the admissible set is tiny
+                const int64_t cand = __ldg(nodes + (pos + step) % n_nodes);
+                const int64_t cg = (cand >= 0 && cand < n_local) ? __ldg(l2g + cand) : -1;
+                if (!sub_known(T, keys, vals, fixed_global, r, cg)) pick = cand;
+            }
+            if (pick >= 0) {
+                if (corrupt_head) h = pick; else t = pick;
+            }
+        }
+        oh[idx] = (int32_t)h; ot[idx] = (int32_t)t; orel[idx] = (int32_t)r;
+    }
+}
+
+int sample_subgraph(mre_ctx *ctx, const mre_index *ix, uint64_t seed, uint64_t step, uint32_t stream_id, const int64_t *edge_h,
+                    const int64_t *edge_t, const int64_t *edge_r, int64_t n_edges, const int64_t *node_list, int64_t n_nodes,
+                    const int64_t *local_to_global, int64_t n_local, int64_t neg, int32_t bern, int32_t filter, int32_t *out_h,
+                    int32_t *out_t, int32_t *out_r, cudaStream_t st) {
+    MRE_CHECK_ARG(ix != nullptr, "index is NULL");
+    MRE_CHECK_ARG(ix->device == ctx->device, "index is not on device %d (call mre_index_to_device)", ctx->device);
+    MRE_CHECK_ARG(n_edges >= 0 && neg >= 0 && n_nodes >= 0 && n_local >= 0, "negative size");
+    MRE_CHECK_ARG(n_edges <= 0xffffffffLL && neg < 65536, "n_edges must fit 32 bits and neg_ent 16 bits of the Philox counter");
+    MRE_CHECK_ARG(stream_id < 65536u, "stream_id must be < 65536");
+    if (n_edges == 0) return MRE_OK;
+    MRE_CHECK_ARG(edge_h && edge_t && edge_r && out_h && out_t && out_r, "NULL edge / output array");
+    MRE_CHECK_ARG(n_nodes == 0 || node_list, "node_list is NULL");
+    MRE_CHECK_ARG(!filter || local_to_global, "filtering needs the local -> global id map");
+    SamplerTables T{ix->d_tr_h, ix->d_tr_r, ix->d_tr_t, ix->d_tr_hr_key, ix->d_tr_tr_key, ix->d_tr_tr_val, ix->d_bern_prob,
+                    ix->n_train, ix->E, ix->R};
+    const uint32_t c2 = (uint32_t)step, c3 = ((uint32_t)(step >> 32) & 0xffffu) | (stream_id << 16);
+    const int64_t n = n_edges * (1 + neg);
+    const int grid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)ctx->sm_count * 8);
+    subgraph_sample_kernel<<<grid, 256, 0, st>>>(T, (uint32_t)seed, (uint32_t)(seed >> 32), c2, c3, edge_h, edge_t, edge_r, n_edges,
+                                                 node_list, n_nodes, local_to_global, n_local, neg, bern, filter, out_h, out_t, out_r);
+    ctx->launches += 1;
+    MRE_CUDA(cudaGetLastError());
+    return MRE_OK;
+}
+
 }  // namespace mre

@@ -39,6 +39,7 @@ __device__ __forceinline__ void for_each_known(const RankParams &p, int tile_q, 
         list = p.filt_idx;
     }
     const GroupDesc &gd = p.groups[p.all_entities ? 0 : group_of_query(p, q)];
+    if (q < gd.q0 || q - gd.q0 >= gd.nq) return;                       // the query's own group was empty (dropped): nothing is scored for it
     const int64_t qt = (q - gd.q0) / tile_q;
     const int row = (int)((q - gd.q0) - qt * tile_q);
     for (int64_t i = lo + lane; i <= hi; i += 32) {        // index hi stands for the true entity itself

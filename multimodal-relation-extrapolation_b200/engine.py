@@ -102,6 +102,27 @@ class KGIndex:
     def find(self, h, t, r):
         return bool(L.lib().mre_index_find(self._h, int(h), int(t), int(r)))
 
+    # ---- type constraints (importTypeFiles, Reader.h:267-317)
+    @property
+    def has_type_constrain(self):
+        return L.lib().mre_index_type_total(self._h, 0) >= 0
+
+    def load_type_constrain(self, path):
+        L.check(L.lib().mre_index_load_type_constrain(self._h, str(path).encode()))
+
+    def set_type_constrain(self, head_ptr, head_idx, tail_ptr, tail_idx):
+        a = [_i64(x) for x in (head_ptr, head_idx, tail_ptr, tail_idx)]
+        L.check(L.lib().mre_index_set_type_constrain(self._h, *(x.ctypes.data for x in a)))
+
+    def type_constrain(self, side):
+        """(ptr [R+1], idx) of the head (side 0) / tail (side 1) lists, each relation's slice sorted and unique"""
+        n = L.lib().mre_index_type_total(self._h, int(side))
+        if n < 0:
+            raise L.MreError("the index holds no type constraints (type_constrain.txt missing)")
+        ptr, idx = np.empty(self.rel_tot + 1, np.int64), np.empty(max(n, 1), np.int64)
+        L.check(L.lib().mre_index_get_type_constrain(self._h, int(side), ptr.ctypes.data, idx.ctypes.data))
+        return ptr, idx[:n]
+
 
 class Context:
     """mre_ctx: scratch buffers and launch accounting for one device."""

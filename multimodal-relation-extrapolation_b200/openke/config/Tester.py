@@ -57,13 +57,42 @@ class Tester(object):
         counts = m.ranker().rank(m.scorer, tabs, to(q_h), to(q_t), to(q_r), side_d, index=dl.index, **m.rank_kwargs())
         return counts, side_d
 
+    def rank_counts_constrained(self, dist=None):
+        """type-constrained counts (Test.h:88-98,153-163): one grouped job per side, a candidate group per relation over
+        the relation's head / tail list of type_constrain.txt; the true entity's score is the threshold even when the
+        true entity is not in the list, exactly as `minimal = con[h]` is taken before the constraint test"""
+        if not self.use_gpu:
+            raise engine.L.MreError("mre_b200 ranks on a B200 only (use_gpu=False has no fallback)")
+        dl, m = self.data_loader, self.model
+        if not dl.index.has_type_constrain:
+            raise engine.L.MreError("type_constrain=True needs type_constrain.txt (importTypeFiles, Reader.h:267-317)")
+        dev = m.device()
+        if dl.index.device is None:
+            dl.index.to_device(dev.index or 0)
+        lo, hi = (0, dl.testTotal) if dist is None else dist.shard(dl.testTotal)
+        to = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+        q_h, q_t, q_r = to(dl.test_h[lo:hi]), to(dl.test_t[lo:hi]), to(dl.test_r[lo:hi])
+        tabs = tuple(t.detach().contiguous() for t in m.tables())
+        out = []
+        for side in (0, 1):
+            groups = dl.type_groups(side, dev, lo, hi)
+            out.append(m.ranker().rank(m.scorer, tabs, q_h, q_t, q_r, side, index=dl.index, groups=groups, **m.rank_kwargs()))
+        return out
+
     def run_link_prediction(self, type_constrain=False, dist=None):              # Tester.py:70-91
-        if type_constrain:
-            raise NotImplementedError("type-constrained ranking (Test.h:88-98, type_constrain.txt) is a 'next' row, not built yet")
         self.data_loader.set_sampling_mode("link")
-        counts, side_d = self.rank_counts(dist)
-        out = self.model.ranker().metrics(counts, side_d, "strict")
-        sums, rr = out["sums"], out["rr"]
+        if type_constrain:
+            # the reference fills both metric sets in this mode and returns the constrained one (Test.h:352-390)
+            sums = torch.zeros((2, 8), dtype=torch.int64, device=self.model.device())
+            rr = torch.zeros(2, dtype=torch.float64, device=self.model.device())
+            for side, counts in enumerate(self.rank_counts_constrained(dist)):
+                o = self.model.ranker().metrics(counts, side, "strict")
+                sums += o["sums"]
+                rr += o["rr"]
+        else:
+            counts, side_d = self.rank_counts(dist)
+            out = self.model.ranker().metrics(counts, side_d, "strict")
+            sums, rr = out["sums"], out["rr"]
         if dist is not None:
             sums, rr = dist.all_reduce_metrics(sums, rr)
         sums, rr = sums.cpu().numpy(), rr.cpu().numpy()

@@ -33,8 +33,8 @@ class TestDataLoader(object):
     def __init__(self, in_path="./", sampling_mode="link", type_constrain=True, index=None):
         self.in_path = in_path
         self.sampling_mode = sampling_mode
-        self.type_constrain = type_constrain   # type_constrain.txt ranking is a "next" row (Test.h:88-98)
-        self.index = index if index is not None else engine.KGIndex.from_dir(in_path)
+        self.index = index if index is not None else engine.KGIndex.from_dir(in_path)   # loads type_constrain.txt if present
+        self.type_constrain = type_constrain and self.index.has_type_constrain          # importTypeFiles, Reader.h:267-317
         self.relTotal, self.entTotal, self.testTotal = self.index.rel_tot, self.index.ent_tot, self.index.test_tot
         self.test_h, self.test_t, self.test_r = self.index.test_triples()
         self._ar = np.arange(self.entTotal, dtype=np.int64)
@@ -45,6 +45,14 @@ class TestDataLoader(object):
         q_h, q_t, q_r = np.repeat(self.test_h, 2), np.repeat(self.test_t, 2), np.repeat(self.test_r, 2)
         side = np.tile(np.array([0, 1], np.uint8), self.testTotal)
         return q_h, q_t, q_r, side
+
+    def type_groups(self, side, device, lo=0, hi=None):
+        """CandidateGroups over the relation blocks of test triples [lo, hi) for the head (0) / tail (1) type lists"""
+        hi = self.testTotal if hi is None else hi
+        ptr, idx = self.index.type_constrain(side)
+        r = self.test_r[lo:hi]
+        qptr = np.searchsorted(r, np.arange(self.relTotal + 1), side="left")
+        return engine.CandidateGroups(qptr, ptr, engine.torch.from_numpy(idx).to(device))
 
     def sampling_lp(self):
         i = self._cursor

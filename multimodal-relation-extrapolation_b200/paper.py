@@ -1,6 +1,8 @@
 """The paper-side (main.py / module/) entry points of the hot path, mirrored over the library:
   evaluate(...)          main.evaluate (main.py:217-272): TransE-L1 candidate ranking, ties//2, MRR + Hits@1/3/10
   PaperScorer            module.NegativeSampling._calc / .evaluate (module/NegativeSampling.py:142-168, 294-305)
+  NegativeSampling       the sampler + structural-loss half of module.NegativeSampling (:114-140, 177-185, 196-229,
+                         307-314, 321-375): neg_sample_fn / generate_eval_list / scoring_fn / regularization
   build_test_candidates  utils/gen_mode_candidates.py:15-39 (regenerates the missing {mode}_candidates.json)
   zsl_rank_metrics       ZSLmodule.eval's rank/metric block (module/zsl_module.py:699-745): Hits@10/5/1 + MRR
 """
@@ -40,6 +42,95 @@ class PaperScorer:
             print("invalid scoring model!")
             return None
         return self._calc(h, t, r)
+
+
+class NegativeSampling(PaperScorer):
+    """module.NegativeSampling without the feature producers (UnifiedModel = M3AE + RGCN is out of scope): the caller
+    passes the node features `x` and relation embeddings the model produced.  Same constructor keywords; `whole_triples`
+    is the reference's (h, r, t) tuple of GLOBAL train ids (main.py:55-68).  The sampler runs on the GPU
+    (mre_sample_subgraph): distributionally the reference's random.sample + np.in1d loop, bit-reproducible per
+    (seed, call number) instead of Python's unseeded `random`."""
+
+    def __init__(self, args=None, whole_triples=None, model=None, loss_fn=None, regul_rate=0.5, neg_ent=1,
+                 sampling_mode="normal", bern_flag=False, filter_flag=True, score_norm_flag=False, *, num_entities=None,
+                 num_relations=None, seed=0, device=0, index=None):
+        super().__init__(p_norm=1, score_norm_flag=score_norm_flag, device=device)
+        if sampling_mode != "normal":
+            raise NotImplementedError("the reference only implements sampling_mode='normal' (module/NegativeSampling.py:119)")
+        self.args, self.model, self.loss_fn, self.regul_rate = args, model, loss_fn, regul_rate
+        self.neg_ent, self.bern_flag, self.filter_flag, self.sampling_mode = neg_ent, bern_flag, filter_flag, sampling_mode
+        self.seed, self.calls = int(seed), 0
+        self.index = index
+        if index is None and whole_triples is not None:
+            h, r, t = (np.ascontiguousarray(np.asarray(x), dtype=np.int64) for x in whole_triples)
+            E = int(num_entities) if num_entities is not None else int(max(h.max(), t.max())) + 1
+            R = int(num_relations) if num_relations is not None else int(r.max()) + 1
+            self.index = engine.KGIndex.from_arrays(E, R, (h, t, r))
+        if self.index is not None and self.index.device is None:
+            self.index.to_device(device)
+
+    @staticmethod
+    def _l2g_array(local_global_id):
+        if isinstance(local_global_id, dict):
+            n = max(local_global_id) + 1 if local_global_id else 0
+            a = np.full(n, -1, np.int64)
+            for k, v in local_global_id.items():
+                a[int(k)] = int(v)
+            return a
+        return np.ascontiguousarray(np.asarray(local_global_id), dtype=np.int64)
+
+    def neg_sample_fn(self, local_global_id, node_list, edge_index, edge_type, *, device_out=False):
+        """-> (expand_edge_index int32 [2, n(1+neg_ent)], expand_edge_type int32 [n(1+neg_ent)]), CPU tensors as the
+        reference returns them (device tensors with device_out=True, saving the round trip the reference then undoes)"""
+        assert edge_index.shape[0] == 2
+        if self.index is None:
+            raise L.MreError("neg_sample_fn needs the train triples (whole_triples=...)")
+        dev = self.device
+        to = lambda a: torch.as_tensor(np.asarray(a) if not isinstance(a, torch.Tensor) else a).to(dev, torch.int64).contiguous()
+        eh, et, er = to(edge_index[0]), to(edge_index[1]), to(edge_type)
+        nodes = to(node_list)
+        l2g = to(self._l2g_array(local_global_id))
+        n = eh.numel()
+        out = torch.empty((3, n * (1 + self.neg_ent)), dtype=torch.int32, device=dev)
+        L.check(L.lib().mre_sample_subgraph(
+            self.ctx._h, self.index._h, self.seed, self.calls, 0, eh.data_ptr(), et.data_ptr(), er.data_ptr(), n,
+            nodes.data_ptr(), nodes.numel(), l2g.data_ptr(), l2g.numel(), self.neg_ent, int(bool(self.bern_flag)),
+            int(bool(self.filter_flag)), out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(),
+            torch.cuda.current_stream().cuda_stream))
+        self.calls += 1
+        if device_out:
+            return out[:2], out[2]
+        o = out.cpu()
+        return o[:2], o[2]
+
+    def generate_eval_list(self, local_global_id, edge_index, edge_type):
+        mapped_node_list = torch.arange(int(torch.as_tensor(edge_index).max()))      # excludes the max id, as :210 does
+        return self.neg_sample_fn(local_global_id, mapped_node_list, edge_index, edge_type)
+
+    def scoring_fn(self, local_global_id, x, relations, edge_index, edge_type):
+        return self._calc(h=x[edge_index[0].long()], t=x[edge_index[1].long()], r=relations)
+
+    def _get_positive_score(self, score, num_pos_samples):
+        return score[:num_pos_samples].view(-1, num_pos_samples).permute(1, 0)
+
+    def _get_negative_score(self, score, num_pos_samples):
+        return score[num_pos_samples:].view(-1, num_pos_samples).permute(1, 0)
+
+    def regularization(self, x, relations, edge_index, edge_type):
+        bh, bt = x[edge_index[0].long()], x[edge_index[1].long()]
+        return (torch.mean(bh ** 2) + torch.mean(bt ** 2) + torch.mean(relations ** 2)) / 3
+
+    def struct_loss(self, local_global_id, x, rel_emb, edge_index, edge_type):
+        """forward's structural part (:196-229): sample, score, margin loss (+ regul_rate * regularization)"""
+        node_list = torch.arange(int(torch.as_tensor(edge_index).max()))
+        ei, etype = self.neg_sample_fn(local_global_id, node_list, edge_index, edge_type, device_out=True)
+        rel_expand = rel_emb.repeat(1 + self.neg_ent, 1).to(self.device)
+        score = self.scoring_fn(local_global_id, x.to(self.device), rel_expand, ei, etype)
+        n = len(edge_type)
+        loss = self.loss_fn(self._get_positive_score(score, n), self._get_negative_score(score, n))
+        if self.regul_rate != 0:
+            loss = loss + self.regul_rate * self.regularization(x.to(self.device), rel_expand, ei, etype)
+        return loss
 
 
 def build_test_candidates(triples, rel2candidates, e1rel_e2):

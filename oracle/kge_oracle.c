@@ -195,6 +195,30 @@ void orc_rank_from_scores(const orc_index *ix, const float *con, int side,
 }
 
 /*
+ * Type-constrained counts (Test.h:88-98 / 153-163): the same comparison restricted to the relation's head (side 0) or
+ * tail (side 1) candidate set from type_constrain.txt (Reader.h:267-317: sorted per relation), walked with the
+ * reference's merge pointer, so duplicates in the list count once and the true entity is excluded by index.
+ */
+void orc_rank_from_scores_constrained(const orc_index *ix, const float *con, int side, int64_t h, int64_t t, int64_t r,
+                                      const int64_t *type_sorted, int64_t n_type, int64_t *raw, int64_t *filt) {
+    int64_t truth = side == 0 ? h : t;
+    float minimal = con[truth];
+    int64_t s = 0, fs = 0, lef = 0;
+    for (int64_t j = 0; j < ix->E; j++) {
+        if (j == truth) continue;
+        while (lef < n_type && type_sorted[lef] < j) lef++;
+        if (lef < n_type && j == type_sorted[lef]) {
+            if (con[j] < minimal) {
+                s++;
+                int known = side == 0 ? orc_find(ix, j, t, r) : orc_find(ix, h, j, r);
+                if (!known) fs++;
+            }
+        }
+    }
+    *raw = s; *filt = fs;
+}
+
+/*
  * Metric accumulation exactly as the reference does it -- float32 globals (Test.h:13-20),
  * thresholds <10/<3/<1 (:102-107), rank = count+1 and 1.0/rank added in double then rounded to
  * float (:109-112), division by testTotal and (head+tail)/2 of the FILTERED values (:232-277).
@@ -356,6 +380,66 @@ void orc_sample_philox(const orc_index *ix, uint64_t seed, uint64_t step, uint32
             if (keep_head) { bh[o] = p.h; bt[o] = orc_corrupt_head(ix, p.h, p.r, word); }
             else           { bh[o] = orc_corrupt_tail(ix, p.t, p.r, word); bt[o] = p.t; }
             br[o] = p.r; by[o] = -1;
+        }
+    }
+}
+
+/*
+ * CPU replay of the product's SUBGRAPH sampler (the paper's neg_sample_fn, module/NegativeSampling.py:114-140 with
+ * __normal_batch :321-349 and __corrupt_head/__corrupt_tail :351-375), same Philox stream as the kernel:
+ *   ctr = (edge b, slot | attempt << 16, step_lo, (step_hi & 0xffff) | stream << 16)
+ *   attempt 0, slot j = 1..neg : decision j : to_head = (x0 >> 8) * 2^-24 < prob   (prob 0.5, or hpt/(hpt+tph) with bern)
+ *   nh = number of to_head decisions; output slot k <= nh corrupts the head, k > nh the tail (heads first, :128-133)
+ *   attempt a >= 1, slot k : position (x1:x0) % n_nodes of node_list; rejected while the candidate's GLOBAL id completes a
+ *   train triple with the kept entity (np.in1d against h_of_tr / t_of_hr, :360,373); 64 attempts, then a scan.
+ * Layout: slot k of edge b at k * n_edges + b (the reference transposes its [n, 1+neg] arrays, :134-136); int32 (:138-139).
+ */
+static int train_has(const orc_index *ix, int64_t h, int64_t r, int64_t t) {
+    orc_triple key = { h, r, t };
+    return bsearch(&key, ix->train_head, (size_t)ix->n_train, sizeof(orc_triple), cmp_hrt) != NULL;
+}
+void orc_sample_subgraph_philox(const orc_index *ix, uint64_t seed, uint64_t step, uint32_t stream,
+                                const int64_t *eh, const int64_t *et, const int64_t *er, int64_t n_edges,
+                                const int64_t *nodes, int64_t n_nodes, const int64_t *l2g, int64_t n_local,
+                                int64_t neg, int bern, int filter, int32_t *oh, int32_t *ot, int32_t *orel) {
+    uint32_t key[2] = { (uint32_t)seed, (uint32_t)(seed >> 32) };
+    uint32_t c2 = (uint32_t)step, c3 = ((uint32_t)(step >> 32) & 0xffffu) | (stream << 16);
+    for (int64_t b = 0; b < n_edges; b++) {
+        int64_t h = eh[b], t = et[b], r = er[b];
+        oh[b] = (int32_t)h; ot[b] = (int32_t)t; orel[b] = (int32_t)r;
+        float prob = 0.5f;
+        if (bern && r >= 0 && r < ix->R) prob = bern_prob(ix, r, 1) * 1e-3f;
+        uint32_t ctr[4] = { (uint32_t)b, 0, c2, c3 }, x[4];
+        int64_t nh = 0;
+        for (int64_t j = 1; j <= neg; j++) {
+            ctr[1] = (uint32_t)j;
+            orc_philox4x32_10(ctr, key, x);
+            nh += ((float)(x[0] >> 8) * 5.9604644775390625e-8f < prob) ? 1 : 0;
+        }
+        for (int64_t k = 1; k <= neg; k++) {
+            int64_t o = k * n_edges + b, nhd = h, ntl = t;
+            if (n_nodes > 0) {
+                int corrupt_head = k <= nh;
+                int64_t fixed_local = corrupt_head ? t : h;
+                int64_t fg = (fixed_local >= 0 && fixed_local < n_local && l2g) ? l2g[fixed_local] : -1;
+                int64_t pick = -1, pos = 0;
+#define KNOWN(cand) ({ int64_t cg_ = ((cand) >= 0 && (cand) < n_local && l2g) ? l2g[(cand)] : -1; \
+                       (fg >= 0 && fg < ix->E && cg_ >= 0) ? (corrupt_head ? train_has(ix, cg_, r, fg) : train_has(ix, fg, r, cg_)) : 0; })
+                for (int a = 0; a < 64 && pick < 0; a++) {
+                    ctr[1] = (uint32_t)k | ((uint32_t)(a + 1) << 16);
+                    orc_philox4x32_10(ctr, key, x);
+                    pos = (int64_t)((((uint64_t)x[1] << 32) | x[0]) % (uint64_t)n_nodes);
+                    int64_t cand = nodes[pos];
+                    if (!filter || !KNOWN(cand)) pick = cand;
+                }
+                for (int64_t st = 1; st <= n_nodes && pick < 0; st++) {
+                    int64_t cand = nodes[(pos + st) % n_nodes];
+                    if (!KNOWN(cand)) pick = cand;
+                }
+#undef KNOWN
+                if (pick >= 0) { if (corrupt_head) nhd = pick; else ntl = pick; }
+            }
+            oh[o] = (int32_t)nhd; ot[o] = (int32_t)ntl; orel[o] = (int32_t)r;
         }
     }
 }

@@ -44,6 +44,8 @@ def lib():
     L.orc_find.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int64]
     L.orc_rank_from_scores.argtypes = [C.c_void_p, _f32p, C.c_int, C.c_int64, C.c_int64, C.c_int64,
                                        C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    L.orc_rank_from_scores_constrained.argtypes = [C.c_void_p, _f32p, C.c_int, C.c_int64, C.c_int64, C.c_int64, _i64p, C.c_int64,
+                                                   C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.orc_metrics_add.argtypes = [_f32p, C.c_int64, C.c_int64]
     L.orc_metrics_final.argtypes = [_f32p, _f32p, C.c_int64, _f32p]
     L.orc_corrupt_head.restype = C.c_int64
@@ -54,6 +56,9 @@ def lib():
                                  C.c_int, C.c_int, _i64p, _i64p, _i64p, _f32p]
     L.orc_sample_philox.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_int64, C.c_int64,
                                     C.c_int, C.c_int, _i64p, _i64p, _i64p, _f32p]
+    _i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+    L.orc_sample_subgraph_philox.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, _i64p, _i64p, _i64p, C.c_int64,
+                                             _i64p, C.c_int64, _i64p, C.c_int64, C.c_int64, C.c_int, C.c_int, _i32p, _i32p, _i32p]
     L.orc_count_train_leaks.restype = C.c_int64
     L.orc_count_train_leaks.argtypes = [C.c_void_p, _i64p, _i64p, _i64p, C.c_int64, C.c_int64]
     L.orc_philox_selftest.restype = C.c_int
@@ -128,6 +133,14 @@ class OracleIndex:
         lib().orc_rank_from_scores(self._h, _f32(con), int(side), int(h), int(t), int(r), C.byref(raw), C.byref(filt))
         return raw.value, filt.value
 
+    def rank_from_scores_constrained(self, con, side, h, t, r, type_sorted):
+        """Test.h:88-98: counts restricted to the relation's type-constraint candidate list (sorted)"""
+        raw, filt = C.c_int64(), C.c_int64()
+        ts = _i64(type_sorted)
+        lib().orc_rank_from_scores_constrained(self._h, _f32(con), int(side), int(h), int(t), int(r), ts, len(ts),
+                                               C.byref(raw), C.byref(filt))
+        return raw.value, filt.value
+
     def corrupt_head(self, h, r, rnd):
         return lib().orc_corrupt_head(self._h, int(h), int(r), C.c_uint64(int(rnd)))
 
@@ -156,6 +169,15 @@ class OracleIndex:
         lib().orc_sample_philox(self._h, C.c_uint64(seed), C.c_uint64(step), C.c_uint32(stream), B, neg, mode, bern,
                                 bh, bt, br, by)
         return bh, bt, br, by
+
+    def sample_subgraph_philox(self, seed, step, eh, et, er, nodes, l2g, neg, bern=0, filt=1, stream=0):
+        """CPU replay of mre_sample_subgraph -> (edge_index int32 [2, n(1+neg)], edge_type int32 [n(1+neg)])"""
+        n = len(eh) * (1 + neg)
+        oh, ot, orl = np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(n, np.int32)
+        lib().orc_sample_subgraph_philox(self._h, C.c_uint64(seed), C.c_uint64(step), C.c_uint32(stream), _i64(eh), _i64(et),
+                                         _i64(er), len(eh), _i64(nodes), len(nodes), _i64(l2g), len(l2g), neg, int(bern),
+                                         int(filt), oh, ot, orl)
+        return np.stack([oh, ot]), orl
 
     def count_train_leaks(self, bh, bt, br, start, stop):
         return lib().orc_count_train_leaks(self._h, _i64(bh), _i64(bt), _i64(br), start, stop)

@@ -51,3 +51,57 @@ def summarize(ranks, ks):
     """main.py:263-266 / zsl_module.py:739-745: MRR and Hits@k as plain means over all test triples."""
     ranks = np.asarray(ranks, np.float64)
     return float((1.0 / ranks).mean()), [float((ranks <= k).mean()) for k in ks]
+
+
+class ReferenceSubgraphSampler:
+    """Restatement of module/NegativeSampling.py's sampler with the reference's own control flow and Python `random`
+    (neg_sample_fn :114-140, __normal_batch :321-349, __corrupt_head/__corrupt_tail :351-375, __count_htr :59-93), ids as
+    ints.  The reference's RNG is unseeded Python `random`, so its output is a DISTRIBUTION, not a vector: tests compare
+    the product's sampler with this one statistically (head/tail split, uniformity over the admissible nodes, no leaks)."""
+
+    def __init__(self, whole_triples, neg_ent=1, filter_flag=True, rng=None):
+        import random
+        self.random = rng or random.Random(0)
+        self.neg_ent, self.filter_flag = neg_ent, filter_flag
+        self.h_of_tr, self.t_of_hr = {}, {}
+        h, r, t = whole_triples
+        for hh, tt, rr in zip(h, t, r):
+            self.t_of_hr.setdefault((int(hh), int(rr)), []).append(int(tt))
+            self.h_of_tr.setdefault((int(tt), int(rr)), []).append(int(hh))
+        self.h_of_tr = {k: np.array(list(set(v))) for k, v in self.h_of_tr.items()}
+        self.t_of_hr = {k: np.array(list(set(v))) for k, v in self.t_of_hr.items()}
+
+    def _corrupt(self, table, key, local_global_id, node_list, num_max):
+        try:
+            tmp = np.asarray(self.random.sample(list(node_list), k=num_max), np.int64)
+        except ValueError:
+            tmp = np.asarray(self.random.sample(list(node_list), k=len(node_list)), np.int64)
+        if not self.filter_flag:
+            return tmp
+        compare = np.asarray([local_global_id[int(x)] for x in tmp], np.int64)
+        mask = np.isin(compare, table.get(key, np.zeros(0, np.int64)), invert=True)
+        return tmp[mask]
+
+    def _normal_batch(self, local_global_id, node_list, h, t, r, neg_size):
+        nh = sum(1 for _ in range(neg_size) if self.random.random() < 0.5)
+        nt = neg_size - nh
+        out = []
+        for table, key, want in ((self.h_of_tr, (local_global_id[t], r), nh), (self.t_of_hr, (local_global_id[h], r), nt)):
+            got, cur = [], 0
+            while cur < want:
+                tmp = self._corrupt(table, key, local_global_id, node_list, (want - cur) * 2)
+                got.append(tmp)
+                cur += len(tmp)
+            out.append(np.concatenate(got)[:want] if got else np.zeros(0, np.int64))
+        return out
+
+    def neg_sample_fn(self, local_global_id, node_list, edge_index, edge_type):
+        bh, bt, br = (np.asarray(x, np.int64) for x in (edge_index[0], edge_index[1], edge_type))
+        hs, ts, rs = (np.repeat(x.reshape(-1, 1), 1 + self.neg_ent, axis=-1) for x in (bh, bt, br))
+        for i, (h, t, r) in enumerate(zip(bh.tolist(), bt.tolist(), br.tolist())):
+            last = 1
+            neg_head, neg_tail = self._normal_batch(local_global_id, node_list, h, t, r, self.neg_ent)
+            hs[i][last:last + len(neg_head)] = neg_head
+            last += len(neg_head)
+            ts[i][last:last + len(neg_tail)] = neg_tail
+        return np.stack([hs.T.flatten(), ts.T.flatten()]).astype(np.int32), rs.T.flatten().astype(np.int32)

@@ -23,6 +23,29 @@ def available():
     return os.path.exists(REF_LIB)
 
 
+def write_type_constrain(path, R, head_lists, tail_lists):
+    """type_constrain.txt in the format importTypeFiles reads (Reader.h:267-317; produced by benchmarks/*/n-n.py):
+    a count line, then per relation "rel n ids..." for the heads and the same for the tails."""
+    with open(os.path.join(path, "type_constrain.txt"), "w") as f:
+        f.write(f"{R}\n")
+        for r in range(R):
+            for lst in (head_lists[r], tail_lists[r]):
+                f.write("\t".join([str(r), str(len(lst))] + [str(int(x)) for x in lst]) + "\n")
+
+
+def read_type_constrain(path):
+    """-> (head_lists, tail_lists): dict rel -> sorted unique int64 array"""
+    toks = open(os.path.join(path, "type_constrain.txt")).read().split()
+    n, pos = int(toks[0]), 1
+    heads, tails = {}, {}
+    for _ in range(n):
+        for dst in (heads, tails):
+            rel, tot = int(toks[pos]), int(toks[pos + 1])
+            dst[rel] = np.unique(np.asarray(toks[pos + 2:pos + 2 + tot], dtype=np.int64))
+            pos += 2 + tot
+    return heads, tails
+
+
 def write_benchmark_dir(path, E, R, train, valid, test):
     """Materialise OpenKE's text format (count line, then 'h t r' rows: OpenKE/README.md:126-141)."""
     os.makedirs(path, exist_ok=True)
@@ -87,9 +110,11 @@ class RefOpenKE:
         self.L.sampling(h.ctypes.data, t.ctypes.data, r.ctypes.data, y.ctypes.data, B, neg, 0, mode, 1, 0, 0)
         return h, t, r, y
 
-    def load_test(self):
+    def load_test(self, type_files=False):
         if not self._test_loaded:
             self.L.importTestFiles()
+            if type_files:
+                self.L.importTypeFiles()      # Reader.h:267-317 (needs type_constrain.txt in the benchmark directory)
             self._test_loaded = True
         self.test_tot = self.L.getTestTotal()
         self.L.initTest()
@@ -104,17 +129,18 @@ class RefOpenKE:
         self.L.getTailBatch(self._bh.ctypes.data, self._bt.ctypes.data, self._br.ctypes.data)
         return {"batch_h": self._bh[:1], "batch_t": self._bt, "batch_r": self._br[:1], "mode": "tail_batch"}
 
-    def test_head(self, score, index):
+    def test_head(self, score, index, type_constrain=0):
         score = np.ascontiguousarray(score, np.float32)
-        self.L.testHead(score.ctypes.data, index, 0)
+        self.L.testHead(score.ctypes.data, index, type_constrain)
 
-    def test_tail(self, score, index):
+    def test_tail(self, score, index, type_constrain=0):
         score = np.ascontiguousarray(score, np.float32)
-        self.L.testTail(score.ctypes.data, index, 0)
+        self.L.testTail(score.ctypes.data, index, type_constrain)
 
-    def finish(self):
+    def finish(self, type_constrain=0):
         """-> (mrr, mr, hit10, hit3, hit1), Tester.py:83-91.  (The C side printf's its table.)"""
         L = self.L
-        L.test_link_prediction(0)
-        return (L.getTestLinkMRR(0), L.getTestLinkMR(0), L.getTestLinkHit10(0), L.getTestLinkHit3(0),
-                L.getTestLinkHit1(0))
+        L.test_link_prediction(type_constrain)
+        tc = type_constrain
+        return (L.getTestLinkMRR(tc), L.getTestLinkMR(tc), L.getTestLinkHit10(tc), L.getTestLinkHit3(tc),
+                L.getTestLinkHit1(tc))

@@ -11,6 +11,7 @@ Fixtures written (all small, integer ids re-encoded; no reference source is copi
                        own modules -> Base.so testHead/testTail) on seeded weights, for a spread of test
                        triples: raw/filtered counts, s_true, tie-band interval, score probes, metric tuples
   golden_sampler.npz   Base.so `sampling` output with its LCG pinned (srand(1)), 2 threads
+  golden_type_constrain.npz  FB15K237's type_constrain.txt sets + Base.so's type-constrained metric tuples (Test.h:88-98)
 While generating, this script ASSERTS that the oracle restatements agree with the reference:
 oracle/openke_torch.py bit-identical to the reference modules; oracle/kge_oracle.c counts -> the same metric
 tuple as Base.so; orc_sample_lcg bit-identical to Base.so's sampler.
@@ -183,12 +184,49 @@ def main():
     probe = np.random.default_rng(7).choice(E, PROBE, replace=False).astype(np.int64)
     probe.sort()
     out = {"qidx": qidx, "probe": probe, "D": D}
-    ref.load_test()
+    ref.load_test(type_files=True)
 
     for wname, wfn in gu.WEIGHT_SETS.items():
         golden_for_weights(wname, wfn, out, ref, ix, (th, tt, trr), qidx, probe, heads_of, tails_of, E, R, D,
                            (TransE, DistMult, ComplEx))
     np.savez_compressed(os.path.join(HERE, "golden_fb15k237.npz"), **out)
+
+    # ---- type-constrained ranking (Test.h:88-98) on the real type_constrain.txt: metric tuples of Base.so + the type sets
+    heads, tails = rd.read_type_constrain(bench_dir)
+    tc = {"R": R}
+    tc["head_ptr"] = np.concatenate([[0], np.cumsum([len(heads[r]) for r in range(R)])]).astype(np.int64)
+    tc["tail_ptr"] = np.concatenate([[0], np.cumsum([len(tails[r]) for r in range(R)])]).astype(np.int64)
+    tc["head_idx"] = np.concatenate([heads[r] for r in range(R)]).astype(np.uint16)
+    tc["tail_idx"] = np.concatenate([tails[r] for r in range(R)]).astype(np.uint16)
+    tc["qidx"] = qidx
+    ar = np.arange(E, dtype=np.int64)
+    for wname, wfn in gu.WEIGHT_SETS.items():
+        ent, rel, ent_im, rel_im = wfn(gu.SEED, [(E, D), (R, D), (E, D), (R, D)])
+        for name, kind, kw in (("transe_l1_norm", "transe", dict(p_norm=1, norm_flag=True)), ("distmult", "distmult", {})):
+            tables = (torch.from_numpy(ent), torch.from_numpy(rel))
+            ref.L.initTest()
+            acc = ko.MetricAccumulator()
+            raws, filts = [], []
+            for i in qidx.tolist():
+                h, t, r = int(th[i]), int(tt[i]), int(trr[i])
+                for side in (0, 1):
+                    data = ({"batch_h": ar, "batch_t": np.array([t]), "batch_r": np.array([r]), "mode": "head_batch"} if side == 0
+                            else {"batch_h": np.array([h]), "batch_t": ar, "batch_r": np.array([r]), "mode": "tail_batch"})
+                    tdata = {k: (torch.from_numpy(v) if k != "mode" else v) for k, v in data.items()}
+                    with torch.no_grad():
+                        s = ot.predict(kind, tables, tdata, **kw).numpy()
+                    (ref.test_head if side == 0 else ref.test_tail)(s, i, 1)
+                    raw, filt = ix.rank_from_scores_constrained(s, side, h, t, r, heads[r] if side == 0 else tails[r])
+                    acc.add(side, raw, filt)
+                    raws.append(raw); filts.append(filt)
+            tup_ref = ref.finish(1)
+            tup_orc = acc.final(ix.test_total)
+            assert tup_ref == tup_orc, (wname, name, tup_ref, tup_orc)
+            tc[f"{wname}_{name}_tuple"] = np.asarray(tup_ref, np.float32)
+            tc[f"{wname}_{name}_raw"] = np.asarray(raws, np.int32).reshape(-1, 2)
+            tc[f"{wname}_{name}_filt"] = np.asarray(filts, np.int32).reshape(-1, 2)
+            print("type-constrained", wname, name, tup_ref)
+    np.savez_compressed(os.path.join(HERE, "golden_type_constrain.npz"), **tc)
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))
