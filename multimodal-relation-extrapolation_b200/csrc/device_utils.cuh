@@ -36,6 +36,20 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         if (!ok && ++tries > 1000u) __trap();
     } while (!ok);
 }
+// the same without the suspend-time hint: the thread polls (each try_wait blocks for a short, hardware-bounded time).  For
+// kernels whose issue slots are not the bottleneck this wakes up faster than the suspended form.
+__device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    uint32_t tries = 0;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (!ok && ++tries > 400000000u) __trap();   // a pipeline bug must surface as a launch failure, never as a hung GPU
+    } while (!ok);
+}
 // TMA tiled load of one 2-D box (SASS: UTMALDG): coordinates are (inner element index, row)
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const void *tmap, int c0, int c1, uint32_t bar) {
     asm volatile(
@@ -61,6 +75,13 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
                  "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
 }
+
+// 8-byte asynchronous copy global -> shared (SASS: LDGSTS), no register staging
+__device__ __forceinline__ void cp_async_8(uint32_t dst, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 // ---- tcgen05 / TMEM (5th-generation tensor cores) ----
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }

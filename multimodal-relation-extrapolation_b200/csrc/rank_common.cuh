@@ -12,8 +12,8 @@ struct GroupDesc {
     int64_t q0, nq;      // query range of the group
     int64_t c0, nc;      // candidate range in cand_idx (c0 = 0, nc = E for the all-entity group)
     int64_t item0;       // first work item of the group
+    int64_t s0;          // first query SLOT of the group (even): the TransE kernel's pair-interleaved query-vector layout
     int32_t n_qt, n_et;  // tiles along queries / candidates
-    int32_t pad0, pad1;
 };
 
 struct RankParams {
@@ -33,6 +33,7 @@ struct RankParams {
     int32_t all_entities;  // 1 => single group over [0, E), cand_idx unused
     const int64_t *cand_idx;
     int64_t total_items;
+    int64_t total_slots;   // query slots over all groups (each group rounded up to an even count)
     // filter
     int32_t filter;
     const int64_t *hr_key, *hr_val, *tr_key, *tr_val;
@@ -40,6 +41,8 @@ struct RankParams {
     const int64_t *filt_ptr, *filt_idx;
     // known-true pairs per work item (tile_filter.cu): pairs[ptr[item] .. ptr[item+1]) = (row << 16 | col)
     const uint32_t *tf_ptr, *tf_pairs;
+    // per-SM arrival counters (zeroed per launch): a CTA's arrival order on its SM decides its start phase
+    uint32_t *sm_slots;
     // outputs [4][Q]
     int32_t *counts;
 };

@@ -15,11 +15,17 @@
 // operands stream into a 3-stage shared-memory ring through TMA (cp.async.bulk.tensor, 128-byte swizzle, mbarrier
 // complete_tx; candidate lists are gathered into a dense table by a pre-pass), issued by whichever warp is last
 // to release a stage; the eight warps hold an 8x8 register micro-tile per thread and read the ring with
-// conflict-free 128-bit LDS.  The
+// conflict-free 128-bit LDS.  The arithmetic is PACKED: query vectors are stored pair-interleaved ([slot / 2][d][slot & 1])
+// so one 64-bit register pair holds element d of two adjacent queries, and each (subtract, add-|.|) step is one
+// sub.f32x2 + one add.f32x2 (SASS FADD2, the entity value as a scalar-broadcast operand) for two (query, entity) pairs:
+// half the issue slots of the scalar form, which leaves the FP32 pipe -- not instruction issue -- as the bound, with the
+// LDS / barrier / address instructions issuing in the shadow of the two-cycle packed instructions.  Per (q, e) pair the
+// accumulation is still sequential over d with the same roundings, so counts stay bit-identical to the oracle.  The
 // epilogue compares the 64 accumulators against the per-query thresholds, masks the known-true slots routed to this
 // tile by tile_filter.cu (raw and filtered counts come from the SAME registers), reduces the counts with warp
 // shuffles and adds them to the per-query counters.  The kernel is bound by the FP32 pipe: 2 lane-ops per (q, e, d).
 #include <math.h>
+#include <stdlib.h>
 
 #include <vector>
 
@@ -32,24 +38,36 @@ namespace mre {
 
 constexpr int CHUNK = 32;            // floats of D per pipeline stage (128 B per row)
 constexpr int STAGES = 3;
-constexpr int CONSUMER_WARPS = 8;
+#ifndef MRE_RANK_WARPS
+#define MRE_RANK_WARPS 8      // 4 (a 16-query x 8-entity register tile per thread, 241 registers) measured 20 % slower on B200
+#endif
+constexpr int CONSUMER_WARPS = MRE_RANK_WARPS;
 constexpr int RANK_THREADS = CONSUMER_WARPS * 32;
-constexpr uint32_t STAGE_BYTES = (TILE_Q + TILE_E) * CHUNK * 4;  // two 16 KiB TMA boxes
-constexpr size_t RANK_SMEM = 1024 + (size_t)STAGES * STAGE_BYTES + STAGES * sizeof(uint64_t) + 4 * sizeof(int) + CONSUMER_WARPS * 32 * sizeof(unsigned long long) + 64;
+constexpr int NTQ = RANK_THREADS / 16;              // threads along the query dimension of the tile
+constexpr int NI = (TILE_Q / 2) / NTQ;              // query PAIR-rows per thread (4 with 8 warps: an 8-query x 8-entity register tile)
+constexpr int KW = (NI * 16 + 63) / 64;             // 64-bit words of one thread's known-true mask
+constexpr uint32_t QBOX_BYTES = (TILE_Q / 2) * 128;             // 64 query pair-rows x 128 B (16 d-values of two queries)
+constexpr uint32_t STAGE_BYTES = (TILE_Q + TILE_E) * CHUNK * 4;  // two 8 KiB query-pair boxes + one 16 KiB candidate box
+constexpr size_t RANK_SMEM = 1024 + (size_t)STAGES * STAGE_BYTES + STAGES * sizeof(uint64_t) + 4 * sizeof(int) + CONSUMER_WARPS * 32 * KW * sizeof(unsigned long long) + (size_t)TILE_Q * sizeof(float2) + 64;
 
 // ------------------------------------------------------------------------------------------ scalar scorer
-// The one definition of a TransE accumulator: sequential over d, acc = acc + |v - e| (p = 1) or fma(u, u, acc) (p = 2).
-// Query vectors are stored PAIR-SWAPPED (element d at position d ^ 1): a 128-bit load then puts v[d] in a register
-// of the opposite even/odd bank to e[d], so the tile kernel's `v[d] - e[d]` never reads two same-bank registers.
+// The one definition of a TransE accumulator: sequential over d, acc = acc + |v - e| (p = 1) or fma(u, u, acc) (p = 2), with
+// v_d = h_d + r_d (tail query) or -(r_d - t_d) (head query), so that |v_d - e_d| is bit-identical to the reference's element
+// (|(h + r) - e| and |e + (r - t)|, TransE.py:55-58).  `a` is the fixed entity's row, `r` the relation's row.
 template <int P>
-__device__ __forceinline__ float transe_acc(const float *__restrict__ v, const float *__restrict__ e, int64_t D) {
+__device__ __forceinline__ float transe_acc(const float *__restrict__ a, const float *__restrict__ r, int side,
+                                            const float *__restrict__ e, int64_t D) {
     float acc = 0.f;
     const int n = (int)D;
-#pragma unroll 8
-    for (int d = 0; d < n; d += 4) {   // unrolled: the row fetches of 8 steps are in flight together (latency-bound callers)
-        float4 a = __ldg(reinterpret_cast<const float4 *>(v + d));
-        float4 b = __ldg(reinterpret_cast<const float4 *>(e + d));
-        float u0 = a.y - b.x, u1 = a.x - b.y, u2 = a.w - b.z, u3 = a.z - b.w;
+#pragma unroll 4
+    for (int d = 0; d < n; d += 4) {   // unrolled: the row fetches of several steps are in flight together (latency-bound callers)
+        const float4 x = __ldg(reinterpret_cast<const float4 *>(a + d));
+        const float4 y = __ldg(reinterpret_cast<const float4 *>(r + d));
+        const float4 b = __ldg(reinterpret_cast<const float4 *>(e + d));
+        float v0, v1, v2, v3;
+        if (side) { v0 = x.x + y.x; v1 = x.y + y.y; v2 = x.z + y.z; v3 = x.w + y.w; }
+        else { v0 = -(y.x - x.x); v1 = -(y.y - x.y); v2 = -(y.z - x.z); v3 = -(y.w - x.w); }
+        const float u0 = v0 - b.x, u1 = v1 - b.y, u2 = v2 - b.z, u3 = v3 - b.w;
         if (P == 1) {
             acc = acc + fabsf(u0); acc = acc + fabsf(u1); acc = acc + fabsf(u2); acc = acc + fabsf(u3);
         } else {
@@ -79,20 +97,22 @@ __global__ void normalize_rows_kernel(const float *__restrict__ x, int64_t n, in
     for (int64_t d = D; d < Dp; d++) o[d] = 0.f;
 }
 
-// v_q = h + r (tail query) or -(r - t) (head query), stored pair-swapped; grid-stride over Q * D elements
-__global__ void transe_qvec_kernel(const float *__restrict__ ent, const float *__restrict__ rel, int64_t D,
-                                   const int64_t *__restrict__ q_h, const int64_t *__restrict__ q_t,
-                                   const int64_t *__restrict__ q_r, const uint8_t *__restrict__ q_side, int side,
-                                   int64_t Q, float *__restrict__ qvec) {
-    int64_t total = Q * D;
+// v_q = h + r (tail query) or -(r - t) (head query), written PAIR-INTERLEAVED by slot: a query's slot is its position in
+// its candidate group counted from the group's (even) first slot, element d of slot s lives at [s / 2][d][s & 1].
+// Queries of dropped (empty) groups own no slot.  Grid-stride over Q * D elements.
+__global__ void transe_qvec_kernel(const RankParams p, const float *__restrict__ rel, float *__restrict__ qvec) {
+    const int64_t D = p.D, total = p.Q * D;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        int64_t q = i / D, d = i - q * D;
-        int s = q_side ? (int)q_side[q] : side;
-        float rv = rel[q_r[q] * D + d];
+        const int64_t q = i / D, d = i - q * D;
+        const GroupDesc &gd = p.groups[p.n_groups > 1 ? group_of_query(p, q) : 0];
+        if (q < gd.q0 || q - gd.q0 >= gd.nq) continue;
+        const int64_t slot = gd.s0 + (q - gd.q0);
+        const int s = query_side(p, q);
+        const float rv = rel[p.q_r[q] * D + d];
         float v;
-        if (s) v = ent[q_h[q] * D + d] + rv;
-        else v = -(rv - ent[q_t[q] * D + d]);
-        qvec[i ^ 1] = v;
+        if (s) v = p.ent[p.q_h[q] * D + d] + rv;
+        else v = -(rv - p.ent[p.q_t[q] * D + d]);
+        qvec[(slot >> 1) * (2 * D) + 2 * d + (slot & 1)] = v;
     }
 }
 
@@ -100,14 +120,15 @@ __global__ void transe_qvec_kernel(const float *__restrict__ ent, const float *_
 // compares the square roots, so lo = min{x : sqrt(x) >= s_true}, hi = min{x : sqrt(x) > s_true} (sqrt is monotone),
 // which lets the tile kernel compare raw accumulators and still agree with sqrtf(acc_j) < sqrtf(acc_true) exactly.
 template <int P>
-__global__ void transe_threshold_kernel(const float *__restrict__ ent, int64_t D, const int64_t *__restrict__ q_h,
-                                        const int64_t *__restrict__ q_t, const uint8_t *__restrict__ q_side, int side,
-                                        int64_t Q, const float *__restrict__ qvec, float2 *__restrict__ thr) {
+__global__ void transe_threshold_kernel(const float *__restrict__ ent, const float *__restrict__ rel, int64_t D,
+                                        const int64_t *__restrict__ q_h, const int64_t *__restrict__ q_t,
+                                        const int64_t *__restrict__ q_r, const uint8_t *__restrict__ q_side, int side,
+                                        int64_t Q, float2 *__restrict__ thr) {
     int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= Q) return;
     int s = q_side ? (int)q_side[q] : side;
-    int64_t truth = s ? q_t[q] : q_h[q];
-    float acc = transe_acc<P>(qvec + q * D, ent + truth * D, D);
+    int64_t truth = s ? q_t[q] : q_h[q], fixed = s ? q_h[q] : q_t[q];
+    float acc = transe_acc<P>(ent + fixed * D, rel + q_r[q] * D, s, ent + truth * D, D);
     float lo = acc, hi = acc;
     if (acc >= 0.f && acc < INFINITY) {
         if (P == 1) {
@@ -132,23 +153,68 @@ __global__ void transe_threshold_kernel(const float *__restrict__ ent, int64_t D
 
 // Model.predict for one query: the materialised float32[E] score vector (tests / drop-in callers only)
 template <int P>
-__global__ void transe_predict_kernel(const float *__restrict__ ent, int64_t E, int64_t D, const float *__restrict__ qv,
+__global__ void transe_predict_kernel(const float *__restrict__ ent, const float *__restrict__ rel, int64_t E, int64_t D,
+                                      const int64_t *__restrict__ q_h, const int64_t *__restrict__ q_t,
+                                      const int64_t *__restrict__ q_r, const uint8_t *__restrict__ q_side, int side,
                                       float *__restrict__ out) {
     int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= E) return;
-    float acc = transe_acc<P>(qv, ent + j * D, D);
+    const int s = q_side ? (int)q_side[0] : side;
+    const int64_t fixed = s ? q_h[0] : q_t[0];
+    float acc = transe_acc<P>(ent + fixed * D, rel + q_r[0] * D, s, ent + j * D, D);
     out[j] = P == 1 ? acc : __fsqrt_rn(acc);
 }
 
 // ------------------------------------------------------------------------------------------ main kernel
+// acc (two queries' accumulators against one entity) <- one more element d: u = q - e ; acc + |u|  (p = 1) | fma(u, u, acc)
+// ptxas turns the {e, e} pair into a scalar-broadcast operand and folds the |.| into the add: FADD2 R, R.F32x2, -R.F32 ;
+// FADD2 R, R.F32x2, |R|.F32x2  (FFMA2 for p = 2): two instructions for four lane-ops.
+#ifndef MRE_VOLATILE
+#define MRE_VOLATILE 1
+#endif
+#if MRE_VOLATILE
+#define MRE_ASM asm volatile   // keeps the source order of the packed instructions: ptxas otherwise pulls dependent pairs together
+#else
+#define MRE_ASM asm
+#endif
 template <int P>
-__device__ __forceinline__ float upd(float acc, float q, float e) {
-    float u = q - e;
-    return P == 1 ? acc + fabsf(u) : fmaf(u, u, acc);
+__device__ __forceinline__ unsigned long long sub2(unsigned long long q, float e) {
+    unsigned long long u;
+    MRE_ASM("{\n\t.reg .b64 t;\n\tmov.b64 t, {%2, %2};\n\tsub.f32x2 %0, %1, t;\n\t}" : "=l"(u) : "l"(q), "f"(e));
+    return u;
 }
+template <int P>
+__device__ __forceinline__ void acc2(unsigned long long &acc, unsigned long long u) {
+    if (P == 1) {
+        MRE_ASM("{\n\t.reg .b64 a;\n\t.reg .b32 lo, hi;\n\tmov.b64 {lo, hi}, %1;\n\tabs.f32 lo, lo;\n\tabs.f32 hi, hi;\n\tmov.b64 a, {lo, hi};\n\t"
+            "add.f32x2 %0, %0, a;\n\t}" : "+l"(acc) : "l"(u));
+    } else {
+        MRE_ASM("fma.rn.f32x2 %0, %1, %1, %0;" : "+l"(acc) : "l"(u));
+    }
+}
+#ifndef MRE_K4_UNROLL
+#define MRE_K4_UNROLL 4
+#endif
+constexpr int K4_UNROLL = MRE_K4_UNROLL;
+#ifndef MRE_STAGGER
+#define MRE_STAGGER 0      // experiment (no effect measured: the two CTAs of an SM de-phase on their own): start-phase offset of
+#endif                     // the second CTA on an SM, in percent of one work item's duration
+#ifndef MRE_DIAG_NOWAIT
+#define MRE_DIAG_NOWAIT 0
+#endif
+#ifndef MRE_DIAG_NOEPI
+#define MRE_DIAG_NOEPI 0
+#endif
+#ifndef MRE_WAIT_SPIN
+#define MRE_WAIT_SPIN 1
+#endif
+#ifndef MRE_GROUP
+#define MRE_GROUP 4        // subtractions issued together before their dependent adds: hides the FADD2 latency inside ONE warp
+#endif
 
-// One pipeline chunk = CHUNK floats (128 B) of every row of one work item's two operands = two TMA boxes of
-// 128 rows x 128 B, written into shared memory with the hardware 128-byte swizzle.  Issued by ONE thread.
+// One pipeline chunk = CHUNK floats of d of every row of one work item's two operands: the interleaved query pairs as two
+// boxes of 64 pair-rows x 128 B (16 d-values of two queries each), the candidates as one box of 128 rows x 128 B, all
+// written into shared memory with the hardware 128-byte swizzle.  Issued by ONE thread.
 __device__ __forceinline__ void issue_chunk(const RankParams &p, const CUtensorMap *tm_q, const CUtensorMap *tm_e, int64_t flat,
                                             int n_chunks, uint32_t ring_u32, uint32_t full0) {
     const int64_t item = blockIdx.x + (flat / n_chunks) * (int64_t)gridDim.x;
@@ -157,14 +223,15 @@ __device__ __forceinline__ void issue_chunk(const RankParams &p, const CUtensorM
     int g, qt, et;
     decode_item(p, item, g, qt, et);
     const GroupDesc &gd = p.groups[g];
-    const int qrow = (int)(gd.q0 + (int64_t)qt * TILE_Q);
+    const int prow = (int)((gd.s0 + (int64_t)qt * TILE_Q) >> 1);
     const int erow = (int)(gd.c0 + (int64_t)et * TILE_E);
     const int stage = (int)(flat % STAGES);
     const uint32_t full = full0 + 8 * stage;
     const uint32_t sq = ring_u32 + (uint32_t)stage * STAGE_BYTES;
     mbar_arrive_expect_tx(full, STAGE_BYTES);
-    tma_load_2d(sq, tm_q, c * CHUNK, qrow, full);
-    tma_load_2d(sq + TILE_Q * CHUNK * 4, tm_e, c * CHUNK, erow, full);
+    tma_load_2d(sq, tm_q, c * (2 * CHUNK), prow, full);
+    tma_load_2d(sq + QBOX_BYTES, tm_q, c * (2 * CHUNK) + CHUNK, prow, full);
+    tma_load_2d(sq + 2 * QBOX_BYTES, tm_e, c * CHUNK, erow, full);
 }
 
 template <int P, bool NEED_EQ>
@@ -176,8 +243,9 @@ transe_rank_kernel(const RankParams p, const __grid_constant__ CUtensorMap tm_q,
     unsigned char *ring = smem_raw + (ring_u32 - smem_u32(smem_raw));
     uint64_t *bars = reinterpret_cast<uint64_t *>(ring + (size_t)STAGES * STAGE_BYTES);
     int *done = reinterpret_cast<int *>(bars + STAGES);  // per-stage count of warps that finished reading the stage
-    // per-warp known-true masks: bit (i * 8 + j) of lane l's word marks accumulator (i, j) of that thread
-    unsigned long long *wmask = reinterpret_cast<unsigned long long *>(done + 4) + (threadIdx.x >> 5) * 32;
+    // per-warp known-true masks: bit (row slot * 8 + j) of lane l's word marks one accumulator of that thread
+    unsigned long long *wmask = reinterpret_cast<unsigned long long *>(done + 4) + (threadIdx.x >> 5) * 32 * KW;   // [lane][KW]
+    float2 *thr_s = reinterpret_cast<float2 *>(reinterpret_cast<unsigned long long *>(done + 4) + CONSUMER_WARPS * 32 * KW);   // [warps][4 NI rows]
     const uint32_t full0 = smem_u32(bars);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_chunks = (int)((p.D + CHUNK - 1) / CHUNK);
@@ -192,11 +260,24 @@ transe_rank_kernel(const RankParams p, const __grid_constant__ CUtensorMap tm_q,
         fence_barrier_init();
         fence_proxy_async();
         for (int s = 0; s < STAGES; s++) issue_chunk(p, &tm_q, &tm_e, s, n_chunks, ring_u32, full0);
+        // The two CTAs of an SM run identical, deterministic work: left alone they reach their (FP32-idle) epilogues
+        // together.  The second CTA to arrive on an SM therefore starts half an item late -- its partner has the FP32
+        // pipe to itself meanwhile, so nothing is lost -- and from then on one CTA's epilogue overlaps the other's tile loop.
+        uint32_t smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        done[3] = (MRE_STAGGER > 0 && p.sm_slots) ? (int)(atomicAdd(p.sm_slots + smid, 1u) & 1u) : 0;
     }
     __syncthreads();
+    if (MRE_STAGGER > 0 && done[3] && p.total_items > (int64_t)gridDim.x) {
+        // one chunk of one CTA alone on the SM takes TILE_Q * TILE_E * CHUNK * 2 / 128 lanes = 8192 cycles
+        const long long delay = (long long)n_chunks * 8192ll * MRE_STAGGER / 100;
+        const long long t0 = clock64();
+        while (clock64() - t0 < delay) __nanosleep(2000);
+    }
 
-    // entity rows te + 16 j, query rows tq + 16 i.  Row r keeps its logical 16-byte chunk k at (k ^ (r & 7)), and
-    // (te + 16 j) & 7 == te & 7: eight consecutive rows read eight distinct bank groups => conflict-free LDS.128.
+    // entity rows te + 16 j (j < 8); query PAIR-rows tq + NTQ i (i < NI) = tile rows 2 (tq + NTQ i) and 2 (tq + NTQ i) + 1.
+    // A row keeps its logical 16-byte chunk k at (k ^ (row & 7)), and (te + 16 j) & 7 == te & 7: the sixteen rows one
+    // LDS.128 touches split into two conflict-free wavefronts; the two pair-rows a warp reads are broadcasts.
     const int te = threadIdx.x & 15, tq = threadIdx.x >> 4;
     const int xe = te & 7, xq = tq & 7;
     int64_t it = 0;
@@ -210,43 +291,71 @@ transe_rank_kernel(const RankParams p, const __grid_constant__ CUtensorMap tm_q,
         // this item's known-true pairs; the first 32 are fetched now so the epilogue does not wait on them
         const uint32_t pf0 = __ldg(p.tf_ptr + item), pf1 = __ldg(p.tf_ptr + item + 1);
         const uint32_t pair0 = pf0 + lane < pf1 ? __ldg(p.tf_pairs + pf0 + lane) : 0xffffffffu;
+        // thresholds of this warp's 16 query rows -> shared memory (asynchronous copy: nobody waits for it before the epilogue);
+        // slot k of the warp = row 2 ((2 warp + k / 2NI) + NTQ ((k % 2NI) / 2)) + k % 2; rows past the group's end get -inf (never counted)
+        if (lane < 4 * NI) {
+            const int k2 = lane % (2 * NI);
+            const int ql = 2 * ((2 * warp + lane / (2 * NI)) + NTQ * (k2 >> 1)) + (k2 & 1);
+            float2 *dst = thr_s + warp * (4 * NI) + lane;
+            if (ql < nq) cp_async_8(smem_u32(dst), p.thr + qbase + ql);
+            else *dst = make_float2(-INFINITY, -INFINITY);
+        }
+        cp_async_commit();
 
-        float acc[8][8];
+        unsigned long long acc[NI][8];   // acc[i][j] = (row 2 (tq + NTQ i), row 2 (tq + NTQ i) + 1) x entity te + 16 j
 #pragma unroll
-        for (int i = 0; i < 8; i++)
+        for (int i = 0; i < NI; i++)
 #pragma unroll
-            for (int j = 0; j < 8; j++) acc[i][j] = 0.f;
+            for (int j = 0; j < 8; j++) acc[i][j] = 0ull;
 
         for (int c = 0; c < n_chunks; c++, it++) {
             const int stage = (int)(it % STAGES);
+#if MRE_DIAG_NOWAIT
+            // diagnostic build only (wrong results): compute on whatever is in the ring
+#elif MRE_WAIT_SPIN
+            mbar_wait_spin(full0 + 8 * stage, (uint32_t)((it / STAGES) & 1));
+#else
             mbar_wait(full0 + 8 * stage, (uint32_t)((it / STAGES) & 1));
-            const unsigned char *sQ = ring + (size_t)stage * STAGE_BYTES + tq * (CHUNK * 4);
-            const unsigned char *sE = ring + (size_t)stage * STAGE_BYTES + (TILE_Q + te) * (CHUNK * 4);
+#endif
+            const unsigned char *sQ = ring + (size_t)stage * STAGE_BYTES + tq * 128;
+            const unsigned char *sE = ring + (size_t)stage * STAGE_BYTES + 2 * QBOX_BYTES + te * 128;
             const int nk4 = (int)min((int64_t)CHUNK, p.D - (int64_t)c * CHUNK) >> 2;
-#pragma unroll 2
+#pragma unroll K4_UNROLL
             for (int k4 = 0; k4 < nk4; k4++) {
-                const int oe = (k4 ^ xe) << 4, oq = (k4 ^ xq) << 4;
+                const int oe = (k4 ^ xe) << 4;
+                // four d-values of a query pair = 32 B = 16-byte chunks 2 (k4 & 3) and 2 (k4 & 3) + 1 of box k4 >> 2
+                const int qb = (k4 >> 2) * (int)QBOX_BYTES;
+                const int oq0 = qb + ((((k4 & 3) << 1) ^ xq) << 4), oq1 = qb + (((((k4 & 3) << 1) | 1) ^ xq) << 4);
                 float4 ev[8];
 #pragma unroll
-                for (int j = 0; j < 8; j++) ev[j] = *reinterpret_cast<const float4 *>(sE + j * (16 * CHUNK * 4) + oe);
+                for (int j = 0; j < 8; j++) ev[j] = *reinterpret_cast<const float4 *>(sE + j * (16 * 128) + oe);
 #pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    const float4 qv = *reinterpret_cast<const float4 *>(sQ + i * (16 * CHUNK * 4) + oq);
+                for (int i = 0; i < NI; i++) {
+                    const ulonglong2 qa = *reinterpret_cast<const ulonglong2 *>(sQ + i * (NTQ * 128) + oq0);
+                    const ulonglong2 qc = *reinterpret_cast<const ulonglong2 *>(sQ + i * (NTQ * 128) + oq1);
+                    // per accumulator the order is d, d+1, d+2, d+3 (sequential sum); across accumulators the work is
+                    // grouped MRE_GROUP subtractions, then their MRE_GROUP adds
 #pragma unroll
-                    for (int j = 0; j < 8; j++) {
-                        float a = acc[i][j];
-                        a = upd<P>(a, qv.y, ev[j].x);  // pair-swapped query layout: element d sits at d ^ 1
-                        a = upd<P>(a, qv.x, ev[j].y);
-                        a = upd<P>(a, qv.w, ev[j].z);
-                        a = upd<P>(a, qv.z, ev[j].w);
-                        acc[i][j] = a;
+                    for (int dd = 0; dd < 4; dd++) {
+                        const unsigned long long qd = dd == 0 ? qa.x : dd == 1 ? qa.y : dd == 2 ? qc.x : qc.y;
+#pragma unroll
+                        for (int j0 = 0; j0 < 8; j0 += MRE_GROUP) {
+                            unsigned long long u[MRE_GROUP];
+#pragma unroll
+                            for (int j = 0; j < MRE_GROUP; j++) {
+                                const float4 e4 = ev[j0 + j];
+                                u[j] = sub2<P>(qd, dd == 0 ? e4.x : dd == 1 ? e4.y : dd == 2 ? e4.z : e4.w);
+                            }
+#pragma unroll
+                            for (int j = 0; j < MRE_GROUP; j++) acc2<P>(acc[i][j0 + j], u[j]);
+                        }
                     }
                 }
             }
             // Release the stage.  The LAST warp to finish reading it refills it with the chunk STAGES ahead: no
             // dedicated producer warp, no empty-barrier spinning, and warps may drift up to STAGES-1 chunks apart.
             __syncwarp();
-            if (lane == 0) {
+            if (lane == 0 && !MRE_DIAG_NOWAIT) {
                 __threadfence_block();
                 const int old = atomicAdd(&done[stage], 1);
                 if ((old & (CONSUMER_WARPS - 1)) == CONSUMER_WARPS - 1) {
@@ -257,61 +366,102 @@ transe_rank_kernel(const RankParams p, const __grid_constant__ CUtensorMap tm_q,
             }
         }
 
+#if MRE_DIAG_NOEPI
+        {   // diagnostic build only (wrong results): keep the accumulators live, skip the compare / count epilogue
+            unsigned long long x = 0;
+#pragma unroll
+            for (int i = 0; i < NI; i++)
+#pragma unroll
+                for (int j = 0; j < 8; j++) x ^= acc[i][j];
+            if (x == 0x123456789abcdefull) atomicAdd(p.counts, 1);
+            continue;
+        }
+#endif
         // ---- known-true mask of this warp's 32 threads: every pair routed to this item by tile_filter.cu
-        unsigned long long known = 0ull;
+        cp_async_wait_all();
+        unsigned long long known[KW];
+#pragma unroll
+        for (int k = 0; k < KW; k++) known[k] = 0ull;
         if (pf1 > pf0) {
-            wmask[lane] = 0ull;
+#pragma unroll
+            for (int k = 0; k < KW; k++) wmask[lane * KW + k] = 0ull;
             __syncwarp();
             for (uint32_t k = pf0 + lane; k < pf1; k += 32) {
                 const uint32_t pr = k < pf0 + 32 ? pair0 : __ldg(p.tf_pairs + k);
                 const int row = (int)(pr >> 16), col = (int)(pr & 0xffffu);
-                const int otq = row & 15;                    // owner thread: tq = row % 16, te = col % 16
-                if ((otq >> 1) == warp)
-                    atomicOr(&wmask[((otq & 1) << 4) | (col & 15)], 1ull << (((row >> 4) << 3) | (col >> 4)));
+                const int prw = row >> 1;                    // pair-row; owner thread: tq = prw % NTQ, te = col % 16
+                const int otq = prw % NTQ;
+                if ((otq >> 1) == warp) {
+                    const int bit = ((((prw / NTQ) << 1) | (row & 1)) << 3) | (col >> 4);   // (2 i + half) * 8 + j
+                    atomicOr(&wmask[(((otq & 1) << 4) | (col & 15)) * KW + (bit >> 6)], 1ull << (bit & 63));
+                }
             }
             __syncwarp();
-            known = wmask[lane];
+#pragma unroll
+            for (int k = 0; k < KW; k++) known[k] = wmask[lane * KW + k];
         }
-        // ---- epilogue: compare against the per-query thresholds, count raw and known hits, reduce over the 16 lanes
-        // sharing a query row (four 8-bit counters packed in one word: each is at most 128 after the reduction)
-        const bool any_known = __any_sync(0xffffffffu, known != 0ull);   // warp-uniform: most warps of most tiles hold none
-        bool ev_ok[8];
+        // ---- epilogue: compare against the per-query thresholds, count, reduce over the 16 lanes sharing a query row.
+        // lt <=> s < th.x ; eq <=> th.x <= s < th.y, so eq = #(s < th.y) - #(s < th.x): two independent compare-and-count
+        // chains per accumulator.  The thresholds of the warp's 16 rows were staged in shared memory at item start.
+        unsigned long long known_or = 0ull;
 #pragma unroll
-        for (int j = 0; j < 8; j++) ev_ok[j] = (te + 16 * j) < ne;
+        for (int k = 0; k < KW; k++) known_or |= known[k];
+        const bool any_known = __any_sync(0xffffffffu, known_or != 0ull);   // warp-uniform: most warps of most tiles hold none
+        __syncwarp();
+        const float2 *th_w = thr_s + warp * (4 * NI) + (tq & 1) * (2 * NI);
+        if (!any_known && ne == TILE_E) {
+            // fast path (nearly every tile): no known-true slot in this warp, no candidate padding.  Two rows share one
+            // word (four 8-bit counters, each at most 128 after the reduction), so 4 shuffles serve 2 rows.
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-            const int ql = tq + 16 * i;
-            const bool q_ok = ql < nq;
-            float2 th = make_float2(-INFINITY, -INFINITY);
-            if (q_ok) th = __ldg(p.thr + qbase + ql);
-            uint32_t packed = 0;
-            if (any_known) {
+            for (int i = 0; i < NI; i++) {
+                const float2 t0 = th_w[2 * i], t1 = th_w[2 * i + 1];
+                uint32_t a_x = 0, a_y = 0, b_x = 0, b_y = 0;
 #pragma unroll
                 for (int j = 0; j < 8; j++) {
-                    const float s = acc[i][j];
-                    const bool lt = ev_ok[j] && s < th.x;
-                    const bool eq = NEED_EQ && ev_ok[j] && !lt && s < th.y;
-                    const bool kn = (known >> (i * 8 + j)) & 1ull;
-                    packed += (lt ? 1u : 0u) + (eq ? 0x100u : 0u) + ((lt && kn) ? 0x10000u : 0u) + ((eq && kn) ? 0x1000000u : 0u);
+                    const float s0 = __uint_as_float((uint32_t)acc[i][j]), s1 = __uint_as_float((uint32_t)(acc[i][j] >> 32));
+                    a_x += s0 < t0.x ? 1u : 0u; a_y += s0 < t0.y ? 1u : 0u;
+                    b_x += s1 < t1.x ? 1u : 0u; b_y += s1 < t1.y ? 1u : 0u;
                 }
-            } else {
+                uint32_t packed = a_x | ((a_y - a_x) << 8) | (b_x << 16) | ((b_y - b_x) << 24);
 #pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    const float s = acc[i][j];
-                    const bool lt = ev_ok[j] && s < th.x;
-                    const bool eq = NEED_EQ && ev_ok[j] && !lt && s < th.y;
-                    packed += (lt ? 1u : 0u) + (eq ? 0x100u : 0u);
+                for (int m = 1; m < 16; m <<= 1) packed += __shfl_xor_sync(0xffffffffu, packed, m);
+                if (te == 0 && packed) {
+                    const int ql = 2 * (tq + NTQ * i);
+                    const int64_t q = qbase + ql;
+                    const int lt0 = packed & 0xff, eq0 = (packed >> 8) & 0xff, lt1 = (packed >> 16) & 0xff, eq1 = packed >> 24;
+                    if (lt0) { atomicAdd(p.counts + q, lt0); atomicAdd(p.counts + 2 * p.Q + q, lt0); }
+                    if (NEED_EQ && eq0) { atomicAdd(p.counts + p.Q + q, eq0); atomicAdd(p.counts + 3 * p.Q + q, eq0); }
+                    if (lt1) { atomicAdd(p.counts + q + 1, lt1); atomicAdd(p.counts + 2 * p.Q + q + 1, lt1); }
+                    if (NEED_EQ && eq1) { atomicAdd(p.counts + p.Q + q + 1, eq1); atomicAdd(p.counts + 3 * p.Q + q + 1, eq1); }
                 }
             }
+        } else {
+            // general path: candidate padding of a group's last tile and / or known-true slots to take out of the filtered counts
 #pragma unroll
-            for (int m = 1; m < 16; m <<= 1) packed += __shfl_xor_sync(0xffffffffu, packed, m);
-            if (q_ok && te == 0 && packed) {
-                const int64_t q = qbase + ql;
-                const int n_lt = packed & 0xff, n_eq = (packed >> 8) & 0xff, k_lt = (packed >> 16) & 0xff, k_eq = packed >> 24;
-                if (n_lt) atomicAdd(p.counts + q, n_lt);
-                if (n_eq) atomicAdd(p.counts + p.Q + q, n_eq);
-                if (n_lt - k_lt) atomicAdd(p.counts + 2 * p.Q + q, n_lt - k_lt);
-                if (n_eq - k_eq) atomicAdd(p.counts + 3 * p.Q + q, n_eq - k_eq);
+            for (int i2 = 0; i2 < 2 * NI; i2++) {             // i2 = 2 i + half (unrolled: register arrays need static indices)
+                const int ql = 2 * (tq + NTQ * (i2 >> 1)) + (i2 & 1);
+                const float2 th = th_w[i2];
+                uint32_t packed = 0;
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const unsigned long long a2 = acc[i2 >> 1][j];
+                    const float sc = __uint_as_float((i2 & 1) ? (uint32_t)(a2 >> 32) : (uint32_t)a2);
+                    const bool ok = (te + 16 * j) < ne;
+                    const bool lt = ok && sc < th.x;
+                    const bool eq = NEED_EQ && ok && !lt && sc < th.y;
+                    const bool kn = (known[(i2 * 8) >> 6] >> ((i2 * 8 + j) & 63)) & 1ull;
+                    packed += (lt ? 1u : 0u) + (eq ? 0x100u : 0u) + ((lt && kn) ? 0x10000u : 0u) + ((eq && kn) ? 0x1000000u : 0u);
+                }
+#pragma unroll
+                for (int m = 1; m < 16; m <<= 1) packed += __shfl_xor_sync(0xffffffffu, packed, m);
+                if (te == 0 && packed) {
+                    const int64_t q = qbase + ql;
+                    const int n_lt = packed & 0xff, n_eq = (packed >> 8) & 0xff, k_lt = (packed >> 16) & 0xff, k_eq = packed >> 24;
+                    if (n_lt) atomicAdd(p.counts + q, n_lt);
+                    if (n_eq) atomicAdd(p.counts + p.Q + q, n_eq);
+                    if (n_lt - k_lt) atomicAdd(p.counts + 2 * p.Q + q, n_lt - k_lt);
+                    if (n_eq - k_eq) atomicAdd(p.counts + 3 * p.Q + q, n_eq - k_eq);
+                }
             }
         }
     }
@@ -319,15 +469,16 @@ transe_rank_kernel(const RankParams p, const __grid_constant__ CUtensorMap tm_q,
 
 // ------------------------------------------------------------------------------------------ host side
 static int build_groups(mre_ctx *ctx, const mre_rank_job *job, int tile_q, int tile_e, std::vector<GroupDesc> &groups,
-                        int64_t *total_items) {
+                        int64_t *total_items, int64_t *total_slots) {
     groups.clear();
-    int64_t items = 0;
+    int64_t items = 0, slots = 0;
     if (job->n_groups <= 0) {
         GroupDesc g{};
         g.q0 = 0; g.nq = job->Q; g.c0 = 0; g.nc = job->E; g.item0 = 0;
         g.n_qt = (int32_t)((job->Q + tile_q - 1) / tile_q);
         g.n_et = (int32_t)((job->E + tile_e - 1) / tile_e);
         items = (int64_t)g.n_qt * g.n_et;
+        slots = (job->Q + 1) & ~(int64_t)1;
         groups.push_back(g);
     } else {
         MRE_CHECK_ARG(job->group_qptr && job->group_cptr && job->cand_idx, "candidate groups need group_qptr, group_cptr, cand_idx");
@@ -339,6 +490,8 @@ static int build_groups(mre_ctx *ctx, const mre_rank_job *job, int tile_q, int t
             MRE_CHECK_ARG(g.nq >= 0 && g.nc >= 0, "group %d has a negative size", i);
             if (g.nq == 0 || g.nc == 0) continue;
             g.item0 = items;
+            g.s0 = slots;
+            slots += (g.nq + 1) & ~(int64_t)1;
             g.n_qt = (int32_t)((g.nq + tile_q - 1) / tile_q);
             g.n_et = (int32_t)((g.nc + tile_e - 1) / tile_e);
             items += (int64_t)g.n_qt * g.n_et;
@@ -350,6 +503,7 @@ static int build_groups(mre_ctx *ctx, const mre_rank_job *job, int tile_q, int t
         }
     }
     *total_items = items;
+    *total_slots = slots;
     (void)ctx;
     return MRE_OK;
 }
@@ -357,8 +511,8 @@ static int build_groups(mre_ctx *ctx, const mre_rank_job *job, int tile_q, int t
 int fill_rank_params(mre_ctx *ctx, const mre_index *ix, const mre_rank_job *job, int tile_q, int tile_e, cudaStream_t st,
                      RankParams &p) {
     std::vector<GroupDesc> groups;
-    int64_t items = 0;
-    MRE_TRY(build_groups(ctx, job, tile_q, tile_e, groups, &items));
+    int64_t items = 0, slots = 0;
+    MRE_TRY(build_groups(ctx, job, tile_q, tile_e, groups, &items, &slots));
     MRE_TRY(ctx->tiles.reserve(groups.size() * sizeof(GroupDesc)));
     MRE_CUDA(cudaMemcpyAsync(ctx->tiles.p, groups.data(), groups.size() * sizeof(GroupDesc), cudaMemcpyHostToDevice, st));
     // the descriptor vector dies with this frame; the copy above is from pageable memory and therefore staged
@@ -370,6 +524,7 @@ int fill_rank_params(mre_ctx *ctx, const mre_index *ix, const mre_rank_job *job,
     p.all_entities = job->n_groups <= 0 ? 1 : 0;
     p.cand_idx = job->cand_idx;
     p.total_items = items;
+    p.total_slots = slots;
     p.filter = job->filter;
     p.hr_key = p.hr_val = p.tr_key = p.tr_val = nullptr;
     p.n_all = 0;
@@ -388,8 +543,9 @@ int fill_rank_params(mre_ctx *ctx, const mre_index *ix, const mre_rank_job *job,
     return MRE_OK;
 }
 
-template <int P>
-static int transe_prepass(mre_ctx *ctx, const mre_rank_job *job, cudaStream_t st, const float **ent_out, int64_t *Dp_out) {
+// normalised / zero-padded copies of the tables when the job asks for them (else the caller's tables are read in place)
+static int transe_tables(mre_ctx *ctx, const mre_rank_job *job, cudaStream_t st, const float **ent_out, const float **rel_out,
+                         int64_t *Dp_out) {
     const int64_t D = job->D, Dp = (D + 3) & ~(int64_t)3;
     const float *ent = job->ent, *rel = job->rel;
     if (job->normalize || Dp != D) {
@@ -401,17 +557,24 @@ static int transe_prepass(mre_ctx *ctx, const mre_rank_job *job, cudaStream_t st
         ent = ctx->ent_n.as<float>();
         rel = ctx->rel_n.as<float>();
     }
-    if (job->Q > 0) {
-        MRE_TRY(ctx->qvec.reserve((size_t)job->Q * Dp * sizeof(float)));
-        MRE_TRY(ctx->thr.reserve((size_t)job->Q * sizeof(float2)));
-        transe_qvec_kernel<<<grid_for(job->Q * Dp, 256), 256, 0, st>>>(ent, rel, Dp, job->q_h, job->q_t, job->q_r, job->q_side,
-                                                                       job->side, job->Q, ctx->qvec.as<float>());
-        transe_threshold_kernel<P><<<(unsigned)((job->Q + 127) / 128), 128, 0, st>>>(
-            ent, Dp, job->q_h, job->q_t, job->q_side, job->side, job->Q, ctx->qvec.as<float>(), ctx->thr.as<float2>());
-        ctx->launches += 2;
-    }
     *ent_out = ent;
+    *rel_out = rel;
     *Dp_out = Dp;
+    MRE_CUDA(cudaGetLastError());
+    return MRE_OK;
+}
+
+// per-query thresholds + the pair-interleaved query vectors (p.ent, p.D, p.groups, p.total_slots already set)
+template <int P>
+static int transe_queries(mre_ctx *ctx, const RankParams &p, const float *rel, cudaStream_t st) {
+    const size_t qbytes = (size_t)std::max<int64_t>(p.total_slots, 2) * p.D * sizeof(float);
+    MRE_TRY(ctx->qvec.reserve(qbytes));
+    MRE_TRY(ctx->thr.reserve((size_t)p.Q * sizeof(float2)));
+    if (p.total_slots != p.Q) MRE_CUDA(cudaMemsetAsync(ctx->qvec.p, 0, qbytes, st));   // the odd halves no query owns
+    transe_qvec_kernel<<<grid_for(p.Q * p.D, 256), 256, 0, st>>>(p, rel, ctx->qvec.as<float>());
+    transe_threshold_kernel<P><<<(unsigned)((p.Q + 127) / 128), 128, 0, st>>>(p.ent, rel, p.D, p.q_h, p.q_t, p.q_r, p.q_side, p.side,
+                                                                               p.Q, ctx->thr.as<float2>());
+    ctx->launches += 2;
     MRE_CUDA(cudaGetLastError());
     return MRE_OK;
 }
@@ -424,7 +587,9 @@ static int launch_rank(mre_ctx *ctx, const RankParams &p, const CUtensorMap &tm_
         MRE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RANK_SMEM));
         configured = true;
     }
-    int grid = (int)std::max<int64_t>(1, std::min<int64_t>(p.total_items, (int64_t)ctx->sm_count * 2));
+    int per_sm = 2;
+    if (const char *e = getenv("MRE_DEV_CTAS_PER_SM")) per_sm = atoi(e) > 0 ? atoi(e) : 2;   // developer experiments only
+    int grid = (int)std::max<int64_t>(1, std::min<int64_t>(p.total_items, (int64_t)ctx->sm_count * per_sm));
     kern<<<grid, RANK_THREADS, RANK_SMEM, st>>>(p, tm_q, tm_e);
     ctx->launches += 1;
     MRE_CUDA(cudaGetLastError());
@@ -433,17 +598,18 @@ static int launch_rank(mre_ctx *ctx, const RankParams &p, const CUtensorMap &tm_
 
 int rank_transe(mre_ctx *ctx, const mre_index *ix, const mre_rank_job *job, cudaStream_t st) {
     MRE_CHECK_ARG(job->p_norm == 1 || job->p_norm == 2, "p_norm must be 1 or 2");
-    const float *ent = nullptr;
+    const float *ent = nullptr, *rel = nullptr;
     int64_t Dp = 0;
-    if (job->p_norm == 1) MRE_TRY(transe_prepass<1>(ctx, job, st, &ent, &Dp));
-    else MRE_TRY(transe_prepass<2>(ctx, job, st, &ent, &Dp));
+    MRE_TRY(transe_tables(ctx, job, st, &ent, &rel, &Dp));
     RankParams p{};
     MRE_TRY(fill_rank_params(ctx, ix, job, TILE_Q, TILE_E, st, p));
     p.ent = ent;
     p.D = Dp;
+    if (job->Q == 0) return MRE_OK;
+    if (job->p_norm == 1) MRE_TRY(transe_queries<1>(ctx, p, rel, st));
+    else MRE_TRY(transe_queries<2>(ctx, p, rel, st));
     p.qvec = ctx->qvec.as<float>();
     p.thr = ctx->thr.as<float2>();
-    if (job->Q == 0) return MRE_OK;
     // the table the candidate tiles stream from: the entity table itself, or the gathered candidate rows
     const float *cand_table = ent;
     int64_t cand_rows = job->E;
@@ -462,8 +628,12 @@ int rank_transe(mre_ctx *ctx, const mre_index *ix, const mre_rank_job *job, cuda
     ctx->launches += 1;
     MRE_TRY(build_tile_filter(ctx, job, p, TILE_Q, TILE_E, st));
     CUtensorMap tm_q, tm_e;
-    MRE_TRY(make_tmap_f32_2d(&tm_q, p.qvec, job->Q, Dp, Dp, TILE_Q, CHUNK));
+    // query vectors: [slots / 2 pair-rows][2 Dp floats], box = 64 pair-rows x 32 floats (16 d-values of two queries)
+    MRE_TRY(make_tmap_f32_2d(&tm_q, p.qvec, std::max<int64_t>(p.total_slots / 2, 1), 2 * Dp, 2 * Dp, TILE_Q / 2, CHUNK));
     MRE_TRY(make_tmap_f32_2d(&tm_e, cand_table, std::max<int64_t>(cand_rows, 1), Dp, Dp, TILE_E, CHUNK));
+    MRE_TRY(ctx->sm_slots.reserve(1024 * sizeof(uint32_t)));
+    MRE_CUDA(cudaMemsetAsync(ctx->sm_slots.p, 0, 1024 * sizeof(uint32_t), st));
+    p.sm_slots = ctx->sm_slots.as<uint32_t>();
     MRE_TRY(ctx->time_begin(st));
     // the tie count is always on: one extra compare per score, in the epilogue only
     if (job->p_norm == 1) MRE_TRY((launch_rank<1, true>(ctx, p, tm_q, tm_e, st)));
@@ -473,17 +643,17 @@ int rank_transe(mre_ctx *ctx, const mre_index *ix, const mre_rank_job *job, cuda
 }
 
 int predict_transe(mre_ctx *ctx, const mre_rank_job *job, int64_t query, float *scores_out, cudaStream_t st) {
-    mre_rank_job one = *job;
-    one.q_h = job->q_h + query; one.q_t = job->q_t + query; one.q_r = job->q_r + query;
-    one.q_side = job->q_side ? job->q_side + query : nullptr;
-    one.Q = 1;
-    const float *ent = nullptr;
+    const float *ent = nullptr, *rel = nullptr;
     int64_t Dp = 0;
-    if (job->p_norm == 1) MRE_TRY(transe_prepass<1>(ctx, &one, st, &ent, &Dp));
-    else MRE_TRY(transe_prepass<2>(ctx, &one, st, &ent, &Dp));
+    MRE_TRY(transe_tables(ctx, job, st, &ent, &rel, &Dp));
+    const uint8_t *qs = job->q_side ? job->q_side + query : nullptr;
     unsigned grid = (unsigned)((job->E + 127) / 128);
-    if (job->p_norm == 1) transe_predict_kernel<1><<<grid, 128, 0, st>>>(ent, job->E, Dp, ctx->qvec.as<float>(), scores_out);
-    else transe_predict_kernel<2><<<grid, 128, 0, st>>>(ent, job->E, Dp, ctx->qvec.as<float>(), scores_out);
+    if (job->p_norm == 1)
+        transe_predict_kernel<1><<<grid, 128, 0, st>>>(ent, rel, job->E, Dp, job->q_h + query, job->q_t + query, job->q_r + query, qs,
+                                                       job->side, scores_out);
+    else
+        transe_predict_kernel<2><<<grid, 128, 0, st>>>(ent, rel, job->E, Dp, job->q_h + query, job->q_t + query, job->q_r + query, qs,
+                                                       job->side, scores_out);
     ctx->launches += 1;
     MRE_CUDA(cudaGetLastError());
     return MRE_OK;
