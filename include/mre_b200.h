@@ -278,10 +278,12 @@ int mre_transe_backward(mre_ctx *ctx, const float *ent, const float *rel, int64_
 int mre_sgd_update(mre_ctx *ctx, float *w, float *g, int64_t n, float lr, void *stream);
 
 /* ------------------------------------------------------------------------------------------- probes */
-/* FP32 FADD issue-rate microbenchmark: returns lane-ops per second in *lane_ops_per_s (the TransE roofline
+/* FP32 add-rate microbenchmark (the better of a scalar FADD and a packed FADD2 stream): lane-ops per second in *lane_ops_per_s (the TransE roofline
  * denominator) and the SM clock-independent instruction count used. Synchronous. */
 int mre_probe_fp32_peak(mre_ctx *ctx, double *lane_ops_per_s);
-/* TF32 tcgen05 dense MMA microbenchmark: flops per second (the DistMult/ComplEx roofline denominator) */
+/* tcgen05 dense MMA microbenchmarks, flops per second: kind::f16 with BF16 operands (what the DistMult / ComplEx kernel
+ * issues -- its roofline denominator when MEASURED_PEAKS.json is absent) and kind::tf32 (for reference) */
+int mre_probe_bf16_peak(mre_ctx *ctx, double *flops_per_s);
 int mre_probe_tf32_peak(mre_ctx *ctx, double *flops_per_s);
 /* Per-launch device timing of the dominant kernel (the fused score+rank kernel of mre_rank / mre_rank_host, or the
  * train-step kernel): while enabled, every such launch is bracketed by a CUDA event pair recorded on the launching

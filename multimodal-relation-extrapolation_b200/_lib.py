@@ -122,6 +122,7 @@ def lib():
     L.mre_transe_backward.argtypes = [vp, vp, vp, i64, vp, vp, vp, i64, i32, i32, vp, vp, vp, vp, vp]
     L.mre_probe_fp32_peak.argtypes = [vp, P(C.c_double)]
     L.mre_probe_tf32_peak.argtypes = [vp, P(C.c_double)]
+    L.mre_probe_bf16_peak.argtypes = [vp, P(C.c_double)]
     L.mre_ctx_timing.argtypes = [vp, i32]
     L.mre_ctx_timing_read.argtypes = [vp, P(C.c_double), P(i64)]
     _lib = L

@@ -65,6 +65,25 @@ __global__ void __launch_bounds__(256) fadd_probe_kernel(float *out, int iters, 
     if (s == 12345.678f) out[0] = s;  // never true in practice; keeps the chain live
 }
 
+// the packed form (add.f32x2 -> FADD2: two lane-ops per lane per instruction, two pipe cycles): what the TransE tile loop issues
+__global__ void __launch_bounds__(256) fadd2_probe_kernel(float *out, int iters, float c) {
+    unsigned long long a[PROBE_ACC];
+#pragma unroll
+    for (int i = 0; i < PROBE_ACC; i++) a[i] = (unsigned long long)(threadIdx.x + i);
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+#pragma unroll
+            for (int i = 0; i < PROBE_ACC; i++)
+                asm volatile("{.reg .b64 t; mov.b64 t, {%1, %1}; add.f32x2 %0, %0, t;}" : "+l"(a[i]) : "f"(c));
+        }
+    }
+    unsigned long long s = 0;
+#pragma unroll
+    for (int i = 0; i < PROBE_ACC; i++) s += a[i];
+    if (s == 12345ull) out[0] = 1.f;  // never true in practice; keeps the chain live
+}
+
 int probe_fp32_peak(mre_ctx *ctx, double *lane_ops_per_s) {
     MRE_CHECK_ARG(lane_ops_per_s != nullptr, "NULL output");
     MRE_TRY(ctx->misc.reserve(256));
@@ -80,7 +99,17 @@ int probe_fp32_peak(mre_ctx *ctx, double *lane_ops_per_s) {
         double ops = (double)blocks * threads * iters * 8.0 * PROBE_ACC;
         if (rep > 0) best = std::max(best, ops / (ms * 1e-3));
     }
-    ctx->launches += 5;
+    for (int rep = 0; rep < 5; rep++) {   // the peak is the better of the scalar and the packed instruction streams
+        MRE_CUDA(cudaEventRecord(ctx->ev0, 0));
+        fadd2_probe_kernel<<<blocks, threads>>>(ctx->misc.as<float>(), iters, 1e-7f);
+        MRE_CUDA(cudaEventRecord(ctx->ev1, 0));
+        MRE_CUDA(cudaEventSynchronize(ctx->ev1));
+        float ms = 0;
+        MRE_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        double ops = (double)blocks * threads * iters * 8.0 * PROBE_ACC * 2.0;
+        if (rep > 0) best = std::max(best, ops / (ms * 1e-3));
+    }
+    ctx->launches += 10;
     *lane_ops_per_s = best;
     return MRE_OK;
 }
@@ -235,6 +264,12 @@ int mre_probe_tf32_peak(mre_ctx *ctx, double *flops_per_s) {
     MRE_CHECK_ARG(ctx != nullptr, "ctx is NULL");
     MRE_CUDA(cudaSetDevice(ctx->device));
     return probe_tf32_peak(ctx, flops_per_s);
+}
+
+int mre_probe_bf16_peak(mre_ctx *ctx, double *flops_per_s) {
+    MRE_CHECK_ARG(ctx != nullptr, "ctx is NULL");
+    MRE_CUDA(cudaSetDevice(ctx->device));
+    return probe_bf16_peak(ctx, flops_per_s);
 }
 
 int mre_ctx_timing(mre_ctx *ctx, int32_t enable) {

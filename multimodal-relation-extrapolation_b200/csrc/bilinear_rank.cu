@@ -15,15 +15,19 @@
 // back with tcgen05.ld (one query row per thread), compare against the query's true score and count, taking the
 // known-true columns routed to the tile by tile_filter.cu back out of the filtered count; columns closer to the true
 // score than an error guard are re-scored in scalar FP32, which makes the COUNTS those of the sequential FP32 scorer.
-// Precision: the reference is FP32.  kind::tf32 keeps 11 significant bits, which would move ranks well outside the
-// 1e-5 tie band, so every operand is split x ~= hi + lo (hi = rn_tf32(x), lo = rn_tf32(x - hi): 22 significant bits,
-// both exactly representable so the MMA's operand truncation loses nothing) and each product is issued as THREE TF32
-// MMAs  hi*hi + lo*hi + hi*lo  (the dropped terms are <= 2^-22 relative and unbiased).
-// Algorithmic flops are counted once (2*Q*E*K); the tensor pipe executes 3x that.
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one elected thread),
-// warps 2..5 = epilogue (TMEM lane quarter = warp % 4).  Shared memory: 2 stages x {A_hi, A_lo: 128 x 128 B;
-// B_hi, B_lo: 256 x 128 B}, 128-byte swizzle, K-major, fed by TMA tensor tiles.
+// Precision: the reference is FP32, and the COUNTS must be those of the FP32 scorer.  The tensor cores only have to decide
+// every column that is not a near-tie, so every operand is split x ~= hi + lo into two BF16 values (hi = rn(x),
+// lo = rn(x - hi): 16 significant bits) and each product is issued as THREE kind::f16 BF16 MMAs  hi*hi + lo*hi + hi*lo
+// with FP32 accumulation: relative error <= ~2^-16 of sum|v_d e_d|, at half the tensor-pipe time and half the operand
+// bytes of the 3xTF32 form this kernel used first (that form ran into the L2 -> SM feed limit, ~42 B/clk/SM, at 71 % of
+// the TF32 pipe).  A rigorous error guard then routes the (rare) columns within the guard of s_true to the exact scalar
+// re-score.  Algorithmic flops are counted once (2*Q*E*K); the tensor pipe executes 3x that.
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one elected thread),
+// warps 2..9 = epilogue (TMEM lane quarter = warp % 4, two warps per quarter: one per 128-column half of the tile).  Shared memory: 2 stages x {A_hi, A_lo: 128 x 128 B;
+// B_hi, B_lo: 256 x 128 B} (64 BF16 of K per row), 128-byte swizzle, K-major, fed by TMA tensor tiles.
+#include <cuda_bf16.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <vector>
@@ -33,63 +37,78 @@
 #include "rank_host.h"
 #include "tma_host.h"
 
+#ifndef MRE_DIAG_BIL_NOEPI
+#define MRE_DIAG_BIL_NOEPI 0
+#endif
+
 namespace mre {
 
 constexpr int BN = 256;                 // entities per tile (UMMA N)
 constexpr int BM = 128;                 // queries per tile (UMMA M)
-constexpr int BK = 32;                  // floats of K per stage = one 128-byte swizzle atom
-constexpr int UK = 8;                   // floats of K per tcgen05.mma kind::tf32
-constexpr int B_STAGES = 2;
-constexpr uint32_t A_BYTES = BM * BK * 4;   // 16 KiB
-constexpr uint32_t B_BYTES = BN * BK * 4;   // 32 KiB
-constexpr uint32_t BSTAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-constexpr int BIL_THREADS = 192;
+constexpr int BK = 64;                  // BF16 elements of K per stage = one 128-byte swizzle atom
+constexpr int UK = 16;                  // elements of K per tcgen05.mma kind::f16
+constexpr int TF_BK = 32, TF_UK = 8;    // the same for the kind::tf32 peak probe
+constexpr uint32_t A_BYTES = BM * BK * 2;   // 16 KiB
+constexpr uint32_t B_BYTES = BN * BK * 2;   // 32 KiB
+// one CTA per tile: a stage holds A_hi, A_lo (128 rows) and B_hi, B_lo (256 rows) = 96 KiB, 2 stages.
+// CTA pair (cta_group::2): M = 256 over two CTAs, each CTA stages its own 128 query rows and HALF of the candidate tile
+// (128 rows) -- 64 KiB per stage, 3 stages -- and the pair's MMA reads both halves: a third less L2 -> SM traffic per flop.
+template <bool PAIR> struct StageCfg {
+    static constexpr int STAGES = PAIR ? 3 : 2;
+    static constexpr uint32_t B_HALF = PAIR ? B_BYTES / 2 : B_BYTES;
+    static constexpr uint32_t BYTES = 2 * A_BYTES + 2 * B_HALF;
+};
+constexpr int MAX_STAGES = 3;
+#ifndef MRE_EPI_WARPS
+#define MRE_EPI_WARPS 4
+#endif
+constexpr int EPI_WARPS = MRE_EPI_WARPS;     // 4: one per TMEM lane quarter; 8: two per quarter, one per 128-column half (measured slower)
+constexpr int RESCORE_WARPS = 4;             // one per epilogue warp of the first column slice
+constexpr int BIL_THREADS = (2 + EPI_WARPS + RESCORE_WARPS) * 32;
 constexpr int EPI_WARP0 = 2;
+constexpr int PEND_CAP = 128;                // per epilogue warp: ring of near-ties handed to its re-score warp through shared memory
 constexpr int MASK_STRIDE = 9;               // words per row of the per-warp known-true mask (8 + 1 pad: conflict-free)
-constexpr size_t BIL_SMEM = 1024 + (size_t)B_STAGES * BSTAGE_BYTES + 16 * sizeof(uint64_t) + 4 * 32 * MASK_STRIDE * 4 + 64;
+constexpr size_t BIL_SMEM = 1024 + (size_t)2 * (2 * A_BYTES + 2 * B_BYTES) + 16 * sizeof(uint64_t) + EPI_WARPS * 32 * MASK_STRIDE * 4 + RESCORE_WARPS * (PEND_CAP * sizeof(uint2) + 16) + 64;   // both configurations: 192 KiB of stages
 constexpr uint32_t TMEM_COLS = 512;     // two 256-column accumulator buffers
 
 struct BilParams {
     RankParams r;            // r.ent = full-precision [E, K] table (scalar scorer), r.qvec = full-precision query vectors
     const float *delta;      // [Q] near-tie guard: |s_mma - s_true| <= delta => the column is re-scored in scalar FP32
-    uint2 *tie_queue;        // [gridDim.x][tie_cap] (query, entity) pairs awaiting the exact re-score
-    uint32_t tie_cap;        // queue entries per CTA
+    int64_t k8;              // K padded to a multiple of 8: row pitch (elements) of the BF16 hi / lo tables
     float *store;            // STORE mode only: [Q, store_ld] tensor-core similarities are written instead of counted
     int64_t store_ld;
 };
 
 // ------------------------------------------------------------------------------------------ pre-pass kernels
-__device__ __forceinline__ float tf32_rn(float x) {
-    uint32_t u;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-    return __uint_as_float(u);
+// x ~= hi + lo with hi = rn_bf16(x), lo = rn_bf16(x - hi)
+__device__ __forceinline__ void bf16_split(float x, __nv_bfloat16 &hi, __nv_bfloat16 &lo) {
+    hi = __float2bfloat16_rn(x);
+    lo = __float2bfloat16_rn(x - __bfloat162float(hi));
 }
 
-// entity table -> [rows, Kp] full-precision copy (ComplEx: [re | im]; zero padded) + TF32 hi / lo splits
+// entity table -> BF16 hi / lo splits [rows, K8] (ComplEx: [re | im]; zero padded) + optional full-precision copy [rows, Kp]
 __global__ void bil_split_table_kernel(const float *__restrict__ re, const float *__restrict__ im, int64_t rows, int64_t D,
-                                       int64_t K, int64_t Kp, float *__restrict__ full, float *__restrict__ hi,
-                                       float *__restrict__ lo) {
-    const int64_t total = rows * Kp;
+                                       int64_t K, int64_t Kp, int64_t K8, float *__restrict__ full, __nv_bfloat16 *__restrict__ hi,
+                                       __nv_bfloat16 *__restrict__ lo) {
+    const int64_t total = rows * K8;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t row = i / Kp, d = i - row * Kp;
+        const int64_t row = i / K8, d = i - row * K8;
         float x = 0.f;
         if (d < K) x = d < D ? re[row * D + d] : im[row * D + (d - D)];
-        const float h = tf32_rn(x);
-        if (full) full[i] = x;
-        hi[i] = h;
-        lo[i] = tf32_rn(x - h);   // exactly representable: the MMA's operand truncation then loses nothing
+        if (full && d < Kp) full[row * Kp + d] = x;
+        bf16_split(x, hi[i], lo[i]);
     }
 }
 
-// per-query vector (see the header comment), full precision + hi / lo
+// per-query vector (see the header comment), full precision [Q, Kp] + BF16 hi / lo [Q, K8]
 __global__ void bil_qvec_kernel(int scorer, const float *__restrict__ ent, const float *__restrict__ ent_im,
                                 const float *__restrict__ rel, const float *__restrict__ rel_im, int64_t D, int64_t K, int64_t Kp,
-                                const int64_t *__restrict__ q_h, const int64_t *__restrict__ q_t, const int64_t *__restrict__ q_r,
-                                const uint8_t *__restrict__ q_side, int side, int64_t Q, float *__restrict__ qv,
-                                float *__restrict__ qhi, float *__restrict__ qlo) {
-    const int64_t total = Q * Kp;
+                                int64_t K8, const int64_t *__restrict__ q_h, const int64_t *__restrict__ q_t,
+                                const int64_t *__restrict__ q_r, const uint8_t *__restrict__ q_side, int side, int64_t Q,
+                                float *__restrict__ qv, __nv_bfloat16 *__restrict__ qhi, __nv_bfloat16 *__restrict__ qlo) {
+    const int64_t total = Q * K8;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t q = i / Kp, d = i - q * Kp;
+        const int64_t q = i / K8, d = i - q * K8;
         const int s = q_side ? (int)q_side[q] : side;
         const int64_t e = s ? q_h[q] : q_t[q];   // the entity that stays fixed in the query
         const int64_t r = q_r[q];
@@ -104,10 +123,8 @@ __global__ void bil_qvec_kernel(int scorer, const float *__restrict__ ent, const
                 else v = d < D ? ere * rre + eim * rim : eim * rre - ere * rim;
             }
         }
-        const float h = tf32_rn(v);
-        qv[i] = v;
-        qhi[i] = h;
-        qlo[i] = tf32_rn(v - h);
+        if (d < Kp) qv[q * Kp + d] = v;
+        bf16_split(v, qhi[i], qlo[i]);
     }
 }
 
@@ -144,14 +161,13 @@ __global__ void bil_max_rownorm_kernel(const float *__restrict__ ent, int64_t E,
 }
 
 // per query: threshold pair on the predict scale (p = -sim: lower is better) and the near-tie guard.
-// Guard: the tensor-core value differs from the sequential FP32 value by the split error (<= 3 * 2^-22), the
-// accumulator's rounding over <= 3K/8 MMAs and the scalar sum's own rounding, all relative to
-// sum_d |v_d e_d| <= ||v|| * max_j ||e_j||.  The all-errors-aligned worst case is ~2^-15 (K = 256); rounding errors
-// do not align, and the largest discrepancy measured on any test table is < 2^-22 (tests/test_bilinear_gpu.py asserts
-// it stays 4x under the guard), so the guard is 2^-18 (scaled linearly beyond K = 256).  Every column closer than the
-// guard to s_true is re-scored with the scalar scorer, so the COUNTS are exactly those of the FP32 scorer whenever the
-// discrepancy is below the guard; if it ever were not, only columns within 2^-18 relative of s_true could flip --
-// well inside the 1e-5 tie band the reference itself cannot resolve.
+// Guard (rigorous, relative to sum_d |v_d e_d| <= ||v|| * max_j ||e_j||): the tensor-core value differs from the
+// sequential FP32 value by
+//   the split: x - hi - lo <= 2^-18 |x| per operand and the dropped lo*lo <= 2^-18  ->  <= 3 * 2^-18 = 1.15e-5,
+//   the FP32 accumulation of the 3K/16 MMAs and the scalar scorer's own K roundings  ->  <= (K + 3K/16) * 2^-24 < K * 0.72e-7,
+// so guard = (1.3e-5 + 1.2e-7 K) ||v|| max||e|| (4.4e-5 at K = 256) bounds it with margin for ANY table; the measured
+// discrepancy is ~50x smaller (tests/test_bilinear_gpu.py).  Every column closer than the guard to s_true is re-scored
+// with the scalar scorer, so the COUNTS are exactly those of the FP32 scorer; on Gaussian tables ~5e-4 of the columns.
 __global__ void bil_threshold_kernel(const RankParams p, const unsigned int *__restrict__ max_norm, float2 *__restrict__ thr,
                                      float *__restrict__ delta) {
     const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -165,8 +181,7 @@ __global__ void bil_threshold_kernel(const RankParams p, const unsigned int *__r
     thr[q] = make_float2(pt, hi);
     float ss = 0.f;
     for (int64_t d = 0; d < p.D; d++) ss = fmaf(v[d], v[d], ss);
-    const float scale = p.D > 256 ? (float)p.D / 256.f : 1.f;
-    delta[q] = 3.814697265625e-06f * scale * sqrtf(ss) * __uint_as_float(*max_norm);   // 2^-18
+    delta[q] = (1.3e-5f + 1.2e-7f * (float)p.D) * sqrtf(ss) * __uint_as_float(*max_norm);
 }
 
 __global__ void bil_predict_kernel(const float *__restrict__ ent, int64_t E, int64_t K, const float *__restrict__ qv,
@@ -176,37 +191,66 @@ __global__ void bil_predict_kernel(const float *__restrict__ ent, int64_t E, int
 }
 
 // ------------------------------------------------------------------------------------------ main kernel
-template <bool STORE>
+// pair work item -> (group, query-tile PAIR, candidate tile); pairs vary fastest (as decode_item does with query tiles)
+__device__ __forceinline__ void decode_pitem(const RankParams &p, int64_t item, int &g, int &qp, int &et) {
+    int lo = 0, hi = p.n_groups;
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (p.groups[mid].pitem0 <= item) lo = mid; else hi = mid;
+    }
+    g = lo;
+    const int n_qp = (p.groups[g].n_qt + 1) >> 1;
+    const int64_t local = item - p.groups[g].pitem0;
+    qp = (int)(local % n_qp);
+    et = (int)(local / n_qp);
+}
+
+template <bool STORE, bool PAIR>
 __global__ void __launch_bounds__(BIL_THREADS, 1)
 bilinear_rank_kernel(const BilParams bp, const __grid_constant__ CUtensorMap tm_ahi, const __grid_constant__ CUtensorMap tm_alo,
                      const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ CUtensorMap tm_blo) {
+    using Cfg = StageCfg<PAIR>;
+    constexpr int B_STAGES = Cfg::STAGES;
+    constexpr uint32_t BSTAGE_BYTES = Cfg::BYTES, B_HALF = Cfg::B_HALF;
     const RankParams &p = bp.r;
     extern __shared__ unsigned char smem_raw[];
     const uint32_t ring_u32 = (smem_u32(smem_raw) + 1023u) & ~1023u;
     unsigned char *ring = smem_raw + (ring_u32 - smem_u32(smem_raw));
     uint64_t *bars = reinterpret_cast<uint64_t *>(ring + (size_t)B_STAGES * BSTAGE_BYTES);
-    // bars: full[2], empty[2], tmem_full[2], tmem_empty[2]; then the TMEM base address word
-    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + 2), tfull0 = smem_u32(bars + 4), tempty0 = smem_u32(bars + 6);
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 8);
-    uint32_t *tie_count = reinterpret_cast<uint32_t *>(bars + 9);      // near-ties queued by this CTA
+    // bars: full[3], empty[3], tmem_full[2], tmem_empty[2]; then the TMEM base address word
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + MAX_STAGES), tfull0 = smem_u32(bars + 2 * MAX_STAGES),
+                   tempty0 = smem_u32(bars + 2 * MAX_STAGES + 2);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * MAX_STAGES + 4);
     uint32_t *mask_all = reinterpret_cast<uint32_t *>(bars + 16);      // per epilogue warp: [32 rows][MASK_STRIDE] known-true bits
+    uint2 *pend_all = reinterpret_cast<uint2 *>(mask_all + EPI_WARPS * 32 * MASK_STRIDE);   // per epilogue warp: [PEND_CAP] ring of near-ties
+    volatile uint32_t *pend_ctl = reinterpret_cast<volatile uint32_t *>(pend_all + RESCORE_WARPS * PEND_CAP);   // per ring: published, consumed, done
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_kb = (int)((p.D + BK - 1) / BK);
+    const int n_kb = (int)((bp.k8 + BK - 1) / BK);
+    // work distribution: a CTA walks tiles on its own, a CTA pair walks two-query-tile items together
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+    const int64_t worker = PAIR ? (blockIdx.x >> 1) : blockIdx.x, n_workers = PAIR ? (gridDim.x >> 1) : gridDim.x;
+    const int64_t n_items = PAIR ? p.total_pitems : p.total_items;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < B_STAGES; s++) {
             mbar_init(full0 + 8 * s, 1);
             mbar_init(empty0 + 8 * s, 1);
-            mbar_init(tfull0 + 8 * s, 1);
-            mbar_init(tempty0 + 8 * s, 4);
         }
-        *tie_count = 0;
+        for (int k = 0; k < RESCORE_WARPS * 4; k++) pend_ctl[k] = 0u;
+        for (int s = 0; s < 2; s++) {
+            mbar_init(tfull0 + 8 * s, 1);
+            mbar_init(tempty0 + 8 * s, PAIR ? 2 * EPI_WARPS : EPI_WARPS);     // the pair's leader collects the epilogue warps of both CTAs
+        }
         fence_barrier_init();
         tma_prefetch_desc(&tm_ahi); tma_prefetch_desc(&tm_alo); tma_prefetch_desc(&tm_bhi); tma_prefetch_desc(&tm_blo);
     }
-    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+    if (warp == 1) {
+        if (PAIR) tmem_alloc_pair(smem_u32(tmem_slot), TMEM_COLS);
+        else tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+    }
     tc_fence_before();
-    __syncthreads();
+    if (PAIR) cluster_sync_all();      // both CTAs' barriers are initialised before either signals the other's
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -214,34 +258,49 @@ bilinear_rank_kernel(const BilParams bp, const __grid_constant__ CUtensorMap tm_
         // ================================================= TMA producer =================================================
         if (lane == 0) {
             uint32_t it = 0;
-            for (int64_t item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+            const uint32_t full_leader0 = PAIR ? mapa_shared(full0, 0) : full0;   // TMA bytes of both CTAs are counted by the leader
+            for (int64_t item = worker; item < n_items; item += n_workers) {
                 int g, qt, et;
-                decode_item(p, item, g, qt, et);
+                if (PAIR) {
+                    decode_pitem(p, item, g, qt, et);
+                    qt = 2 * qt + (int)rank;
+                } else {
+                    decode_item(p, item, g, qt, et);
+                }
                 const GroupDesc &gd = p.groups[g];
                 const int qrow = (int)(gd.q0 + (int64_t)qt * BM);
-                const int erow = (int)(gd.c0 + (int64_t)et * BN);
+                const int erow = (int)(gd.c0 + (int64_t)et * BN) + (PAIR ? (int)rank * (BN / 2) : 0);
                 for (int kb = 0; kb < n_kb; kb++, it++) {
                     const int s = it % B_STAGES;
                     mbar_wait(empty0 + 8 * s, ((it / B_STAGES) & 1) ^ 1);
-                    const uint32_t full = full0 + 8 * s;
                     const uint32_t base = ring_u32 + (uint32_t)s * BSTAGE_BYTES;
-                    mbar_arrive_expect_tx(full, BSTAGE_BYTES);
                     // query tiles are re-read for every candidate tile of the sweep: keep them in L2 (evict-last) so the
-                    // streaming candidate tiles (each shared by the ~128 CTAs of one round, then dead) cannot push them out
-                    tma_load_2d_hint(base, &tm_ahi, kb * BK, qrow, full, L2_EVICT_LAST);
-                    tma_load_2d_hint(base + A_BYTES, &tm_alo, kb * BK, qrow, full, L2_EVICT_LAST);
-                    tma_load_2d_hint(base + 2 * A_BYTES, &tm_bhi, kb * BK, erow, full, L2_EVICT_NORMAL);
-                    tma_load_2d_hint(base + 2 * A_BYTES + B_BYTES, &tm_blo, kb * BK, erow, full, L2_EVICT_NORMAL);
+                    // streaming candidate tiles (each shared by the CTAs of one round, then dead) cannot push them out
+                    if (PAIR) {
+                        const uint32_t full = full_leader0 + 8 * s;
+                        if (rank == 0) mbar_arrive_expect_tx(full0 + 8 * s, 2 * BSTAGE_BYTES);
+                        tma_load_2d_pair(base, &tm_ahi, kb * BK, qrow, full, L2_EVICT_LAST);
+                        tma_load_2d_pair(base + A_BYTES, &tm_alo, kb * BK, qrow, full, L2_EVICT_LAST);
+                        tma_load_2d_pair(base + 2 * A_BYTES, &tm_bhi, kb * BK, erow, full, L2_EVICT_NORMAL);
+                        tma_load_2d_pair(base + 2 * A_BYTES + B_HALF, &tm_blo, kb * BK, erow, full, L2_EVICT_NORMAL);
+                    } else {
+                        const uint32_t full = full0 + 8 * s;
+                        mbar_arrive_expect_tx(full, BSTAGE_BYTES);
+                        tma_load_2d_hint(base, &tm_ahi, kb * BK, qrow, full, L2_EVICT_LAST);
+                        tma_load_2d_hint(base + A_BYTES, &tm_alo, kb * BK, qrow, full, L2_EVICT_LAST);
+                        tma_load_2d_hint(base + 2 * A_BYTES, &tm_bhi, kb * BK, erow, full, L2_EVICT_NORMAL);
+                        tma_load_2d_hint(base + 2 * A_BYTES + B_HALF, &tm_blo, kb * BK, erow, full, L2_EVICT_NORMAL);
+                    }
                 }
             }
         }
         __syncwarp();
     } else if (warp == 1) {
         // ================================================= MMA issuer ===================================================
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_tf32(BM, BN);
+        if (lane == 0 && rank == 0) {      // in a pair only the leader CTA issues: one instruction drives both SMs' tensor cores
+            constexpr uint32_t idesc = umma_idesc_bf16(PAIR ? 2 * BM : BM, BN);
             uint32_t it = 0, tile = 0;
-            for (int64_t item = blockIdx.x; item < p.total_items; item += gridDim.x, tile++) {
+            for (int64_t item = worker; item < n_items; item += n_workers, tile++) {
                 const uint32_t buf = tile & 1;
                 mbar_wait(tempty0 + 8 * buf, ((tile >> 1) & 1) ^ 1);   // epilogue has drained this accumulator buffer
                 tc_fence_after();
@@ -251,27 +310,54 @@ bilinear_rank_kernel(const BilParams bp, const __grid_constant__ CUtensorMap tm_
                     mbar_wait(full0 + 8 * s, (it / B_STAGES) & 1);
                     tc_fence_after();
                     const uint32_t base = ring_u32 + (uint32_t)s * BSTAGE_BYTES;
-                    const int n_ks = (int)min((int64_t)(BK / UK), (p.D - (int64_t)kb * BK + UK - 1) / UK);
+                    const int n_ks = (int)min((int64_t)(BK / UK), (bp.k8 - (int64_t)kb * BK + UK - 1) / UK);
                     for (int ks = 0; ks < n_ks; ks++) {
-                        const uint32_t koff = ks * UK * 4;   // bytes along K inside the 128-byte swizzle atom
+                        const uint32_t koff = ks * UK * 2;   // bytes along K inside the 128-byte swizzle atom
                         const uint64_t ahi = umma_desc_k128(base + koff), alo = umma_desc_k128(base + A_BYTES + koff);
                         const uint64_t bhi = umma_desc_k128(base + 2 * A_BYTES + koff);
-                        const uint64_t blo = umma_desc_k128(base + 2 * A_BYTES + B_BYTES + koff);
-                        umma_tf32(d_tmem, ahi, bhi, idesc, (kb | ks) != 0);
-                        umma_tf32(d_tmem, alo, bhi, idesc, 1);
-                        umma_tf32(d_tmem, ahi, blo, idesc, 1);
+                        const uint64_t blo = umma_desc_k128(base + 2 * A_BYTES + B_HALF + koff);
+                        if (PAIR) {
+                            umma_bf16_pair(d_tmem, ahi, bhi, idesc, (kb | ks) != 0);
+                            umma_bf16_pair(d_tmem, alo, bhi, idesc, 1);
+                            umma_bf16_pair(d_tmem, ahi, blo, idesc, 1);
+                        } else {
+                            umma_bf16(d_tmem, ahi, bhi, idesc, (kb | ks) != 0);
+                            umma_bf16(d_tmem, alo, bhi, idesc, 1);
+                            umma_bf16(d_tmem, ahi, blo, idesc, 1);
+                        }
                     }
-                    umma_commit(empty0 + 8 * s);        // shared-memory stage reusable once these MMAs retire
+                    // shared-memory stage reusable (in both CTAs of a pair) once these MMAs retire
+                    if (PAIR) umma_commit_pair(empty0 + 8 * s, 3);
+                    else umma_commit(empty0 + 8 * s);
                 }
-                umma_commit(tfull0 + 8 * buf);          // accumulator tile complete
+                // accumulator tile complete (each CTA of a pair holds its own 128 rows)
+                if (PAIR) umma_commit_pair(tfull0 + 8 * buf, 3);
+                else umma_commit(tfull0 + 8 * buf);
             }
         }
         __syncwarp();
-    } else {
+    } else if (warp < EPI_WARP0 + EPI_WARPS) {
         // ================================================= epilogue warps ===============================================
         const int quarter = warp & 3;                   // TMEM lanes [32 * quarter, 32 * quarter + 32)
+        const int chalf = (warp - EPI_WARP0) >> 2;      // which column slice of the accumulator tile this warp compares
         const int row = quarter * 32 + lane;            // query row of the tile owned by this thread
-        uint2 *my_queue = bp.tie_queue + (size_t)blockIdx.x * bp.tie_cap;
+        // Near-ties (columns within the guard of s_true) are handed, as (query, entity | known << 31), to this warp's RE-SCORE
+        // warp through a small shared-memory ring; the exact scalar re-score (two row gathers per entry: pure latency) thus
+        // never sits on the epilogue's critical path.  published / consumed are monotonic counters.
+        static_assert(EPI_WARPS == RESCORE_WARPS, "one re-score warp per epilogue warp");
+        const uint32_t tempty_leader0 = PAIR ? mapa_shared(tempty0, 0) : tempty0;
+        const int ring_id = warp - EPI_WARP0;
+        uint2 *pend = pend_all + ring_id * PEND_CAP;
+        volatile uint32_t *ctl = pend_ctl + ring_id * 4;
+        uint32_t n_pub = 0;                             // warp-uniform copy of ctl[0]
+        auto rescore = [&](uint2 it2) {
+            const int64_t q2 = it2.x, ent_id = it2.y & 0x7fffffffu;
+            const bool kn = (it2.y >> 31) != 0u;
+            const float s2 = bil_dot(p.qvec + q2 * p.D, p.ent + ent_id * p.D, p.D);
+            const float st = -__ldg(&p.thr[q2].x);
+            if (s2 > st) { atomicAdd(p.counts + q2, 1); if (!kn) atomicAdd(p.counts + 2 * p.Q + q2, 1); }
+            if (s2 == st) { atomicAdd(p.counts + p.Q + q2, 1); if (!kn) atomicAdd(p.counts + 3 * p.Q + q2, 1); }
+        };
         uint32_t *mask = mask_all + (warp - EPI_WARP0) * 32 * MASK_STRIDE;
         // Per-tile metadata (tile geometry, this row's true score and guard, the tile's known-true pair range) is
         // fetched ONE TILE AHEAD: a lone epilogue warp per SM sub-partition cannot hide dependent global-load latency,
@@ -287,7 +373,17 @@ bilinear_rank_kernel(const BilParams bp, const __grid_constant__ CUtensorMap tm_
             TileMeta m;
             int g = 0, qt, et;
             GroupDesc gd = gd0;
-            if (p.n_groups > 1) {
+            if (PAIR) {
+                if (p.n_groups > 1) {
+                    decode_pitem(p, item, g, qt, et);
+                    gd = p.groups[g];
+                } else {
+                    const int n_qp = (gd0.n_qt + 1) >> 1;
+                    qt = (int)(item % n_qp);
+                    et = (int)(item / n_qp);
+                }
+                qt = 2 * qt + (int)rank;           // this CTA's query tile of the pair (past the group's end when n_qt is odd)
+            } else if (p.n_groups > 1) {
                 decode_item(p, item, g, qt, et);
                 gd = p.groups[g];
             } else {
@@ -304,16 +400,20 @@ bilinear_rank_kernel(const BilParams bp, const __grid_constant__ CUtensorMap tm_
                 m.sim_true = -__ldg(&p.thr[m.qbase + row].x);
                 m.guard = __ldg(bp.delta + m.qbase + row);
             }
-            m.pf0 = __ldg(p.tf_ptr + item);
-            m.pf1 = __ldg(p.tf_ptr + item + 1);
+            m.pf0 = m.pf1 = 0;
+            if (qt < gd.n_qt) {                    // the known-true pairs were routed per (query tile, candidate tile)
+                const int64_t fitem = PAIR ? gd.item0 + (int64_t)et * gd.n_qt + qt : item;
+                m.pf0 = __ldg(p.tf_ptr + fitem);
+                m.pf1 = __ldg(p.tf_ptr + fitem + 1);
+            }
             return m;
         };
         uint32_t tile = 0;
         TileMeta nxt{};
-        if ((int64_t)blockIdx.x < p.total_items) nxt = load_meta(blockIdx.x);
-        for (int64_t item = blockIdx.x; item < p.total_items; item += gridDim.x, tile++) {
+        if (worker < n_items) nxt = load_meta(worker);
+        for (int64_t item = worker; item < n_items; item += n_workers, tile++) {
             const TileMeta cur = nxt;
-            if (item + gridDim.x < p.total_items) nxt = load_meta(item + gridDim.x);
+            if (item + n_workers < n_items) nxt = load_meta(item + n_workers);
             const int64_t qbase = cur.qbase;
             const int nq = cur.nq, ne = cur.ne;
             const bool q_ok = row < nq;
@@ -353,55 +453,98 @@ bilinear_rank_kernel(const BilParams bp, const __grid_constant__ CUtensorMap tm_
                     }
                     return;
                 }
-                uint32_t gtm = 0u, gem = 0u;                    // bit c: column c0 + c beats thr_hi / reaches thr_lo
+                // bit c of gtm: column c0 + c beats thr_hi; bit c of ltm: it falls short of thr_lo.  Both are SIGN bits:
+                // x > y <=> (y - x) < 0 exactly (a difference of distinct floats never rounds to zero), so each compare is one
+                // FADD and one funnel shift that collects the sign -- no predicates, four independent 8-column chains per mask.
+                uint32_t g4[4] = {0u, 0u, 0u, 0u}, l4[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
-                for (int c = 0; c < 32; c++) {
-                    const float sc = __uint_as_float(v[c]);
-                    gtm |= sc > thr_hi ? (1u << c) : 0u;
-                    gem |= sc >= thr_lo ? (1u << c) : 0u;
+                for (int k = 0; k < 4; k++) {
+#pragma unroll
+                    for (int c = 7; c >= 0; c--) {              // descending: column 8 k + c ends up at bit c of the byte
+                        const float sc = __uint_as_float(v[8 * k + c]);
+                        g4[k] = __funnelshift_l(__float_as_uint(thr_hi - sc), g4[k], 1);
+                        l4[k] = __funnelshift_l(__float_as_uint(sc - thr_lo), l4[k], 1);
+                    }
                 }
                 const uint32_t valid = left >= 32 ? 0xffffffffu : ((1u << left) - 1u);   // padding of the last candidate tile
-                gtm &= valid;
-                gem &= valid;
+                const uint32_t gtm = (g4[0] | (g4[1] << 8) | (g4[2] << 16) | (g4[3] << 24)) & valid;
+                const uint32_t gem = ~(l4[0] | (l4[1] << 8) | (l4[2] << 16) | (l4[3] << 24)) & valid;
                 const uint32_t mw = has_mask ? mask[lane * MASK_STRIDE + (c0 >> 5)] : 0u;   // known-true columns of this chunk
                 r_lt += __popc(gtm);
                 f_lt += __popc(gtm & ~mw);
-                uint32_t near = gem & ~gtm;                     // rare: queue the near-ties for the exact re-score
-                while (near) {
-                    const int c = __ffs(near) - 1;
-                    near &= near - 1;
-                    const uint32_t kn = (mw >> c) & 1u;
-                    const int64_t crow = cur.crow0 + c0 + c;
-                    const int64_t ent_id = p.all_entities ? crow : __ldg(p.cand_idx + crow);
-                    const uint32_t slot = atomicAdd(tie_count, 1u);
-                    if (slot < bp.tie_cap) {
-                        my_queue[slot] = make_uint2((uint32_t)(qbase + row), (uint32_t)ent_id | (kn << 31));
-                    } else {                                    // queue full (pathological ties): re-score in place
-                        const float s2 = bil_dot(p.qvec + (qbase + row) * p.D, p.ent + ent_id * p.D, p.D);
-                        r_lt += s2 > sim_true ? 1 : 0;
-                        r_eq += s2 == sim_true ? 1 : 0;
-                        f_lt += (!kn && s2 > sim_true) ? 1 : 0;
-                        f_eq += (!kn && s2 == sim_true) ? 1 : 0;
+                uint32_t near = gem & ~gtm;                     // rare: park the near-ties for the exact re-score
+                if (__any_sync(0xffffffffu, near != 0u)) {
+                    // slots by a warp prefix sum of the per-lane counts: no atomics
+                    const int mine = __popc(near);
+                    int incl = mine;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const int up = __shfl_up_sync(0xffffffffu, incl, d);
+                        if (lane >= d) incl += up;
                     }
+                    const int total = __shfl_sync(0xffffffffu, incl, 31);
+                    if (total <= PEND_CAP) {
+                        while (n_pub + total - ctl[1] > (uint32_t)PEND_CAP) __nanosleep(64);   // ring full: the re-score warp is draining it
+                        uint32_t slot = n_pub + incl - mine;
+                        while (near) {
+                            const int c = __ffs(near) - 1;
+                            near &= near - 1;
+                            const uint32_t kn = (mw >> c) & 1u;
+                            const int64_t crow = cur.crow0 + c0 + c;
+                            const int64_t ent_id = p.all_entities ? crow : __ldg(p.cand_idx + crow);
+                            pend[(slot++) & (PEND_CAP - 1)] = make_uint2((uint32_t)(qbase + row), (uint32_t)ent_id | (kn << 31));
+                        }
+                        n_pub += total;
+                        __syncwarp();
+                        __threadfence_block();                  // entries before the counter
+                        if (lane == 0) ctl[0] = n_pub;
+                    } else {                                    // a chunk with more near-ties than the ring holds (mass ties): in place
+                        while (near) {
+                            const int c = __ffs(near) - 1;
+                            near &= near - 1;
+                            const uint32_t kn = (mw >> c) & 1u;
+                            const int64_t crow = cur.crow0 + c0 + c;
+                            const int64_t ent_id = p.all_entities ? crow : __ldg(p.cand_idx + crow);
+                            rescore(make_uint2((uint32_t)(qbase + row), (uint32_t)ent_id | (kn << 31)));
+                        }
+                    }
+                    __syncwarp();
                 }
             };
             // two register buffers: the TMEM load of the next 32 columns is in flight while this chunk is compared
             uint32_t va[32], vb[32];
-            tmem_ld_32x32(taddr, va);
+            constexpr int CSLICE = BN / (EPI_WARPS / 4);
+            const int cbeg = chalf * CSLICE, cend = min(ne, cbeg + CSLICE);   // this warp's slice of the tile's columns
+#if MRE_DIAG_BIL_NOEPI
+            if (false)      // diagnostic build only (wrong results): hand the accumulator buffer straight back
+#endif
+#if MRE_DIAG_BIL_NOEPI == 2      // diagnostic (wrong results): TMEM loads only
+            for (int c0 = cbeg; c0 < cend; c0 += 32) { tmem_ld_32x32(taddr + c0, va); tmem_ld_wait(); }
+            if (va[0] == 0x12345678u && va[31] == 0x9abcdef0u) r_lt++;
+#elif MRE_DIAG_BIL_NOEPI == 3    // diagnostic (wrong results): compares only, no TMEM loads
+#pragma unroll
+            for (int c = 0; c < 32; c++) { va[c] = (uint32_t)(row * c + tile); vb[c] = va[c] ^ 0x3f800000u; }
+            for (int c0 = cbeg; c0 < cend; c0 += 64) { process(va, c0); process(vb, c0 + 32); }
+#else
+            if (cbeg < cend) tmem_ld_32x32(taddr + cbeg, va);
 #pragma unroll 1
-            for (int c0 = 0; c0 < ne; c0 += 64) {               // ne is warp-uniform: the collective loads stay aligned
+            for (int c0 = cbeg; c0 < (MRE_DIAG_BIL_NOEPI ? 0 : cend); c0 += 64) {          // cend is warp-uniform: the collective loads stay aligned
                 tmem_ld_wait();
-                if (c0 + 32 < ne) tmem_ld_32x32(taddr + c0 + 32, vb);
+                if (c0 + 32 < cend) tmem_ld_32x32(taddr + c0 + 32, vb);
                 process(va, c0);
-                if (c0 + 32 < ne) {
+                if (c0 + 32 < cend) {
                     tmem_ld_wait();
-                    if (c0 + 64 < ne) tmem_ld_32x32(taddr + c0 + 64, va);
+                    if (c0 + 64 < cend) tmem_ld_32x32(taddr + c0 + 64, va);
                     process(vb, c0 + 32);
                 }
             }
+#endif
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
+            if (lane == 0) {     // relaxed: the TMEM reads are complete (wait::ld); nothing in global memory is ordered by this barrier
+                if (PAIR) mbar_arrive_cluster_relaxed(tempty_leader0 + 8 * buf);
+                else mbar_arrive_relaxed(tempty0 + 8 * buf);
+            }
             if (q_ok) {
                 const int64_t q = qbase + row;
                 if (r_lt) atomicAdd(p.counts + q, r_lt);
@@ -410,13 +553,27 @@ bilinear_rank_kernel(const BilParams bp, const __grid_constant__ CUtensorMap tm_
                 if (f_eq) atomicAdd(p.counts + 3 * p.Q + q, f_eq);
             }
         }
-        // exact FP32 re-score of this CTA's queued near-ties: off the tile loop's critical path, one per thread, so the
-        // row fetches of ~128 items are in flight together.  Known-true entities only enter the RAW counts.
-        asm volatile("bar.sync 1, 128;" ::: "memory");          // the four epilogue warps have finished pushing
-        if (!STORE) {
-            const uint32_t n_tie = min(*tie_count, bp.tie_cap);
-            for (uint32_t i = (warp - EPI_WARP0) * 32 + lane; i < n_tie; i += 128) {
-                const uint2 it2 = my_queue[i];
+        __syncwarp();
+        __threadfence_block();
+        if (lane == 0) ctl[2] = 1u;                       // no more entries will be published
+    } else {
+        // ================================================= re-score warps ===============================================
+        const int ring_id = warp - EPI_WARP0 - EPI_WARPS;
+        const uint2 *pend = pend_all + ring_id * PEND_CAP;
+        volatile uint32_t *ctl = pend_ctl + ring_id * 4;
+        uint32_t cons = 0;
+        for (;;) {
+            const uint32_t done = ctl[2];               // read BEFORE the counter: done => the counter is final
+            const uint32_t pub = ctl[0];
+            if (pub == cons) {
+                if (done) break;
+                __nanosleep(200);
+                continue;
+            }
+            __threadfence_block();                      // the counter before the entries
+            const uint32_t n_new = pub - cons;          // <= PEND_CAP
+            for (uint32_t k = lane; k < n_new; k += 32) {
+                const uint2 it2 = pend[(cons + k) & (PEND_CAP - 1)];
                 const int64_t q2 = it2.x, ent_id = it2.y & 0x7fffffffu;
                 const bool kn = (it2.y >> 31) != 0u;
                 const float s2 = bil_dot(p.qvec + q2 * p.D, p.ent + ent_id * p.D, p.D);
@@ -424,19 +581,25 @@ bilinear_rank_kernel(const BilParams bp, const __grid_constant__ CUtensorMap tm_
                 if (s2 > st) { atomicAdd(p.counts + q2, 1); if (!kn) atomicAdd(p.counts + 2 * p.Q + q2, 1); }
                 if (s2 == st) { atomicAdd(p.counts + p.Q + q2, 1); if (!kn) atomicAdd(p.counts + 3 * p.Q + q2, 1); }
             }
+            __syncwarp();
+            cons = pub;
+            if (lane == 0) ctl[1] = cons;               // the ring slots may be reused
         }
     }
 
     tc_fence_before();
-    __syncthreads();
+    if (PAIR) cluster_sync_all();      // neither CTA may retire while its partner can still touch its barriers / shared memory
+    else __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, TMEM_COLS);
+        if (PAIR) tmem_dealloc_pair(tmem_base, TMEM_COLS);
+        else tmem_dealloc(tmem_base, TMEM_COLS);
     }
 }
 
-// ------------------------------------------------------------------------------------------ TF32 MMA peak probe
-__global__ void __launch_bounds__(128, 1) tf32_probe_kernel(int iters) {
+// ------------------------------------------------------------------------------------------ dense MMA peak probes
+template <bool BF16>
+__global__ void __launch_bounds__(128, 1) mma_probe_kernel(int iters) {
     extern __shared__ unsigned char smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     unsigned char *al = smem_raw + (base - smem_u32(smem_raw));
@@ -451,10 +614,11 @@ __global__ void __launch_bounds__(128, 1) tf32_probe_kernel(int iters) {
     tc_fence_after();
     const uint32_t tmem = *slot;
     if (threadIdx.x == 0) {
-        constexpr uint32_t idesc = umma_idesc_tf32(BM, BN);
+        constexpr uint32_t idesc = BF16 ? umma_idesc_bf16(BM, BN) : umma_idesc_tf32(BM, BN);
         for (int i = 0; i < iters; i++) {
-            const uint32_t koff = (i & 3) * UK * 4;
-            umma_tf32(tmem, umma_desc_k128(base + koff), umma_desc_k128(base + A_BYTES + koff), idesc, i != 0);
+            const uint32_t koff = (i & 3) * 32;   // one k-step = 32 bytes of the 128-byte swizzle atom in both kinds
+            if (BF16) umma_bf16(tmem, umma_desc_k128(base + koff), umma_desc_k128(base + A_BYTES + koff), idesc, i != 0);
+            else umma_tf32(tmem, umma_desc_k128(base + koff), umma_desc_k128(base + A_BYTES + koff), idesc, i != 0);
         }
         umma_commit(smem_u32(bar));
         mbar_wait(smem_u32(bar), 0);
@@ -464,20 +628,21 @@ __global__ void __launch_bounds__(128, 1) tf32_probe_kernel(int iters) {
     if (threadIdx.x < 32) { tc_fence_after(); tmem_dealloc(tmem, 256); }
 }
 
-int probe_tf32_peak(mre_ctx *ctx, double *flops_per_s) {
+template <bool BF16>
+static int probe_mma_peak(mre_ctx *ctx, double *flops_per_s) {
     MRE_CHECK_ARG(flops_per_s != nullptr, "NULL output");
     const size_t smem = 1024 + A_BYTES + B_BYTES + 64;
-    MRE_CUDA(cudaFuncSetAttribute(tf32_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MRE_CUDA(cudaFuncSetAttribute(mma_probe_kernel<BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int iters = 8192;
     double best = 0;
     for (int rep = 0; rep < 4; rep++) {
         MRE_CUDA(cudaEventRecord(ctx->ev0, 0));
-        tf32_probe_kernel<<<ctx->sm_count, 128, smem>>>(iters);
+        mma_probe_kernel<BF16><<<ctx->sm_count, 128, smem>>>(iters);
         MRE_CUDA(cudaEventRecord(ctx->ev1, 0));
         MRE_CUDA(cudaEventSynchronize(ctx->ev1));
         float ms = 0;
         MRE_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
-        const double flops = (double)ctx->sm_count * iters * 2.0 * BM * BN * UK;
+        const double flops = (double)ctx->sm_count * iters * 2.0 * BM * BN * (BF16 ? UK : TF_UK);
         if (rep > 0) best = std::max(best, flops / (ms * 1e-3));
     }
     ctx->launches += 4;
@@ -486,36 +651,41 @@ int probe_tf32_peak(mre_ctx *ctx, double *flops_per_s) {
     return MRE_OK;
 }
 
+int probe_tf32_peak(mre_ctx *ctx, double *flops_per_s) { return probe_mma_peak<false>(ctx, flops_per_s); }
+int probe_bf16_peak(mre_ctx *ctx, double *flops_per_s) { return probe_mma_peak<true>(ctx, flops_per_s); }
+
 // ------------------------------------------------------------------------------------------ host side
 struct BilScratch {
-    const float *ent_full;   // [E, Kp]
-    const float *ent_hi, *ent_lo;
-    int64_t K, Kp;
+    const float *ent_full;   // [E, Kp] full precision (the scalar scorer's table)
+    const __nv_bfloat16 *ent_hi, *ent_lo;   // [E, K8]
+    int64_t K, Kp, K8;
 };
 
 static int bil_prepass(mre_ctx *ctx, const mre_rank_job *job, cudaStream_t st, BilScratch &sc) {
     const int64_t D = job->D;
     sc.K = job->scorer == MRE_COMPLEX ? 2 * D : D;
     sc.Kp = (sc.K + 3) & ~(int64_t)3;
-    const size_t tbl = (size_t)job->E * sc.Kp * sizeof(float);
+    sc.K8 = (sc.K + 7) & ~(int64_t)7;
+    const size_t half = ((size_t)job->E * sc.K8 * sizeof(__nv_bfloat16) + 255) & ~(size_t)255;
     // layout of ctx->ent_n: [hi | lo | full (only when a repacked full-precision copy is needed)]
     const bool need_full = job->scorer == MRE_COMPLEX || sc.Kp != D;
-    MRE_TRY(ctx->ent_n.reserve(tbl * (need_full ? 3 : 2)));
-    float *hi = ctx->ent_n.as<float>(), *lo = hi + (size_t)job->E * sc.Kp;
-    float *full = need_full ? lo + (size_t)job->E * sc.Kp : nullptr;
-    bil_split_table_kernel<<<grid_for(job->E * sc.Kp, 256), 256, 0, st>>>(job->ent, job->ent_im, job->E, D, sc.K, sc.Kp, full, hi, lo);
+    MRE_TRY(ctx->ent_n.reserve(2 * half + (need_full ? (size_t)job->E * sc.Kp * sizeof(float) : 0)));
+    char *base = ctx->ent_n.as<char>();
+    __nv_bfloat16 *hi = reinterpret_cast<__nv_bfloat16 *>(base), *lo = reinterpret_cast<__nv_bfloat16 *>(base + half);
+    float *full = need_full ? reinterpret_cast<float *>(base + 2 * half) : nullptr;
+    bil_split_table_kernel<<<grid_for(job->E * sc.K8, 256), 256, 0, st>>>(job->ent, job->ent_im, job->E, D, sc.K, sc.Kp, sc.K8, full, hi, lo);
     ctx->launches += 1;
     sc.ent_full = need_full ? full : job->ent;
     sc.ent_hi = hi;
     sc.ent_lo = lo;
     if (job->Q > 0) {
-        const size_t qb = (size_t)job->Q * sc.Kp * sizeof(float);
-        MRE_TRY(ctx->qvec.reserve(qb));
-        MRE_TRY(ctx->qvec2.reserve(2 * qb));
-        bil_qvec_kernel<<<grid_for(job->Q * sc.Kp, 256), 256, 0, st>>>(job->scorer, job->ent, job->ent_im, job->rel, job->rel_im, D, sc.K,
-                                                                     sc.Kp, job->q_h, job->q_t, job->q_r, job->q_side, job->side, job->Q,
-                                                                     ctx->qvec.as<float>(), ctx->qvec2.as<float>(),
-                                                                     ctx->qvec2.as<float>() + (size_t)job->Q * sc.Kp);
+        const size_t qhalf = ((size_t)job->Q * sc.K8 * sizeof(__nv_bfloat16) + 255) & ~(size_t)255;
+        MRE_TRY(ctx->qvec.reserve((size_t)job->Q * sc.Kp * sizeof(float)));
+        MRE_TRY(ctx->qvec2.reserve(2 * qhalf));
+        __nv_bfloat16 *qhi = ctx->qvec2.as<__nv_bfloat16>(), *qlo = reinterpret_cast<__nv_bfloat16 *>(ctx->qvec2.as<char>() + qhalf);
+        bil_qvec_kernel<<<grid_for(job->Q * sc.K8, 256), 256, 0, st>>>(job->scorer, job->ent, job->ent_im, job->rel, job->rel_im, D, sc.K,
+                                                                     sc.Kp, sc.K8, job->q_h, job->q_t, job->q_r, job->q_side, job->side,
+                                                                     job->Q, ctx->qvec.as<float>(), qhi, qlo);
         ctx->launches += 1;
     }
     MRE_CUDA(cudaGetLastError());
@@ -530,6 +700,7 @@ static int run_bilinear(mre_ctx *ctx, const mre_index *ix, const mre_rank_job *j
     MRE_TRY(fill_rank_params(ctx, ix, job, BM, BN, st, p));
     p.ent = sc.ent_full;
     p.D = sc.Kp;
+    bp.k8 = sc.K8;
     p.qvec = ctx->qvec.as<float>();
     if (job->Q == 0) return MRE_OK;
     MRE_TRY(ctx->thr.reserve((size_t)job->Q * (sizeof(float2) + sizeof(float)) + 16));
@@ -543,17 +714,21 @@ static int run_bilinear(mre_ctx *ctx, const mre_index *ix, const mre_rank_job *j
     bil_threshold_kernel<<<(unsigned)((job->Q + 127) / 128), 128, 0, st>>>(p, max_norm, thr, delta);
     ctx->launches += 2;
     // candidate tables the B tiles stream from
-    const float *b_hi = sc.ent_hi, *b_lo = sc.ent_lo;
+    const __nv_bfloat16 *b_hi = sc.ent_hi, *b_lo = sc.ent_lo;
     int64_t cand_rows = job->E;
     if (!p.all_entities) {
         cand_rows = job->group_cptr[job->n_groups];
         MRE_CHECK_ARG(cand_rows < (1LL << 31), "too many candidate rows");
-        const size_t cb = (size_t)std::max<int64_t>(cand_rows, 1) * sc.Kp * sizeof(float);
+        const size_t cb = ((size_t)std::max<int64_t>(cand_rows, 1) * sc.K8 * sizeof(__nv_bfloat16) + 255) & ~(size_t)255;
         MRE_TRY(ctx->ent_aux.reserve(2 * cb));
-        float *g_hi = ctx->ent_aux.as<float>(), *g_lo = g_hi + (size_t)std::max<int64_t>(cand_rows, 1) * sc.Kp;
+        __nv_bfloat16 *g_hi = ctx->ent_aux.as<__nv_bfloat16>(), *g_lo = reinterpret_cast<__nv_bfloat16 *>(ctx->ent_aux.as<char>() + cb);
         if (cand_rows > 0) {
-            gather_rows_kernel<<<grid_for(cand_rows * (sc.Kp >> 2), 256), 256, 0, st>>>(sc.ent_hi, sc.Kp, job->cand_idx, cand_rows, g_hi);
-            gather_rows_kernel<<<grid_for(cand_rows * (sc.Kp >> 2), 256), 256, 0, st>>>(sc.ent_lo, sc.Kp, job->cand_idx, cand_rows, g_lo);
+            // a BF16 row of K8 elements is K8 / 2 floats (a multiple of 4): the float4 row gather serves it unchanged
+            const int64_t row_f = sc.K8 >> 1;
+            gather_rows_kernel<<<grid_for(cand_rows * (row_f >> 2), 256), 256, 0, st>>>(reinterpret_cast<const float *>(sc.ent_hi), row_f,
+                                                                                        job->cand_idx, cand_rows, reinterpret_cast<float *>(g_hi));
+            gather_rows_kernel<<<grid_for(cand_rows * (row_f >> 2), 256), 256, 0, st>>>(reinterpret_cast<const float *>(sc.ent_lo), row_f,
+                                                                                        job->cand_idx, cand_rows, reinterpret_cast<float *>(g_lo));
             ctx->launches += 2;
         }
         b_hi = g_hi;
@@ -562,29 +737,49 @@ static int run_bilinear(mre_ctx *ctx, const mre_index *ix, const mre_rank_job *j
     init_counts_kernel<<<grid_for(4 * job->Q, 256), 256, 0, st>>>(job->counts, 4 * job->Q);
     ctx->launches += 1;
     MRE_TRY(build_tile_filter(ctx, job, p, BM, BN, st));
-    const float *q_hi = ctx->qvec2.as<float>(), *q_lo = q_hi + (size_t)job->Q * sc.Kp;
+    const size_t qhalf = ((size_t)job->Q * sc.K8 * sizeof(__nv_bfloat16) + 255) & ~(size_t)255;
+    const __nv_bfloat16 *q_hi = ctx->qvec2.as<__nv_bfloat16>();
+    const __nv_bfloat16 *q_lo = reinterpret_cast<const __nv_bfloat16 *>(ctx->qvec2.as<char>() + qhalf);
+    // CTA pairs (cta_group::2) whenever there is more than one query tile; a lone CTA per tile otherwise
+    bool pair = p.total_items > p.total_pitems && ctx->sm_count >= 2;
+    if (const char *e = getenv("MRE_DEV_BIL_PAIR")) pair = pair && atoi(e) != 0;     // developer A/B switch
     CUtensorMap tm_ahi, tm_alo, tm_bhi, tm_blo;
-    MRE_TRY(make_tmap_f32_2d(&tm_ahi, q_hi, job->Q, sc.Kp, sc.Kp, BM, BK));
-    MRE_TRY(make_tmap_f32_2d(&tm_alo, q_lo, job->Q, sc.Kp, sc.Kp, BM, BK));
-    MRE_TRY(make_tmap_f32_2d(&tm_bhi, b_hi, std::max<int64_t>(cand_rows, 1), sc.Kp, sc.Kp, BN, BK));
-    MRE_TRY(make_tmap_f32_2d(&tm_blo, b_lo, std::max<int64_t>(cand_rows, 1), sc.Kp, sc.Kp, BN, BK));
+    MRE_TRY(make_tmap_bf16_2d(&tm_ahi, q_hi, job->Q, sc.K8, sc.K8, BM, BK));
+    MRE_TRY(make_tmap_bf16_2d(&tm_alo, q_lo, job->Q, sc.K8, sc.K8, BM, BK));
+    MRE_TRY(make_tmap_bf16_2d(&tm_bhi, b_hi, std::max<int64_t>(cand_rows, 1), sc.K8, sc.K8, pair ? BN / 2 : BN, BK));
+    MRE_TRY(make_tmap_bf16_2d(&tm_blo, b_lo, std::max<int64_t>(cand_rows, 1), sc.K8, sc.K8, pair ? BN / 2 : BN, BK));
     static bool configured = false;
     if (!configured) {
-        MRE_CUDA(cudaFuncSetAttribute(bilinear_rank_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BIL_SMEM));
-        MRE_CUDA(cudaFuncSetAttribute(bilinear_rank_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BIL_SMEM));
+        MRE_CUDA(cudaFuncSetAttribute(bilinear_rank_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BIL_SMEM));
+        MRE_CUDA(cudaFuncSetAttribute(bilinear_rank_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BIL_SMEM));
+        MRE_CUDA(cudaFuncSetAttribute(bilinear_rank_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BIL_SMEM));
+        MRE_CUDA(cudaFuncSetAttribute(bilinear_rank_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BIL_SMEM));
         configured = true;
     }
-    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(p.total_items, ctx->sm_count));
+    const int grid = pair ? 2 * (int)std::max<int64_t>(1, std::min<int64_t>(p.total_pitems, ctx->sm_count / 2))
+                          : (int)std::max<int64_t>(1, std::min<int64_t>(p.total_items, ctx->sm_count));
     bp.store = store;
     bp.store_ld = cand_rows;
-    // near-tie queue: expected Q*E*P(near) entries with P(near) ~ 5e-5; 10x headroom, at least 4096 per CTA
-    const int64_t cap_total = std::min<int64_t>(std::max<int64_t>(job->Q * std::max<int64_t>(cand_rows, 1) / 2048, (int64_t)grid * 4096), 1LL << 26);
-    bp.tie_cap = (uint32_t)(cap_total / grid);
-    MRE_TRY(ctx->tie_queue.reserve((size_t)bp.tie_cap * grid * sizeof(uint2)));
-    bp.tie_queue = ctx->tie_queue.as<uint2>();
     MRE_TRY(ctx->time_begin(st));
-    if (store) bilinear_rank_kernel<true><<<grid, BIL_THREADS, BIL_SMEM, st>>>(bp, tm_ahi, tm_alo, tm_bhi, tm_blo);
-    else bilinear_rank_kernel<false><<<grid, BIL_THREADS, BIL_SMEM, st>>>(bp, tm_ahi, tm_alo, tm_bhi, tm_blo);
+    if (pair) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)grid);
+        cfg.blockDim = dim3(BIL_THREADS);
+        cfg.dynamicSmemBytes = BIL_SMEM;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        if (store) MRE_CUDA(cudaLaunchKernelEx(&cfg, bilinear_rank_kernel<true, true>, bp, tm_ahi, tm_alo, tm_bhi, tm_blo));
+        else MRE_CUDA(cudaLaunchKernelEx(&cfg, bilinear_rank_kernel<false, true>, bp, tm_ahi, tm_alo, tm_bhi, tm_blo));
+    } else {
+        if (store) bilinear_rank_kernel<true, false><<<grid, BIL_THREADS, BIL_SMEM, st>>>(bp, tm_ahi, tm_alo, tm_bhi, tm_blo);
+        else bilinear_rank_kernel<false, false><<<grid, BIL_THREADS, BIL_SMEM, st>>>(bp, tm_ahi, tm_alo, tm_bhi, tm_blo);
+    }
     MRE_TRY(ctx->time_end(st));
     ctx->launches += 1;
     MRE_CUDA(cudaGetLastError());

@@ -146,4 +146,5 @@ int transe_backward(mre_ctx *ctx, const float *ent, const float *rel, int64_t D,
                     float *grad_rel, cudaStream_t st);
 int probe_fp32_peak(mre_ctx *ctx, double *lane_ops_per_s);
 int probe_tf32_peak(mre_ctx *ctx, double *flops_per_s);
+int probe_bf16_peak(mre_ctx *ctx, double *flops_per_s);
 }  // namespace mre

@@ -13,6 +13,7 @@ struct GroupDesc {
     int64_t c0, nc;      // candidate range in cand_idx (c0 = 0, nc = E for the all-entity group)
     int64_t item0;       // first work item of the group
     int64_t s0;          // first query SLOT of the group (even): the TransE kernel's pair-interleaved query-vector layout
+    int64_t pitem0;      // first CTA-PAIR work item of the group (two query tiles x one candidate tile): bilinear pair kernel
     int32_t n_qt, n_et;  // tiles along queries / candidates
 };
 
@@ -34,6 +35,7 @@ struct RankParams {
     const int64_t *cand_idx;
     int64_t total_items;
     int64_t total_slots;   // query slots over all groups (each group rounded up to an even count)
+    int64_t total_pitems;  // CTA-pair work items over all groups
     // filter
     int32_t filter;
     const int64_t *hr_key, *hr_val, *tr_key, *tr_val;

@@ -469,15 +469,16 @@ transe_rank_kernel(const RankParams p, const __grid_constant__ CUtensorMap tm_q,
 
 // ------------------------------------------------------------------------------------------ host side
 static int build_groups(mre_ctx *ctx, const mre_rank_job *job, int tile_q, int tile_e, std::vector<GroupDesc> &groups,
-                        int64_t *total_items, int64_t *total_slots) {
+                        int64_t *total_items, int64_t *total_slots, int64_t *total_pitems) {
     groups.clear();
-    int64_t items = 0, slots = 0;
+    int64_t items = 0, slots = 0, pitems = 0;
     if (job->n_groups <= 0) {
         GroupDesc g{};
         g.q0 = 0; g.nq = job->Q; g.c0 = 0; g.nc = job->E; g.item0 = 0;
         g.n_qt = (int32_t)((job->Q + tile_q - 1) / tile_q);
         g.n_et = (int32_t)((job->E + tile_e - 1) / tile_e);
         items = (int64_t)g.n_qt * g.n_et;
+        pitems = (int64_t)((g.n_qt + 1) / 2) * g.n_et;
         slots = (job->Q + 1) & ~(int64_t)1;
         groups.push_back(g);
     } else {
@@ -495,6 +496,8 @@ static int build_groups(mre_ctx *ctx, const mre_rank_job *job, int tile_q, int t
             g.n_qt = (int32_t)((g.nq + tile_q - 1) / tile_q);
             g.n_et = (int32_t)((g.nc + tile_e - 1) / tile_e);
             items += (int64_t)g.n_qt * g.n_et;
+            g.pitem0 = pitems;
+            pitems += (int64_t)((g.n_qt + 1) / 2) * g.n_et;
             groups.push_back(g);
         }
         if (groups.empty()) {  // nothing to count; keep one empty descriptor so lookups stay in range
@@ -504,6 +507,7 @@ static int build_groups(mre_ctx *ctx, const mre_rank_job *job, int tile_q, int t
     }
     *total_items = items;
     *total_slots = slots;
+    *total_pitems = pitems;
     (void)ctx;
     return MRE_OK;
 }
@@ -511,8 +515,8 @@ static int build_groups(mre_ctx *ctx, const mre_rank_job *job, int tile_q, int t
 int fill_rank_params(mre_ctx *ctx, const mre_index *ix, const mre_rank_job *job, int tile_q, int tile_e, cudaStream_t st,
                      RankParams &p) {
     std::vector<GroupDesc> groups;
-    int64_t items = 0, slots = 0;
-    MRE_TRY(build_groups(ctx, job, tile_q, tile_e, groups, &items, &slots));
+    int64_t items = 0, slots = 0, pitems = 0;
+    MRE_TRY(build_groups(ctx, job, tile_q, tile_e, groups, &items, &slots, &pitems));
     MRE_TRY(ctx->tiles.reserve(groups.size() * sizeof(GroupDesc)));
     MRE_CUDA(cudaMemcpyAsync(ctx->tiles.p, groups.data(), groups.size() * sizeof(GroupDesc), cudaMemcpyHostToDevice, st));
     // the descriptor vector dies with this frame; the copy above is from pageable memory and therefore staged
@@ -525,6 +529,7 @@ int fill_rank_params(mre_ctx *ctx, const mre_index *ix, const mre_rank_job *job,
     p.cand_idx = job->cand_idx;
     p.total_items = items;
     p.total_slots = slots;
+    p.total_pitems = pitems;
     p.filter = job->filter;
     p.hr_key = p.hr_val = p.tr_key = p.tr_val = nullptr;
     p.n_all = 0;

@@ -6,8 +6,8 @@ import mre_b200
 eng = mre_b200.engine
 ctx = eng.Context(0)
 rk = eng.Ranker(ctx)
-peak = ctx.probe_tf32_peak()
-print("tf32 MMA peak flop/s %.4g" % peak)
+peak = ctx.probe_bf16_peak()
+print("bf16 MMA peak flop/s %.4g (tf32 %.4g)" % (peak, ctx.probe_tf32_peak()))
 for (kind, E, D, Q) in [("distmult", 14208, 200, 17596), ("complex", 14208, 200, 17596), ("distmult", 2_000_000, 256, 8192), ("distmult", 200_000, 256, 65536)]:
     g = torch.Generator(device="cuda").manual_seed(1)
     mk = lambda n: torch.randn(n, D, device="cuda", generator=g) / D ** 0.5

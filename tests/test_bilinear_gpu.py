@@ -1,6 +1,6 @@
 """GPU parity of the tcgen05 DistMult / ComplEx contraction + rank path (mre_rank with scorer distmult|complex).
 
-The tensor-core path computes 3xTF32 split products, but every column closer to s_true than a rigorous error guard is
+The tensor-core path computes BF16x3 split products, but every column closer to s_true than a rigorous error guard is
 re-scored with the sequential FP32 scorer, so the COUNTS must equal the FP32 oracle's BIT FOR BIT (DistMult, whose
 oracle uses the same association) -- and sit inside the reference's (torch) tie band of SURVEY Appendix F, exactly equal
 where the band is empty, with MRR / Hits within 1e-4."""
@@ -152,8 +152,9 @@ def test_bilinear_candidate_groups(mre):
 
 @pytest.mark.parametrize("kind", ["distmult", "complex"])
 def test_tensor_core_discrepancy_stays_far_under_the_guard(env, fb15k237, kind):
-    """the 3xTF32 tensor-core similarity vs the sequential FP32 scorer, relative to ||v|| * max||e||: the near-tie guard
-    is 2^-18 of that scale; the measured discrepancy must stay at least 4x below it"""
+    """the BF16x3 tensor-core similarity vs the sequential FP32 scorer, relative to ||v|| * max||e||: the near-tie guard
+    is (1.3e-5 + 1.2e-7 K) of that scale (a rigorous bound); the measured discrepancy must stay at least 4x below it
+    """
     eng, ix, rk = env
     E, R, D = fb15k237.E, fb15k237.R, 200
     th, tt, tr = fb15k237.oracle.test_triples()
@@ -181,4 +182,6 @@ def test_tensor_core_discrepancy_stays_far_under_the_guard(env, fb15k237, kind):
                 v = np.concatenate([a, b])
             scale = np.linalg.norm(v.astype(np.float64)) * max_norm
             worst = max(worst, float(np.abs(mma[q].astype(np.float64) - seq.astype(np.float64)).max() / scale))
-    assert worst < 2.0 ** -20, worst
+    K = D * (2 if kind == "complex" else 1)
+    assert worst < (1.3e-5 + 1.2e-7 * K) / 4, worst
+    print(f"{kind}: worst tensor-core discrepancy {worst:.3e} of ||v|| max||e|| (guard {(1.3e-5 + 1.2e-7 * K):.3e})")
