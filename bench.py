@@ -449,6 +449,17 @@ def main():
                 "algorithmic": "2*Q*E*K flops counted ONCE; to stay FP32-faithful the kernel issues 3 BF16 MMAs per product "
                                "(hi*hi + lo*hi + hi*lo), so frac <= 1/3 by construction; pipe_frac = executed flops / peak"}
 
+    # DRAM traffic of the dominant kernel per launch, from the committed `ncu --set full` capture of this workload's shape
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_traffic.json")) as f:
+            tr = json.load(f).get(w.name)
+        if tr and tr.get("dram_bytes_read") is not None:
+            roof["traffic"] = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+            roof["traffic_source"] = tr["source"]
+            roof["algorithmic_bytes"] = 4.0 * (w.E + Q) * w.D
+    except Exception:  # noqa: BLE001
+        pass
+
     extra = {}
     cpu_base = None
     if rank == 0 and not args.no_extra:
