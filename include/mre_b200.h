@@ -250,6 +250,45 @@ int mre_sample_subgraph(mre_ctx *ctx, const mre_index *ix, uint64_t seed, uint64
                         int64_t neg_ent, int32_t bern, int32_t filter,
                         int32_t *out_h, int32_t *out_t, int32_t *out_r, void *stream);
 
+/* ------------------------------------------------------------------------------------------ ZSL scorer */
+/*
+ * The ZSL candidate scorer of ZSLmodule.eval (module/zsl_module.py:662-745): Extractor.forward (zsl_module.py:46-106, with
+ * SupportEncoder, module/submodule.py:240-258) on every (head, candidate) pair of every test triple, cosine similarity
+ * against the relation's generated vectors averaged over them (sklearn cosine_similarity(...).mean(axis=1), :699-701), and
+ * the rank of the true candidate (index 0 of its list, :705-706).  All pointers are device pointers.  Tensor names follow the
+ * reference's state_dict: symbol_emb.weight [n_symbols + 1, D] (last row = padding, zeros), gcn_w / fc1 / fc2 .weight [D/2, D]
+ * and .bias [D/2], reshape_layer.weight [D, 2D] / .bias [D], support_encoder.proj1.weight [2D, D] / .bias [2D],
+ * support_encoder.proj2.weight [D, 2D] / .bias [D], support_encoder.layer_norm.weight / .bias [D] (eps 1e-5).
+ */
+typedef struct mre_zsl_model {
+    int64_t D;                 /* emb_dim, args.py:41 (200); a multiple of 8, at most 256 */
+    const float *symbol_emb;
+    const float *gcn_w, *gcn_b, *fc1_w, *fc1_b, *fc2_w, *fc2_b;
+    const float *reshape_w, *reshape_b;
+    const float *proj1_w, *proj1_b, *proj2_w, *proj2_b;
+    const float *ln_g, *ln_b;
+    float ln_eps;
+} mre_zsl_model;
+/*
+ * Per-entity halves of the pair encoder: reshape_layer([N_h | tanh fc1(h) | tanh fc2(c) | N_c]) = A[h] + B[c], where
+ * N_e = tanh(sum_j gcn_w(symbol_emb[conn[e][j]]) / deg[e]) is neighbor_encoder (zsl_module.py:46-59; conn holds the
+ * NEIGHBOUR symbol ids, connections[e, :, 1] of build_connection :239-268, padded with the pad id; deg = e1_degrees).
+ * ent_symbol[e] = symbol id of entity e.  A, B: float32 [n_ent, D].
+ */
+int mre_zsl_entity_features(mre_ctx *ctx, const mre_zsl_model *model, const int64_t *ent_symbol, const int64_t *conn,
+                            const float *deg, int64_t n_ent, int32_t max_neighbor, float *A, float *B, void *stream);
+/*
+ * Scores + ranks of T test triples.  Triple t has head entity q_head[t], relation slot q_rel[t] (row of rel_vecs
+ * [n_rel, n_vec, D], the generator's test_sample vectors per relation, :657-660) and candidate entities
+ * cand_idx[cand_ptr[t] .. cand_ptr[t+1]) with the TRUE tail first (test_candidates.json, :665-682); P = cand_ptr[T].
+ * scores (nullable): float32 [P].  counts: int32 [4][T] in mre_metrics' layout -- rows 0 and 2 = #candidates scoring
+ * HIGHER than the true one, rows 1 and 3 = #exact ties: rank = counts[0] + 1 (ties resolved for the true candidate) up to
+ * counts[0] + counts[1] + 1 (MRE_RANK_PESSIMISTIC); the reference's argsort leaves exact ties unpinned.
+ */
+int mre_zsl_rank(mre_ctx *ctx, const mre_zsl_model *model, const float *A, const float *B, const int64_t *q_head,
+                 const int64_t *q_rel, const int64_t *cand_ptr, const int64_t *cand_idx, int64_t T, int64_t P,
+                 const float *rel_vecs, int64_t n_rel, int32_t n_vec, float *scores, int32_t *counts, void *stream);
+
 /* ------------------------------------------------------------------------------------------ training */
 /*
  * Fused TransE margin-loss step, forward + backward, on one sampled batch (n = B*(1+neg) triples):

@@ -14,7 +14,7 @@ BUILD_DIR = os.path.join(_HERE, "build")
 LIB_PATH = os.environ.get("MRE_B200_LIB") or os.path.join(BUILD_DIR, "libmre_b200.so")   # override: A/B timing of two builds
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include", "mre_b200.h")
 
-SOURCES = ["index.cpp", "tma_host.cpp", "abi.cu", "transe_rank.cu", "metrics.cu", "sampler.cu", "train_step.cu", "bilinear_rank.cu", "tile_filter.cu"]
+SOURCES = ["index.cpp", "tma_host.cpp", "abi.cu", "transe_rank.cu", "metrics.cu", "sampler.cu", "train_step.cu", "bilinear_rank.cu", "tile_filter.cu", "zsl_rank.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
               "-Xcompiler", "-fPIC,-O2", "-shared"]
 
@@ -29,6 +29,15 @@ SPLIT_TRAIN, SPLIT_VALID, SPLIT_TEST = 0, 1, 2
 
 class MreError(RuntimeError):
     pass
+
+
+class ZslModel(C.Structure):
+    """struct mre_zsl_model"""
+    _fields_ = [("D", C.c_int64), ("symbol_emb", C.c_void_p),
+                ("gcn_w", C.c_void_p), ("gcn_b", C.c_void_p), ("fc1_w", C.c_void_p), ("fc1_b", C.c_void_p),
+                ("fc2_w", C.c_void_p), ("fc2_b", C.c_void_p), ("reshape_w", C.c_void_p), ("reshape_b", C.c_void_p),
+                ("proj1_w", C.c_void_p), ("proj1_b", C.c_void_p), ("proj2_w", C.c_void_p), ("proj2_b", C.c_void_p),
+                ("ln_g", C.c_void_p), ("ln_b", C.c_void_p), ("ln_eps", C.c_float)]
 
 
 class RankJob(C.Structure):
@@ -116,6 +125,8 @@ def lib():
     L.mre_sample.argtypes = samp
     L.mre_sample_host.argtypes = samp
     L.mre_sample_subgraph.argtypes = [vp, vp, u64, u64, u32, vp, vp, vp, i64, vp, i64, vp, i64, i64, i32, i32, vp, vp, vp, vp]
+    L.mre_zsl_entity_features.argtypes = [vp, P(ZslModel), vp, vp, vp, i64, i32, vp, vp, vp]
+    L.mre_zsl_rank.argtypes = [vp, P(ZslModel), vp, vp, vp, vp, vp, vp, i64, i64, vp, i64, i32, vp, vp, vp]
     L.mre_transe_margin_step.argtypes = [vp, vp, vp, i64, i64, i64, vp, vp, vp, i64, i64, f32, i32, i32, vp, vp, vp, vp, vp]
     L.mre_sgd_update.argtypes = [vp, vp, vp, i64, f32, vp]
     L.mre_score_triples.argtypes = [vp, i32, vp, vp, vp, vp, i64, vp, vp, vp, i64, i32, i32, vp, vp]

@@ -5,6 +5,7 @@
                          307-314, 321-375): neg_sample_fn / generate_eval_list / scoring_fn / regularization
   build_test_candidates  utils/gen_mode_candidates.py:15-39 (regenerates the missing {mode}_candidates.json)
   zsl_rank_metrics       ZSLmodule.eval's rank/metric block (module/zsl_module.py:699-745): Hits@10/5/1 + MRR
+  ZSLEvaluator           ZSLmodule.eval end to end (module/zsl_module.py:635-745): Extractor + cosine-mean + rank on the GPU
 """
 import numpy as np
 import torch
@@ -202,3 +203,93 @@ def zsl_rank_metrics(score_lists):
     reference).  Returns (hits10, hits5, mrr) -- the tuple ZSLmodule.eval returns -- plus hits1."""
     ranks = np.asarray([list(np.argsort(s))[::-1].index(0) + 1 for s in score_lists], np.float64)
     return float((ranks <= 10).mean()), float((ranks <= 5).mean()), float((1.0 / ranks).mean()), float((ranks <= 1).mean())
+
+
+class ZSLEvaluator:
+    """ZSLmodule.eval (module/zsl_module.py:635-745) over the library: the Extractor's per-entity halves are computed once
+    (mre_zsl_entity_features), then every (head, candidate) pair of every test triple is scored and ranked in one sweep
+    (mre_zsl_rank) instead of one Extractor forward per triple.
+
+    extractor_state: the reference Extractor's state_dict (tensors or numpy), names symbol_emb.weight, gcn_w.*, fc1.*, fc2.*,
+    reshape_layer.*, support_encoder.proj1.*, support_encoder.proj2.*, support_encoder.layer_norm.*;
+    connections [num_ents, max_neighbor, 2] and e1_degrees as ZSLmodule.build_connection leaves them (:239-268);
+    ent_symbol[e] = symbol2id of the entity whose ent2id is e."""
+
+    STATE = (("symbol_emb", "symbol_emb.weight"), ("gcn_w", "gcn_w.weight"), ("gcn_b", "gcn_w.bias"), ("fc1_w", "fc1.weight"),
+             ("fc1_b", "fc1.bias"), ("fc2_w", "fc2.weight"), ("fc2_b", "fc2.bias"), ("reshape_w", "reshape_layer.weight"),
+             ("reshape_b", "reshape_layer.bias"), ("proj1_w", "support_encoder.proj1.weight"), ("proj1_b", "support_encoder.proj1.bias"),
+             ("proj2_w", "support_encoder.proj2.weight"), ("proj2_b", "support_encoder.proj2.bias"),
+             ("ln_g", "support_encoder.layer_norm.weight"), ("ln_b", "support_encoder.layer_norm.bias"))
+
+    def __init__(self, extractor_state, connections, e1_degrees, ent_symbol, device=0):
+        self.ctx = engine.Context(device)
+        self.device = torch.device("cuda", device)
+        to = lambda a, dt: torch.as_tensor(np.asarray(a) if not isinstance(a, torch.Tensor) else a).to(self.device, dt).contiguous()
+        self._w = {f: to(extractor_state[k], torch.float32) for f, k in self.STATE}
+        self.D = int(self._w["symbol_emb"].shape[1])
+        self.model = L.ZslModel(D=self.D, ln_eps=1e-5, **{f: t.data_ptr() for f, t in self._w.items()})
+        conn = np.asarray(connections)
+        self.conn = to(conn[:, :, 1] if conn.ndim == 3 else conn, torch.int64)              # neighbour symbols only (:51)
+        n_ent = self.conn.shape[0]
+        deg = e1_degrees
+        if isinstance(deg, dict):
+            deg = [deg.get(i, 0) for i in range(n_ent)]
+        self.deg = to(deg, torch.float32)
+        self.ent_symbol = to(ent_symbol, torch.int64)
+        self.A = torch.empty((n_ent, self.D), dtype=torch.float32, device=self.device)
+        self.B = torch.empty_like(self.A)
+        L.check(L.lib().mre_zsl_entity_features(self.ctx._h, self.model, self.ent_symbol.data_ptr(), self.conn.data_ptr(),
+                                                self.deg.data_ptr(), n_ent, int(self.conn.shape[1]), self.A.data_ptr(),
+                                                self.B.data_ptr(), torch.cuda.current_stream().cuda_stream))
+
+    def rank(self, q_head, q_rel, cand_lists, rel_vecs, want_scores=False):
+        """q_head [T] entity ids, q_rel [T] rows of rel_vecs [n_rel, n_vec, D], cand_lists: T arrays of entity ids (true first)
+        -> (counts int32 [4, T] on the device, scores float32 [P] or None)"""
+        to = lambda a, dt: torch.as_tensor(np.asarray(a) if not isinstance(a, torch.Tensor) else a).to(self.device, dt).contiguous()
+        T = len(cand_lists)
+        ptr = np.concatenate([[0], np.cumsum([len(c) for c in cand_lists])]).astype(np.int64)
+        P = int(ptr[-1])
+        flat = np.concatenate([np.asarray(c, np.int64) for c in cand_lists]) if P else np.zeros(0, np.int64)
+        d_ptr, d_idx, d_head, d_rel = to(ptr, torch.int64), to(flat, torch.int64), to(q_head, torch.int64), to(q_rel, torch.int64)
+        rv = to(rel_vecs, torch.float32)
+        assert rv.dim() == 3 and rv.shape[2] == self.D
+        counts = torch.zeros((4, max(T, 1)), dtype=torch.int32, device=self.device)[:, :T].contiguous()
+        scores = torch.empty(max(P, 1), dtype=torch.float32, device=self.device) if want_scores else None
+        L.check(L.lib().mre_zsl_rank(self.ctx._h, self.model, self.A.data_ptr(), self.B.data_ptr(), d_head.data_ptr(), d_rel.data_ptr(),
+                                     d_ptr.data_ptr(), d_idx.data_ptr(), T, P, rv.data_ptr(), rv.shape[0], rv.shape[1],
+                                     scores.data_ptr() if want_scores else None, counts.data_ptr(),
+                                     torch.cuda.current_stream().cuda_stream))
+        return counts, (scores[:P] if want_scores else None)
+
+    def eval(self, test_candidates, relation_vecs, ent2id, mode="test", verbose=True, ties="pessimistic"):
+        """test_candidates: {relation: {"head\trel\ttail": [true tail, candidates...]}} ({mode}_candidates.json, :647-649);
+        relation_vecs: {relation: [test_sample, D] array} = generate_model.generate(...) per relation (:657-660).
+        Returns (hits10, hits5, mrr) as ZSLmodule.eval does (:745) and prints its lines."""
+        rels = list(test_candidates.keys())
+        rv = np.stack([np.asarray(relation_vecs[r], np.float32) for r in rels]) if rels else np.zeros((0, 1, self.D), np.float32)
+        q_head, q_rel, lists, per_rel = [], [], [], []
+        for ri, rel in enumerate(rels):
+            n0 = len(lists)
+            for key, cands in test_candidates[rel].items():
+                head = key.split("\t")[0]
+                q_head.append(ent2id[head]); q_rel.append(ri)
+                lists.append(np.fromiter((ent2id[c] for c in cands), np.int64, len(cands)))
+            per_rel.append((rel, n0, len(lists)))
+        counts, _ = self.rank(np.asarray(q_head, np.int64), np.asarray(q_rel, np.int64), lists, rv)
+        c = counts.cpu().numpy()
+        ranks = (c[0] + 1 + (c[1] if ties == "pessimistic" else 0)).astype(np.float64)
+        if verbose:
+            print("##EVALUATING ON %s DATA" % mode.upper())
+            for rel, a, b in per_rel:
+                r = ranks[a:b]
+                if len(r):
+                    print("{} Hits10:{:.3f}, Hits5:{:.3f}, Hits1:{:.3f} MRR:{:.3f}".format(
+                        mode + rel, (r <= 10).mean(), (r <= 5).mean(), (r <= 1).mean(), (1.0 / r).mean()))
+        if len(ranks) == 0:
+            return float("nan"), float("nan"), float("nan")
+        h10, h5, h1, mrr = (ranks <= 10).mean(), (ranks <= 5).mean(), (ranks <= 1).mean(), (1.0 / ranks).mean()
+        if verbose:
+            print("############   " + mode + "    #############")
+            print("HITS10: {:.3f}".format(h10)); print("HITS5: {:.3f}".format(h5)); print("HITS1: {:.3f}".format(h1))
+            print("MAP: {:.3f}".format(mrr)); print("###################################")
+        return float(h10), float(h5), float(mrr)

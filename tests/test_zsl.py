@@ -1,0 +1,123 @@
+"""ZSL candidate scorer (ZSLmodule.eval, module/zsl_module.py:635-745 -> mre_zsl_entity_features + mre_zsl_rank).
+
+Fixture tests/golden/golden_zsl.npz: scores and ranks produced by the REFERENCE's own Extractor class + sklearn
+cosine_similarity on a seeded synthetic graph (tests/golden/make_golden_zsl.py asserts oracle/zsl_oracle.py restates the
+Extractor bit for bit).  CPU: the oracle's separable form (what the kernels compute) against the reference scores.
+GPU: entity halves and scores against the oracle (FP32 rounding: 2e-5 absolute on cosine means in [-1, 1]), ranks inside the
+interval the reference's scores leave open at that tolerance and equal to the reference's rank wherever it is empty,
+(hits10, hits5, mrr) within 1e-4 when no rank is in doubt.
+"""
+import numpy as np
+import pytest
+import torch
+
+import golden_util as gu
+from oracle import zsl_oracle as zo
+
+TOL = 1e-6
+
+
+@pytest.fixture(scope="module")
+def setup():
+    g = gu.load("golden_zsl.npz")
+    n_symbols, conn, deg, heads, rels, cands, rel_vecs = zo.synthetic_zsl_setup(int(g["seed"]), int(g["n_ent"]), int(g["n_rel"]),
+                                                                                int(g["D"]), int(g["max_nb"]), len(g["ranks"]))
+    w = zo.seeded_extractor_weights(int(g["seed"]), n_symbols, int(g["D"]))
+    return g, w, conn, deg, heads, rels, cands, rel_vecs
+
+
+def test_separable_form_matches_reference_scores(setup):
+    g, w, conn, deg, heads, rels, cands, rel_vecs = setup
+    n_ent = int(g["n_ent"])
+    A, B = zo.entity_halves(w, np.arange(n_ent), conn[:, :, 1], deg)
+    for t in range(len(cands)):
+        ref = g["scores"][g["ptr"][t]:g["ptr"][t + 1]]
+        mine = zo.separable_scores(w, A, B, int(heads[t]), cands[t], rel_vecs[rels[t]])
+        assert np.abs(mine - ref).max() < TOL
+        lo, hi = zo.rank_interval(ref)
+        assert lo <= g["ranks"][t] <= hi
+    # the planted exact tie with the true candidate leaves the reference's rank genuinely open
+    lo, hi = zo.rank_interval(g["scores"][g["ptr"][3]:g["ptr"][4]])
+    assert hi == lo + 1
+
+
+def rank_bounds(ref_scores, tol):
+    """ranks the reference scores allow when every score may move by tol"""
+    s0 = ref_scores[0]
+    lo = int((ref_scores[1:] > s0 + 2 * tol).sum()) + 1
+    hi = int((ref_scores[1:] >= s0 - 2 * tol).sum()) + 1
+    return lo, hi
+
+
+@pytest.mark.gpu
+def test_zsl_kernels_vs_reference(mre, setup):
+    g, w, conn, deg, heads, rels, cands, rel_vecs = setup
+    n_ent = int(g["n_ent"])
+    ev = mre.paper.ZSLEvaluator(w, conn, deg, np.arange(n_ent), device=0)
+    A, B = zo.entity_halves(w, np.arange(n_ent), conn[:, :, 1], deg)
+    assert np.abs(ev.A.cpu().numpy() - A).max() < 1e-5 and np.abs(ev.B.cpu().numpy() - B).max() < 1e-5
+    counts, scores = ev.rank(heads, rels, cands, rel_vecs, want_scores=True)
+    c, s = counts.cpu().numpy(), scores.cpu().numpy()
+    err = float(np.abs(s - g["scores"]).max())
+    print(f"max |score - reference score| = {err:.3e}")
+    assert err < TOL                                                 # against the reference's own scores
+    exact = 0
+    for t in range(len(cands)):
+        ref = g["scores"][g["ptr"][t]:g["ptr"][t + 1]]
+        lo, hi = rank_bounds(ref, err + 1e-7)                        # what the reference's scores allow at the measured deviation
+        assert lo <= c[0][t] + 1 and c[0][t] + c[1][t] + 1 <= hi, t
+        if lo == hi:
+            exact += 1
+            assert c[0][t] + 1 == g["ranks"][t] and c[1][t] == 0
+        # the kernel's own counts are consistent with its own scores
+        mine = s[g["ptr"][t]:g["ptr"][t + 1]]
+        assert (c[0][t], c[1][t]) == (int((mine[1:] > mine[0]).sum()), int((mine[1:] == mine[0]).sum()))
+    assert exact >= len(cands) - 3
+    assert c[1][3] >= 1                                              # the planted duplicate candidate ties exactly
+    # metrics through mre_metrics (pessimistic = a stable descending sort's answer)
+    rk = mre.engine.Ranker(ev.ctx)
+    m = rk.metrics(counts, 1, "pessimistic")
+    sums, rr = m["sums"].cpu().numpy(), m["rr"].cpu().numpy()
+    ranks = (c[0] + c[1] + 1).astype(np.float64)
+    assert sums[1][0] == len(cands) and np.isclose(rr[1], (1.0 / ranks).sum(), rtol=1e-12)
+    assert sums[1][5] == (ranks <= 10).sum() and sums[1][4] == (ranks <= 5).sum()
+
+
+@pytest.mark.gpu
+def test_zsl_eval_dropin(mre, setup, capsys):
+    """ZSLmodule.eval's contract: {relation: {"head\\trel\\ttail": [true, cands...]}} in, (hits10, hits5, mrr) out"""
+    g, w, conn, deg, heads, rels, cands, rel_vecs = setup
+    n_ent = int(g["n_ent"])
+    ent2id = {f"e{i}": i for i in range(n_ent)}
+    order = np.argsort(rels, kind="stable")
+    test_candidates, relation_vecs = {}, {}
+    for t in order.tolist():
+        rel = f"r{int(rels[t])}"
+        key = "\t".join((f"e{int(heads[t])}", rel, f"e{int(cands[t][0])}")) + f"#{t}"      # keys must be unique per triple
+        test_candidates.setdefault(rel, {})[key] = [f"e{int(x)}" for x in cands[t]]
+        relation_vecs[rel] = rel_vecs[rels[t]]
+    ev = mre.paper.ZSLEvaluator(w, conn, deg, np.arange(n_ent), device=0)
+    h10, h5, mrr = ev.eval(test_candidates, relation_vecs, ent2id, mode="test", ties="optimistic")
+    out = capsys.readouterr().out
+    assert "HITS10" in out and "MAP" in out
+    ref = g["metrics"]
+    # one triple carries a planted exact tie: allow its rank to differ by one
+    assert abs(h10 - ref[0]) <= 1 / len(cands) + 1e-9 and abs(h5 - ref[1]) <= 1 / len(cands) + 1e-9 and abs(mrr - ref[2]) < 5e-3
+
+
+@pytest.mark.gpu
+def test_zsl_ragged_and_empty(mre, setup):
+    g, w, conn, deg, heads, rels, cands, rel_vecs = setup
+    n_ent = int(g["n_ent"])
+    ev = mre.paper.ZSLEvaluator(w, conn, deg, np.arange(n_ent), device=0)
+    counts, scores = ev.rank(np.zeros(0, np.int64), np.zeros(0, np.int64), [], rel_vecs, want_scores=True)
+    assert counts.shape == (4, 0)
+    # a list holding only the true candidate ranks first; a longer sweep crosses the 64-row tile edge mid-list
+    lists = [cands[0], np.arange(n_ent, dtype=np.int64), cands[1]]
+    counts, scores = ev.rank(heads[:3], rels[:3], lists, rel_vecs, want_scores=True)
+    c = counts.cpu().numpy()
+    assert c[0][0] == 0 and c[1][0] == 0
+    A, B = zo.entity_halves(w, np.arange(n_ent), conn[:, :, 1], deg)
+    want = zo.separable_scores(w, A, B, int(heads[1]), lists[1], rel_vecs[rels[1]])
+    got = scores.cpu().numpy()[1:1 + n_ent]
+    assert np.abs(got - want).max() < TOL
