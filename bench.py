@@ -295,6 +295,9 @@ def main():
     if args.workload == "train":
         import bench_train
         return bench_train.main(args, rank, world, local)
+    if args.workload == "zsl":
+        import bench_zsl
+        return bench_zsl.main(args, rank, world, local)
 
     w = load_workload(args.workload, rank)
     if args.impl == "reference":

@@ -112,7 +112,7 @@ __device__ __forceinline__ void zsl_mma_tile(const float *__restrict__ sa, const
 }
 
 // layer 1: Hid[p, n] = relu(sum_k X[p, k] W1[n, k] + b1[n]),  X[p, :] = A[head(p), :] + B[cand(p), :].  128 x 128 tiles.
-__global__ void __launch_bounds__(256) zsl_layer1_kernel(const mre_zsl_model m, const float *__restrict__ A, const float *__restrict__ B,
+__global__ void __launch_bounds__(256, 2) zsl_layer1_kernel(const mre_zsl_model m, const float *__restrict__ A, const float *__restrict__ B,
                                                          const int64_t *__restrict__ q_head, const int64_t *__restrict__ cand,
                                                          const int32_t *__restrict__ pair_triple, int64_t p0, int64_t P,
                                                          float *__restrict__ hid) {
@@ -138,23 +138,41 @@ __global__ void __launch_bounds__(256) zsl_layer1_kernel(const mre_zsl_model m, 
     for (int i = 0; i < 8; i++)
 #pragma unroll
         for (int j = 0; j < 8; j++) acc[i][j] = 0.f;
-    for (int k0 = 0; k0 < D; k0 += ZBK) {
+    // the next k-slice travels global -> registers while the current one is multiplied out of shared memory
+    float4 nx[2], nw[2];
+    auto fetch = [&](int k0) {
 #pragma unroll
         for (int u = 0; u < 2; u++) {
             const int k = k0 + (lq + u) * 4;
-            float4 x = make_float4(0.f, 0.f, 0.f, 0.f), w = x;
+            nx[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            nw[u] = nx[u];
             if (row_ok && k < D) {
                 const float4 p = *reinterpret_cast<const float4 *>(xa + k), q = *reinterpret_cast<const float4 *>(xb + k);
-                x = make_float4(p.x + q.x, p.y + q.y, p.z + q.z, p.w + q.w);
+                nx[u] = make_float4(p.x + q.x, p.y + q.y, p.z + q.z, p.w + q.w);
             }
-            if (wrow && k < D) w = *reinterpret_cast<const float4 *>(wrow + k);
-            const int kk = (lq + u) * 4;
-            sa[(kk + 0) * BM + lr] = x.x; sa[(kk + 1) * BM + lr] = x.y; sa[(kk + 2) * BM + lr] = x.z; sa[(kk + 3) * BM + lr] = x.w;
-            sb[(kk + 0) * BN + lr] = w.x; sb[(kk + 1) * BN + lr] = w.y; sb[(kk + 2) * BN + lr] = w.z; sb[(kk + 3) * BN + lr] = w.w;
+            if (wrow && k < D) nw[u] = *reinterpret_cast<const float4 *>(wrow + k);
         }
-        __syncthreads();
+    };
+    auto stage = [&]() {
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            const int kk = (lq + u) * 4;
+            sa[(kk + 0) * BM + lr] = nx[u].x; sa[(kk + 1) * BM + lr] = nx[u].y; sa[(kk + 2) * BM + lr] = nx[u].z; sa[(kk + 3) * BM + lr] = nx[u].w;
+            sb[(kk + 0) * BN + lr] = nw[u].x; sb[(kk + 1) * BN + lr] = nw[u].y; sb[(kk + 2) * BN + lr] = nw[u].z; sb[(kk + 3) * BN + lr] = nw[u].w;
+        }
+    };
+    fetch(0);
+    stage();
+    __syncthreads();
+    for (int k0 = 0; k0 < D; k0 += ZBK) {
+        const bool more = k0 + ZBK < D;
+        if (more) fetch(k0 + ZBK);
         zsl_mma_tile<BM, BN>(sa, sb, ty * 8, tx * 8, acc);
         __syncthreads();
+        if (more) {
+            stage();
+            __syncthreads();
+        }
     }
 #pragma unroll
     for (int i = 0; i < 8; i++) {
@@ -171,7 +189,7 @@ __global__ void __launch_bounds__(256) zsl_layer1_kernel(const mre_zsl_model m, 
 
 // layer 2 + LayerNorm + cosine mean: score[p] = mean_k cos(LN(Hid[p, :] W2^T + b2 + X[p, :]), r_k).  64 x 256 tiles: a warp owns
 // 8 whole rows (lane = 8-column slice), so every row reduction is a warp shuffle.
-__global__ void __launch_bounds__(256) zsl_layer2_kernel(const mre_zsl_model m, const float *__restrict__ A, const float *__restrict__ B,
+__global__ void __launch_bounds__(256, 2) zsl_layer2_kernel(const mre_zsl_model m, const float *__restrict__ A, const float *__restrict__ B,
                                                          const int64_t *__restrict__ q_head, const int64_t *__restrict__ q_rel,
                                                          const int64_t *__restrict__ cand, const int32_t *__restrict__ pair_triple,
                                                          const float *__restrict__ hid, const float *__restrict__ rel_vecs,
@@ -191,22 +209,37 @@ __global__ void __launch_bounds__(256) zsl_layer2_kernel(const mre_zsl_model m, 
     const int ar = tid >> 2, aq = (tid & 3) * 4;
     const int64_t arow = row0 + ar;
     const float *hrow = arow < p0 + P ? hid + (arow - p0) * K : nullptr;
-    for (int k0 = 0; k0 < K; k0 += ZBK) {
-        {
-            float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (hrow && k0 + aq < K) x = *reinterpret_cast<const float4 *>(hrow + k0 + aq);
-            sa[(aq + 0) * BM + ar] = x.x; sa[(aq + 1) * BM + ar] = x.y; sa[(aq + 2) * BM + ar] = x.z; sa[(aq + 3) * BM + ar] = x.w;
-        }
+    float4 nh, nw[4];
+    auto fetch = [&](int k0) {
+        nh = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (hrow && k0 + aq < K) nh = *reinterpret_cast<const float4 *>(hrow + k0 + aq);
 #pragma unroll
         for (int u = 0; u < 4; u++) {
             const int f = tid + u * 256, n = f >> 2, kq = (f & 3) * 4;
-            float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (n < D && k0 + kq < K) w = *reinterpret_cast<const float4 *>(m.proj2_w + (int64_t)n * K + k0 + kq);
-            sb[(kq + 0) * BN + n] = w.x; sb[(kq + 1) * BN + n] = w.y; sb[(kq + 2) * BN + n] = w.z; sb[(kq + 3) * BN + n] = w.w;
+            nw[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (n < D && k0 + kq < K) nw[u] = *reinterpret_cast<const float4 *>(m.proj2_w + (int64_t)n * K + k0 + kq);
         }
-        __syncthreads();
+    };
+    auto stage = [&]() {
+        sa[(aq + 0) * BM + ar] = nh.x; sa[(aq + 1) * BM + ar] = nh.y; sa[(aq + 2) * BM + ar] = nh.z; sa[(aq + 3) * BM + ar] = nh.w;
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int f = tid + u * 256, n = f >> 2, kq = (f & 3) * 4;
+            sb[(kq + 0) * BN + n] = nw[u].x; sb[(kq + 1) * BN + n] = nw[u].y; sb[(kq + 2) * BN + n] = nw[u].z; sb[(kq + 3) * BN + n] = nw[u].w;
+        }
+    };
+    fetch(0);
+    stage();
+    __syncthreads();
+    for (int k0 = 0; k0 < K; k0 += ZBK) {
+        const bool more = k0 + ZBK < K;
+        if (more) fetch(k0 + ZBK);
         zsl_mma_tile<BM, BN>(sa, sb, ty * 8, tx * 8, acc);
         __syncthreads();
+        if (more) {
+            stage();
+            __syncthreads();
+        }
     }
     // ---- epilogue: this lane holds columns c0 .. c0 + 7 of eight rows
     const int c0 = tx * 8;
@@ -219,10 +252,10 @@ __global__ void __launch_bounds__(256) zsl_layer2_kernel(const mre_zsl_model m, 
         be[j] = col_ok ? m.ln_b[c0 + j] : 0.f;
     }
     const float inv_d = 1.f / (float)D;
-#pragma unroll 1
+#pragma unroll                                                      // (static indices: the accumulators stay in registers)
     for (int i = 0; i < 8; i++) {
         const int64_t p = row0 + ty * 8 + i;
-        if (p >= p0 + P) break;                                     // warp-uniform
+        if (p >= p0 + P) continue;                                  // warp-uniform
         const int t = pair_triple[p];
         const float *xa = A + q_head[t] * D, *xb = B + cand[p] * D;
         float y[8], s = 0.f;
