@@ -259,13 +259,36 @@ def run_reference(args, w):
     v = tot_q / tot_s
     sample = f"{per_step} test triples per step ({tot_q} queries in {tot_s:.1f} s), torch-CPU scoring + " + \
              ("unmodified Base.so rank" if kind == "reference" else "C restatement of Test.h")
-    print(json.dumps({
+    emit(({
         "impl": "reference", "metric": "filtered-rank eval queries/sec", "value": v, "unit": "queries/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": w.name, "desc": w.desc, "E": w.E, "D": w.D},
         "cpu_baseline": {"value": v, "unit": "queries/s", "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": v, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+# ------------------------------------------------------------------------------------------------- the one JSON line
+_JSON_FD = None
+
+
+def claim_stdout():
+    """Keep fd 1 for the ONE JSON line: everything else that writes to stdout (NCCL's version banner, Base.so's printf tables,
+    library chatter) is sent to stderr from here on."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    sys.stdout.flush()
+    if _JSON_FD is None:
+        os.write(1, line)
+    else:
+        os.write(_JSON_FD, line)
 
 
 # ------------------------------------------------------------------------------------------------- our arm
@@ -288,6 +311,8 @@ def main():
     ap.add_argument("--no-extra", action="store_true", help="skip the extra (synthetic2m, cpu_baseline) legs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    claim_stdout()
+    args.emit = emit
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -510,7 +535,7 @@ def main():
             "gpu_launches": int(launches), "clocks": clocks.summary(),
             "result": {"tail": summ[1], "head": summ[0]}, "extra": extra,
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

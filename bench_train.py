@@ -57,12 +57,12 @@ def main(args, rank, world, local):
             cpu_reference_step(w, threads, 1)
             s, kind = cpu_reference_step(w, threads, max(1, min(args.steps, 5)))
         v = n / s
-        print(json.dumps({"impl": "reference", "metric": "train triples/sec", "value": v, "unit": "triples/s", "n_gpus": args.gpus,
+        args.emit({"impl": "reference", "metric": "train triples/sec", "value": v, "unit": "triples/s", "n_gpus": args.gpus,
                           "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * s, "higher_is_better": True, "scaling": "weak",
                           "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
                           "cpu_baseline": {"value": v, "unit": "triples/s", "cores": threads, "kind": kind,
                                            "sample": f"{min(args.steps, 5)} full steps: Base.so sampling + torch-CPU forward/backward"},
-                          "e2e": {"value": v, "unit": "triples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+                          "e2e": {"value": v, "unit": "triples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
         return
 
     import torch
@@ -162,7 +162,7 @@ def main(args, rank, world, local):
         cpu_base = {"value": n / s, "unit": "triples/s", "cores": threads, "kind": kind,
                     "sample": "3 full steps: Base.so sampling on all host threads + torch-CPU forward/backward of the reference expressions"}
     if rank == 0:
-        print(json.dumps({
+        args.emit({
             "metric": "train triples/sec", "value": value, "unit": "triples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": config,
@@ -173,6 +173,6 @@ def main(args, rank, world, local):
             "cpu_baseline": cpu_base,
             "e2e": {"value": world * n * args.steps / e2e_s, "unit": "triples/s", "h2d_bytes_per_step": 3 * n * 8, "d2h_bytes_per_step": 3 * n * 8 + n * 4 + 4,
                     "api": "sample_host (reference loader contract: numpy batch on the host) -> pinned H2D -> margin step -> loss.item()"},
-            "gpu_launches": int(launches), "clocks": clocks.summary(), "result": {"last_loss": float(loss.item())}}))
+            "gpu_launches": int(launches), "clocks": clocks.summary(), "result": {"last_loss": float(loss.item())}})
     if world > 1:
         dist.destroy_process_group()

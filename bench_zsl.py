@@ -78,12 +78,12 @@ def main(args, rank, world, local):
         for _ in range(args.steps):
             tot += cpu_reference(wl, threads, rng.integers(0, T, per_step))
         v = per_step * args.steps / tot
-        print(json.dumps({"impl": "reference", "metric": "ZSL eval test triples/sec", "value": v, "unit": "triples/s", "n_gpus": args.gpus,
+        args.emit({"impl": "reference", "metric": "ZSL eval test triples/sec", "value": v, "unit": "triples/s", "n_gpus": args.gpus,
                           "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / args.steps, "higher_is_better": True,
                           "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
                           "cpu_baseline": {"value": v, "unit": "triples/s", "cores": threads, "kind": "port",
                                            "sample": f"{per_step} test triples per step, one torch-CPU Extractor forward per triple (the reference's loop; its class is pinned to this restatement bit for bit)"},
-                          "e2e": {"value": v, "unit": "triples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+                          "e2e": {"value": v, "unit": "triples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
         return
 
     import torch
@@ -180,7 +180,7 @@ def main(args, rank, world, local):
         cpu_base = {"value": n_s / s, "unit": "triples/s", "cores": threads, "kind": "port",
                     "sample": f"{n_s} test triples of the same workload in {s:.1f} s: one torch-CPU Extractor forward per triple (the reference's loop)"}
     if rank == 0:
-        print(json.dumps({
+        args.emit({
             "metric": "ZSL eval test triples/sec", "value": world * T * steps / (ms * 1e-3), "unit": "triples/s", "n_gpus": world,
             "steps": steps, "warmup": warmup, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": config,
@@ -191,4 +191,4 @@ def main(args, rank, world, local):
             "cpu_baseline": cpu_base,
             "e2e": {"value": world * T * steps / e2e_s, "unit": "triples/s", "h2d_bytes_per_step": int(sum(a.numel() * 8 for a in host)),
                     "d2h_bytes_per_step": int(counts_h.numel() * 4), "api": "mre_zsl_entity_features + mre_zsl_rank: pinned host candidate lists in, int32 rank counts out"},
-            "gpu_launches": int(launches), "clocks": clocks.summary(), "result": {"tail": summ[1]}}))
+            "gpu_launches": int(launches), "clocks": clocks.summary(), "result": {"tail": summ[1]}})

@@ -37,18 +37,29 @@
 namespace mre {
 
 constexpr int CHUNK = 32;            // floats of D per pipeline stage (128 B per row)
-constexpr int STAGES = 3;
+#ifndef MRE_TRANSE_TQ
+#define MRE_TRANSE_TQ 128
+#endif
+#ifndef MRE_TRANSE_STAGES
+#define MRE_TRANSE_STAGES 3
+#endif
+#ifndef MRE_TRANSE_CTAS
+#define MRE_TRANSE_CTAS 2
+#endif
+constexpr int TQ = MRE_TRANSE_TQ;                  // queries per work item of this kernel
+constexpr int STAGES = MRE_TRANSE_STAGES;
+constexpr int CTAS_PER_SM = MRE_TRANSE_CTAS;
 #ifndef MRE_RANK_WARPS
 #define MRE_RANK_WARPS 8      // 4 (a 16-query x 8-entity register tile per thread, 241 registers) measured 20 % slower on B200
 #endif
 constexpr int CONSUMER_WARPS = MRE_RANK_WARPS;
 constexpr int RANK_THREADS = CONSUMER_WARPS * 32;
 constexpr int NTQ = RANK_THREADS / 16;              // threads along the query dimension of the tile
-constexpr int NI = (TILE_Q / 2) / NTQ;              // query PAIR-rows per thread (4 with 8 warps: an 8-query x 8-entity register tile)
+constexpr int NI = (TQ / 2) / NTQ;              // query PAIR-rows per thread (4 with 8 warps: an 8-query x 8-entity register tile)
 constexpr int KW = (NI * 16 + 63) / 64;             // 64-bit words of one thread's known-true mask
-constexpr uint32_t QBOX_BYTES = (TILE_Q / 2) * 128;             // 64 query pair-rows x 128 B (16 d-values of two queries)
-constexpr uint32_t STAGE_BYTES = (TILE_Q + TILE_E) * CHUNK * 4;  // two 8 KiB query-pair boxes + one 16 KiB candidate box
-constexpr size_t RANK_SMEM = 1024 + (size_t)STAGES * STAGE_BYTES + STAGES * sizeof(uint64_t) + 4 * sizeof(int) + CONSUMER_WARPS * 32 * KW * sizeof(unsigned long long) + (size_t)TILE_Q * sizeof(float2) + 64;
+constexpr uint32_t QBOX_BYTES = (TQ / 2) * 128;             // 64 query pair-rows x 128 B (16 d-values of two queries)
+constexpr uint32_t STAGE_BYTES = (TQ + TILE_E) * CHUNK * 4;  // two 8 KiB query-pair boxes + one 16 KiB candidate box
+constexpr size_t RANK_SMEM = 1024 + (size_t)STAGES * STAGE_BYTES + STAGES * sizeof(uint64_t) + 4 * sizeof(int) + CONSUMER_WARPS * 32 * KW * sizeof(unsigned long long) + (size_t)TQ * sizeof(float2) + 64;
 
 // ------------------------------------------------------------------------------------------ scalar scorer
 // The one definition of a TransE accumulator: sequential over d, acc = acc + |v - e| (p = 1) or fma(u, u, acc) (p = 2), with
@@ -223,7 +234,7 @@ __device__ __forceinline__ void issue_chunk(const RankParams &p, const CUtensorM
     int g, qt, et;
     decode_item(p, item, g, qt, et);
     const GroupDesc &gd = p.groups[g];
-    const int prow = (int)((gd.s0 + (int64_t)qt * TILE_Q) >> 1);
+    const int prow = (int)((gd.s0 + (int64_t)qt * TQ) >> 1);
     const int erow = (int)(gd.c0 + (int64_t)et * TILE_E);
     const int stage = (int)(flat % STAGES);
     const uint32_t full = full0 + 8 * stage;
@@ -235,7 +246,7 @@ __device__ __forceinline__ void issue_chunk(const RankParams &p, const CUtensorM
 }
 
 template <int P, bool NEED_EQ>
-__global__ void __launch_bounds__(RANK_THREADS, 2)
+__global__ void __launch_bounds__(RANK_THREADS, CTAS_PER_SM)
 transe_rank_kernel(const RankParams p, const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_e) {
     extern __shared__ unsigned char smem_raw[];
     // the 128-byte swizzle pattern is a function of the shared-memory address: tiles must start 1024-byte aligned
@@ -269,7 +280,7 @@ transe_rank_kernel(const RankParams p, const __grid_constant__ CUtensorMap tm_q,
     }
     __syncthreads();
     if (MRE_STAGGER > 0 && done[3] && p.total_items > (int64_t)gridDim.x) {
-        // one chunk of one CTA alone on the SM takes TILE_Q * TILE_E * CHUNK * 2 / 128 lanes = 8192 cycles
+        // one chunk of one CTA alone on the SM takes TQ * TILE_E * CHUNK * 2 / 128 lanes = 8192 cycles
         const long long delay = (long long)n_chunks * 8192ll * MRE_STAGGER / 100;
         const long long t0 = clock64();
         while (clock64() - t0 < delay) __nanosleep(2000);
@@ -285,8 +296,8 @@ transe_rank_kernel(const RankParams p, const __grid_constant__ CUtensorMap tm_q,
         int g, qt, et;
         decode_item(p, item, g, qt, et);
         const GroupDesc gd = p.groups[g];
-        const int64_t qbase = gd.q0 + (int64_t)qt * TILE_Q;
-        const int nq = (int)min((int64_t)TILE_Q, gd.q0 + gd.nq - qbase);
+        const int64_t qbase = gd.q0 + (int64_t)qt * TQ;
+        const int nq = (int)min((int64_t)TQ, gd.q0 + gd.nq - qbase);
         const int ne = (int)min((int64_t)TILE_E, gd.nc - (int64_t)et * TILE_E);
         // this item's known-true pairs; the first 32 are fetched now so the epilogue does not wait on them
         const uint32_t pf0 = __ldg(p.tf_ptr + item), pf1 = __ldg(p.tf_ptr + item + 1);
@@ -592,8 +603,8 @@ static int launch_rank(mre_ctx *ctx, const RankParams &p, const CUtensorMap &tm_
         MRE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RANK_SMEM));
         configured = true;
     }
-    int per_sm = 2;
-    if (const char *e = getenv("MRE_DEV_CTAS_PER_SM")) per_sm = atoi(e) > 0 ? atoi(e) : 2;   // developer experiments only
+    int per_sm = CTAS_PER_SM;
+    if (const char *e = getenv("MRE_DEV_CTAS_PER_SM")) per_sm = atoi(e) > 0 ? atoi(e) : CTAS_PER_SM;   // developer experiments only
     int grid = (int)std::max<int64_t>(1, std::min<int64_t>(p.total_items, (int64_t)ctx->sm_count * per_sm));
     kern<<<grid, RANK_THREADS, RANK_SMEM, st>>>(p, tm_q, tm_e);
     ctx->launches += 1;
@@ -607,7 +618,7 @@ int rank_transe(mre_ctx *ctx, const mre_index *ix, const mre_rank_job *job, cuda
     int64_t Dp = 0;
     MRE_TRY(transe_tables(ctx, job, st, &ent, &rel, &Dp));
     RankParams p{};
-    MRE_TRY(fill_rank_params(ctx, ix, job, TILE_Q, TILE_E, st, p));
+    MRE_TRY(fill_rank_params(ctx, ix, job, TQ, TILE_E, st, p));
     p.ent = ent;
     p.D = Dp;
     if (job->Q == 0) return MRE_OK;
@@ -631,10 +642,10 @@ int rank_transe(mre_ctx *ctx, const mre_index *ix, const mre_rank_job *job, cuda
     }
     init_counts_kernel<<<grid_for(4 * job->Q, 256), 256, 0, st>>>(job->counts, 4 * job->Q);
     ctx->launches += 1;
-    MRE_TRY(build_tile_filter(ctx, job, p, TILE_Q, TILE_E, st));
+    MRE_TRY(build_tile_filter(ctx, job, p, TQ, TILE_E, st));
     CUtensorMap tm_q, tm_e;
     // query vectors: [slots / 2 pair-rows][2 Dp floats], box = 64 pair-rows x 32 floats (16 d-values of two queries)
-    MRE_TRY(make_tmap_f32_2d(&tm_q, p.qvec, std::max<int64_t>(p.total_slots / 2, 1), 2 * Dp, 2 * Dp, TILE_Q / 2, CHUNK));
+    MRE_TRY(make_tmap_f32_2d(&tm_q, p.qvec, std::max<int64_t>(p.total_slots / 2, 1), 2 * Dp, 2 * Dp, TQ / 2, CHUNK));
     MRE_TRY(make_tmap_f32_2d(&tm_e, cand_table, std::max<int64_t>(cand_rows, 1), Dp, Dp, TILE_E, CHUNK));
     MRE_TRY(ctx->sm_slots.reserve(1024 * sizeof(uint32_t)));
     MRE_CUDA(cudaMemsetAsync(ctx->sm_slots.p, 0, 1024 * sizeof(uint32_t), st));
