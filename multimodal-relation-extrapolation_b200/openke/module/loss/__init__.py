@@ -1,3 +1,5 @@
 from .MarginLoss import MarginLoss
+from .SigmoidLoss import SigmoidLoss
+from .SoftplusLoss import SoftplusLoss
 
-__all__ = ["MarginLoss"]
+__all__ = ["MarginLoss", "SigmoidLoss", "SoftplusLoss"]
