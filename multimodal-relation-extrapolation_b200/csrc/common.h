@@ -105,8 +105,6 @@ struct mre_ctx {
     mre::DevBuf counters;            // raw/corr counters, work counters
     mre::DevBuf misc;                // loss partials etc.
     mre::DevBuf misc2;               // known-true pair list of the tile filter
-    mre::DevBuf tie_queue;           // bilinear kernel: near-tie (query, entity) pairs awaiting the exact re-score
-    mre::DevBuf sm_slots;            // per-SM CTA arrival counters of the TransE rank kernel
     mre::DevBuf stage_dev;           // device staging for *_host entry points
     mre::PinnedBuf stage_pin;        // pinned host staging
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;

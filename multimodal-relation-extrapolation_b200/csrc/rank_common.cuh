@@ -43,8 +43,6 @@ struct RankParams {
     const int64_t *filt_ptr, *filt_idx;
     // known-true pairs per work item (tile_filter.cu): pairs[ptr[item] .. ptr[item+1]) = (row << 16 | col)
     const uint32_t *tf_ptr, *tf_pairs;
-    // per-SM arrival counters (zeroed per launch): a CTA's arrival order on its SM decides its start phase
-    uint32_t *sm_slots;
     // outputs [4][Q]
     int32_t *counts;
 };

@@ -207,9 +207,6 @@ __device__ __forceinline__ void acc2(unsigned long long &acc, unsigned long long
 #define MRE_K4_UNROLL 4
 #endif
 constexpr int K4_UNROLL = MRE_K4_UNROLL;
-#ifndef MRE_STAGGER
-#define MRE_STAGGER 0      // experiment (no effect measured: the two CTAs of an SM de-phase on their own): start-phase offset of
-#endif                     // the second CTA on an SM, in percent of one work item's duration
 #ifndef MRE_DIAG_NOWAIT
 #define MRE_DIAG_NOWAIT 0
 #endif
@@ -271,20 +268,8 @@ transe_rank_kernel(const RankParams p, const __grid_constant__ CUtensorMap tm_q,
         fence_barrier_init();
         fence_proxy_async();
         for (int s = 0; s < STAGES; s++) issue_chunk(p, &tm_q, &tm_e, s, n_chunks, ring_u32, full0);
-        // The two CTAs of an SM run identical, deterministic work: left alone they reach their (FP32-idle) epilogues
-        // together.  The second CTA to arrive on an SM therefore starts half an item late -- its partner has the FP32
-        // pipe to itself meanwhile, so nothing is lost -- and from then on one CTA's epilogue overlaps the other's tile loop.
-        uint32_t smid;
-        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-        done[3] = (MRE_STAGGER > 0 && p.sm_slots) ? (int)(atomicAdd(p.sm_slots + smid, 1u) & 1u) : 0;
     }
     __syncthreads();
-    if (MRE_STAGGER > 0 && done[3] && p.total_items > (int64_t)gridDim.x) {
-        // one chunk of one CTA alone on the SM takes TQ * TILE_E * CHUNK * 2 / 128 lanes = 8192 cycles
-        const long long delay = (long long)n_chunks * 8192ll * MRE_STAGGER / 100;
-        const long long t0 = clock64();
-        while (clock64() - t0 < delay) __nanosleep(2000);
-    }
 
     // entity rows te + 16 j (j < 8); query PAIR-rows tq + NTQ i (i < NI) = tile rows 2 (tq + NTQ i) and 2 (tq + NTQ i) + 1.
     // A row keeps its logical 16-byte chunk k at (k ^ (row & 7)), and (te + 16 j) & 7 == te & 7: the sixteen rows one
@@ -647,9 +632,6 @@ int rank_transe(mre_ctx *ctx, const mre_index *ix, const mre_rank_job *job, cuda
     // query vectors: [slots / 2 pair-rows][2 Dp floats], box = 64 pair-rows x 32 floats (16 d-values of two queries)
     MRE_TRY(make_tmap_f32_2d(&tm_q, p.qvec, std::max<int64_t>(p.total_slots / 2, 1), 2 * Dp, 2 * Dp, TQ / 2, CHUNK));
     MRE_TRY(make_tmap_f32_2d(&tm_e, cand_table, std::max<int64_t>(cand_rows, 1), Dp, Dp, TILE_E, CHUNK));
-    MRE_TRY(ctx->sm_slots.reserve(1024 * sizeof(uint32_t)));
-    MRE_CUDA(cudaMemsetAsync(ctx->sm_slots.p, 0, 1024 * sizeof(uint32_t), st));
-    p.sm_slots = ctx->sm_slots.as<uint32_t>();
     MRE_TRY(ctx->time_begin(st));
     // the tie count is always on: one extra compare per score, in the epilogue only
     if (job->p_norm == 1) MRE_TRY((launch_rank<1, true>(ctx, p, tm_q, tm_e, st)));
