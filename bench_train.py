@@ -76,18 +76,23 @@ def main(args, rank, world, local):
     ctx = eng.Context(local)
     ix = eng.KGIndex.from_arrays(E, R, *splits).to_device(local)
     smp = eng.Sampler(ix, ctx=ctx, seed=192, stream_id=rank)
-    ent_d, rel_d = torch.from_numpy(ent).to(dev), torch.from_numpy(rel).to(dev)
-    g_ent, g_rel = torch.zeros_like(ent_d), torch.zeros_like(rel_d)
+    # both tables (and both gradient tables) live back to back in ONE buffer: a data-parallel step is one flat all-reduce
+    # and one SGD kernel with 1/world folded into the learning rate
+    tab = torch.empty((E + R) * D, dtype=torch.float32, device=dev)
+    grad = torch.zeros_like(tab)
+    ent_d, rel_d = tab[:E * D].view(E, D), tab[E * D:].view(R, D)
+    g_ent, g_rel = grad[:E * D].view(E, D), grad[E * D:].view(R, D)
+    ent_d.copy_(torch.from_numpy(ent)); rel_d.copy_(torch.from_numpy(rel))
     state = {"step": 0}
+    lr = 1.0
 
     def step_dev():
         h, t, r, y = smp.sample(state["step"], B, neg)
         state["step"] += 1
         loss, _, _, _ = eng.transe_margin_step(ctx, ent_d, rel_d, h, t, r, B, neg, 5.0, 1, True, grad_ent=g_ent, grad_rel=g_rel)
         if dctx is not None:
-            dctx.all_reduce_grads([g_ent, g_rel])
-        eng.sgd_update(ctx, ent_d, g_ent, 1.0)
-        eng.sgd_update(ctx, rel_d, g_rel, 1.0)
+            dctx.all_reduce_flat(grad)
+        eng.sgd_update(ctx, tab, grad, lr / world)
         return loss
 
     host = [np.empty(n, np.int64) for _ in range(3)] + [np.empty(n, np.float32)]
@@ -102,9 +107,8 @@ def main(args, rank, world, local):
         h, t, r = (p.to(dev, non_blocking=True) for p in pinned)
         loss, _, _, _ = eng.transe_margin_step(ctx, ent_d, rel_d, h, t, r, B, neg, 5.0, 1, True, grad_ent=g_ent, grad_rel=g_rel)
         if dctx is not None:
-            dctx.all_reduce_grads([g_ent, g_rel])
-        eng.sgd_update(ctx, ent_d, g_ent, 1.0)
-        eng.sgd_update(ctx, rel_d, g_rel, 1.0)
+            dctx.all_reduce_flat(grad)
+        eng.sgd_update(ctx, tab, grad, lr / world)
         return float(loss.item())
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)

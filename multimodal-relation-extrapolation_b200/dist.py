@@ -56,6 +56,12 @@ class DistContext:
             dist.all_reduce(g)
             g.mul_(1.0 / self.world)
 
+    def all_reduce_flat(self, flat):
+        """ONE sum all-reduce of a flat gradient buffer holding every table back to back; no scaling here -- the caller folds
+        1/world into its SGD step (w -= (lr / world) * sum g), so a data-parallel step is one collective + one update kernel"""
+        dist.all_reduce(flat)
+        return flat
+
     def barrier(self):
         dist.barrier()
 

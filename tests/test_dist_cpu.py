@@ -32,8 +32,10 @@ def _worker(rank, world, port, ranks_all, out_dir):
     hist2 = d.all_reduce_hist(hist)
     g = [torch.full((4, 3), float(rank + 1)), torch.full((2,), float(10 * (rank + 1)))]
     d.all_reduce_grads(g)
+    flat = torch.arange(6, dtype=torch.float32) * (rank + 1)      # the one-collective form: plain sum, 1/world folded into the SGD step
+    d.all_reduce_flat(flat)
     if rank == 0:
-        torch.save({"sums": sums2, "rr": rr2, "hist": hist2, "g0": g[0], "g1": g[1]}, os.path.join(out_dir, "out.pt"))
+        torch.save({"sums": sums2, "rr": rr2, "hist": hist2, "g0": g[0], "g1": g[1], "flat": flat}, os.path.join(out_dir, "out.pt"))
     d.barrier()
     dist.destroy_process_group()
 
@@ -73,3 +75,4 @@ def test_two_rank_gloo_metrics_equal_single_process(tmp_path):
     assert np.isclose(m["hits10"], (ranks_all <= 10).mean()) and np.isclose(m["hits1"], (ranks_all <= 1).mean())
     # gradient all-reduce: mean over ranks
     assert torch.allclose(out["g0"], torch.full((4, 3), 1.5)) and torch.allclose(out["g1"], torch.full((2,), 15.0))
+    assert torch.equal(out["flat"], torch.arange(6, dtype=torch.float32) * 3)
