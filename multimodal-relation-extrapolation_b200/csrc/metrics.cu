@@ -17,8 +17,8 @@ __global__ void __launch_bounds__(MET_THREADS) metrics_kernel(const int32_t *__r
                                                               int side, int64_t Q, int rank_mode, int raw,
                                                               int64_t *__restrict__ sums_out, double *__restrict__ rr_out,
                                                               unsigned long long *__restrict__ hist, int64_t hist_len) {
-    __shared__ long long s_int[MET_THREADS];
-    __shared__ double s_rr[MET_THREADS];
+    __shared__ long long s_int[MET_THREADS / 32][12];
+    __shared__ double s_rr[MET_THREADS / 32][2];
     const int32_t *lt = counts + (raw ? 0 : 2) * Q;
     const int32_t *eq = counts + (raw ? 1 : 3) * Q;
     long long acc[2][6] = {{0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0}};
@@ -29,32 +29,56 @@ __global__ void __launch_bounds__(MET_THREADS) metrics_kernel(const int32_t *__r
         long long rank = a + 1;
         if (rank_mode == MRE_RANK_TIES_HALF) rank += e / 2;
         else if (rank_mode == MRE_RANK_PESSIMISTIC) rank += e;
-        acc[s][0] += 1;
-        acc[s][1] += rank;
-        acc[s][2] += rank <= 1;
-        acc[s][3] += rank <= 3;
-        acc[s][4] += rank <= 5;
-        acc[s][5] += rank <= 10;
-        rr[s] += 1.0 / (double)rank;
+        const double inv = 1.0 / (double)rank;
+#pragma unroll
+        for (int ss = 0; ss < 2; ss++) {               // static indices: the accumulators stay in registers
+            const long long on = s == ss ? 1 : 0;
+            acc[ss][0] += on;
+            acc[ss][1] += on * rank;
+            acc[ss][2] += on & (rank <= 1);
+            acc[ss][3] += on & (rank <= 3);
+            acc[ss][4] += on & (rank <= 5);
+            acc[ss][5] += on & (rank <= 10);
+            rr[ss] += on ? inv : 0.0;
+        }
         if (hist) atomicAdd(hist + min((long long)hist_len - 1, rank), 1ull);
     }
+    // all 14 quantities together, in a FIXED order: butterfly inside each warp, then the 32 warp partials summed by warp 0
+    // in lane order -- deterministic, two block barriers in total
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
     for (int s = 0; s < 2; s++) {
-        for (int k = 0; k < 7; k++) {
-            if (k < 6) s_int[threadIdx.x] = acc[s][k]; else s_rr[threadIdx.x] = rr[s];
-            __syncthreads();
-            for (int w = MET_THREADS / 2; w > 0; w >>= 1) {
-                if (threadIdx.x < w) {
-                    if (k < 6) s_int[threadIdx.x] += s_int[threadIdx.x + w];
-                    else s_rr[threadIdx.x] += s_rr[threadIdx.x + w];
-                }
-                __syncthreads();
-            }
-            if (threadIdx.x == 0) {
-                if (k < 6) sums_out[s * 8 + k] = s_int[0]; else rr_out[s] = s_rr[0];
-            }
-            __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 6; k++)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc[s][k] += __shfl_xor_sync(0xffffffffu, acc[s][k], o);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) rr[s] += __shfl_xor_sync(0xffffffffu, rr[s], o);
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < 2; s++) {
+#pragma unroll
+            for (int k = 0; k < 6; k++) s_int[warp][s * 6 + k] = acc[s][k];
+            s_rr[warp][s] = rr[s];
         }
-        if (threadIdx.x == 0) { sums_out[s * 8 + 6] = 0; sums_out[s * 8 + 7] = 0; }
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int k = 0; k < 12; k++) {
+            long long v = s_int[lane][k];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) sums_out[(k / 6) * 8 + (k % 6)] = v;
+        }
+#pragma unroll
+        for (int s = 0; s < 2; s++) {
+            double v = s_rr[lane][s];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) { rr_out[s] = v; sums_out[s * 8 + 6] = 0; sums_out[s * 8 + 7] = 0; }
+        }
     }
 }
 

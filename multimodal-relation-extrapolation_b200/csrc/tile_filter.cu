@@ -138,6 +138,38 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_add_kernel(uint32_t *__rest
     if (blockIdx.x == 0 && threadIdx.x == 0) out[n] = *total;     // ptr[n] = number of pairs
 }
 
+// the same exclusive scan in ONE launch when the counters fit one block (n <= 1024 * 16): small jobs are launch-latency bound
+constexpr int SMALL_SCAN_MAX = 1024 * 16;
+__global__ void __launch_bounds__(1024) scan_small_kernel(const uint32_t *__restrict__ in, int n, uint32_t *__restrict__ out,
+                                                          uint32_t *__restrict__ total) {
+    __shared__ uint32_t sh[1024];
+    const int per = (n + 1023) / 1024, base = threadIdx.x * per;
+    uint32_t v[16], sum = 0;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        v[k] = (k < per && base + k < n) ? in[base + k] : 0u;
+        sum += v[k];
+    }
+    sh[threadIdx.x] = sum;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {
+        const uint32_t add = threadIdx.x >= off ? sh[threadIdx.x - off] : 0u;
+        __syncthreads();
+        sh[threadIdx.x] += add;
+        __syncthreads();
+    }
+    uint32_t run = sh[threadIdx.x] - sum;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        if (k < per && base + k < n) out[base + k] = run;
+        run += v[k];
+    }
+    if (threadIdx.x == 1023) {
+        out[n] = sh[1023];
+        *total = sh[1023];
+    }
+}
+
 int build_tile_filter(mre_ctx *ctx, const mre_rank_job *job, RankParams &p, int tile_q, int tile_e, cudaStream_t st) {
     p.tf_ptr = nullptr;
     p.tf_pairs = nullptr;
@@ -151,10 +183,15 @@ int build_tile_filter(mre_ctx *ctx, const mre_rank_job *job, RankParams &p, int 
     MRE_CUDA(cudaMemsetAsync(cnt, 0, (size_t)n * sizeof(uint32_t), st));
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((p.Q + 7) / 8, (int64_t)ctx->sm_count * 8));
     tf_count_kernel<<<grid, 256, 0, st>>>(p, tile_q, tile_e, cnt);
-    scan_blocks_kernel<<<(unsigned)nb, SCAN_THREADS, 0, st>>>(cnt, n, ptr, bsum);
-    scan_sums_kernel<<<1, 1024, 0, st>>>(bsum, nb, total);
-    scan_add_kernel<<<(unsigned)nb, SCAN_THREADS, 0, st>>>(ptr, n, bsum, total);
-    ctx->launches += 4;
+    if (n <= SMALL_SCAN_MAX) {
+        scan_small_kernel<<<1, 1024, 0, st>>>(cnt, (int)n, ptr, total);
+        ctx->launches += 2;
+    } else {
+        scan_blocks_kernel<<<(unsigned)nb, SCAN_THREADS, 0, st>>>(cnt, n, ptr, bsum);
+        scan_sums_kernel<<<1, 1024, 0, st>>>(bsum, nb, total);
+        scan_add_kernel<<<(unsigned)nb, SCAN_THREADS, 0, st>>>(ptr, n, bsum, total);
+        ctx->launches += 4;
+    }
     // capacity of the pair list: the caller's bound when it gave one, else read the exact total back (one small sync)
     int64_t cap = -1;
     if (job->filter == MRE_FILTER_NONE) cap = p.Q;

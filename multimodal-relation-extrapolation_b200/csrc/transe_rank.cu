@@ -70,8 +70,8 @@ __device__ __forceinline__ float transe_acc(const float *__restrict__ a, const f
                                             const float *__restrict__ e, int64_t D) {
     float acc = 0.f;
     const int n = (int)D;
-#pragma unroll 4
-    for (int d = 0; d < n; d += 4) {   // unrolled: the row fetches of several steps are in flight together (latency-bound callers)
+#pragma unroll 16
+    for (int d = 0; d < n; d += 4) {   // unrolled: the row fetches of 16 steps are in flight together (latency-bound callers)
         const float4 x = __ldg(reinterpret_cast<const float4 *>(a + d));
         const float4 y = __ldg(reinterpret_cast<const float4 *>(r + d));
         const float4 b = __ldg(reinterpret_cast<const float4 *>(e + d));
