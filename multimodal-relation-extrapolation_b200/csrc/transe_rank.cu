@@ -11,11 +11,15 @@
 // vector  v_q  such that |v_q[d] - e_j[d]| is bit-identical to the reference's element (tail: v = h + r;
 // head: v = -(r - t), because e + (r - t) == -(v - e) exactly), and computes s_true with the SAME sequential-d
 // accumulation the tile kernel uses, so `s_j < s_true` is decided on identical bits for every j.
-// The main kernel is persistent: each CTA walks 128-query x 128-entity work items; 128-row x 128-byte boxes of both
-// operands stream into a 3-stage shared-memory ring through TMA (cp.async.bulk.tensor, 128-byte swizzle, mbarrier
+// The main kernel is persistent, ONE 16-warp CTA per SM: each CTA walks 256-query x 128-entity work items; boxes of both
+// operands stream into a 4-stage shared-memory ring through TMA (cp.async.bulk.tensor, 128-byte swizzle, mbarrier
 // complete_tx; candidate lists are gathered into a dense table by a pre-pass), issued by whichever warp is last
-// to release a stage; the eight warps hold an 8x8 register micro-tile per thread and read the ring with
-// conflict-free 128-bit LDS.  The arithmetic is PACKED: query vectors are stored pair-interleaved ([slot / 2][d][slot & 1])
+// to release a stage; the sixteen warps hold an 8x8 register micro-tile per thread and read the ring with
+// conflict-free 128-bit LDS.  Why one big CTA: the SM sub-partition arbiter is greedy, so warps sharing a ring drift to
+// the ring's limit and the fast ones sleep; with two 8-warp CTAs per SM each CTA's pace was set by its least-favoured warp
+// on ANY sub-partition and the favoured warps of both CTAs idled together (measured: 0.826 of the FP32 add peak).  With all
+// sixteen warps of the SM on one ring every sub-partition holds the same fixed work per chunk whatever the arbiter prefers,
+// and early finishers run their epilogue while the others still compute (0.855).  The arithmetic is PACKED: query vectors are stored pair-interleaved ([slot / 2][d][slot & 1])
 // so one 64-bit register pair holds element d of two adjacent queries, and each (subtract, add-|.|) step is one
 // sub.f32x2 + one add.f32x2 (SASS FADD2, the entity value as a scalar-broadcast operand) for two (query, entity) pairs:
 // half the issue slots of the scalar form, which leaves the FP32 pipe -- not instruction issue -- as the bound, with the
@@ -38,19 +42,19 @@ namespace mre {
 
 constexpr int CHUNK = 32;            // floats of D per pipeline stage (128 B per row)
 #ifndef MRE_TRANSE_TQ
-#define MRE_TRANSE_TQ 128
+#define MRE_TRANSE_TQ 256
 #endif
 #ifndef MRE_TRANSE_STAGES
-#define MRE_TRANSE_STAGES 3
+#define MRE_TRANSE_STAGES 4
 #endif
 #ifndef MRE_TRANSE_CTAS
-#define MRE_TRANSE_CTAS 2
+#define MRE_TRANSE_CTAS 1
 #endif
 constexpr int TQ = MRE_TRANSE_TQ;                  // queries per work item of this kernel
 constexpr int STAGES = MRE_TRANSE_STAGES;
 constexpr int CTAS_PER_SM = MRE_TRANSE_CTAS;
 #ifndef MRE_RANK_WARPS
-#define MRE_RANK_WARPS 8      // 4 (a 16-query x 8-entity register tile per thread, 241 registers) measured 20 % slower on B200
+#define MRE_RANK_WARPS 16     // one 512-thread CTA per SM, four warps per SM sub-partition, all on ONE ring (see the kernel comment)
 #endif
 constexpr int CONSUMER_WARPS = MRE_RANK_WARPS;
 constexpr int RANK_THREADS = CONSUMER_WARPS * 32;
