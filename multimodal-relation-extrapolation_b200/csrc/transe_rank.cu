@@ -31,6 +31,7 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include <type_traits>
 #include <vector>
 
 #include "common.h"
@@ -288,6 +289,7 @@ transe_rank_kernel(const RankParams p, const __grid_constant__ CUtensorMap tm_q,
         const int64_t qbase = gd.q0 + (int64_t)qt * TQ;
         const int nq = (int)min((int64_t)TQ, gd.q0 + gd.nq - qbase);
         const int ne = (int)min((int64_t)TILE_E, gd.nc - (int64_t)et * TILE_E);
+        const int ni_act = (nq + 2 * NTQ - 1) / (2 * NTQ);    // slabs of NTQ pair-rows (2 NTQ queries) holding at least one query
         // this item's known-true pairs; the first 32 are fetched now so the epilogue does not wait on them
         const uint32_t pf0 = __ldg(p.tf_ptr + item), pf1 = __ldg(p.tf_ptr + item + 1);
         const uint32_t pair0 = pf0 + lane < pf1 ? __ldg(p.tf_pairs + pf0 + lane) : 0xffffffffu;
@@ -308,6 +310,11 @@ transe_rank_kernel(const RankParams p, const __grid_constant__ CUtensorMap tm_q,
 #pragma unroll
             for (int j = 0; j < 8; j++) acc[i][j] = 0ull;
 
+        // Full tiles run the unguarded loop (ptxas hoists the loads of the next slab over the current one's arithmetic); a
+        // partial query tile -- the last tile of a group, frequent with per-relation candidate groups -- runs a second copy
+        // of the loop that skips its empty 64-query slabs with a uniform branch.
+        auto tile_loop = [&](auto guard_tag) {
+        constexpr bool GUARD = decltype(guard_tag)::value;
         for (int c = 0; c < n_chunks; c++, it++) {
             const int stage = (int)(it % STAGES);
 #if MRE_DIAG_NOWAIT
@@ -331,6 +338,7 @@ transe_rank_kernel(const RankParams p, const __grid_constant__ CUtensorMap tm_q,
                 for (int j = 0; j < 8; j++) ev[j] = *reinterpret_cast<const float4 *>(sE + j * (16 * 128) + oe);
 #pragma unroll
                 for (int i = 0; i < NI; i++) {
+                    if (GUARD && i >= ni_act) break;           // uniform: a partial query tile skips its empty 64-query slabs
                     const ulonglong2 qa = *reinterpret_cast<const ulonglong2 *>(sQ + i * (NTQ * 128) + oq0);
                     const ulonglong2 qc = *reinterpret_cast<const ulonglong2 *>(sQ + i * (NTQ * 128) + oq1);
                     // per accumulator the order is d, d+1, d+2, d+3 (sequential sum); across accumulators the work is
@@ -365,6 +373,10 @@ transe_rank_kernel(const RankParams p, const __grid_constant__ CUtensorMap tm_q,
                 }
             }
         }
+
+        };
+        if (ni_act == NI) tile_loop(std::false_type{});
+        else tile_loop(std::true_type{});
 
 #if MRE_DIAG_NOEPI
         {   // diagnostic build only (wrong results): keep the accumulators live, skip the compare / count epilogue
