@@ -95,20 +95,31 @@ __global__ void zsl_relnorm_kernel(const float *__restrict__ rel_vecs, int64_t n
 // ------------------------------------------------------------------------------------------ the two tile GEMMs
 constexpr int ZBK = 16;
 
-// 8 x 8 register micro-tile update from one k-slice held in shared memory (a: [ZBK][BM], b: [ZBK][BN], both k-major)
+// 8 x 8 register micro-tile update from one k-slice held in shared memory (a: [ZBK][BM], b: [ZBK][BN], both k-major).
+// Packed: the accumulators are 8 x 4 pairs of adjacent columns and one step is fma.rn.f32x2 (a, a) * (b_j, b_j+1) + acc
+// (SASS FFMA2 with a scalar-broadcast operand): half the issue slots of 64 scalar FFMAs, same roundings.
+__device__ __forceinline__ void ffma2(unsigned long long &acc, float a, unsigned long long b) {
+    asm("{\n\t.reg .b64 t;\n\tmov.b64 t, {%1, %1};\n\tfma.rn.f32x2 %0, t, %2, %0;\n\t}" : "+l"(acc) : "f"(a), "l"(b));
+}
 template <int BM, int BN>
-__device__ __forceinline__ void zsl_mma_tile(const float *__restrict__ sa, const float *__restrict__ sb, int ra, int cb, float (&acc)[8][8]) {
+__device__ __forceinline__ void zsl_mma_tile(const float *__restrict__ sa, const float *__restrict__ sb, int ra, int cb,
+                                             unsigned long long (&acc)[8][4]) {
 #pragma unroll
     for (int k = 0; k < ZBK; k++) {
         const float4 a0 = *reinterpret_cast<const float4 *>(sa + k * BM + ra), a1 = *reinterpret_cast<const float4 *>(sa + k * BM + ra + 4);
-        const float4 b0 = *reinterpret_cast<const float4 *>(sb + k * BN + cb), b1 = *reinterpret_cast<const float4 *>(sb + k * BN + cb + 4);
+        // the thread's 8 columns are cb .. cb + 3 and BN / 2 + cb .. + 3: each 128-bit load is contiguous across the lanes
+        const ulonglong2 b0 = *reinterpret_cast<const ulonglong2 *>(sb + k * BN + cb), b1 = *reinterpret_cast<const ulonglong2 *>(sb + k * BN + BN / 2 + cb);
         const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-        const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        const unsigned long long b[4] = {b0.x, b0.y, b1.x, b1.y};
 #pragma unroll
         for (int i = 0; i < 8; i++)
 #pragma unroll
-            for (int j = 0; j < 8; j++) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+            for (int j = 0; j < 4; j++) ffma2(acc[i][j], a[i], b[j]);
     }
+}
+// column j of accumulator row i
+__device__ __forceinline__ float zsl_acc(const unsigned long long (&acc)[8][4], int i, int j) {
+    return __uint_as_float((j & 1) ? (uint32_t)(acc[i][j >> 1] >> 32) : (uint32_t)acc[i][j >> 1]);
 }
 
 // layer 1: Hid[p, n] = relu(sum_k X[p, k] W1[n, k] + b1[n]),  X[p, :] = A[head(p), :] + B[cand(p), :].  128 x 128 tiles.
@@ -123,7 +134,7 @@ __global__ void __launch_bounds__(256, 2) zsl_layer1_kernel(const mre_zsl_model 
     const int n0 = blockIdx.y * BN;
     const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
     // loader role: row lr of the tile, k-quad lq (two float4 per thread and operand)
-    const int lr = tid >> 1, lq = (tid & 1) * 2;
+    const int lr = tid & 127, lq = (tid >> 7) * 2;      // a warp stores 32 consecutive rows of one k: conflict-free transposition
     const int64_t prow = row0 + lr;
     const bool row_ok = prow < p0 + P;
     const float *xa = nullptr, *xb = nullptr;
@@ -133,11 +144,11 @@ __global__ void __launch_bounds__(256, 2) zsl_layer1_kernel(const mre_zsl_model 
     }
     const int wn = n0 + lr;
     const float *wrow = wn < N ? m.proj1_w + (int64_t)wn * D : nullptr;
-    float acc[8][8];
+    unsigned long long acc[8][4];
 #pragma unroll
     for (int i = 0; i < 8; i++)
 #pragma unroll
-        for (int j = 0; j < 8; j++) acc[i][j] = 0.f;
+        for (int j = 0; j < 4; j++) acc[i][j] = 0ull;
     // the next k-slice travels global -> registers while the current one is multiplied out of shared memory
     float4 nx[2], nw[2];
     auto fetch = [&](int k0) {
@@ -167,7 +178,7 @@ __global__ void __launch_bounds__(256, 2) zsl_layer1_kernel(const mre_zsl_model 
     for (int k0 = 0; k0 < D; k0 += ZBK) {
         const bool more = k0 + ZBK < D;
         if (more) fetch(k0 + ZBK);
-        zsl_mma_tile<BM, BN>(sa, sb, ty * 8, tx * 8, acc);
+        zsl_mma_tile<BM, BN>(sa, sb, ty * 8, tx * 4, acc);
         __syncthreads();
         if (more) {
             stage();
@@ -178,11 +189,11 @@ __global__ void __launch_bounds__(256, 2) zsl_layer1_kernel(const mre_zsl_model 
     for (int i = 0; i < 8; i++) {
         const int64_t p = row0 + ty * 8 + i;
         if (p >= p0 + P) continue;
-        float *o = hid + (p - p0) * N + n0 + tx * 8;
+        float *o = hid + (p - p0) * N + n0;
 #pragma unroll
         for (int j = 0; j < 8; j++) {
-            const int n = n0 + tx * 8 + j;
-            if (n < N) o[j] = fmaxf(acc[i][j] + m.proj1_b[n], 0.f);
+            const int c = (j < 4 ? 0 : BN / 2) + tx * 4 + (j & 3);
+            if (n0 + c < N) o[c] = fmaxf(zsl_acc(acc, i, j) + m.proj1_b[n0 + c], 0.f);
         }
     }
 }
@@ -200,13 +211,13 @@ __global__ void __launch_bounds__(256, 2) zsl_layer2_kernel(const mre_zsl_model 
     const int D = (int)m.D, K = 2 * D;
     const int64_t row0 = p0 + (int64_t)blockIdx.x * BM;
     const int tid = threadIdx.x, ty = tid >> 5, tx = tid & 31;
-    float acc[8][8];
+    unsigned long long acc[8][4];
 #pragma unroll
     for (int i = 0; i < 8; i++)
 #pragma unroll
-        for (int j = 0; j < 8; j++) acc[i][j] = 0.f;
+        for (int j = 0; j < 4; j++) acc[i][j] = 0ull;
     // loaders: hidden rows 64 x 16 = 256 float4 (one per thread); W2 rows 256 x 16 = 1024 float4 (four per thread)
-    const int ar = tid >> 2, aq = (tid & 3) * 4;
+    const int ar = tid & 63, aq = (tid >> 6) * 4;        // a warp stores 32 consecutive rows of one k
     const int64_t arow = row0 + ar;
     const float *hrow = arow < p0 + P ? hid + (arow - p0) * K : nullptr;
     float4 nh, nw[4];
@@ -215,7 +226,7 @@ __global__ void __launch_bounds__(256, 2) zsl_layer2_kernel(const mre_zsl_model 
         if (hrow && k0 + aq < K) nh = *reinterpret_cast<const float4 *>(hrow + k0 + aq);
 #pragma unroll
         for (int u = 0; u < 4; u++) {
-            const int f = tid + u * 256, n = f >> 2, kq = (f & 3) * 4;
+            const int n = tid, kq = u * 4;
             nw[u] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (n < D && k0 + kq < K) nw[u] = *reinterpret_cast<const float4 *>(m.proj2_w + (int64_t)n * K + k0 + kq);
         }
@@ -224,7 +235,7 @@ __global__ void __launch_bounds__(256, 2) zsl_layer2_kernel(const mre_zsl_model 
         sa[(aq + 0) * BM + ar] = nh.x; sa[(aq + 1) * BM + ar] = nh.y; sa[(aq + 2) * BM + ar] = nh.z; sa[(aq + 3) * BM + ar] = nh.w;
 #pragma unroll
         for (int u = 0; u < 4; u++) {
-            const int f = tid + u * 256, n = f >> 2, kq = (f & 3) * 4;
+            const int n = tid, kq = u * 4;
             sb[(kq + 0) * BN + n] = nw[u].x; sb[(kq + 1) * BN + n] = nw[u].y; sb[(kq + 2) * BN + n] = nw[u].z; sb[(kq + 3) * BN + n] = nw[u].w;
         }
     };
@@ -234,22 +245,24 @@ __global__ void __launch_bounds__(256, 2) zsl_layer2_kernel(const mre_zsl_model 
     for (int k0 = 0; k0 < K; k0 += ZBK) {
         const bool more = k0 + ZBK < K;
         if (more) fetch(k0 + ZBK);
-        zsl_mma_tile<BM, BN>(sa, sb, ty * 8, tx * 8, acc);
+        zsl_mma_tile<BM, BN>(sa, sb, ty * 8, tx * 4, acc);
         __syncthreads();
         if (more) {
             stage();
             __syncthreads();
         }
     }
-    // ---- epilogue: this lane holds columns c0 .. c0 + 7 of eight rows
-    const int c0 = tx * 8;
-    const bool col_ok = c0 < D;                                     // D is a multiple of 8: a lane is all in or all out
+    // ---- epilogue: this lane holds columns 4 tx .. 4 tx + 3 and 128 + 4 tx .. + 3 of eight rows
+    const int ca = tx * 4, cb2 = BN / 2 + tx * 4;                  // first column of the lane's two 4-column groups
+    const bool ok_a = ca < D, ok_b = cb2 < D;                      // D is a multiple of 8 (so of 4): a group is all in or all out
     float b2[8], g[8], be[8];
 #pragma unroll
     for (int j = 0; j < 8; j++) {
-        b2[j] = col_ok ? m.proj2_b[c0 + j] : 0.f;
-        g[j] = col_ok ? m.ln_g[c0 + j] : 0.f;
-        be[j] = col_ok ? m.ln_b[c0 + j] : 0.f;
+        const int c = (j < 4 ? ca : cb2) + (j & 3);
+        const bool ok = j < 4 ? ok_a : ok_b;
+        b2[j] = ok ? m.proj2_b[c] : 0.f;
+        g[j] = ok ? m.ln_g[c] : 0.f;
+        be[j] = ok ? m.ln_b[c] : 0.f;
     }
     const float inv_d = 1.f / (float)D;
 #pragma unroll                                                      // (static indices: the accumulators stay in registers)
@@ -261,7 +274,9 @@ __global__ void __launch_bounds__(256, 2) zsl_layer2_kernel(const mre_zsl_model 
         float y[8], s = 0.f;
 #pragma unroll
         for (int j = 0; j < 8; j++) {
-            y[j] = col_ok ? acc[i][j] + b2[j] + (xa[c0 + j] + xb[c0 + j]) : 0.f;
+            const int c = (j < 4 ? ca : cb2) + (j & 3);
+            const bool ok = j < 4 ? ok_a : ok_b;
+            y[j] = ok ? zsl_acc(acc, i, j) + b2[j] + (xa[c] + xb[c]) : 0.f;
             s += y[j];
         }
 #pragma unroll
@@ -270,7 +285,7 @@ __global__ void __launch_bounds__(256, 2) zsl_layer2_kernel(const mre_zsl_model 
         float v = 0.f;
 #pragma unroll
         for (int j = 0; j < 8; j++) {
-            const float d = col_ok ? y[j] - mu : 0.f;
+            const float d = (j < 4 ? ok_a : ok_b) ? y[j] - mu : 0.f;
             v = fmaf(d, d, v);
         }
 #pragma unroll
@@ -279,7 +294,7 @@ __global__ void __launch_bounds__(256, 2) zsl_layer2_kernel(const mre_zsl_model 
         float ln[8], nn = 0.f;
 #pragma unroll
         for (int j = 0; j < 8; j++) {
-            ln[j] = col_ok ? (y[j] - mu) * rstd * g[j] + be[j] : 0.f;
+            ln[j] = (j < 4 ? ok_a : ok_b) ? (y[j] - mu) * rstd * g[j] + be[j] : 0.f;
             nn = fmaf(ln[j], ln[j], nn);
         }
 #pragma unroll
@@ -289,9 +304,13 @@ __global__ void __launch_bounds__(256, 2) zsl_layer2_kernel(const mre_zsl_model 
         float total = 0.f;
         for (int k = 0; k < n_vec; k++) {
             float d = 0.f;
-            if (col_ok) {
-                const float4 r0 = *reinterpret_cast<const float4 *>(rv + (int64_t)k * D + c0), r1 = *reinterpret_cast<const float4 *>(rv + (int64_t)k * D + c0 + 4);
-                d = ln[0] * r0.x + ln[1] * r0.y + ln[2] * r0.z + ln[3] * r0.w + ln[4] * r1.x + ln[5] * r1.y + ln[6] * r1.z + ln[7] * r1.w;
+            if (ok_a) {
+                const float4 r0 = *reinterpret_cast<const float4 *>(rv + (int64_t)k * D + ca);
+                d = ln[0] * r0.x + ln[1] * r0.y + ln[2] * r0.z + ln[3] * r0.w;
+            }
+            if (ok_b) {
+                const float4 r1 = *reinterpret_cast<const float4 *>(rv + (int64_t)k * D + cb2);
+                d += ln[4] * r1.x + ln[5] * r1.y + ln[6] * r1.z + ln[7] * r1.w;
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
