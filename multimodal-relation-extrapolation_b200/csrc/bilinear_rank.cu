@@ -45,7 +45,10 @@ namespace mre {
 
 constexpr int BN = 256;                 // entities per tile (UMMA N)
 constexpr int BM = 128;                 // queries per tile (UMMA M)
-constexpr int BK = 64;                  // BF16 elements of K per stage = one 128-byte swizzle atom
+#ifndef MRE_BIL_BK
+#define MRE_BIL_BK 64
+#endif
+constexpr int BK = MRE_BIL_BK;          // BF16 elements of K per stage: 64 = one 128-byte swizzle atom per row, 32 = a 64-byte atom (more, smaller stages)
 constexpr int UK = 16;                  // elements of K per tcgen05.mma kind::f16
 constexpr int TF_BK = 32, TF_UK = 8;    // the same for the kind::tf32 peak probe
 constexpr uint32_t A_BYTES = BM * BK * 2;   // 16 KiB
@@ -54,11 +57,12 @@ constexpr uint32_t B_BYTES = BN * BK * 2;   // 32 KiB
 // CTA pair (cta_group::2): M = 256 over two CTAs, each CTA stages its own 128 query rows and HALF of the candidate tile
 // (128 rows) -- 64 KiB per stage, 3 stages -- and the pair's MMA reads both halves: a third less L2 -> SM traffic per flop.
 template <bool PAIR> struct StageCfg {
-    static constexpr int STAGES = PAIR ? 3 : 2;
+    static constexpr int STAGES = (PAIR ? 3 : 2) * (64 / BK);
     static constexpr uint32_t B_HALF = PAIR ? B_BYTES / 2 : B_BYTES;
     static constexpr uint32_t BYTES = 2 * A_BYTES + 2 * B_HALF;
 };
-constexpr int MAX_STAGES = 3;
+constexpr int MAX_STAGES = 3 * (64 / BK);
+__device__ __forceinline__ uint64_t umma_desc_op(uint32_t addr) { return BK == 64 ? umma_desc_k128(addr) : umma_desc_k64(addr); }
 #ifndef MRE_EPI_WARPS
 #define MRE_EPI_WARPS 4
 #endif
@@ -68,7 +72,7 @@ constexpr int BIL_THREADS = (2 + EPI_WARPS + RESCORE_WARPS) * 32;
 constexpr int EPI_WARP0 = 2;
 constexpr int PEND_CAP = 128;                // per epilogue warp: ring of near-ties handed to its re-score warp through shared memory
 constexpr int MASK_STRIDE = 9;               // words per row of the per-warp known-true mask (8 + 1 pad: conflict-free)
-constexpr size_t BIL_SMEM = 1024 + (size_t)2 * (2 * A_BYTES + 2 * B_BYTES) + 16 * sizeof(uint64_t) + EPI_WARPS * 32 * MASK_STRIDE * 4 + RESCORE_WARPS * (PEND_CAP * sizeof(uint2) + 16) + 64;   // both configurations: 192 KiB of stages
+constexpr size_t BIL_SMEM = 1024 + (size_t)2 * (64 / BK) * (2 * A_BYTES + 2 * B_BYTES) + 32 * sizeof(uint64_t) + EPI_WARPS * 32 * MASK_STRIDE * 4 + RESCORE_WARPS * (PEND_CAP * sizeof(uint2) + 16) + 64;   // both configurations: 192 KiB of stages
 constexpr uint32_t TMEM_COLS = 512;     // two 256-column accumulator buffers
 
 struct BilParams {
@@ -221,7 +225,7 @@ bilinear_rank_kernel(const BilParams bp, const __grid_constant__ CUtensorMap tm_
     const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + MAX_STAGES), tfull0 = smem_u32(bars + 2 * MAX_STAGES),
                    tempty0 = smem_u32(bars + 2 * MAX_STAGES + 2);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * MAX_STAGES + 4);
-    uint32_t *mask_all = reinterpret_cast<uint32_t *>(bars + 16);      // per epilogue warp: [32 rows][MASK_STRIDE] known-true bits
+    uint32_t *mask_all = reinterpret_cast<uint32_t *>(bars + 32);      // per epilogue warp: [32 rows][MASK_STRIDE] known-true bits
     uint2 *pend_all = reinterpret_cast<uint2 *>(mask_all + EPI_WARPS * 32 * MASK_STRIDE);   // per epilogue warp: [PEND_CAP] ring of near-ties
     volatile uint32_t *pend_ctl = reinterpret_cast<volatile uint32_t *>(pend_all + RESCORE_WARPS * PEND_CAP);   // per ring: published, consumed, done
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -313,9 +317,9 @@ bilinear_rank_kernel(const BilParams bp, const __grid_constant__ CUtensorMap tm_
                     const int n_ks = (int)min((int64_t)(BK / UK), (bp.k8 - (int64_t)kb * BK + UK - 1) / UK);
                     for (int ks = 0; ks < n_ks; ks++) {
                         const uint32_t koff = ks * UK * 2;   // bytes along K inside the 128-byte swizzle atom
-                        const uint64_t ahi = umma_desc_k128(base + koff), alo = umma_desc_k128(base + A_BYTES + koff);
-                        const uint64_t bhi = umma_desc_k128(base + 2 * A_BYTES + koff);
-                        const uint64_t blo = umma_desc_k128(base + 2 * A_BYTES + B_HALF + koff);
+                        const uint64_t ahi = umma_desc_op(base + koff), alo = umma_desc_op(base + A_BYTES + koff);
+                        const uint64_t bhi = umma_desc_op(base + 2 * A_BYTES + koff);
+                        const uint64_t blo = umma_desc_op(base + 2 * A_BYTES + B_HALF + koff);
                         if (PAIR) {
                             umma_bf16_pair(d_tmem, ahi, bhi, idesc, (kb | ks) != 0);
                             umma_bf16_pair(d_tmem, alo, bhi, idesc, 1);
@@ -598,14 +602,15 @@ bilinear_rank_kernel(const BilParams bp, const __grid_constant__ CUtensorMap tm_
 }
 
 // ------------------------------------------------------------------------------------------ dense MMA peak probes
+constexpr uint32_t PROBE_A = BM * 128, PROBE_B = BN * 128;   // one 128-byte-swizzled k-block of each operand
 template <bool BF16>
 __global__ void __launch_bounds__(128, 1) mma_probe_kernel(int iters) {
     extern __shared__ unsigned char smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     unsigned char *al = smem_raw + (base - smem_u32(smem_raw));
-    uint64_t *bar = reinterpret_cast<uint64_t *>(al + A_BYTES + B_BYTES);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(al + PROBE_A + PROBE_B);
     uint32_t *slot = reinterpret_cast<uint32_t *>(bar + 1);
-    for (uint32_t i = threadIdx.x; i < (A_BYTES + B_BYTES) / 4; i += blockDim.x) reinterpret_cast<float *>(al)[i] = 0.f;
+    for (uint32_t i = threadIdx.x; i < (PROBE_A + PROBE_B) / 4; i += blockDim.x) reinterpret_cast<float *>(al)[i] = 0.f;
     if (threadIdx.x == 0) { mbar_init(smem_u32(bar), 1); fence_barrier_init(); }
     fence_proxy_async();
     if (threadIdx.x < 32) tmem_alloc(smem_u32(slot), 256);
@@ -617,8 +622,8 @@ __global__ void __launch_bounds__(128, 1) mma_probe_kernel(int iters) {
         constexpr uint32_t idesc = BF16 ? umma_idesc_bf16(BM, BN) : umma_idesc_tf32(BM, BN);
         for (int i = 0; i < iters; i++) {
             const uint32_t koff = (i & 3) * 32;   // one k-step = 32 bytes of the 128-byte swizzle atom in both kinds
-            if (BF16) umma_bf16(tmem, umma_desc_k128(base + koff), umma_desc_k128(base + A_BYTES + koff), idesc, i != 0);
-            else umma_tf32(tmem, umma_desc_k128(base + koff), umma_desc_k128(base + A_BYTES + koff), idesc, i != 0);
+            if (BF16) umma_bf16(tmem, umma_desc_k128(base + koff), umma_desc_k128(base + PROBE_A + koff), idesc, i != 0);
+            else umma_tf32(tmem, umma_desc_k128(base + koff), umma_desc_k128(base + PROBE_A + koff), idesc, i != 0);
         }
         umma_commit(smem_u32(bar));
         mbar_wait(smem_u32(bar), 0);
@@ -631,7 +636,7 @@ __global__ void __launch_bounds__(128, 1) mma_probe_kernel(int iters) {
 template <bool BF16>
 static int probe_mma_peak(mre_ctx *ctx, double *flops_per_s) {
     MRE_CHECK_ARG(flops_per_s != nullptr, "NULL output");
-    const size_t smem = 1024 + A_BYTES + B_BYTES + 64;
+    const size_t smem = 1024 + PROBE_A + PROBE_B + 64;
     MRE_CUDA(cudaFuncSetAttribute(mma_probe_kernel<BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int iters = 8192;
     double best = 0;

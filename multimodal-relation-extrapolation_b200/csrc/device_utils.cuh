@@ -197,6 +197,15 @@ __device__ __forceinline__ uint64_t umma_desc_k128(uint32_t smem_addr) {
     d |= (uint64_t)2 << 61;
     return d;
 }
+// the same for 64-byte rows under SWIZZLE_64B (8-row groups 512 B apart, layout code 4)
+__device__ __forceinline__ uint64_t umma_desc_k64(uint32_t smem_addr) {
+    uint64_t d = (uint64_t)((smem_addr >> 4) & 0x3FFFu);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(512 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)4 << 61;
+    return d;
+}
 // instruction descriptor: C = F32 (1 @ bit 4), A = B = TF32 (2 @ bits 7 and 10), both K-major, N >> 3 @ 17, M >> 4 @ 24
 __host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
