@@ -4,6 +4,8 @@
   NegativeSampling       the sampler + structural-loss half of module.NegativeSampling (:114-140, 177-185, 196-229,
                          307-314, 321-375): neg_sample_fn / generate_eval_list / scoring_fn / regularization
   build_test_candidates  utils/gen_mode_candidates.py:15-39 (regenerates the missing {mode}_candidates.json)
+  load_tasks, gen_e1rel_e2, gen_rel2candidates, evaluate_from_dir
+                         module/utils.py:194-207, utils/gen_e1r_e2_all.py:14-19, utils/gen_rel2candidates.py:14-27
   zsl_rank_metrics       ZSLmodule.eval's rank/metric block (module/zsl_module.py:699-745): Hits@10/5/1 + MRR
   ZSLEvaluator           ZSLmodule.eval end to end (module/zsl_module.py:635-745): Extractor + cosine-mean + rank on the GPU
 """
@@ -134,15 +136,73 @@ class NegativeSampling(PaperScorer):
         return loss
 
 
-def build_test_candidates(triples, rel2candidates, e1rel_e2):
+def build_test_candidates(triples, rel2candidates, e1rel_e2, entity2id=None):
     """triples: iterable of (head, rel, tail) symbols -> {rel: {"head\\trel\\ttail": [tail, cand, ...]}} with the true tail
-    first, then every candidate of the relation that is neither a known tail of (head, rel) nor the true tail."""
+    first, then every candidate of the relation that is a known entity (utils/gen_mode_candidates.py:31-32), neither a known
+    tail of (head, rel) nor the true tail (:33-34)."""
     out = {}
     for head, rel, tail in triples:
         known = set(e1rel_e2.get(head + rel, ()))
-        cands = [tail] + [c for c in rel2candidates[rel] if c not in known and c != tail]
+        cands = [tail] + [c for c in rel2candidates[rel]
+                          if (entity2id is None or c in entity2id) and c not in known and c != tail]
         out.setdefault(rel, {})["\t".join((head, rel, tail))] = cands
     return out
+
+
+# ---- the reference's data files (SURVEY 8f-2): loaders and the generators of the artefacts its repository does not bundle
+def load_tasks(data_path, mode="test"):
+    """{mode}_tasks_zsl.json -> (tasks dict, (h, r, t) int64 id arrays, entity2id, relation2id) with entity2ids_zsl.json /
+    relation2ids.json, as load_appendix_data reads them (module/utils.py:194-207)"""
+    import json
+    import os
+    e_id = json.load(open(os.path.join(data_path, "entity2ids_zsl.json")))
+    r_id = json.load(open(os.path.join(data_path, "relation2ids.json")))
+    tasks = json.load(open(os.path.join(data_path, f"{mode}_tasks_zsl.json")))
+    h, r, t = [], [], []
+    for rel in tasks:
+        for head, rela, tail in tasks[rel]:
+            h.append(e_id[head]); r.append(r_id[rela]); t.append(e_id[tail])
+    return tasks, (np.asarray(h, np.int64), np.asarray(r, np.int64), np.asarray(t, np.int64)), e_id, r_id
+
+
+def gen_e1rel_e2(triples):
+    """e1rel_e2_all.json (utils/gen_e1r_e2_all.py:14-19): head + relation symbol -> list of tails, from (head, rel, tail) symbols"""
+    out = {}
+    for head, rel, tail in triples:
+        out.setdefault(head + rel, []).append(tail)
+    return out
+
+
+def gen_rel2candidates(triples, entities, n=300, seed=None):
+    """rel2candidates_all.json (utils/gen_rel2candidates.py:14-27): `n` entities drawn without replacement per relation that
+    occurs in the triples (the reference uses the unseeded `random` module; pass `seed` for a reproducible file)"""
+    import random
+    rng = random.Random(seed)
+    rels = []
+    for _, rel, _ in triples:
+        if rel not in rels:
+            rels.append(rel)
+    entities = list(entities)
+    return {rel: rng.sample(entities, n) for rel in rels}
+
+
+def evaluate_from_dir(data_path, ent_embs, rel_embs, mode="test", hits_at_k=(1, 3, 10), ranker=None, verbose=True):
+    """main.evaluate end to end from a reference dataset directory: reads entity2ids_zsl.json, relation2ids.json,
+    {mode}_tasks_zsl.json, rel2candidates_all.json, uses {mode}_candidates.json / e1rel_e2_all.json when present and
+    regenerates them otherwise (from the tasks themselves -- the bundled ZS datasets carry no train.tsv)."""
+    import json
+    import os
+    tasks, _, e2id, r2id = load_tasks(data_path, mode)
+    cand_file = os.path.join(data_path, f"{mode}_candidates.json")
+    if os.path.exists(cand_file):
+        test_candidates = json.load(open(cand_file))
+    else:
+        rel2cand = json.load(open(os.path.join(data_path, "rel2candidates_all.json")))
+        triples = [tuple(tri) for rel in tasks for tri in tasks[rel]]
+        e1_file = os.path.join(data_path, "e1rel_e2_all.json")
+        e1rel_e2 = json.load(open(e1_file)) if os.path.exists(e1_file) else gen_e1rel_e2(triples)
+        test_candidates = build_test_candidates(triples, rel2cand, e1rel_e2, e2id)
+    return evaluate(ent_embs, rel_embs, e2id, r2id, test_candidates, hits_at_k=hits_at_k, ranker=ranker, verbose=verbose)
 
 
 def _plan_candidates(test_candidates, e2id, r2id):
