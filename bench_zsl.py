@@ -20,18 +20,25 @@ D, MAX_NB, N_VEC = 200, 50, 20
 
 def load(rank=0):
     import golden_util as gu
-    from oracle import zsl_oracle as zo, paper_oracle as po
     z = gu.load("fb15k237_zs.npz")
     E, R = int(z["E"]), int(z["R"])
     h, r, t = (z[k].astype(np.int64) for k in ("test_h", "test_r", "test_t"))
     order = np.argsort(r, kind="stable")
     h, r, t = h[order], r[order], t[order]
     rel2cand = {int(rr): z["cand_ent"][i].astype(np.int64) for i, rr in enumerate(z["cand_rel"])}
-    known = po.known_tails(h, r, t)
-    cands = po.build_candidates(h, r, t, rel2cand, known)                       # true tail first
+    # candidate lists as utils/gen_mode_candidates.py:15-39 builds them: true tail first, then the relation's candidates that are
+    # neither a known tail of (head, relation) nor the true tail
+    known = {}
+    for hh, rr, tt in zip(h.tolist(), r.tolist(), t.tolist()):
+        known.setdefault((hh, rr), set()).add(tt)
+    cands = []
+    for hh, rr, tt in zip(h.tolist(), r.tolist(), t.tolist()):
+        c = rel2cand[rr]
+        keep = c[~np.isin(c, np.fromiter(known[(hh, rr)], np.int64)) & (c != tt)]
+        cands.append(np.concatenate([[tt], keep]).astype(np.int64))
     rng = np.random.default_rng(192 + rank)
     n_symbols = E + R
-    w = zo.seeded_extractor_weights(192, n_symbols, D)
+    w = gu.seeded_extractor_weights(192, n_symbols, D)
     deg = rng.integers(1, MAX_NB + 1, E)
     conn = np.full((E, MAX_NB), n_symbols, np.int64)
     mask = np.arange(MAX_NB)[None, :] < deg[:, None]

@@ -12,30 +12,21 @@ cannot import here stubbed) on seeded weights and asserts `extractor_query_vecto
 tests/golden/golden_zsl.npz holds the reference's scores and ranks.  `separable_scores` is the algebraically equal form the
 CUDA path computes (per-entity halves A_h + B_c); it differs from the reference by FP32 rounding only.
 """
+import os
+import sys
+
 import numpy as np
 import torch
 import torch.nn.functional as F
 
 D_DEFAULT = 200
 
-
-def seeded_extractor_weights(seed, n_symbols, D=D_DEFAULT):
-    """Extractor state (names as in the reference's state_dict) drawn with numpy PCG64: same bits on any box."""
-    rng = np.random.default_rng(seed)
-    def lin(o, i):
-        a = np.sqrt(6.0 / (o + i))
-        return rng.uniform(-a, a, (o, i)).astype(np.float32), rng.uniform(-0.1, 0.1, o).astype(np.float32)
-    w = {}
-    emb = (rng.standard_normal((n_symbols + 1, D)) / np.sqrt(D)).astype(np.float32)
-    emb[n_symbols] = 0.0                                        # padding_idx row
-    w["symbol_emb.weight"] = emb
-    for name, (o, i) in {"gcn_w": (D // 2, D), "fc1": (D // 2, D), "fc2": (D // 2, D), "reshape_layer": (D, 2 * D),
-                         "support_encoder.proj1": (2 * D, D), "support_encoder.proj2": (D, 2 * D)}.items():
-        w[name + ".weight"], w[name + ".bias"] = lin(o, i)
-    w["gcn_b"] = np.zeros(D, np.float32)                        # declared by the reference, never used in forward
-    w["support_encoder.layer_norm.weight"] = (1.0 + 0.1 * rng.standard_normal(D)).astype(np.float32)
-    w["support_encoder.layer_norm.bias"] = (0.1 * rng.standard_normal(D)).astype(np.float32)
-    return w
+# the seeded input generators live with the fixtures (tests/golden/golden_util.py: shared by tests and bench.py, which may not
+# import this package outside its cpu_baseline leg); re-exported here for the golden scripts
+_gdir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+if _gdir not in sys.path:
+    sys.path.insert(0, _gdir)
+from golden_util import seeded_extractor_weights, synthetic_zsl_setup  # noqa: E402,F401
 
 
 def extractor_query_vectors(w, pairs, left_conn, left_deg, right_conn, right_deg):
@@ -103,23 +94,3 @@ def separable_scores(w, A, B, head, cands, rel_vecs):
     r = rel_vecs.astype(np.float64)
     cos = (g @ r.T) / (np.linalg.norm(g, axis=1)[:, None] * np.linalg.norm(r, axis=1)[None, :])
     return cos.mean(1)
-
-
-def synthetic_zsl_setup(seed=192, n_ent=300, n_rel=3, D=D_DEFAULT, max_nb=50, T=14):
-    """The seeded graph of tests/golden/golden_zsl.npz: symbols = entities 0..n_ent-1, then the relations, then the pad id;
-    connections [n_ent, max_nb, 2] (relation symbol, neighbour symbol) padded with the pad id, degrees, T candidate lists."""
-    rng = np.random.default_rng(seed)
-    n_symbols = n_ent + n_rel
-    deg = rng.integers(1, max_nb + 1, n_ent)
-    deg[:5] = [1, 2, max_nb, max_nb, 3]
-    conn = np.full((n_ent, max_nb, 2), n_symbols, np.int64)
-    for e in range(n_ent):
-        conn[e, :deg[e], 0] = n_ent + rng.integers(0, n_rel, deg[e])
-        conn[e, :deg[e], 1] = rng.integers(0, n_ent, deg[e])
-    sizes = [1, 2, 17, 33, 64, 65, 128, 129, 150, 200, 257, 40, 90, 7][:T]
-    heads = rng.integers(0, n_ent, T)
-    rels = rng.integers(0, n_rel, T)
-    cands = [rng.choice(n_ent, s, replace=False).astype(np.int64) for s in sizes]      # candidate 0 = the true tail
-    cands[3][5] = cands[3][0]                                                           # an exact tie with the true candidate
-    rel_vecs = rng.standard_normal((n_rel, 20, D)).astype(np.float32)
-    return n_symbols, conn, deg.astype(np.float32), heads, rels, cands, rel_vecs
