@@ -119,7 +119,7 @@ def main(args, rank, world, local):
                                                 wl["E"], MAX_NB, ev.A.data_ptr(), ev.B.data_ptr(), stream()))
 
     def rank_all(dh, dr, dp, di):
-        L.check(L.lib().mre_zsl_rank(ctx._h, ev.model, ev.A.data_ptr(), ev.B.data_ptr(), dh.data_ptr(), dr.data_ptr(), dp.data_ptr(),
+        L.check(L.lib().mre_zsl_rank(ctx._h, ev.model, ev.A.data_ptr(), ev.B.data_ptr(), wl["E"], dh.data_ptr(), dr.data_ptr(), dp.data_ptr(),
                                      di.data_ptr(), T, P, rv.data_ptr(), rv.shape[0], N_VEC, None, counts.data_ptr(), stream()))
 
     def step_dev():

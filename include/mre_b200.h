@@ -284,10 +284,12 @@ int mre_zsl_entity_features(mre_ctx *ctx, const mre_zsl_model *model, const int6
  * scores (nullable): float32 [P].  counts: int32 [4][T] in mre_metrics' layout -- rows 0 and 2 = #candidates scoring
  * HIGHER than the true one, rows 1 and 3 = #exact ties: rank = counts[0] + 1 (ties resolved for the true candidate) up to
  * counts[0] + counts[1] + 1 (MRE_RANK_PESSIMISTIC); the reference's argsort leaves exact ties unpinned.
+ * A, B: the [n_ent, D] halves mre_zsl_entity_features wrote (n_ent rows: the hidden layer of the support encoder is
+ * split per entity the same way, W1 A + b1 and W1 B, before the per-pair tensor-core contraction with W2).
  */
-int mre_zsl_rank(mre_ctx *ctx, const mre_zsl_model *model, const float *A, const float *B, const int64_t *q_head,
-                 const int64_t *q_rel, const int64_t *cand_ptr, const int64_t *cand_idx, int64_t T, int64_t P,
-                 const float *rel_vecs, int64_t n_rel, int32_t n_vec, float *scores, int32_t *counts, void *stream);
+int mre_zsl_rank(mre_ctx *ctx, const mre_zsl_model *model, const float *A, const float *B, int64_t n_ent,
+                 const int64_t *q_head, const int64_t *q_rel, const int64_t *cand_ptr, const int64_t *cand_idx, int64_t T,
+                 int64_t P, const float *rel_vecs, int64_t n_rel, int32_t n_vec, float *scores, int32_t *counts, void *stream);
 
 /* ------------------------------------------------------------------------------------------ training */
 /*

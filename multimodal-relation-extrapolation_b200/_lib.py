@@ -126,7 +126,7 @@ def lib():
     L.mre_sample_host.argtypes = samp
     L.mre_sample_subgraph.argtypes = [vp, vp, u64, u64, u32, vp, vp, vp, i64, vp, i64, vp, i64, i64, i32, i32, vp, vp, vp, vp]
     L.mre_zsl_entity_features.argtypes = [vp, P(ZslModel), vp, vp, vp, i64, i32, vp, vp, vp]
-    L.mre_zsl_rank.argtypes = [vp, P(ZslModel), vp, vp, vp, vp, vp, vp, i64, i64, vp, i64, i32, vp, vp, vp]
+    L.mre_zsl_rank.argtypes = [vp, P(ZslModel), vp, vp, i64, vp, vp, vp, vp, i64, i64, vp, i64, i32, vp, vp, vp]
     L.mre_transe_margin_step.argtypes = [vp, vp, vp, i64, i64, i64, vp, vp, vp, i64, i64, f32, i32, i32, vp, vp, vp, vp, vp]
     L.mre_sgd_update.argtypes = [vp, vp, vp, i64, f32, vp]
     L.mre_score_triples.argtypes = [vp, i32, vp, vp, vp, vp, i64, vp, vp, vp, i64, i32, i32, vp, vp]

@@ -261,12 +261,12 @@ int mre_zsl_entity_features(mre_ctx *ctx, const mre_zsl_model *model, const int6
     return zsl_entity_features(ctx, model, ent_symbol, conn, deg, n_ent, max_neighbor, A, B, (cudaStream_t)stream);
 }
 
-int mre_zsl_rank(mre_ctx *ctx, const mre_zsl_model *model, const float *A, const float *B, const int64_t *q_head, const int64_t *q_rel,
-                 const int64_t *cand_ptr, const int64_t *cand_idx, int64_t T, int64_t P, const float *rel_vecs, int64_t n_rel,
-                 int32_t n_vec, float *scores, int32_t *counts, void *stream) {
+int mre_zsl_rank(mre_ctx *ctx, const mre_zsl_model *model, const float *A, const float *B, int64_t n_ent, const int64_t *q_head,
+                 const int64_t *q_rel, const int64_t *cand_ptr, const int64_t *cand_idx, int64_t T, int64_t P, const float *rel_vecs,
+                 int64_t n_rel, int32_t n_vec, float *scores, int32_t *counts, void *stream) {
     MRE_CHECK_ARG(ctx != nullptr, "ctx is NULL");
     MRE_CUDA(cudaSetDevice(ctx->device));
-    return zsl_rank(ctx, model, A, B, q_head, q_rel, cand_ptr, cand_idx, T, P, rel_vecs, n_rel, n_vec, scores, counts, (cudaStream_t)stream);
+    return zsl_rank(ctx, model, A, B, n_ent, q_head, q_rel, cand_ptr, cand_idx, T, P, rel_vecs, n_rel, n_vec, scores, counts, (cudaStream_t)stream);
 }
 
 int mre_probe_fp32_peak(mre_ctx *ctx, double *lane_ops_per_s) {

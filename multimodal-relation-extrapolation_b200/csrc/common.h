@@ -144,9 +144,9 @@ int transe_backward(mre_ctx *ctx, const float *ent, const float *rel, int64_t D,
                     float *grad_rel, cudaStream_t st);
 int zsl_entity_features(mre_ctx *ctx, const mre_zsl_model *m, const int64_t *ent_symbol, const int64_t *conn, const float *deg,
                         int64_t n_ent, int32_t max_nb, float *A, float *B, cudaStream_t st);
-int zsl_rank(mre_ctx *ctx, const mre_zsl_model *m, const float *A, const float *B, const int64_t *q_head, const int64_t *q_rel,
-             const int64_t *cand_ptr, const int64_t *cand_idx, int64_t T, int64_t P, const float *rel_vecs, int64_t n_rel,
-             int32_t n_vec, float *scores, int32_t *counts, cudaStream_t st);
+int zsl_rank(mre_ctx *ctx, const mre_zsl_model *m, const float *A, const float *B, int64_t n_ent, const int64_t *q_head,
+             const int64_t *q_rel, const int64_t *cand_ptr, const int64_t *cand_idx, int64_t T, int64_t P, const float *rel_vecs,
+             int64_t n_rel, int32_t n_vec, float *scores, int32_t *counts, cudaStream_t st);
 int probe_fp32_peak(mre_ctx *ctx, double *lane_ops_per_s);
 int probe_tf32_peak(mre_ctx *ctx, double *flops_per_s);
 int probe_bf16_peak(mre_ctx *ctx, double *flops_per_s);

@@ -14,11 +14,13 @@
 // over all pairs of the sweep, the second with LayerNorm + cosine-mean fused in its epilogue (whole rows stay in one warp),
 // and a per-triple compare/count.  FP32 throughout (the reference's arithmetic); scores agree to rounding.
 #include <math.h>
+#include <stdlib.h>
 
 #include <algorithm>
 
 #include "common.h"
 #include "device_utils.cuh"
+#include "tma_host.h"
 
 namespace mre {
 
@@ -126,7 +128,7 @@ __device__ __forceinline__ float zsl_acc(const unsigned long long (&acc)[8][4], 
 __global__ void __launch_bounds__(256, 2) zsl_layer1_kernel(const mre_zsl_model m, const float *__restrict__ A, const float *__restrict__ B,
                                                          const int64_t *__restrict__ q_head, const int64_t *__restrict__ cand,
                                                          const int32_t *__restrict__ pair_triple, int64_t p0, int64_t P,
-                                                         float *__restrict__ hid) {
+                                                         float *__restrict__ hid, int relu, int bias) {
     constexpr int BM = 128, BN = 128;
     __shared__ __align__(16) float sa[ZBK * BM], sb[ZBK * BN];
     const int D = (int)m.D, N = 2 * D;
@@ -139,8 +141,12 @@ __global__ void __launch_bounds__(256, 2) zsl_layer1_kernel(const mre_zsl_model 
     const bool row_ok = prow < p0 + P;
     const float *xa = nullptr, *xb = nullptr;
     if (row_ok) {
-        xa = A + q_head[pair_triple[prow]] * D;
-        xb = B + cand[prow] * D;
+        if (pair_triple) {
+            xa = A + q_head[pair_triple[prow]] * D;
+            xb = B + cand[prow] * D;
+        } else {
+            xa = A + prow * D;                                      // table mode: row p of A alone (the per-entity hidden halves)
+        }
     }
     const int wn = n0 + lr;
     const float *wrow = wn < N ? m.proj1_w + (int64_t)wn * D : nullptr;
@@ -158,7 +164,8 @@ __global__ void __launch_bounds__(256, 2) zsl_layer1_kernel(const mre_zsl_model 
             nx[u] = make_float4(0.f, 0.f, 0.f, 0.f);
             nw[u] = nx[u];
             if (row_ok && k < D) {
-                const float4 p = *reinterpret_cast<const float4 *>(xa + k), q = *reinterpret_cast<const float4 *>(xb + k);
+                const float4 p = *reinterpret_cast<const float4 *>(xa + k);
+                const float4 q = xb ? *reinterpret_cast<const float4 *>(xb + k) : make_float4(0.f, 0.f, 0.f, 0.f);
                 nx[u] = make_float4(p.x + q.x, p.y + q.y, p.z + q.z, p.w + q.w);
             }
             if (wrow && k < D) nw[u] = *reinterpret_cast<const float4 *>(wrow + k);
@@ -193,7 +200,10 @@ __global__ void __launch_bounds__(256, 2) zsl_layer1_kernel(const mre_zsl_model 
 #pragma unroll
         for (int j = 0; j < 8; j++) {
             const int c = (j < 4 ? 0 : BN / 2) + tx * 4 + (j & 3);
-            if (n0 + c < N) o[c] = fmaxf(zsl_acc(acc, i, j) + m.proj1_b[n0 + c], 0.f);
+            if (n0 + c < N) {
+                const float v = zsl_acc(acc, i, j) + (bias ? m.proj1_b[n0 + c] : 0.f);
+                o[c] = relu ? fmaxf(v, 0.f) : v;
+            }
         }
     }
 }
@@ -321,6 +331,309 @@ __global__ void __launch_bounds__(256, 2) zsl_layer2_kernel(const mre_zsl_model 
     }
 }
 
+// ------------------------------------------------------------------------------------------ tensor-core path
+// proj1 is linear too, so the hidden layer splits the same way the pair vector does: relu(W1 (A_h + B_c) + b1) =
+// relu(A1_h + B1_c) with per-ENTITY rows A1 = W1 A + b1, B1 = W1 B (two small FP32 GEMMs over the entity table).  What is left
+// per pair is ONE contraction, Hid[p, :] W2^T (K = 2 D = 400, N = D = 200), run on the 5th-generation tensor cores as 3 x TF32:
+// every FP32 operand is split hi + lo (both round-to-nearest TF32; hi + lo carries 22 significand bits) and the product is
+// hi*hi + hi*lo + lo*hi with FP32 accumulation in TMEM -- the dropped lo*lo term is 2^-22 relative, FP32-level accuracy.
+//   CTA = one SM, persistent over 256-pair tiles (two 128-row accumulators, 2 x NP <= 512 TMEM columns):
+//     warp 0        TMA producer: the W2 hi / lo k-blocks (NP rows x 16 floats, 64-byte swizzle) of every stage
+//     warp 1        MMA issuer: 12 tcgen05.mma (2 sub-tiles x 2 k-steps x 3 split products) per k-block
+//     warps 2-9     operand producers, thread = pair row: gather A1[head], B1[cand] (L2-resident), add, relu, split, store the
+//                   hi / lo rows in the canonical K-major SWIZZLE_64B layout (the score matrix's left operand never sees HBM)
+//     warps 10-17   epilogue, thread = pair row (TMEM lane): + b2 + (A_h + B_c), written back to TMEM, then two more passes
+//                   for the LayerNorm statistics and the normalised dot with sum_k r_k / ||r_k|| (the cosine mean is linear
+//                   in the normalised relation vectors) -- no shuffles, no shared memory
+constexpr int ZT_ROWS = 256, ZT_BK = 16, ZT_STAGES = 3, ZT_PROD_WARPS = 8, ZT_EPI_WARPS = 8;
+constexpr int ZT_THREADS = 32 * (2 + ZT_PROD_WARPS + ZT_EPI_WARPS);
+#ifndef MRE_ZT_DIAG
+#define MRE_ZT_DIAG 0      // developer timing variants: 1 no residual gather, 2 no LayerNorm passes, 4 no B1 gather, 16 no epilogue work
+#endif
+constexpr int ZT_A_BYTES = ZT_ROWS * ZT_BK * 4;                    // one of the hi / lo operand tiles of a stage
+
+struct ZslTcParams {
+    const float *A1, *B1, *A, *B;
+    const int64_t *q_head, *q_rel, *cand;
+    const int32_t *pair_triple;
+    const float *rsum;                                              // [n_rel, D]: sum_k r_k / ||r_k||
+    const float *b2, *ln_g, *ln_b;
+    float ln_eps, inv_nvec;
+    int D, K, NP, nkb;
+    uint32_t idesc;
+    int64_t P, tiles;
+    float *score;
+};
+
+// W2 -> TF32 hi / lo, rows padded with zeros to NP
+__global__ void zsl_split_w2_kernel(const float *__restrict__ w, int D, int K, int NP, float *__restrict__ hi, float *__restrict__ lo) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= NP * K) return;
+    const float v = i < D * K ? w[i] : 0.f;
+    const float h = tf32_rna(v);
+    hi[i] = h;
+    lo[i] = tf32_rna(v - h);
+}
+
+// rsum[r, :] = sum_k rel_vecs[r, k, :] / ||rel_vecs[r, k, :]||   (zero vectors contribute nothing, as sklearn's normalize leaves them)
+__global__ void zsl_relsum_kernel(const float *__restrict__ rel_vecs, int n_vec, int D, float *__restrict__ rsum) {
+    __shared__ float s_inv[64];
+    const int64_t r = blockIdx.x;
+    const float *rv = rel_vecs + r * (int64_t)n_vec * D;
+    for (int k0 = 0; k0 < n_vec; k0 += 64) {
+        const int nk = min(64, n_vec - k0);
+        __syncthreads();
+        if ((int)threadIdx.x < nk) {
+            float s = 0.f;
+            for (int d = 0; d < D; d++) s = fmaf(rv[(int64_t)(k0 + threadIdx.x) * D + d], rv[(int64_t)(k0 + threadIdx.x) * D + d], s);
+            const float n = sqrtf(s);
+            s_inv[threadIdx.x] = n > 0.f ? 1.f / n : 0.f;
+        }
+        __syncthreads();
+        for (int d = threadIdx.x; d < D; d += blockDim.x) {
+            float acc = k0 ? rsum[r * D + d] : 0.f;
+            for (int k = 0; k < nk; k++) acc = fmaf(rv[(int64_t)(k0 + k) * D + d], s_inv[k], acc);
+            rsum[r * D + d] = acc;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(ZT_THREADS, 1) zsl_tc_kernel(const __grid_constant__ CUtensorMap tm_hi,
+                                                               const __grid_constant__ CUtensorMap tm_lo, const ZslTcParams p) {
+    extern __shared__ uint8_t zt_smem[];
+    __shared__ __align__(8) uint64_t bars[2 * ZT_STAGES + 2];
+    __shared__ uint32_t tmem_slot;
+    __shared__ float s_vec[3][256];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t base = (smem_u32(zt_smem) + 1023u) & ~1023u;
+    const uint32_t w_bytes = (uint32_t)p.NP * ZT_BK * 4, stage_bytes = 2 * ZT_A_BYTES + 2 * w_bytes;
+    auto full = [&](int s) { return smem_u32(&bars[s]); };
+    auto empty = [&](int s) { return smem_u32(&bars[ZT_STAGES + s]); };
+    const uint32_t acc_full = smem_u32(&bars[2 * ZT_STAGES]), acc_empty = smem_u32(&bars[2 * ZT_STAGES + 1]);
+    if (tid == 0) {
+        for (int s = 0; s < ZT_STAGES; s++) {
+            mbar_init(full(s), ZT_PROD_WARPS + 1);
+            mbar_init(empty(s), 1);
+        }
+        mbar_init(acc_full, 1);
+        mbar_init(acc_empty, ZT_EPI_WARPS);
+        fence_barrier_init();
+        tma_prefetch_desc(&tm_hi);
+        tma_prefetch_desc(&tm_lo);
+    }
+    for (int i = tid; i < 256; i += ZT_THREADS) {
+        s_vec[0][i] = i < p.D ? p.b2[i] : 0.f;
+        s_vec[1][i] = i < p.D ? p.ln_g[i] : 0.f;
+        s_vec[2][i] = i < p.D ? p.ln_b[i] : 0.f;
+    }
+    if (warp == 1) tmem_alloc(smem_u32(&tmem_slot), 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            for (int64_t tile = blockIdx.x; tile < p.tiles; tile += gridDim.x)
+                for (int kb = 0; kb < p.nkb; kb++) {
+                    mbar_wait(empty(s), ph ^ 1);
+                    mbar_arrive_expect_tx(full(s), 2 * w_bytes);
+                    const uint32_t w = base + s * stage_bytes + 2 * ZT_A_BYTES;
+                    tma_load_2d_hint(w, &tm_hi, kb * ZT_BK, 0, full(s), L2_EVICT_LAST);
+                    tma_load_2d_hint(w + w_bytes, &tm_lo, kb * ZT_BK, 0, full(s), L2_EVICT_LAST);
+                    if (++s == ZT_STAGES) { s = 0; ph ^= 1; }
+                }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0, aph = 0;
+            for (int64_t tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+                mbar_wait(acc_empty, aph ^ 1);
+                tc_fence_after();
+                for (int kb = 0; kb < p.nkb; kb++) {
+                    mbar_wait(full(s), ph);
+                    tc_fence_after();
+                    const uint32_t a_hi = base + s * stage_bytes, a_lo = a_hi + ZT_A_BYTES, w_hi = a_hi + 2 * ZT_A_BYTES, w_lo = w_hi + w_bytes;
+#pragma unroll
+                    for (int sub = 0; sub < 2; sub++) {
+                        const uint32_t d = tmem + (uint32_t)(sub * p.NP);
+#pragma unroll
+                        for (int kk = 0; kk < ZT_BK / 8; kk++) {
+                            const uint64_t da_hi = umma_desc_k64(a_hi + sub * (ZT_A_BYTES / 2)) + kk * 2, da_lo = umma_desc_k64(a_lo + sub * (ZT_A_BYTES / 2)) + kk * 2;
+                            const uint64_t db_hi = umma_desc_k64(w_hi) + kk * 2, db_lo = umma_desc_k64(w_lo) + kk * 2;
+                            umma_tf32(d, da_lo, db_hi, p.idesc, (kb | kk) != 0);     // the small cross terms first
+                            umma_tf32(d, da_hi, db_lo, p.idesc, 1);
+                            umma_tf32(d, da_hi, db_hi, p.idesc, 1);
+                        }
+                    }
+                    umma_commit(empty(s));
+                    if (++s == ZT_STAGES) { s = 0; ph ^= 1; }
+                }
+                umma_commit(acc_full);
+                aph ^= 1;
+            }
+        }
+    } else if (warp < 2 + ZT_PROD_WARPS) {
+        // ---- operand producers
+        const int r = (warp - 2) * 32 + lane;
+        const uint32_t row_off = (uint32_t)r * (ZT_BK * 4), sw = (uint32_t)(r >> 1) & 3u;
+        int s = 0;
+        uint32_t ph = 0;
+        auto row_ptrs = [&](int64_t tile, const float4 *&a1, const float4 *&b1) {
+            const int64_t pr = min(tile * ZT_ROWS + r, p.P - 1);   // rows past the end recompute the last pair; never written
+            a1 = reinterpret_cast<const float4 *>(p.A1 + p.q_head[p.pair_triple[pr]] * p.K);
+            b1 = reinterpret_cast<const float4 *>(p.B1 + p.cand[pr] * p.K);
+        };
+        const float4 *a1, *b1, *na1 = nullptr, *nb1 = nullptr;
+        if ((int64_t)blockIdx.x < p.tiles) row_ptrs(blockIdx.x, a1, b1);
+        for (int64_t tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+            if (tile + gridDim.x < p.tiles) row_ptrs(tile + gridDim.x, na1, nb1);   // the next tile's index chain resolves under this tile
+            float4 bq[3][4];
+            auto ld = [&](float4 (&d)[4], int kb) {
+#pragma unroll
+                for (int j = 0; j < 4; j++) d[j] = (MRE_ZT_DIAG & 4) ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldg(b1 + kb * 4 + j);
+            };
+            auto put = [&](const float4 (&bv)[4], int kb) {
+                float4 av[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) av[j] = __ldg(a1 + kb * 4 + j);
+                mbar_wait(empty(s), ph ^ 1);
+                const uint32_t a_hi = base + s * stage_bytes + row_off, a_lo = a_hi + ZT_A_BYTES;
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const float v0 = fmaxf(av[j].x + bv[j].x, 0.f), v1 = fmaxf(av[j].y + bv[j].y, 0.f);
+                    const float v2 = fmaxf(av[j].z + bv[j].z, 0.f), v3 = fmaxf(av[j].w + bv[j].w, 0.f);
+                    const float h0 = tf32_rna(v0), h1 = tf32_rna(v1), h2 = tf32_rna(v2), h3 = tf32_rna(v3);
+                    const uint32_t off = ((uint32_t)j ^ sw) << 4;
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a_hi + off), "f"(h0), "f"(h1), "f"(h2), "f"(h3) : "memory");
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a_lo + off), "f"(tf32_rna(v0 - h0)), "f"(tf32_rna(v1 - h1)),
+                                 "f"(tf32_rna(v2 - h2)), "f"(tf32_rna(v3 - h3))
+                                 : "memory");
+                }
+                fence_proxy_async();                                // generic-proxy stores -> visible to the tensor core's async proxy
+                __syncwarp();
+                if (lane == 0) mbar_arrive(full(s));
+                if (++s == ZT_STAGES) { s = 0; ph ^= 1; }
+            };
+            ld(bq[0], 0);
+            if (p.nkb > 1) ld(bq[1], 1);
+            for (int kb = 0; kb < p.nkb; kb += 3) {
+#pragma unroll
+                for (int u = 0; u < 3; u++) {
+                    if (kb + u < p.nkb) {
+                        if (kb + u + 2 < p.nkb) ld(bq[(u + 2) % 3], kb + u + 2);
+                        put(bq[u], kb + u);
+                    }
+                }
+            }
+            a1 = na1;
+            b1 = nb1;
+        }
+    } else {
+        // ---- epilogue: thread = TMEM lane = pair row
+        const int q = warp & 3, sub = (warp - 2 - ZT_PROD_WARPS) >> 2, r = sub * 128 + q * 32 + lane;
+        const uint32_t t0 = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(sub * p.NP);
+        const int nch = p.D / 8;
+        const float inv_d = 1.f / (float)p.D;
+        uint32_t aph = 0;
+        for (int64_t tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+            const int64_t pr0 = tile * ZT_ROWS + r, pr = min(pr0, p.P - 1);
+            const int t = p.pair_triple[pr];
+            const float4 *xa = reinterpret_cast<const float4 *>(p.A + p.q_head[t] * p.D), *xb = reinterpret_cast<const float4 *>(p.B + p.cand[pr] * p.D);
+            const float4 *rs = reinterpret_cast<const float4 *>(p.rsum + p.q_rel[t] * p.D);
+            mbar_wait(acc_full, aph);
+            aph ^= 1;
+            tc_fence_after();
+            if (MRE_ZT_DIAG & 16) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(acc_empty);
+                if (pr0 < p.P) p.score[pr0] = (float)t;
+                continue;
+            }
+            constexpr int G = 3;                                    // chunks of 8 columns in flight per wait
+            float sum = 0.f;
+            for (int c0 = 0; c0 < nch; c0 += G) {                   // pass 1: u = (acc + b2) + (A_h + B_c), kept in TMEM
+                uint32_t v[G][8];
+#pragma unroll
+                for (int g = 0; g < G; g++)
+                    if (c0 + g < nch) tmem_ld_32x8(t0 + (c0 + g) * 8, v[g]);
+                tmem_ld_wait();
+#pragma unroll
+                for (int g = 0; g < G; g++)
+                    if (c0 + g < nch) {
+                        const int c = (c0 + g) * 8;
+                        const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                        const float4 a0 = (MRE_ZT_DIAG & 1) ? zero4 : __ldg(xa + c / 4), a1v = (MRE_ZT_DIAG & 1) ? zero4 : __ldg(xa + c / 4 + 1);
+                        const float4 b0 = (MRE_ZT_DIAG & 1) ? zero4 : __ldg(xb + c / 4), b1v = (MRE_ZT_DIAG & 1) ? zero4 : __ldg(xb + c / 4 + 1);
+                        const float x[8] = {a0.x + b0.x, a0.y + b0.y, a0.z + b0.z, a0.w + b0.w, a1v.x + b1v.x, a1v.y + b1v.y, a1v.z + b1v.z, a1v.w + b1v.w};
+#pragma unroll
+                        for (int i = 0; i < 8; i++) {
+                            const float u = (__uint_as_float(v[g][i]) + s_vec[0][c + i]) + x[i];
+                            sum += u;
+                            v[g][i] = __float_as_uint(u);
+                        }
+                        tmem_st_32x8(t0 + c, v[g]);
+                    }
+            }
+            tmem_st_wait();
+            const float mu = sum * inv_d;
+            float var = 0.f;
+            for (int c0 = 0; c0 < ((MRE_ZT_DIAG & 2) ? 0 : nch); c0 += G) {   // pass 2: variance about the mean
+                uint32_t v[G][8];
+#pragma unroll
+                for (int g = 0; g < G; g++)
+                    if (c0 + g < nch) tmem_ld_32x8(t0 + (c0 + g) * 8, v[g]);
+                tmem_ld_wait();
+#pragma unroll
+                for (int g = 0; g < G; g++)
+                    if (c0 + g < nch) {
+#pragma unroll
+                        for (int i = 0; i < 8; i++) {
+                            const float d = __uint_as_float(v[g][i]) - mu;
+                            var = fmaf(d, d, var);
+                        }
+                    }
+            }
+            const float rstd = rsqrtf(var * inv_d + p.ln_eps);
+            float dot = 0.f, nn = 0.f;
+            for (int c0 = 0; c0 < ((MRE_ZT_DIAG & 2) ? 0 : nch); c0 += G) {   // pass 3: LayerNorm output, its norm and its dot with the relation sum
+                uint32_t v[G][8];
+#pragma unroll
+                for (int g = 0; g < G; g++)
+                    if (c0 + g < nch) tmem_ld_32x8(t0 + (c0 + g) * 8, v[g]);
+                tmem_ld_wait();
+#pragma unroll
+                for (int g = 0; g < G; g++)
+                    if (c0 + g < nch) {
+                        const int c = (c0 + g) * 8;
+                        const float4 r0 = __ldg(rs + c / 4), r1 = __ldg(rs + c / 4 + 1);
+                        const float rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+                        for (int i = 0; i < 8; i++) {
+                            const float z = (__uint_as_float(v[g][i]) - mu) * rstd * s_vec[1][c + i] + s_vec[2][c + i];
+                            nn = fmaf(z, z, nn);
+                            dot = fmaf(z, rr[i], dot);
+                        }
+                    }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty);                  // the accumulators are free for the next tile
+            if (pr0 < p.P) {
+                const float den = sqrtf(nn);
+                p.score[pr0] = den > 0.f ? dot / den * p.inv_nvec : 0.f;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
 // per test triple: how many candidates score higher than / equal to the true one (candidate 0 of its list); one warp per triple
 __global__ void __launch_bounds__(256) zsl_count_kernel(const float *__restrict__ score, const int64_t *__restrict__ cand_ptr, int64_t T,
                                                         int32_t *__restrict__ counts) {
@@ -368,37 +681,77 @@ int zsl_entity_features(mre_ctx *ctx, const mre_zsl_model *m, const int64_t *ent
     return MRE_OK;
 }
 
-int zsl_rank(mre_ctx *ctx, const mre_zsl_model *m, const float *A, const float *B, const int64_t *q_head, const int64_t *q_rel,
-             const int64_t *cand_ptr, const int64_t *cand_idx, int64_t T, int64_t P, const float *rel_vecs, int64_t n_rel,
-             int32_t n_vec, float *scores, int32_t *counts, cudaStream_t st) {
+int zsl_rank(mre_ctx *ctx, const mre_zsl_model *m, const float *A, const float *B, int64_t n_ent, const int64_t *q_head,
+             const int64_t *q_rel, const int64_t *cand_ptr, const int64_t *cand_idx, int64_t T, int64_t P, const float *rel_vecs,
+             int64_t n_rel, int32_t n_vec, float *scores, int32_t *counts, cudaStream_t st) {
     MRE_TRY(check_model(m));
-    MRE_CHECK_ARG(T >= 0 && P >= 0 && n_rel >= 0 && n_vec > 0, "bad size");
+    MRE_CHECK_ARG(T >= 0 && P >= 0 && n_rel >= 0 && n_vec > 0 && n_ent >= 0, "bad size");
     if (T == 0) return MRE_OK;
     MRE_CHECK_ARG(A && B && q_head && q_rel && cand_ptr && counts && rel_vecs, "NULL argument");
     MRE_CHECK_ARG(P == 0 || cand_idx, "cand_idx is NULL");
+    MRE_CHECK_ARG(P == 0 || n_ent > 0, "pairs given but the entity table is empty");
     MRE_CHECK_ARG(P < (1LL << 31), "too many (head, candidate) pairs for one call");
-    const int D = (int)m->D;
-    const int64_t chunk = std::min<int64_t>(std::max<int64_t>(P, 1), 1 << 18);
-    // scratch: pair -> triple map, relation-vector norms, scores (when the caller does not want them), hidden activations
-    MRE_TRY(ctx->misc2.reserve((size_t)std::max<int64_t>(P, 1) * (sizeof(int32_t) + sizeof(float)) + (size_t)n_rel * n_vec * sizeof(float) + 64));
+    const int D = (int)m->D, K = 2 * D, NP = (D + 15) / 16 * 16;
+    const char *dev_fp32 = getenv("MRE_DEV_ZSL_FP32");                     // developer switch: the CUDA-core FP32 tile GEMMs
+    const bool fp32_path = dev_fp32 && dev_fp32[0] == '1';
+    const int64_t P1 = (std::max<int64_t>(P, 1) + 3) / 4 * 4;                // keeps the float4-read relation sums 16-byte aligned
+    // scratch: pair -> triple map, scores (when the caller does not want them), relation-vector norms / normalised sums
+    MRE_TRY(ctx->misc2.reserve((size_t)P1 * (sizeof(int32_t) + sizeof(float)) + (size_t)n_rel * std::max(n_vec, D) * sizeof(float) + 64));
     int32_t *pair_triple = ctx->misc2.as<int32_t>();
-    float *sc = scores ? scores : reinterpret_cast<float *>(pair_triple + std::max<int64_t>(P, 1));
-    float *rel_norm = reinterpret_cast<float *>(pair_triple + std::max<int64_t>(P, 1)) + std::max<int64_t>(P, 1);
-    MRE_TRY(ctx->ent_aux.reserve((size_t)chunk * 2 * D * sizeof(float)));
-    float *hid = ctx->ent_aux.as<float>();
+    float *sc = scores ? scores : reinterpret_cast<float *>(pair_triple + P1);
+    float *rel_aux = reinterpret_cast<float *>(pair_triple + P1) + P1;
     if (P > 0) zsl_pair_triple_kernel<<<(unsigned)std::min<int64_t>((P + 255) / 256, 148 * 16), 256, 0, st>>>(cand_ptr, T, P, pair_triple);
-    if (n_rel > 0) zsl_relnorm_kernel<<<(unsigned)((n_rel * n_vec + 127) / 128), 128, 0, st>>>(rel_vecs, n_rel * n_vec, D, rel_norm);
-    ctx->launches += 2;
-    MRE_TRY(ctx->time_begin(st));
-    for (int64_t p0 = 0; p0 < P; p0 += chunk) {
-        const int64_t n = std::min(chunk, P - p0);
-        dim3 g1((unsigned)((n + 127) / 128), (unsigned)((2 * D + 127) / 128));
-        zsl_layer1_kernel<<<g1, 256, 0, st>>>(*m, A, B, q_head, cand_idx, pair_triple, p0, n, hid);
-        zsl_layer2_kernel<<<(unsigned)((n + 63) / 64), 256, 0, st>>>(*m, A, B, q_head, q_rel, cand_idx, pair_triple, hid, rel_vecs, rel_norm,
-                                                                      n_vec, p0, n, sc);
-        ctx->launches += 2;
+    ctx->launches += 1;
+    if (fp32_path) {
+        const int64_t chunk = std::min<int64_t>(P1, 1 << 18);
+        MRE_TRY(ctx->ent_aux.reserve((size_t)chunk * K * sizeof(float)));
+        float *hid = ctx->ent_aux.as<float>();
+        if (n_rel > 0) zsl_relnorm_kernel<<<(unsigned)((n_rel * n_vec + 127) / 128), 128, 0, st>>>(rel_vecs, n_rel * n_vec, D, rel_aux);
+        ctx->launches += 1;
+        MRE_TRY(ctx->time_begin(st));
+        for (int64_t p0 = 0; p0 < P; p0 += chunk) {
+            const int64_t n = std::min(chunk, P - p0);
+            dim3 g1((unsigned)((n + 127) / 128), (unsigned)((K + 127) / 128));
+            zsl_layer1_kernel<<<g1, 256, 0, st>>>(*m, A, B, q_head, cand_idx, pair_triple, p0, n, hid, 1, 1);
+            zsl_layer2_kernel<<<(unsigned)((n + 63) / 64), 256, 0, st>>>(*m, A, B, q_head, q_rel, cand_idx, pair_triple, hid, rel_vecs, rel_aux,
+                                                                          n_vec, p0, n, sc);
+            ctx->launches += 2;
+        }
+        MRE_TRY(ctx->time_end(st));
+    } else if (P > 0) {
+        // per-entity hidden halves A1 = W1 A + b1, B1 = W1 B, and the TF32 hi / lo split of W2 (rows zero-padded to NP)
+        MRE_TRY(ctx->ent_aux.reserve(((size_t)2 * n_ent * K + (size_t)2 * NP * K) * sizeof(float) + 256));
+        float *A1 = ctx->ent_aux.as<float>(), *B1 = A1 + n_ent * K, *w_hi = B1 + n_ent * K, *w_lo = w_hi + (size_t)NP * K;
+        dim3 g1((unsigned)((n_ent + 127) / 128), (unsigned)((K + 127) / 128));
+        zsl_layer1_kernel<<<g1, 256, 0, st>>>(*m, A, nullptr, nullptr, nullptr, nullptr, 0, n_ent, A1, 0, 1);
+        zsl_layer1_kernel<<<g1, 256, 0, st>>>(*m, B, nullptr, nullptr, nullptr, nullptr, 0, n_ent, B1, 0, 0);
+        zsl_split_w2_kernel<<<(NP * K + 255) / 256, 256, 0, st>>>(m->proj2_w, D, K, NP, w_hi, w_lo);
+        if (n_rel > 0) zsl_relsum_kernel<<<(unsigned)n_rel, 128, 0, st>>>(rel_vecs, n_vec, D, rel_aux);
+        ctx->launches += 4;
+        CUtensorMap tm_hi, tm_lo;
+        MRE_TRY(make_tmap_f32_2d(&tm_hi, w_hi, NP, K, K, NP, ZT_BK));
+        MRE_TRY(make_tmap_f32_2d(&tm_lo, w_lo, NP, K, K, NP, ZT_BK));
+        ZslTcParams tp;
+        tp.A1 = A1; tp.B1 = B1; tp.A = A; tp.B = B;
+        tp.q_head = q_head; tp.q_rel = q_rel; tp.cand = cand_idx; tp.pair_triple = pair_triple;
+        tp.rsum = rel_aux; tp.b2 = m->proj2_b; tp.ln_g = m->ln_g; tp.ln_b = m->ln_b;
+        tp.ln_eps = m->ln_eps; tp.inv_nvec = 1.f / (float)n_vec;
+        tp.D = D; tp.K = K; tp.NP = NP; tp.nkb = K / ZT_BK;
+        tp.idesc = umma_idesc_tf32(128, NP);
+        tp.P = P; tp.tiles = (P + ZT_ROWS - 1) / ZT_ROWS;
+        tp.score = sc;
+        const size_t smem = (size_t)ZT_STAGES * (2 * ZT_A_BYTES + 2 * (size_t)NP * ZT_BK * 4) + 1024;
+        static bool attr_set = false;
+        if (!attr_set) {
+            MRE_CUDA(cudaFuncSetAttribute(zsl_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            attr_set = true;
+        }
+        const int sms = ctx->sm_count > 0 ? ctx->sm_count : 148;
+        MRE_TRY(ctx->time_begin(st));
+        zsl_tc_kernel<<<(unsigned)std::min<int64_t>(tp.tiles, sms), ZT_THREADS, smem, st>>>(tm_hi, tm_lo, tp);
+        ctx->launches += 1;
+        MRE_TRY(ctx->time_end(st));
     }
-    MRE_TRY(ctx->time_end(st));
     zsl_count_kernel<<<(unsigned)((T + 7) / 8), 256, 0, st>>>(sc, cand_ptr, T, counts);
     ctx->launches += 1;
     MRE_CUDA(cudaGetLastError());

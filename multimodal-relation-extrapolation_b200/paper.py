@@ -315,7 +315,7 @@ class ZSLEvaluator:
         assert rv.dim() == 3 and rv.shape[2] == self.D
         counts = torch.zeros((4, max(T, 1)), dtype=torch.int32, device=self.device)[:, :T].contiguous()
         scores = torch.empty(max(P, 1), dtype=torch.float32, device=self.device) if want_scores else None
-        L.check(L.lib().mre_zsl_rank(self.ctx._h, self.model, self.A.data_ptr(), self.B.data_ptr(), d_head.data_ptr(), d_rel.data_ptr(),
+        L.check(L.lib().mre_zsl_rank(self.ctx._h, self.model, self.A.data_ptr(), self.B.data_ptr(), self.A.shape[0], d_head.data_ptr(), d_rel.data_ptr(),
                                      d_ptr.data_ptr(), d_idx.data_ptr(), T, P, rv.data_ptr(), rv.shape[0], rv.shape[1],
                                      scores.data_ptr() if want_scores else None, counts.data_ptr(),
                                      torch.cuda.current_stream().cuda_stream))
