@@ -337,26 +337,29 @@ __global__ void __launch_bounds__(256, 2) zsl_layer2_kernel(const mre_zsl_model 
 // per pair is ONE contraction, Hid[p, :] W2^T (K = 2 D = 400, N = D = 200), run on the 5th-generation tensor cores as 3 x TF32:
 // every FP32 operand is split hi + lo (both round-to-nearest TF32; hi + lo carries 22 significand bits) and the product is
 // hi*hi + hi*lo + lo*hi with FP32 accumulation in TMEM -- the dropped lo*lo term is 2^-22 relative, FP32-level accuracy.
-//   CTA = one SM, persistent over 256-pair tiles (two 128-row accumulators, 2 x NP <= 512 TMEM columns):
-//     warp 0        TMA producer: the W2 hi / lo k-blocks (NP rows x 16 floats, 64-byte swizzle) of every stage
-//     warp 1        MMA issuer: 12 tcgen05.mma (2 sub-tiles x 2 k-steps x 3 split products) per k-block
-//     warps 2-9     operand producers, thread = pair row: gather A1[head], B1[cand] (L2-resident), add, relu, split, store the
-//                   hi / lo rows in the canonical K-major SWIZZLE_64B layout (the score matrix's left operand never sees HBM)
-//     warps 10-17   epilogue, thread = pair row (TMEM lane): + b2 + (A_h + B_c), written back to TMEM, then two more passes
-//                   for the LayerNorm statistics and the normalised dot with sum_k r_k / ||r_k|| (the cosine mean is linear
-//                   in the normalised relation vectors) -- no shuffles, no shared memory
+// W2 carries one extra output row, its column sums, so accumulator column D is sum_d y[d]: the LayerNorm mean is known before
+// the row is read, and the whole epilogue is ONE pass over TMEM on centred values d = u - mu:
+//     var = sum d^2 / D,  z = d rstd g + be,  z . rsum = rstd sum (d g) rsum + be . rsum,  |z|^2 = rstd^2 sum (d g)^2 + 2 rstd sum (d g) be + |be|^2
+// (rsum = sum_k r_k / ||r_k||: the cosine mean is linear in the normalised relation vectors).
+//   CTA = one SM, persistent over 256-pair tiles (two 128-row accumulators, 2 x NP <= 512 TMEM columns), 16 warps:
+//     warps 0-7     operand producers, thread = pair row: gather A1[head], B1[cand] (L2-resident), add, relu, split, store the
+//                   hi / lo rows in the canonical K-major SWIZZLE_64B layout (the contraction's left operand never sees HBM);
+//                   lane 0 of warp 0 also issues the TMA loads of the W2 hi / lo k-blocks (NP rows x 16 floats) of each stage
+//     warps 8-15    epilogue, thread = pair row (TMEM lane); warp 8 first issues the tile's tcgen05.mma (12 per k-block:
+//                   2 sub-tiles x 2 k-steps x 3 split products) -- with one accumulator set the two phases alternate anyway
 constexpr int ZT_ROWS = 256, ZT_BK = 16, ZT_STAGES = 3, ZT_PROD_WARPS = 8, ZT_EPI_WARPS = 8;
-constexpr int ZT_THREADS = 32 * (2 + ZT_PROD_WARPS + ZT_EPI_WARPS);
+constexpr int ZT_THREADS = 32 * (ZT_PROD_WARPS + ZT_EPI_WARPS);
 #ifndef MRE_ZT_DIAG
-#define MRE_ZT_DIAG 0      // developer timing variants: 1 no residual gather, 2 no LayerNorm passes, 4 no B1 gather, 16 no epilogue work
+#define MRE_ZT_DIAG 0      // developer timing variants: 1 no residual gather, 4 no B1 gather, 16 no epilogue work
 #endif
+constexpr int ZT_XPITCH = 36;                                      // floats per staged residual row (32 + 4: conflict-free both ways)
 constexpr int ZT_A_BYTES = ZT_ROWS * ZT_BK * 4;                    // one of the hi / lo operand tiles of a stage
 
 struct ZslTcParams {
-    const float *A1, *B1, *A, *B;
+    const float *A1, *B1, *A, *B, *sA, *sB;                         // sA / sB: row sums of A / B
     const int64_t *q_head, *q_rel, *cand;
     const int32_t *pair_triple;
-    const float *rsum;                                              // [n_rel, D]: sum_k r_k / ||r_k||
+    const float *rsum, *bR;                                         // [n_rel, D]: sum_k r_k / ||r_k||;  [n_rel]: ln_b . rsum
     const float *b2, *ln_g, *ln_b;
     float ln_eps, inv_nvec;
     int D, K, NP, nkb;
@@ -365,18 +368,35 @@ struct ZslTcParams {
     float *score;
 };
 
-// W2 -> TF32 hi / lo, rows padded with zeros to NP
+// W2 -> TF32 hi / lo; row D holds the column sums (accumulator column D = sum of the row's outputs), the rest of the padding zeros
 __global__ void zsl_split_w2_kernel(const float *__restrict__ w, int D, int K, int NP, float *__restrict__ hi, float *__restrict__ lo) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= NP * K) return;
-    const float v = i < D * K ? w[i] : 0.f;
+    const int row = i / K, k = i - row * K;
+    float v = 0.f;
+    if (row < D) v = w[i];
+    else if (row == D)
+        for (int d = 0; d < D; d++) v += w[d * K + k];
     const float h = tf32_rna(v);
     hi[i] = h;
     lo[i] = tf32_rna(v - h);
 }
 
-// rsum[r, :] = sum_k rel_vecs[r, k, :] / ||rel_vecs[r, k, :]||   (zero vectors contribute nothing, as sklearn's normalize leaves them)
-__global__ void zsl_relsum_kernel(const float *__restrict__ rel_vecs, int n_vec, int D, float *__restrict__ rsum) {
+// out[i] = sum of row i (one warp per row, fixed order)
+__global__ void zsl_rowsum_kernel(const float *__restrict__ tab, int64_t n, int D, float *__restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= n) return;
+    float s = 0.f;
+    for (int d = threadIdx.x & 31; d < D; d += 32) s += tab[i * D + d];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) out[i] = s;
+}
+
+// rsum[r, :] = sum_k rel_vecs[r, k, :] / ||rel_vecs[r, k, :]||   (zero vectors contribute nothing, as sklearn's normalize leaves
+// them);  bR[r] = ln_b . rsum[r, :]
+__global__ void zsl_relsum_kernel(const float *__restrict__ rel_vecs, int n_vec, int D, const float *__restrict__ ln_b,
+                                  float *__restrict__ rsum, float *__restrict__ bR) {
     __shared__ float s_inv[64];
     const int64_t r = blockIdx.x;
     const float *rv = rel_vecs + r * (int64_t)n_vec * D;
@@ -396,6 +416,12 @@ __global__ void zsl_relsum_kernel(const float *__restrict__ rel_vecs, int n_vec,
             rsum[r * D + d] = acc;
         }
     }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0.f;
+        for (int d = 0; d < D; d++) s = fmaf(ln_b[d], rsum[r * D + d], s);
+        bR[r] = s;
+    }
 }
 
 __global__ void __launch_bounds__(ZT_THREADS, 1) zsl_tc_kernel(const __grid_constant__ CUtensorMap tm_hi,
@@ -403,7 +429,10 @@ __global__ void __launch_bounds__(ZT_THREADS, 1) zsl_tc_kernel(const __grid_cons
     extern __shared__ uint8_t zt_smem[];
     __shared__ __align__(8) uint64_t bars[2 * ZT_STAGES + 2];
     __shared__ uint32_t tmem_slot;
-    __shared__ float s_vec[3][256];
+    __shared__ __align__(16) float s_vec[3][256];
+    __shared__ float s_scal[2];
+    __shared__ __align__(16) float s_stage[ZT_EPI_WARPS][32][ZT_XPITCH];   // per epilogue warp: 32 rows x 32 residual columns, transposed on the way
+    __shared__ int s_cand[ZT_EPI_WARPS][32];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t base = (smem_u32(zt_smem) + 1023u) & ~1023u;
     const uint32_t w_bytes = (uint32_t)p.NP * ZT_BK * 4, stage_bytes = 2 * ZT_A_BYTES + 2 * w_bytes;
@@ -426,88 +455,69 @@ __global__ void __launch_bounds__(ZT_THREADS, 1) zsl_tc_kernel(const __grid_cons
         s_vec[1][i] = i < p.D ? p.ln_g[i] : 0.f;
         s_vec[2][i] = i < p.D ? p.ln_b[i] : 0.f;
     }
-    if (warp == 1) tmem_alloc(smem_u32(&tmem_slot), 512);
+    if (warp == 1) {                                                // sum b2 and |ln_b|^2
+        float a = 0.f, b = 0.f;
+        for (int d = lane; d < p.D; d += 32) {
+            a += p.b2[d];
+            b = fmaf(p.ln_b[d], p.ln_b[d], b);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            a += __shfl_xor_sync(0xffffffffu, a, o);
+            b += __shfl_xor_sync(0xffffffffu, b, o);
+        }
+        if (lane == 0) { s_scal[0] = a; s_scal[1] = b; }
+    }
+    if (warp == ZT_PROD_WARPS) tmem_alloc(smem_u32(&tmem_slot), 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_slot;
 
-    if (warp == 0) {
-        if (lane == 0) {
-            int s = 0;
-            uint32_t ph = 0;
-            for (int64_t tile = blockIdx.x; tile < p.tiles; tile += gridDim.x)
-                for (int kb = 0; kb < p.nkb; kb++) {
-                    mbar_wait(empty(s), ph ^ 1);
-                    mbar_arrive_expect_tx(full(s), 2 * w_bytes);
-                    const uint32_t w = base + s * stage_bytes + 2 * ZT_A_BYTES;
-                    tma_load_2d_hint(w, &tm_hi, kb * ZT_BK, 0, full(s), L2_EVICT_LAST);
-                    tma_load_2d_hint(w + w_bytes, &tm_lo, kb * ZT_BK, 0, full(s), L2_EVICT_LAST);
-                    if (++s == ZT_STAGES) { s = 0; ph ^= 1; }
-                }
-        }
-    } else if (warp == 1) {
-        if (lane == 0) {
-            int s = 0;
-            uint32_t ph = 0, aph = 0;
-            for (int64_t tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
-                mbar_wait(acc_empty, aph ^ 1);
-                tc_fence_after();
-                for (int kb = 0; kb < p.nkb; kb++) {
-                    mbar_wait(full(s), ph);
-                    tc_fence_after();
-                    const uint32_t a_hi = base + s * stage_bytes, a_lo = a_hi + ZT_A_BYTES, w_hi = a_hi + 2 * ZT_A_BYTES, w_lo = w_hi + w_bytes;
-#pragma unroll
-                    for (int sub = 0; sub < 2; sub++) {
-                        const uint32_t d = tmem + (uint32_t)(sub * p.NP);
-#pragma unroll
-                        for (int kk = 0; kk < ZT_BK / 8; kk++) {
-                            const uint64_t da_hi = umma_desc_k64(a_hi + sub * (ZT_A_BYTES / 2)) + kk * 2, da_lo = umma_desc_k64(a_lo + sub * (ZT_A_BYTES / 2)) + kk * 2;
-                            const uint64_t db_hi = umma_desc_k64(w_hi) + kk * 2, db_lo = umma_desc_k64(w_lo) + kk * 2;
-                            umma_tf32(d, da_lo, db_hi, p.idesc, (kb | kk) != 0);     // the small cross terms first
-                            umma_tf32(d, da_hi, db_lo, p.idesc, 1);
-                            umma_tf32(d, da_hi, db_hi, p.idesc, 1);
-                        }
-                    }
-                    umma_commit(empty(s));
-                    if (++s == ZT_STAGES) { s = 0; ph ^= 1; }
-                }
-                umma_commit(acc_full);
-                aph ^= 1;
-            }
-        }
-    } else if (warp < 2 + ZT_PROD_WARPS) {
-        // ---- operand producers
-        const int r = (warp - 2) * 32 + lane;
-        const uint32_t row_off = (uint32_t)r * (ZT_BK * 4), sw = (uint32_t)(r >> 1) & 3u;
+    if (warp < ZT_PROD_WARPS) {
+        // ---- operand producers (+ the W2 loads).  Four lanes share a pair row (one 16-byte quarter of its 64-byte k-block each),
+        // so a warp-wide load touches 8 rows x 64 contiguous bytes instead of 32 scattered 16-byte pieces; a warp owns 32 rows
+        // and covers them in four passes of 8.
+        const int rr = lane >> 2, j = lane & 3;
+        const uint32_t sw = (uint32_t)(rr >> 1) & 3u;
+        const uint32_t row_off = (uint32_t)(warp * 32 + rr) * (ZT_BK * 4) + (((uint32_t)j ^ sw) << 4);
         int s = 0;
         uint32_t ph = 0;
-        auto row_ptrs = [&](int64_t tile, const float4 *&a1, const float4 *&b1) {
-            const int64_t pr = min(tile * ZT_ROWS + r, p.P - 1);   // rows past the end recompute the last pair; never written
-            a1 = reinterpret_cast<const float4 *>(p.A1 + p.q_head[p.pair_triple[pr]] * p.K);
-            b1 = reinterpret_cast<const float4 *>(p.B1 + p.cand[pr] * p.K);
+        const float4 *a1[4], *b1[4], *na1[4], *nb1[4];
+        auto row_ptrs = [&](int64_t tile, const float4 *(&pa)[4], const float4 *(&pb)[4]) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int64_t pr = min(tile * ZT_ROWS + warp * 32 + i * 8 + rr, p.P - 1);   // rows past the end recompute the last pair
+                pa[i] = reinterpret_cast<const float4 *>(p.A1 + p.q_head[p.pair_triple[pr]] * p.K) + j;
+                pb[i] = reinterpret_cast<const float4 *>(p.B1 + p.cand[pr] * p.K) + j;
+            }
         };
-        const float4 *a1, *b1, *na1 = nullptr, *nb1 = nullptr;
         if ((int64_t)blockIdx.x < p.tiles) row_ptrs(blockIdx.x, a1, b1);
         for (int64_t tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
             if (tile + gridDim.x < p.tiles) row_ptrs(tile + gridDim.x, na1, nb1);   // the next tile's index chain resolves under this tile
-            float4 bq[3][4];
+            float4 bq[4][4];
             auto ld = [&](float4 (&d)[4], int kb) {
 #pragma unroll
-                for (int j = 0; j < 4; j++) d[j] = (MRE_ZT_DIAG & 4) ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldg(b1 + kb * 4 + j);
+                for (int i = 0; i < 4; i++) d[i] = (MRE_ZT_DIAG & 4) ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldg(b1[i] + kb * 4);
             };
             auto put = [&](const float4 (&bv)[4], int kb) {
                 float4 av[4];
 #pragma unroll
-                for (int j = 0; j < 4; j++) av[j] = __ldg(a1 + kb * 4 + j);
+                for (int i = 0; i < 4; i++) av[i] = __ldg(a1[i] + kb * 4);
                 mbar_wait(empty(s), ph ^ 1);
+                if (warp == 0 && lane == 0) {
+                    mbar_arrive_expect_tx(full(s), 2 * w_bytes);
+                    const uint32_t w = base + s * stage_bytes + 2 * ZT_A_BYTES;
+                    tma_load_2d_hint(w, &tm_hi, kb * ZT_BK, 0, full(s), L2_EVICT_LAST);
+                    tma_load_2d_hint(w + w_bytes, &tm_lo, kb * ZT_BK, 0, full(s), L2_EVICT_LAST);
+                }
                 const uint32_t a_hi = base + s * stage_bytes + row_off, a_lo = a_hi + ZT_A_BYTES;
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const float v0 = fmaxf(av[j].x + bv[j].x, 0.f), v1 = fmaxf(av[j].y + bv[j].y, 0.f);
-                    const float v2 = fmaxf(av[j].z + bv[j].z, 0.f), v3 = fmaxf(av[j].w + bv[j].w, 0.f);
+                for (int i = 0; i < 4; i++) {
+                    const float v0 = fmaxf(av[i].x + bv[i].x, 0.f), v1 = fmaxf(av[i].y + bv[i].y, 0.f);
+                    const float v2 = fmaxf(av[i].z + bv[i].z, 0.f), v3 = fmaxf(av[i].w + bv[i].w, 0.f);
                     const float h0 = tf32_rna(v0), h1 = tf32_rna(v1), h2 = tf32_rna(v2), h3 = tf32_rna(v3);
-                    const uint32_t off = ((uint32_t)j ^ sw) << 4;
+                    const uint32_t off = (uint32_t)i * 8 * (ZT_BK * 4);
                     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a_hi + off), "f"(h0), "f"(h1), "f"(h2), "f"(h3) : "memory");
                     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a_lo + off), "f"(tf32_rna(v0 - h0)), "f"(tf32_rna(v1 - h1)),
                                  "f"(tf32_rna(v2 - h2)), "f"(tf32_rna(v3 - h3))
@@ -520,30 +530,77 @@ __global__ void __launch_bounds__(ZT_THREADS, 1) zsl_tc_kernel(const __grid_cons
             };
             ld(bq[0], 0);
             if (p.nkb > 1) ld(bq[1], 1);
-            for (int kb = 0; kb < p.nkb; kb += 3) {
+            if (p.nkb > 2) ld(bq[2], 2);
+            for (int kb = 0; kb < p.nkb; kb += 4) {
 #pragma unroll
-                for (int u = 0; u < 3; u++) {
+                for (int u = 0; u < 4; u++) {
                     if (kb + u < p.nkb) {
-                        if (kb + u + 2 < p.nkb) ld(bq[(u + 2) % 3], kb + u + 2);
+                        if (kb + u + 3 < p.nkb) ld(bq[(u + 3) % 4], kb + u + 3);
                         put(bq[u], kb + u);
                     }
                 }
             }
-            a1 = na1;
-            b1 = nb1;
+#pragma unroll
+            for (int i = 0; i < 4; i++) { a1[i] = na1[i]; b1[i] = nb1[i]; }
         }
     } else {
-        // ---- epilogue: thread = TMEM lane = pair row
-        const int q = warp & 3, sub = (warp - 2 - ZT_PROD_WARPS) >> 2, r = sub * 128 + q * 32 + lane;
+        // ---- MMA issue (warp 8) and epilogue: thread = TMEM lane = pair row
+        const int ew = warp - ZT_PROD_WARPS, q = warp & 3, sub = ew >> 2, r = sub * 128 + q * 32 + lane;
         const uint32_t t0 = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(sub * p.NP);
-        const int nch = p.D / 8;
         const float inv_d = 1.f / (float)p.D;
-        uint32_t aph = 0;
+        const int ngrp = (p.D + 31) / 32;
+        float (*stg)[ZT_XPITCH] = s_stage[ew];
+        const int lr = lane >> 3, lc = (lane & 7) * 4;             // coalesced residual loads: 8 lanes cover 128 bytes of one row
+        int s = 0;
+        uint32_t ph = 0, aph = 0;
         for (int64_t tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
             const int64_t pr0 = tile * ZT_ROWS + r, pr = min(pr0, p.P - 1);
             const int t = p.pair_triple[pr];
-            const float4 *xa = reinterpret_cast<const float4 *>(p.A + p.q_head[t] * p.D), *xb = reinterpret_cast<const float4 *>(p.B + p.cand[pr] * p.D);
-            const float4 *rs = reinterpret_cast<const float4 *>(p.rsum + p.q_rel[t] * p.D);
+            const int64_t head = p.q_head[t], cnd = p.cand[pr], rel = p.q_rel[t];
+            const float4 *xa = reinterpret_cast<const float4 *>(p.A + head * p.D);
+            const float4 *rs = reinterpret_cast<const float4 *>(p.rsum + rel * p.D);
+            const float sum_x = p.sA[head] + p.sB[cnd], b_r = p.bR[rel];
+            __syncwarp();
+            s_cand[ew][lane] = (int)cnd;
+            __syncwarp();
+            const float *xrow[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) xrow[i] = p.B + (int64_t)s_cand[ew][4 * i + lr] * p.D + lc;
+            float4 xr[8];                                           // the candidates' residual columns of the next 32-column group
+            auto ldx = [&](int g) {
+#pragma unroll
+                for (int i = 0; i < 8; i++)
+                    xr[i] = (!(MRE_ZT_DIAG & 1) && g * 32 + lc < p.D) ? __ldg(reinterpret_cast<const float4 *>(xrow[i] + g * 32))
+                                                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+            };
+            ldx(0);
+            if (ew == 0) {
+                mbar_wait(acc_empty, aph ^ 1);
+                tc_fence_after();
+                for (int kb = 0; kb < p.nkb; kb++) {
+                    mbar_wait(full(s), ph);
+                    tc_fence_after();
+                    if (lane == 0) {
+                        const uint32_t a_hi = base + s * stage_bytes, a_lo = a_hi + ZT_A_BYTES, w_hi = a_hi + 2 * ZT_A_BYTES, w_lo = w_hi + w_bytes;
+#pragma unroll
+                        for (int sb = 0; sb < 2; sb++) {
+                            const uint32_t d = tmem + (uint32_t)(sb * p.NP);
+#pragma unroll
+                            for (int kk = 0; kk < ZT_BK / 8; kk++) {
+                                const uint64_t da_hi = umma_desc_k64(a_hi + sb * (ZT_A_BYTES / 2)) + kk * 2, da_lo = umma_desc_k64(a_lo + sb * (ZT_A_BYTES / 2)) + kk * 2;
+                                const uint64_t db_hi = umma_desc_k64(w_hi) + kk * 2, db_lo = umma_desc_k64(w_lo) + kk * 2;
+                                umma_tf32(d, da_lo, db_hi, p.idesc, (kb | kk) != 0);     // the small cross terms first
+                                umma_tf32(d, da_hi, db_lo, p.idesc, 1);
+                                umma_tf32(d, da_hi, db_hi, p.idesc, 1);
+                            }
+                        }
+                        umma_commit(empty(s));
+                        if (kb == p.nkb - 1) umma_commit(acc_full);
+                    }
+                    __syncwarp();
+                    if (++s == ZT_STAGES) { s = 0; ph ^= 1; }
+                }
+            }
             mbar_wait(acc_full, aph);
             aph ^= 1;
             tc_fence_after();
@@ -551,72 +608,52 @@ __global__ void __launch_bounds__(ZT_THREADS, 1) zsl_tc_kernel(const __grid_cons
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(acc_empty);
-                if (pr0 < p.P) p.score[pr0] = (float)t;
+                if (pr0 < p.P) p.score[pr0] = (float)t + xr[0].x;
                 continue;
             }
-            constexpr int G = 3;                                    // chunks of 8 columns in flight per wait
-            float sum = 0.f;
-            for (int c0 = 0; c0 < nch; c0 += G) {                   // pass 1: u = (acc + b2) + (A_h + B_c), kept in TMEM
-                uint32_t v[G][8];
-#pragma unroll
-                for (int g = 0; g < G; g++)
-                    if (c0 + g < nch) tmem_ld_32x8(t0 + (c0 + g) * 8, v[g]);
+            float mu;
+            {
+                uint32_t v[8];
+                tmem_ld_32x8(t0 + p.D, v);                          // column D: sum_d (Hid W2^T)[d], from the column-sum row of W2
                 tmem_ld_wait();
-#pragma unroll
-                for (int g = 0; g < G; g++)
-                    if (c0 + g < nch) {
-                        const int c = (c0 + g) * 8;
-                        const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                        const float4 a0 = (MRE_ZT_DIAG & 1) ? zero4 : __ldg(xa + c / 4), a1v = (MRE_ZT_DIAG & 1) ? zero4 : __ldg(xa + c / 4 + 1);
-                        const float4 b0 = (MRE_ZT_DIAG & 1) ? zero4 : __ldg(xb + c / 4), b1v = (MRE_ZT_DIAG & 1) ? zero4 : __ldg(xb + c / 4 + 1);
-                        const float x[8] = {a0.x + b0.x, a0.y + b0.y, a0.z + b0.z, a0.w + b0.w, a1v.x + b1v.x, a1v.y + b1v.y, a1v.z + b1v.z, a1v.w + b1v.w};
-#pragma unroll
-                        for (int i = 0; i < 8; i++) {
-                            const float u = (__uint_as_float(v[g][i]) + s_vec[0][c + i]) + x[i];
-                            sum += u;
-                            v[g][i] = __float_as_uint(u);
-                        }
-                        tmem_st_32x8(t0 + c, v[g]);
-                    }
+                mu = ((__uint_as_float(v[0]) + s_scal[0]) + sum_x) * inv_d;
             }
-            tmem_st_wait();
-            const float mu = sum * inv_d;
-            float var = 0.f;
-            for (int c0 = 0; c0 < ((MRE_ZT_DIAG & 2) ? 0 : nch); c0 += G) {   // pass 2: variance about the mean
-                uint32_t v[G][8];
+            float var = 0.f, q2 = 0.f, sgb = 0.f, dotp = 0.f;
+            for (int g = 0; g < ngrp; g++) {
+                const int c0 = g * 32;
+                __syncwarp();                                       // the previous group's rows have been read
 #pragma unroll
-                for (int g = 0; g < G; g++)
-                    if (c0 + g < nch) tmem_ld_32x8(t0 + (c0 + g) * 8, v[g]);
+                for (int i = 0; i < 8; i++) *reinterpret_cast<float4 *>(&stg[4 * i + lr][lc]) = xr[i];
+                __syncwarp();
+                if (g + 1 < ngrp) ldx(g + 1);
+                uint32_t v[4][8];
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if (c0 + 8 * k < p.D) tmem_ld_32x8(t0 + c0 + 8 * k, v[k]);
                 tmem_ld_wait();
 #pragma unroll
-                for (int g = 0; g < G; g++)
-                    if (c0 + g < nch) {
+                for (int k = 0; k < 4; k++)
+                    if (c0 + 8 * k < p.D) {
 #pragma unroll
-                        for (int i = 0; i < 8; i++) {
-                            const float d = __uint_as_float(v[g][i]) - mu;
-                            var = fmaf(d, d, var);
-                        }
-                    }
-            }
-            const float rstd = rsqrtf(var * inv_d + p.ln_eps);
-            float dot = 0.f, nn = 0.f;
-            for (int c0 = 0; c0 < ((MRE_ZT_DIAG & 2) ? 0 : nch); c0 += G) {   // pass 3: LayerNorm output, its norm and its dot with the relation sum
-                uint32_t v[G][8];
+                        for (int h = 0; h < 2; h++) {
+                            const int c = c0 + 8 * k + 4 * h;
+                            const float4 a = (MRE_ZT_DIAG & 1) ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldg(xa + c / 4);
+                            const float4 b = *reinterpret_cast<const float4 *>(&stg[lane][8 * k + 4 * h]), rr4 = __ldg(rs + c / 4);
+                            const float4 b2 = *reinterpret_cast<const float4 *>(&s_vec[0][c]);
+                            const float4 gg = *reinterpret_cast<const float4 *>(&s_vec[1][c]);
+                            const float4 be = *reinterpret_cast<const float4 *>(&s_vec[2][c]);
+                            const float xs[4] = {a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w};
+                            const float b2s[4] = {b2.x, b2.y, b2.z, b2.w}, gs[4] = {gg.x, gg.y, gg.z, gg.w};
+                            const float bes[4] = {be.x, be.y, be.z, be.w}, rrs[4] = {rr4.x, rr4.y, rr4.z, rr4.w};
 #pragma unroll
-                for (int g = 0; g < G; g++)
-                    if (c0 + g < nch) tmem_ld_32x8(t0 + (c0 + g) * 8, v[g]);
-                tmem_ld_wait();
-#pragma unroll
-                for (int g = 0; g < G; g++)
-                    if (c0 + g < nch) {
-                        const int c = (c0 + g) * 8;
-                        const float4 r0 = __ldg(rs + c / 4), r1 = __ldg(rs + c / 4 + 1);
-                        const float rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-#pragma unroll
-                        for (int i = 0; i < 8; i++) {
-                            const float z = (__uint_as_float(v[g][i]) - mu) * rstd * s_vec[1][c + i] + s_vec[2][c + i];
-                            nn = fmaf(z, z, nn);
-                            dot = fmaf(z, rr[i], dot);
+                            for (int i = 0; i < 4; i++) {
+                                const float u = (__uint_as_float(v[k][4 * h + i]) + b2s[i]) + xs[i];
+                                const float d = u - mu, e = d * gs[i];
+                                var = fmaf(d, d, var);
+                                q2 = fmaf(e, e, q2);
+                                sgb = fmaf(e, bes[i], sgb);
+                                dotp = fmaf(e, rrs[i], dotp);
+                            }
                         }
                     }
             }
@@ -624,14 +661,16 @@ __global__ void __launch_bounds__(ZT_THREADS, 1) zsl_tc_kernel(const __grid_cons
             __syncwarp();
             if (lane == 0) mbar_arrive(acc_empty);                  // the accumulators are free for the next tile
             if (pr0 < p.P) {
-                const float den = sqrtf(nn);
-                p.score[pr0] = den > 0.f ? dot / den * p.inv_nvec : 0.f;
+                const float rstd = rsqrtf(var * inv_d + p.ln_eps);
+                const float dot = fmaf(rstd, dotp, b_r);
+                const float nn = fmaf(rstd * rstd, q2, fmaf(2.f * rstd, sgb, s_scal[1]));
+                p.score[pr0] = nn > 0.f ? dot / sqrtf(nn) * p.inv_nvec : 0.f;
             }
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem, 512);
+    if (warp == ZT_PROD_WARPS) tmem_dealloc(tmem, 512);
 }
 
 // per test triple: how many candidates score higher than / equal to the true one (candidate 0 of its list); one warp per triple
@@ -691,12 +730,12 @@ int zsl_rank(mre_ctx *ctx, const mre_zsl_model *m, const float *A, const float *
     MRE_CHECK_ARG(P == 0 || cand_idx, "cand_idx is NULL");
     MRE_CHECK_ARG(P == 0 || n_ent > 0, "pairs given but the entity table is empty");
     MRE_CHECK_ARG(P < (1LL << 31), "too many (head, candidate) pairs for one call");
-    const int D = (int)m->D, K = 2 * D, NP = (D + 15) / 16 * 16;
+    const int D = (int)m->D, K = 2 * D, NP = (D + 16) / 16 * 16;   // >= D + 1: one spare output row for the column sums
     const char *dev_fp32 = getenv("MRE_DEV_ZSL_FP32");                     // developer switch: the CUDA-core FP32 tile GEMMs
-    const bool fp32_path = dev_fp32 && dev_fp32[0] == '1';
+    const bool fp32_path = (dev_fp32 && dev_fp32[0] == '1') || NP > 224;  // (three operand stages of wider tiles do not fit the SM's shared memory)
     const int64_t P1 = (std::max<int64_t>(P, 1) + 3) / 4 * 4;                // keeps the float4-read relation sums 16-byte aligned
     // scratch: pair -> triple map, scores (when the caller does not want them), relation-vector norms / normalised sums
-    MRE_TRY(ctx->misc2.reserve((size_t)P1 * (sizeof(int32_t) + sizeof(float)) + (size_t)n_rel * std::max(n_vec, D) * sizeof(float) + 64));
+    MRE_TRY(ctx->misc2.reserve((size_t)P1 * (sizeof(int32_t) + sizeof(float)) + (size_t)n_rel * std::max(n_vec, D + 1) * sizeof(float) + 64));
     int32_t *pair_triple = ctx->misc2.as<int32_t>();
     float *sc = scores ? scores : reinterpret_cast<float *>(pair_triple + P1);
     float *rel_aux = reinterpret_cast<float *>(pair_triple + P1) + P1;
@@ -720,32 +759,32 @@ int zsl_rank(mre_ctx *ctx, const mre_zsl_model *m, const float *A, const float *
         MRE_TRY(ctx->time_end(st));
     } else if (P > 0) {
         // per-entity hidden halves A1 = W1 A + b1, B1 = W1 B, and the TF32 hi / lo split of W2 (rows zero-padded to NP)
-        MRE_TRY(ctx->ent_aux.reserve(((size_t)2 * n_ent * K + (size_t)2 * NP * K) * sizeof(float) + 256));
+        const int64_t n4 = (n_ent + 3) / 4 * 4;
+        MRE_TRY(ctx->ent_aux.reserve(((size_t)2 * n_ent * K + (size_t)2 * NP * K + 2 * n4) * sizeof(float) + 256));
         float *A1 = ctx->ent_aux.as<float>(), *B1 = A1 + n_ent * K, *w_hi = B1 + n_ent * K, *w_lo = w_hi + (size_t)NP * K;
+        float *sA = w_lo + (size_t)NP * K, *sB = sA + n4;
         dim3 g1((unsigned)((n_ent + 127) / 128), (unsigned)((K + 127) / 128));
         zsl_layer1_kernel<<<g1, 256, 0, st>>>(*m, A, nullptr, nullptr, nullptr, nullptr, 0, n_ent, A1, 0, 1);
         zsl_layer1_kernel<<<g1, 256, 0, st>>>(*m, B, nullptr, nullptr, nullptr, nullptr, 0, n_ent, B1, 0, 0);
         zsl_split_w2_kernel<<<(NP * K + 255) / 256, 256, 0, st>>>(m->proj2_w, D, K, NP, w_hi, w_lo);
-        if (n_rel > 0) zsl_relsum_kernel<<<(unsigned)n_rel, 128, 0, st>>>(rel_vecs, n_vec, D, rel_aux);
-        ctx->launches += 4;
+        zsl_rowsum_kernel<<<(unsigned)((n_ent + 7) / 8), 256, 0, st>>>(A, n_ent, D, sA);
+        zsl_rowsum_kernel<<<(unsigned)((n_ent + 7) / 8), 256, 0, st>>>(B, n_ent, D, sB);
+        if (n_rel > 0) zsl_relsum_kernel<<<(unsigned)n_rel, 128, 0, st>>>(rel_vecs, n_vec, D, m->ln_b, rel_aux, rel_aux + n_rel * D);
+        ctx->launches += 6;
         CUtensorMap tm_hi, tm_lo;
         MRE_TRY(make_tmap_f32_2d(&tm_hi, w_hi, NP, K, K, NP, ZT_BK));
         MRE_TRY(make_tmap_f32_2d(&tm_lo, w_lo, NP, K, K, NP, ZT_BK));
         ZslTcParams tp;
-        tp.A1 = A1; tp.B1 = B1; tp.A = A; tp.B = B;
+        tp.A1 = A1; tp.B1 = B1; tp.A = A; tp.B = B; tp.sA = sA; tp.sB = sB;
         tp.q_head = q_head; tp.q_rel = q_rel; tp.cand = cand_idx; tp.pair_triple = pair_triple;
-        tp.rsum = rel_aux; tp.b2 = m->proj2_b; tp.ln_g = m->ln_g; tp.ln_b = m->ln_b;
+        tp.rsum = rel_aux; tp.bR = rel_aux + n_rel * D; tp.b2 = m->proj2_b; tp.ln_g = m->ln_g; tp.ln_b = m->ln_b;
         tp.ln_eps = m->ln_eps; tp.inv_nvec = 1.f / (float)n_vec;
         tp.D = D; tp.K = K; tp.NP = NP; tp.nkb = K / ZT_BK;
         tp.idesc = umma_idesc_tf32(128, NP);
         tp.P = P; tp.tiles = (P + ZT_ROWS - 1) / ZT_ROWS;
         tp.score = sc;
         const size_t smem = (size_t)ZT_STAGES * (2 * ZT_A_BYTES + 2 * (size_t)NP * ZT_BK * 4) + 1024;
-        static bool attr_set = false;
-        if (!attr_set) {
-            MRE_CUDA(cudaFuncSetAttribute(zsl_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            attr_set = true;
-        }
+        MRE_CUDA(cudaFuncSetAttribute(zsl_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const int sms = ctx->sm_count > 0 ? ctx->sm_count : 148;
         MRE_TRY(ctx->time_begin(st));
         zsl_tc_kernel<<<(unsigned)std::min<int64_t>(tp.tiles, sms), ZT_THREADS, smem, st>>>(tm_hi, tm_lo, tp);
