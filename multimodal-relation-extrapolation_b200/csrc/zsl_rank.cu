@@ -341,19 +341,27 @@ __global__ void __launch_bounds__(256, 2) zsl_layer2_kernel(const mre_zsl_model 
 // the row is read, and the whole epilogue is ONE pass over TMEM on centred values d = u - mu:
 //     var = sum d^2 / D,  z = d rstd g + be,  z . rsum = rstd sum (d g) rsum + be . rsum,  |z|^2 = rstd^2 sum (d g)^2 + 2 rstd sum (d g) be + |be|^2
 // (rsum = sum_k r_k / ||r_k||: the cosine mean is linear in the normalised relation vectors).
-//   CTA = one SM, persistent over 256-pair tiles (two 128-row accumulators, 2 x NP <= 512 TMEM columns), 16 warps:
-//     warps 0-7     operand producers, thread = pair row: gather A1[head], B1[cand] (L2-resident), add, relu, split, store the
-//                   hi / lo rows in the canonical K-major SWIZZLE_64B layout (the contraction's left operand never sees HBM);
-//                   lane 0 of warp 0 also issues the TMA loads of the W2 hi / lo k-blocks (NP rows x 16 floats) of each stage
-//     warps 8-15    epilogue, thread = pair row (TMEM lane); warp 8 first issues the tile's tcgen05.mma (12 per k-block:
-//                   2 sub-tiles x 2 k-steps x 3 split products) -- with one accumulator set the two phases alternate anyway
-constexpr int ZT_ROWS = 256, ZT_BK = 16, ZT_STAGES = 3, ZT_PROD_WARPS = 8, ZT_EPI_WARPS = 8;
-constexpr int ZT_THREADS = 32 * (ZT_PROD_WARPS + ZT_EPI_WARPS);
+//   Two CTAs (a cluster, cta_group::2) walk 256-pair tiles together: each stages its own 128 pair rows and HALF of every W2
+//   k-block (NP / 2 rows x 16 floats, hi and lo), one tcgen05.mma of the leader drives both SMs' tensor cores (M = 256), and each
+//   CTA keeps two 128 x NP accumulators in TMEM, so the epilogue of tile i runs under the MMAs of tile i + 1.  17 warps per CTA:
+//     warps 0-7     operand producers: four lanes share a pair row (one 16-byte quarter of its 64-byte k-block each); gather
+//                   A1[head], B1[cand] (L2-resident), add, relu, split, store the hi / lo rows in the canonical K-major
+//                   SWIZZLE_64B layout (the contraction's left operand never sees HBM), then arrive on the LEADER's full
+//                   barrier; lane 0 of warp 0 also issues the TMA loads of this CTA's W2 half
+//     warps 8-15    epilogue, thread = pair row (TMEM lane), two warps per 32-lane quarter splitting the columns; partial sums
+//                   meet in shared memory
+//     warp 16       MMA issuer (leader CTA): 6 tcgen05.mma per k-block (2 k-steps x 3 split products), commits multicast to both
+#ifndef MRE_ZT_STAGES
+#define MRE_ZT_STAGES 6
+#endif
+constexpr int ZT_ROWS = 256, ZT_CTA_ROWS = 128, ZT_BK = 16, ZT_STAGES = MRE_ZT_STAGES, ZT_PROD_WARPS = 8, ZT_EPI_WARPS = 8;
+constexpr int ZT_PASSES = ZT_CTA_ROWS / (ZT_PROD_WARPS * 8);      // a producer warp covers its rows 8 at a time
+constexpr int ZT_THREADS = 32 * (ZT_PROD_WARPS + ZT_EPI_WARPS + 1);
 #ifndef MRE_ZT_DIAG
 #define MRE_ZT_DIAG 0      // developer timing variants: 1 no residual gather, 4 no B1 gather, 16 no epilogue work
 #endif
 constexpr int ZT_XPITCH = 36;                                      // floats per staged residual row (32 + 4: conflict-free both ways)
-constexpr int ZT_A_BYTES = ZT_ROWS * ZT_BK * 4;                    // one of the hi / lo operand tiles of a stage
+constexpr int ZT_A_BYTES = ZT_CTA_ROWS * ZT_BK * 4;                // one of the hi / lo operand tiles of a stage (this CTA's rows)
 
 struct ZslTcParams {
     const float *A1, *B1, *A, *B, *sA, *sB;                         // sA / sB: row sums of A / B
@@ -424,28 +432,46 @@ __global__ void zsl_relsum_kernel(const float *__restrict__ rel_vecs, int n_vec,
     }
 }
 
+// round-to-nearest (ties away) TF32 of a finite non-negative float in two integer ops (cvt.rna.tf32 adds an inf / nan guard)
+__device__ __forceinline__ float tf32_hi(float v) { return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u); }
+
+// D[tmem of both CTAs] (+)= A * B^T, kind::tf32, over a CTA pair (M = 256, each CTA holds 128 rows of A / D and half of B's rows)
+__device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
 __global__ void __launch_bounds__(ZT_THREADS, 1) zsl_tc_kernel(const __grid_constant__ CUtensorMap tm_hi,
                                                                const __grid_constant__ CUtensorMap tm_lo, const ZslTcParams p) {
     extern __shared__ uint8_t zt_smem[];
-    __shared__ __align__(8) uint64_t bars[2 * ZT_STAGES + 2];
+    __shared__ __align__(8) uint64_t bars[2 * ZT_STAGES + 4];
     __shared__ uint32_t tmem_slot;
     __shared__ __align__(16) float s_vec[3][256];
     __shared__ float s_scal[2];
     __shared__ __align__(16) float s_stage[ZT_EPI_WARPS][32][ZT_XPITCH];   // per epilogue warp: 32 rows x 32 residual columns, transposed on the way
     __shared__ int s_cand[ZT_EPI_WARPS][32];
+    __shared__ __align__(16) float4 s_part[2][4][32];                      // [tile parity][quarter][row]: the upper column half's partial sums
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int64_t worker = blockIdx.x >> 1, n_workers = gridDim.x >> 1;
     const uint32_t base = (smem_u32(zt_smem) + 1023u) & ~1023u;
-    const uint32_t w_bytes = (uint32_t)p.NP * ZT_BK * 4, stage_bytes = 2 * ZT_A_BYTES + 2 * w_bytes;
+    const uint32_t w_bytes = (uint32_t)(p.NP / 2) * ZT_BK * 4, stage_bytes = 2 * ZT_A_BYTES + 2 * w_bytes;
     auto full = [&](int s) { return smem_u32(&bars[s]); };
     auto empty = [&](int s) { return smem_u32(&bars[ZT_STAGES + s]); };
-    const uint32_t acc_full = smem_u32(&bars[2 * ZT_STAGES]), acc_empty = smem_u32(&bars[2 * ZT_STAGES + 1]);
+    auto acc_full = [&](int b) { return smem_u32(&bars[2 * ZT_STAGES + b]); };
+    auto acc_empty = [&](int b) { return smem_u32(&bars[2 * ZT_STAGES + 2 + b]); };
     if (tid == 0) {
         for (int s = 0; s < ZT_STAGES; s++) {
-            mbar_init(full(s), ZT_PROD_WARPS + 1);
+            mbar_init(full(s), 2 * ZT_PROD_WARPS + 1);              // (leader's copy is the one used) both CTAs' producer warps + the expect_tx arrive
             mbar_init(empty(s), 1);
         }
-        mbar_init(acc_full, 1);
-        mbar_init(acc_empty, ZT_EPI_WARPS);
+        for (int b = 0; b < 2; b++) {
+            mbar_init(acc_full(b), 1);
+            mbar_init(acc_empty(b), 2 * ZT_EPI_WARPS);              // (leader's copy) the epilogue warps of both CTAs
+        }
         fence_barrier_init();
         tma_prefetch_desc(&tm_hi);
         tma_prefetch_desc(&tm_lo);
@@ -468,64 +494,66 @@ __global__ void __launch_bounds__(ZT_THREADS, 1) zsl_tc_kernel(const __grid_cons
         }
         if (lane == 0) { s_scal[0] = a; s_scal[1] = b; }
     }
-    if (warp == ZT_PROD_WARPS) tmem_alloc(smem_u32(&tmem_slot), 512);
+    constexpr int MMA_WARP = ZT_PROD_WARPS + ZT_EPI_WARPS;
+    if (warp == MMA_WARP) tmem_alloc_pair(smem_u32(&tmem_slot), 512);
     tc_fence_before();
-    __syncthreads();
+    cluster_sync_all();                                             // both CTAs' barriers are initialised before either signals the other's
     tc_fence_after();
     const uint32_t tmem = tmem_slot;
 
     if (warp < ZT_PROD_WARPS) {
-        // ---- operand producers (+ the W2 loads).  Four lanes share a pair row (one 16-byte quarter of its 64-byte k-block each),
-        // so a warp-wide load touches 8 rows x 64 contiguous bytes instead of 32 scattered 16-byte pieces; a warp owns 32 rows
-        // and covers them in four passes of 8.
+        // ---- operand producers (+ this CTA's W2 half)
         const int rr = lane >> 2, j = lane & 3;
         const uint32_t sw = (uint32_t)(rr >> 1) & 3u;
-        const uint32_t row_off = (uint32_t)(warp * 32 + rr) * (ZT_BK * 4) + (((uint32_t)j ^ sw) << 4);
+        const uint32_t row_off = (uint32_t)(warp * 8 * ZT_PASSES + rr) * (ZT_BK * 4) + (((uint32_t)j ^ sw) << 4);
+        const uint32_t full_leader0 = mapa_shared(full(0), 0);
         int s = 0;
         uint32_t ph = 0;
-        const float4 *a1[4], *b1[4], *na1[4], *nb1[4];
-        auto row_ptrs = [&](int64_t tile, const float4 *(&pa)[4], const float4 *(&pb)[4]) {
+        const float4 *a1[ZT_PASSES], *b1[ZT_PASSES], *na1[ZT_PASSES], *nb1[ZT_PASSES];
+        auto row_ptrs = [&](int64_t tile, const float4 *(&pa)[ZT_PASSES], const float4 *(&pb)[ZT_PASSES]) {
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const int64_t pr = min(tile * ZT_ROWS + warp * 32 + i * 8 + rr, p.P - 1);   // rows past the end recompute the last pair
+            for (int i = 0; i < ZT_PASSES; i++) {
+                const int64_t pr = min(tile * ZT_ROWS + rank * ZT_CTA_ROWS + warp * 8 * ZT_PASSES + i * 8 + rr, p.P - 1);   // rows past the end recompute the last pair
                 pa[i] = reinterpret_cast<const float4 *>(p.A1 + p.q_head[p.pair_triple[pr]] * p.K) + j;
                 pb[i] = reinterpret_cast<const float4 *>(p.B1 + p.cand[pr] * p.K) + j;
             }
         };
-        if ((int64_t)blockIdx.x < p.tiles) row_ptrs(blockIdx.x, a1, b1);
-        for (int64_t tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
-            if (tile + gridDim.x < p.tiles) row_ptrs(tile + gridDim.x, na1, nb1);   // the next tile's index chain resolves under this tile
-            float4 bq[4][4];
-            auto ld = [&](float4 (&d)[4], int kb) {
+        if (worker < p.tiles) row_ptrs(worker, a1, b1);
+        for (int64_t tile = worker; tile < p.tiles; tile += n_workers) {
+            if (tile + n_workers < p.tiles) row_ptrs(tile + n_workers, na1, nb1);   // the next tile's index chain resolves under this tile
+            float4 bq[4][2 * ZT_PASSES];                           // [.][2 i] = the candidate's quarter k-block, [.][2 i + 1] = the head's
+            auto ld = [&](float4 (&d)[2 * ZT_PASSES], int kb) {
 #pragma unroll
-                for (int i = 0; i < 4; i++) d[i] = (MRE_ZT_DIAG & 4) ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldg(b1[i] + kb * 4);
+                for (int i = 0; i < ZT_PASSES; i++) {
+                    d[2 * i] = (MRE_ZT_DIAG & 4) ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldg(b1[i] + kb * 4);
+                    d[2 * i + 1] = __ldg(a1[i] + kb * 4);
+                }
             };
-            auto put = [&](const float4 (&bv)[4], int kb) {
-                float4 av[4];
-#pragma unroll
-                for (int i = 0; i < 4; i++) av[i] = __ldg(a1[i] + kb * 4);
+            auto put = [&](const float4 (&q)[2 * ZT_PASSES], int kb) {
                 mbar_wait(empty(s), ph ^ 1);
-                if (warp == 0 && lane == 0) {
-                    mbar_arrive_expect_tx(full(s), 2 * w_bytes);
-                    const uint32_t w = base + s * stage_bytes + 2 * ZT_A_BYTES;
-                    tma_load_2d_hint(w, &tm_hi, kb * ZT_BK, 0, full(s), L2_EVICT_LAST);
-                    tma_load_2d_hint(w + w_bytes, &tm_lo, kb * ZT_BK, 0, full(s), L2_EVICT_LAST);
+                if (warp == 0 && lane == 0) {                       // the bytes of both CTAs' halves are counted by the leader's barrier
+                    if (rank == 0) mbar_arrive_expect_tx(full(s), 4 * w_bytes);
+                    const uint32_t w = base + s * stage_bytes + 2 * ZT_A_BYTES, fl = full_leader0 + 8 * s;
+                    tma_load_2d_pair(w, &tm_hi, kb * ZT_BK, (int)rank * (p.NP / 2), fl, L2_EVICT_LAST);
+                    tma_load_2d_pair(w + w_bytes, &tm_lo, kb * ZT_BK, (int)rank * (p.NP / 2), fl, L2_EVICT_LAST);
                 }
                 const uint32_t a_hi = base + s * stage_bytes + row_off, a_lo = a_hi + ZT_A_BYTES;
 #pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    const float v0 = fmaxf(av[i].x + bv[i].x, 0.f), v1 = fmaxf(av[i].y + bv[i].y, 0.f);
-                    const float v2 = fmaxf(av[i].z + bv[i].z, 0.f), v3 = fmaxf(av[i].w + bv[i].w, 0.f);
-                    const float h0 = tf32_rna(v0), h1 = tf32_rna(v1), h2 = tf32_rna(v2), h3 = tf32_rna(v3);
+                for (int i = 0; i < ZT_PASSES; i++) {
+                    const float v0 = fmaxf(q[2 * i + 1].x + q[2 * i].x, 0.f), v1 = fmaxf(q[2 * i + 1].y + q[2 * i].y, 0.f);
+                    const float v2 = fmaxf(q[2 * i + 1].z + q[2 * i].z, 0.f), v3 = fmaxf(q[2 * i + 1].w + q[2 * i].w, 0.f);
+                    const float h0 = tf32_hi(v0), h1 = tf32_hi(v1), h2 = tf32_hi(v2), h3 = tf32_hi(v3);
                     const uint32_t off = (uint32_t)i * 8 * (ZT_BK * 4);
                     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a_hi + off), "f"(h0), "f"(h1), "f"(h2), "f"(h3) : "memory");
-                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a_lo + off), "f"(tf32_rna(v0 - h0)), "f"(tf32_rna(v1 - h1)),
-                                 "f"(tf32_rna(v2 - h2)), "f"(tf32_rna(v3 - h3))
+                    // lo = v - hi is exact in FP32; the tensor core reads its leading 11 significand bits (2^-21 |v| at worst)
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a_lo + off), "f"(v0 - h0), "f"(v1 - h1), "f"(v2 - h2), "f"(v3 - h3)
                                  : "memory");
                 }
                 fence_proxy_async();                                // generic-proxy stores -> visible to the tensor core's async proxy
                 __syncwarp();
-                if (lane == 0) mbar_arrive(full(s));
+                // (relaxed: a release.cluster arrive costs a MEMBAR.ALL.GPU per k-block; the proxy fence above has already made
+                // the rows visible to the tensor core before the arrive is issued)
+                if (lane == 0) mbar_arrive_cluster_relaxed(full_leader0 + 8 * s);
                 if (++s == ZT_STAGES) { s = 0; ph ^= 1; }
             };
             ld(bq[0], 0);
@@ -541,20 +569,52 @@ __global__ void __launch_bounds__(ZT_THREADS, 1) zsl_tc_kernel(const __grid_cons
                 }
             }
 #pragma unroll
-            for (int i = 0; i < 4; i++) { a1[i] = na1[i]; b1[i] = nb1[i]; }
+            for (int i = 0; i < ZT_PASSES; i++) { a1[i] = na1[i]; b1[i] = nb1[i]; }
         }
+    } else if (warp == MMA_WARP) {
+        // ---- MMA issuer: only the leader CTA issues, one instruction drives both SMs' tensor cores
+        if (rank == 0 && lane == 0) {
+            int s = 0;
+            uint32_t ph = 0, n = 0;
+            for (int64_t tile = worker; tile < p.tiles; tile += n_workers, n++) {
+                const uint32_t buf = n & 1;
+                mbar_wait(acc_empty(buf), ((n >> 1) & 1) ^ 1);      // both CTAs' epilogues have drained this accumulator buffer
+                tc_fence_after();
+                const uint32_t d = tmem + buf * (uint32_t)p.NP;
+                for (int kb = 0; kb < p.nkb; kb++) {
+                    mbar_wait(full(s), ph);
+                    tc_fence_after();
+                    const uint32_t a_hi = base + s * stage_bytes, a_lo = a_hi + ZT_A_BYTES, w_hi = a_hi + 2 * ZT_A_BYTES, w_lo = w_hi + w_bytes;
+#pragma unroll
+                    for (int kk = 0; kk < ZT_BK / 8; kk++) {
+                        const uint64_t da_hi = umma_desc_k64(a_hi) + kk * 2, da_lo = umma_desc_k64(a_lo) + kk * 2;
+                        const uint64_t db_hi = umma_desc_k64(w_hi) + kk * 2, db_lo = umma_desc_k64(w_lo) + kk * 2;
+                        umma_tf32_pair(d, da_lo, db_hi, p.idesc, (kb | kk) != 0);     // the small cross terms first
+                        umma_tf32_pair(d, da_hi, db_lo, p.idesc, 1);
+                        umma_tf32_pair(d, da_hi, db_hi, p.idesc, 1);
+                    }
+                    umma_commit_pair(empty(s), 3);                  // the stage is reusable in both CTAs once these MMAs retire
+                    if (++s == ZT_STAGES) { s = 0; ph ^= 1; }
+                }
+                umma_commit_pair(acc_full(buf), 3);
+            }
+        }
+        __syncwarp();
     } else {
-        // ---- MMA issue (warp 8) and epilogue: thread = TMEM lane = pair row
-        const int ew = warp - ZT_PROD_WARPS, q = warp & 3, sub = ew >> 2, r = sub * 128 + q * 32 + lane;
-        const uint32_t t0 = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(sub * p.NP);
+        // ---- epilogue: thread = TMEM lane = pair row; the two warps of a lane quarter split the columns
+        const int ew = warp - ZT_PROD_WARPS, q = warp & 3, half = ew >> 2, r = q * 32 + lane;
+        const int nch = p.D / 8, c_split = ((nch + 1) / 2) * 8;
+        const int c_lo = half ? c_split : 0, c_hi = half ? p.D : c_split;
+        const int ngrp = (c_hi - c_lo + 31) / 32;
+        const uint32_t t_lane = tmem + ((uint32_t)(q * 32) << 16);
         const float inv_d = 1.f / (float)p.D;
-        const int ngrp = (p.D + 31) / 32;
         float (*stg)[ZT_XPITCH] = s_stage[ew];
         const int lr = lane >> 3, lc = (lane & 7) * 4;             // coalesced residual loads: 8 lanes cover 128 bytes of one row
-        int s = 0;
-        uint32_t ph = 0, aph = 0;
-        for (int64_t tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
-            const int64_t pr0 = tile * ZT_ROWS + r, pr = min(pr0, p.P - 1);
+        const uint32_t acc_empty_leader0 = mapa_shared(acc_empty(0), 0);
+        uint32_t n = 0;
+        for (int64_t tile = worker; tile < p.tiles; tile += n_workers, n++) {
+            const uint32_t buf = n & 1;
+            const int64_t pr0 = tile * ZT_ROWS + rank * ZT_CTA_ROWS + r, pr = min(pr0, p.P - 1);
             const int t = p.pair_triple[pr];
             const int64_t head = p.q_head[t], cnd = p.cand[pr], rel = p.q_rel[t];
             const float4 *xa = reinterpret_cast<const float4 *>(p.A + head * p.D);
@@ -563,104 +623,78 @@ __global__ void __launch_bounds__(ZT_THREADS, 1) zsl_tc_kernel(const __grid_cons
             __syncwarp();
             s_cand[ew][lane] = (int)cnd;
             __syncwarp();
-            const float *xrow[8];
-#pragma unroll
-            for (int i = 0; i < 8; i++) xrow[i] = p.B + (int64_t)s_cand[ew][4 * i + lr] * p.D + lc;
             float4 xr[8];                                           // the candidates' residual columns of the next 32-column group
             auto ldx = [&](int g) {
 #pragma unroll
                 for (int i = 0; i < 8; i++)
-                    xr[i] = (!(MRE_ZT_DIAG & 1) && g * 32 + lc < p.D) ? __ldg(reinterpret_cast<const float4 *>(xrow[i] + g * 32))
-                                                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+                    xr[i] = (!(MRE_ZT_DIAG & 1) && c_lo + g * 32 + lc < c_hi)
+                                ? __ldg(reinterpret_cast<const float4 *>(p.B + (int64_t)s_cand[ew][4 * i + lr] * p.D + (c_lo + g * 32 + lc)))
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
             };
             ldx(0);
-            if (ew == 0) {
-                mbar_wait(acc_empty, aph ^ 1);
-                tc_fence_after();
-                for (int kb = 0; kb < p.nkb; kb++) {
-                    mbar_wait(full(s), ph);
-                    tc_fence_after();
-                    if (lane == 0) {
-                        const uint32_t a_hi = base + s * stage_bytes, a_lo = a_hi + ZT_A_BYTES, w_hi = a_hi + 2 * ZT_A_BYTES, w_lo = w_hi + w_bytes;
-#pragma unroll
-                        for (int sb = 0; sb < 2; sb++) {
-                            const uint32_t d = tmem + (uint32_t)(sb * p.NP);
-#pragma unroll
-                            for (int kk = 0; kk < ZT_BK / 8; kk++) {
-                                const uint64_t da_hi = umma_desc_k64(a_hi + sb * (ZT_A_BYTES / 2)) + kk * 2, da_lo = umma_desc_k64(a_lo + sb * (ZT_A_BYTES / 2)) + kk * 2;
-                                const uint64_t db_hi = umma_desc_k64(w_hi) + kk * 2, db_lo = umma_desc_k64(w_lo) + kk * 2;
-                                umma_tf32(d, da_lo, db_hi, p.idesc, (kb | kk) != 0);     // the small cross terms first
-                                umma_tf32(d, da_hi, db_lo, p.idesc, 1);
-                                umma_tf32(d, da_hi, db_hi, p.idesc, 1);
-                            }
-                        }
-                        umma_commit(empty(s));
-                        if (kb == p.nkb - 1) umma_commit(acc_full);
-                    }
-                    __syncwarp();
-                    if (++s == ZT_STAGES) { s = 0; ph ^= 1; }
-                }
-            }
-            mbar_wait(acc_full, aph);
-            aph ^= 1;
+            mbar_wait(acc_full(buf), (n >> 1) & 1);
             tc_fence_after();
-            if (MRE_ZT_DIAG & 16) {
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(acc_empty);
-                if (pr0 < p.P) p.score[pr0] = (float)t + xr[0].x;
-                continue;
-            }
-            float mu;
-            {
-                uint32_t v[8];
-                tmem_ld_32x8(t0 + p.D, v);                          // column D: sum_d (Hid W2^T)[d], from the column-sum row of W2
-                tmem_ld_wait();
-                mu = ((__uint_as_float(v[0]) + s_scal[0]) + sum_x) * inv_d;
-            }
+            const uint32_t t0 = t_lane + buf * (uint32_t)p.NP;
             float var = 0.f, q2 = 0.f, sgb = 0.f, dotp = 0.f;
-            for (int g = 0; g < ngrp; g++) {
-                const int c0 = g * 32;
-                __syncwarp();                                       // the previous group's rows have been read
+            if (!(MRE_ZT_DIAG & 16)) {
+                float mu;
+                {
+                    uint32_t v[8];
+                    tmem_ld_32x8(t0 + p.D, v);                      // column D: sum_d (Hid W2^T)[d], from the column-sum row of W2
+                    tmem_ld_wait();
+                    mu = ((__uint_as_float(v[0]) + s_scal[0]) + sum_x) * inv_d;
+                }
+                for (int g = 0; g < ngrp; g++) {
+                    const int c0 = c_lo + g * 32;
+                    __syncwarp();                                   // the previous group's rows have been read
 #pragma unroll
-                for (int i = 0; i < 8; i++) *reinterpret_cast<float4 *>(&stg[4 * i + lr][lc]) = xr[i];
-                __syncwarp();
-                if (g + 1 < ngrp) ldx(g + 1);
-                uint32_t v[4][8];
+                    for (int i = 0; i < 8; i++) *reinterpret_cast<float4 *>(&stg[4 * i + lr][lc]) = xr[i];
+                    __syncwarp();
+                    if (g + 1 < ngrp) ldx(g + 1);
+                    uint32_t v[4][8];
 #pragma unroll
-                for (int k = 0; k < 4; k++)
-                    if (c0 + 8 * k < p.D) tmem_ld_32x8(t0 + c0 + 8 * k, v[k]);
-                tmem_ld_wait();
+                    for (int k = 0; k < 4; k++)
+                        if (c0 + 8 * k < c_hi) tmem_ld_32x8(t0 + c0 + 8 * k, v[k]);
+                    tmem_ld_wait();
 #pragma unroll
-                for (int k = 0; k < 4; k++)
-                    if (c0 + 8 * k < p.D) {
+                    for (int k = 0; k < 4; k++)
+                        if (c0 + 8 * k < c_hi) {
 #pragma unroll
-                        for (int h = 0; h < 2; h++) {
-                            const int c = c0 + 8 * k + 4 * h;
-                            const float4 a = (MRE_ZT_DIAG & 1) ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldg(xa + c / 4);
-                            const float4 b = *reinterpret_cast<const float4 *>(&stg[lane][8 * k + 4 * h]), rr4 = __ldg(rs + c / 4);
-                            const float4 b2 = *reinterpret_cast<const float4 *>(&s_vec[0][c]);
-                            const float4 gg = *reinterpret_cast<const float4 *>(&s_vec[1][c]);
-                            const float4 be = *reinterpret_cast<const float4 *>(&s_vec[2][c]);
-                            const float xs[4] = {a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w};
-                            const float b2s[4] = {b2.x, b2.y, b2.z, b2.w}, gs[4] = {gg.x, gg.y, gg.z, gg.w};
-                            const float bes[4] = {be.x, be.y, be.z, be.w}, rrs[4] = {rr4.x, rr4.y, rr4.z, rr4.w};
+                            for (int h = 0; h < 2; h++) {
+                                const int c = c0 + 8 * k + 4 * h;
+                                const float4 a = (MRE_ZT_DIAG & 1) ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldg(xa + c / 4);
+                                const float4 b = *reinterpret_cast<const float4 *>(&stg[lane][8 * k + 4 * h]), rr4 = __ldg(rs + c / 4);
+                                const float4 b2 = *reinterpret_cast<const float4 *>(&s_vec[0][c]);
+                                const float4 gg = *reinterpret_cast<const float4 *>(&s_vec[1][c]);
+                                const float4 be = *reinterpret_cast<const float4 *>(&s_vec[2][c]);
+                                const float xs[4] = {a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w};
+                                const float b2s[4] = {b2.x, b2.y, b2.z, b2.w}, gs[4] = {gg.x, gg.y, gg.z, gg.w};
+                                const float bes[4] = {be.x, be.y, be.z, be.w}, rrs[4] = {rr4.x, rr4.y, rr4.z, rr4.w};
 #pragma unroll
-                            for (int i = 0; i < 4; i++) {
-                                const float u = (__uint_as_float(v[k][4 * h + i]) + b2s[i]) + xs[i];
-                                const float d = u - mu, e = d * gs[i];
-                                var = fmaf(d, d, var);
-                                q2 = fmaf(e, e, q2);
-                                sgb = fmaf(e, bes[i], sgb);
-                                dotp = fmaf(e, rrs[i], dotp);
+                                for (int i = 0; i < 4; i++) {
+                                    const float u = (__uint_as_float(v[k][4 * h + i]) + b2s[i]) + xs[i];
+                                    const float d = u - mu, e = d * gs[i];
+                                    var = fmaf(d, d, var);
+                                    q2 = fmaf(e, e, q2);
+                                    sgb = fmaf(e, bes[i], sgb);
+                                    dotp = fmaf(e, rrs[i], dotp);
+                                }
                             }
                         }
-                    }
+                }
+            } else {
+                dotp = xr[0].x;
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(acc_empty);                  // the accumulators are free for the next tile
-            if (pr0 < p.P) {
+            if (lane == 0) mbar_arrive_cluster_relaxed(acc_empty_leader0 + 8 * buf);   // this warp is done with the accumulator buffer
+            // the upper column half hands its partial sums to the lower one (buffers alternate with the tile parity: the
+            // writer can be at most one tile ahead of the reader)
+            if (half) s_part[n & 1][q][lane] = make_float4(var, q2, sgb, dotp);
+            asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+            if (!half && pr0 < p.P) {
+                const float4 o = s_part[n & 1][q][lane];
+                var += o.x; q2 += o.y; sgb += o.z; dotp += o.w;
                 const float rstd = rsqrtf(var * inv_d + p.ln_eps);
                 const float dot = fmaf(rstd, dotp, b_r);
                 const float nn = fmaf(rstd * rstd, q2, fmaf(2.f * rstd, sgb, s_scal[1]));
@@ -669,8 +703,11 @@ __global__ void __launch_bounds__(ZT_THREADS, 1) zsl_tc_kernel(const __grid_cons
         }
     }
     tc_fence_before();
-    __syncthreads();
-    if (warp == ZT_PROD_WARPS) tmem_dealloc(tmem, 512);
+    cluster_sync_all();                                             // neither CTA may retire while its partner can still touch its barriers / shared memory
+    if (warp == MMA_WARP) {
+        tc_fence_after();
+        tmem_dealloc_pair(tmem, 512);
+    }
 }
 
 // per test triple: how many candidates score higher than / equal to the true one (candidate 0 of its list); one warp per triple
@@ -772,22 +809,34 @@ int zsl_rank(mre_ctx *ctx, const mre_zsl_model *m, const float *A, const float *
         if (n_rel > 0) zsl_relsum_kernel<<<(unsigned)n_rel, 128, 0, st>>>(rel_vecs, n_vec, D, m->ln_b, rel_aux, rel_aux + n_rel * D);
         ctx->launches += 6;
         CUtensorMap tm_hi, tm_lo;
-        MRE_TRY(make_tmap_f32_2d(&tm_hi, w_hi, NP, K, K, NP, ZT_BK));
-        MRE_TRY(make_tmap_f32_2d(&tm_lo, w_lo, NP, K, K, NP, ZT_BK));
+        MRE_TRY(make_tmap_f32_2d(&tm_hi, w_hi, NP, K, K, NP / 2, ZT_BK));   // a CTA of the pair loads half of the rows
+        MRE_TRY(make_tmap_f32_2d(&tm_lo, w_lo, NP, K, K, NP / 2, ZT_BK));
         ZslTcParams tp;
         tp.A1 = A1; tp.B1 = B1; tp.A = A; tp.B = B; tp.sA = sA; tp.sB = sB;
         tp.q_head = q_head; tp.q_rel = q_rel; tp.cand = cand_idx; tp.pair_triple = pair_triple;
         tp.rsum = rel_aux; tp.bR = rel_aux + n_rel * D; tp.b2 = m->proj2_b; tp.ln_g = m->ln_g; tp.ln_b = m->ln_b;
         tp.ln_eps = m->ln_eps; tp.inv_nvec = 1.f / (float)n_vec;
         tp.D = D; tp.K = K; tp.NP = NP; tp.nkb = K / ZT_BK;
-        tp.idesc = umma_idesc_tf32(128, NP);
+        tp.idesc = umma_idesc_tf32(256, NP);
         tp.P = P; tp.tiles = (P + ZT_ROWS - 1) / ZT_ROWS;
         tp.score = sc;
-        const size_t smem = (size_t)ZT_STAGES * (2 * ZT_A_BYTES + 2 * (size_t)NP * ZT_BK * 4) + 1024;
+        const size_t smem = (size_t)ZT_STAGES * (2 * ZT_A_BYTES + 2 * (size_t)(NP / 2) * ZT_BK * 4) + 1024;
         MRE_CUDA(cudaFuncSetAttribute(zsl_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const int sms = ctx->sm_count > 0 ? ctx->sm_count : 148;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2u * (unsigned)std::max<int64_t>(1, std::min<int64_t>(tp.tiles, sms / 2)));
+        cfg.blockDim = dim3(ZT_THREADS);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
         MRE_TRY(ctx->time_begin(st));
-        zsl_tc_kernel<<<(unsigned)std::min<int64_t>(tp.tiles, sms), ZT_THREADS, smem, st>>>(tm_hi, tm_lo, tp);
+        MRE_CUDA(cudaLaunchKernelEx(&cfg, zsl_tc_kernel, tm_hi, tm_lo, tp));
         ctx->launches += 1;
         MRE_TRY(ctx->time_end(st));
     }
