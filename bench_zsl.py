@@ -67,7 +67,7 @@ def cpu_reference(wl, threads, sample):
 
 
 def main(args, rank, world, local):
-    from bench import ClockSampler, stdout_to_stderr
+    from bench import ClockSampler, measured_peaks, stdout_to_stderr
     wl = load(rank)
     T = len(wl["heads"])
     P = int(sum(len(c) for c in wl["cands"]))
@@ -174,10 +174,17 @@ def main(args, rank, world, local):
     if dctx is not None:
         sums, rr = dctx.all_reduce_metrics(sums, rr)
     summ = mre_b200.engine.summarize(sums.cpu().numpy(), rr.cpu().numpy())
-    flops = 2.0 * P * (2 * D * 2 * D)                       # the two support-encoder GEMMs: 2 x (D x 2D) MACs per pair
+    # per pair ONE 2D -> D contraction is left (the hidden layer is split per entity); it runs as 3 x TF32 on the tensor cores
+    flops = 2.0 * P * (2 * D * D)
     kms = kern_ms / max(kern_n, 1)
     achieved = flops / (kms * 1e-3) / 1e12
-    peak = 2.0 * fp32_peak / 1e12                           # one FMA = 2 flops per lane per clock
+    tf32_probe = ctx.probe_tf32_peak() / 1e12
+    mp = measured_peaks()
+    if mp and mp.get("bf16_tflops"):
+        peak = float(mp["bf16_tflops"]) / 2.0
+        peak_src = f"half of MEASURED_PEAKS.json bf16_tflops (TF32 runs at half the BF16 rate; no TF32 figure in the file); in-process tcgen05 kind::tf32 probe: {tf32_probe:.0f} TFLOP/s"
+    else:
+        peak, peak_src = tf32_probe, "tcgen05 kind::tf32 dense MMA microbenchmark run in this process (mre_probe_tf32_peak); MEASURED_PEAKS.json absent"
     cpu_base = None
     if rank == 0 and not args.no_extra:
         rng = np.random.default_rng(0)
@@ -191,10 +198,12 @@ def main(args, rank, world, local):
             "metric": "ZSL eval test triples/sec", "value": world * T * steps / (ms * 1e-3), "unit": "triples/s", "n_gpus": world,
             "steps": steps, "warmup": warmup, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": config,
-            "roofline": {"bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
-                         "kernel": "zsl_layer1_kernel + zsl_layer2_kernel", "kernel_ms": kms, "launches_timed": kern_n,
-                         "peak_source": "2 x the FP32 add-rate microbenchmark of this process (one FFMA = 2 flops per lane per clock)",
-                         "algorithmic": "2 * pairs * (D * 2D + 2D * D) flops of the support encoder; LayerNorm / cosine epilogue not counted"},
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                         "kernel": "zsl_tc_kernel", "kernel_ms": kms, "launches_timed": kern_n, "peak_source": peak_src,
+                         "pipe_frac": 3 * 208.0 / 200.0 * achieved / peak,
+                         "algorithmic": "2 * pairs * 2D * D flops: the one per-pair contraction left after the per-entity split of the hidden layer; "
+                                        "FP32-exact results need 3 TF32 products per FP32 product and N is padded 200 -> 208, so frac <= 0.32 by "
+                                        "construction; pipe_frac = executed flops / peak.  LayerNorm / cosine epilogue and the operand gather not counted"},
             "cpu_baseline": cpu_base,
             "e2e": {"value": world * T * steps / e2e_s, "unit": "triples/s", "h2d_bytes_per_step": int(sum(a.numel() * 8 for a in host)),
                     "d2h_bytes_per_step": int(counts_h.numel() * 4), "api": "mre_zsl_entity_features + mre_zsl_rank: pinned host candidate lists in, int32 rank counts out"},

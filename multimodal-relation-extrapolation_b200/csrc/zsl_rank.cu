@@ -29,47 +29,74 @@ struct ZslDims {
 };
 
 // ------------------------------------------------------------------------------------------ per-entity halves
-// one CTA per entity; dot products are per-thread sequential fmaf over the weight row (tiny work: ~140 K MAC per entity)
+// ZE_TILE entities per CTA: every weight element a thread reads feeds ZE_TILE accumulators (the weights, 560 KB, do not fit
+// L1: one entity per CTA re-read them from L2 14 208 times and took 4.5 ms).  Dot products stay per-thread sequential fmaf
+// over the weight row, in the same order for every entity, so the halves do not depend on the tiling.
+constexpr int ZE_TILE = 8;
 __global__ void __launch_bounds__(128) zsl_entity_kernel(const mre_zsl_model m, const int64_t *__restrict__ ent_symbol,
                                                          const int64_t *__restrict__ conn, const float *__restrict__ deg,
                                                          int64_t n_ent, int max_nb, float *__restrict__ A, float *__restrict__ B) {
-    extern __shared__ float sh[];
+    extern __shared__ __align__(16) float sh[];
     const int D = (int)m.D, H = D / 2;
-    float *s_sum = sh, *s_self = sh + D, *s_N = sh + 2 * D, *s_T1 = s_N + H, *s_T2 = s_T1 + H;
-    const int64_t e = blockIdx.x;
-    if (e >= n_ent) return;
-    const int64_t sym = ent_symbol[e];
-    for (int d = threadIdx.x; d < D; d += blockDim.x) {
-        float acc = 0.f;
-        for (int j = 0; j < max_nb; j++) acc += m.symbol_emb[conn[e * max_nb + j] * D + d];   // pad id -> the zero row
-        s_sum[d] = acc;
-        s_self[d] = m.symbol_emb[sym * D + d];
+    float *s_sum = sh, *s_self = sh + ZE_TILE * D, *s_N = sh + 2 * ZE_TILE * D, *s_T1 = s_N + ZE_TILE * H, *s_T2 = s_T1 + ZE_TILE * H;
+    const int64_t e0 = (int64_t)blockIdx.x * ZE_TILE;
+    const int ne = (int)min((int64_t)ZE_TILE, n_ent - e0);
+    for (int i = threadIdx.x; i < ZE_TILE * D; i += blockDim.x) {
+        const int te = i / D, d = i - te * D;
+        float acc = 0.f, self = 0.f;
+        if (te < ne) {
+            const int64_t e = e0 + te;
+            for (int j = 0; j < max_nb; j++) acc += m.symbol_emb[conn[e * max_nb + j] * D + d];   // pad id -> the zero row
+            self = m.symbol_emb[ent_symbol[e] * D + d];
+        }
+        s_sum[i] = acc;
+        s_self[i] = self;
     }
     __syncthreads();
-    const float dg = deg[e];
     for (int o = threadIdx.x; o < H; o += blockDim.x) {
-        float g = 0.f, a = 0.f, b = 0.f;
-        for (int d = 0; d < D; d++) {
-            g = fmaf(m.gcn_w[o * D + d], s_sum[d], g);
-            a = fmaf(m.fc1_w[o * D + d], s_self[d], a);
-            b = fmaf(m.fc2_w[o * D + d], s_self[d], b);
+        float g[ZE_TILE], a[ZE_TILE], b[ZE_TILE];
+#pragma unroll
+        for (int te = 0; te < ZE_TILE; te++) g[te] = a[te] = b[te] = 0.f;
+        for (int d = 0; d < D; d += 4) {
+            const float4 wg = *reinterpret_cast<const float4 *>(m.gcn_w + o * D + d), wa = *reinterpret_cast<const float4 *>(m.fc1_w + o * D + d);
+            const float4 wb = *reinterpret_cast<const float4 *>(m.fc2_w + o * D + d);
+#pragma unroll
+            for (int te = 0; te < ZE_TILE; te++) {
+                const float4 ss = *reinterpret_cast<const float4 *>(s_sum + te * D + d), sf = *reinterpret_cast<const float4 *>(s_self + te * D + d);
+                g[te] = fmaf(wg.w, ss.w, fmaf(wg.z, ss.z, fmaf(wg.y, ss.y, fmaf(wg.x, ss.x, g[te]))));
+                a[te] = fmaf(wa.w, sf.w, fmaf(wa.z, sf.z, fmaf(wa.y, sf.y, fmaf(wa.x, sf.x, a[te]))));
+                b[te] = fmaf(wb.w, sf.w, fmaf(wb.z, sf.z, fmaf(wb.y, sf.y, fmaf(wb.x, sf.x, b[te]))));
+            }
         }
-        s_N[o] = tanhf((g + (float)max_nb * m.gcn_b[o]) / dg);      // every neighbour slot (pads too) carries the Linear's bias
-        s_T1[o] = tanhf(a + m.fc1_b[o]);
-        s_T2[o] = tanhf(b + m.fc2_b[o]);
+#pragma unroll
+        for (int te = 0; te < ZE_TILE; te++) {
+            const float dg = te < ne ? deg[e0 + te] : 1.f;
+            s_N[te * H + o] = tanhf((g[te] + (float)max_nb * m.gcn_b[o]) / dg);   // every neighbour slot (pads too) carries the Linear's bias
+            s_T1[te * H + o] = tanhf(a[te] + m.fc1_b[o]);
+            s_T2[te * H + o] = tanhf(b[te] + m.fc2_b[o]);
+        }
     }
     __syncthreads();
     for (int k = threadIdx.x; k < D; k += blockDim.x) {
         const float *w = m.reshape_w + (int64_t)k * 2 * D;          // [D, 2 D]: columns [N_left | T1 | T2 | N_right]
-        float a = 0.f, b = 0.f;
+        float a[ZE_TILE], b[ZE_TILE];
+#pragma unroll
+        for (int te = 0; te < ZE_TILE; te++) a[te] = b[te] = 0.f;
         for (int o = 0; o < H; o++) {
-            a = fmaf(w[o], s_N[o], a);
-            a = fmaf(w[H + o], s_T1[o], a);
-            b = fmaf(w[2 * H + o], s_T2[o], b);
-            b = fmaf(w[3 * H + o], s_N[o], b);
+            const float w0 = w[o], w1 = w[H + o], w2 = w[2 * H + o], w3 = w[3 * H + o];
+#pragma unroll
+            for (int te = 0; te < ZE_TILE; te++) {
+                const float n = s_N[te * H + o];
+                a[te] = fmaf(w1, s_T1[te * H + o], fmaf(w0, n, a[te]));
+                b[te] = fmaf(w3, n, fmaf(w2, s_T2[te * H + o], b[te]));
+            }
         }
-        A[e * D + k] = a;
-        B[e * D + k] = b + m.reshape_b[k];
+#pragma unroll
+        for (int te = 0; te < ZE_TILE; te++)
+            if (te < ne) {
+                A[(e0 + te) * D + k] = a[te];
+                B[(e0 + te) * D + k] = b[te] + m.reshape_b[k];
+            }
     }
 }
 
@@ -352,7 +379,7 @@ __global__ void __launch_bounds__(256, 2) zsl_layer2_kernel(const mre_zsl_model 
 //                   meet in shared memory
 //     warp 16       MMA issuer (leader CTA): 6 tcgen05.mma per k-block (2 k-steps x 3 split products), commits multicast to both
 #ifndef MRE_ZT_STAGES
-#define MRE_ZT_STAGES 6
+#define MRE_ZT_STAGES 4
 #endif
 constexpr int ZT_ROWS = 256, ZT_CTA_ROWS = 128, ZT_BK = 16, ZT_STAGES = MRE_ZT_STAGES, ZT_PROD_WARPS = 8, ZT_EPI_WARPS = 8;
 constexpr int ZT_PASSES = ZT_CTA_ROWS / (ZT_PROD_WARPS * 8);      // a producer warp covers its rows 8 at a time
@@ -750,8 +777,8 @@ int zsl_entity_features(mre_ctx *ctx, const mre_zsl_model *m, const int64_t *ent
     MRE_CHECK_ARG(n_ent >= 0 && max_nb >= 0, "negative size");
     if (n_ent == 0) return MRE_OK;
     MRE_CHECK_ARG(ent_symbol && conn && deg && A && B, "NULL argument");
-    const size_t smem = (size_t)(2 * m->D + 3 * (m->D / 2)) * sizeof(float);
-    zsl_entity_kernel<<<(unsigned)n_ent, 128, smem, st>>>(*m, ent_symbol, conn, deg, n_ent, max_nb, A, B);
+    const size_t smem = (size_t)ZE_TILE * (2 * m->D + 3 * (m->D / 2)) * sizeof(float);
+    zsl_entity_kernel<<<(unsigned)((n_ent + ZE_TILE - 1) / ZE_TILE), 128, smem, st>>>(*m, ent_symbol, conn, deg, n_ent, max_nb, A, B);
     ctx->launches += 1;
     MRE_CUDA(cudaGetLastError());
     return MRE_OK;
