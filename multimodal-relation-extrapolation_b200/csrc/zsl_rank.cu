@@ -629,6 +629,8 @@ __global__ void __launch_bounds__(ZT_THREADS, 1) zsl_tc_kernel(const __grid_cons
         __syncwarp();
     } else {
         // ---- epilogue: thread = TMEM lane = pair row; the two warps of a lane quarter split the columns
+        // (17 warps cap the kernel at 96 registers per thread -- 5 warps on one scheduler; setmaxnreg.inc cannot help: it draws
+        // from the CTA's own pool, and the gather warps have nothing to give back)
         const int ew = warp - ZT_PROD_WARPS, q = warp & 3, half = ew >> 2, r = q * 32 + lane;
         const int nch = p.D / 8, c_split = ((nch + 1) / 2) * 8;
         const int c_lo = half ? c_split : 0, c_hi = half ? p.D : c_split;
