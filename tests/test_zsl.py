@@ -156,3 +156,30 @@ def test_zsl_tensor_core_path_vs_fp32_path_fullsize(mre, monkeypatch):
             same += 1
             assert ctc[0][t] == c32[0][t] and ctc[1][t] == 0
     assert same > 0.5 * T                                            # (1 000 scores in a narrow range: a fifth of the triples have a near-tie)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("D", [8, 104, 216])
+def test_zsl_tensor_core_path_other_dims(mre, monkeypatch, D):
+    """model dimensions other than the reference's 200 (odd chunk counts, one k-block, the widest tile that fits): the
+    tensor-core kernel against the FP32 CUDA-core kernels, ragged lists, a tile tail and a single-candidate list"""
+    E, R, NB, T = 700, 5, 12, 9
+    rng = np.random.default_rng(D)
+    w = gu.seeded_extractor_weights(11, E + R, D)
+    conn = rng.integers(0, E, (E, NB)).astype(np.int64)
+    deg = rng.integers(1, NB + 1, E).astype(np.float32)
+    ev = mre.paper.ZSLEvaluator(w, conn, deg, np.arange(E), device=0)
+    heads, rels = rng.integers(0, E, T), rng.integers(0, R, T)
+    sizes = [1, 300, 129, 127, 256, 257, 3, 511, 64]
+    cands = [rng.choice(E, s, replace=False) for s in sizes]
+    rel_vecs = rng.standard_normal((R, 20, D)).astype(np.float32)
+    monkeypatch.setenv("MRE_DEV_ZSL_FP32", "1")
+    c32, s32 = ev.rank(heads, rels, cands, rel_vecs, want_scores=True)
+    monkeypatch.setenv("MRE_DEV_ZSL_FP32", "0")
+    ctc, stc = ev.rank(heads, rels, cands, rel_vecs, want_scores=True)
+    s32, stc, ctc = s32.cpu().numpy(), stc.cpu().numpy(), ctc.cpu().numpy()
+    assert np.isfinite(stc).all() and np.abs(s32 - stc).max() < TOL
+    ptr = np.concatenate([[0], np.cumsum(sizes)])
+    for t in range(T):
+        b = stc[ptr[t]:ptr[t + 1]]
+        assert (ctc[0][t], ctc[1][t]) == (int((b[1:] > b[0]).sum()), int((b[1:] == b[0]).sum()))
