@@ -23,6 +23,23 @@ int mre_ctx::time_end(cudaStream_t st) {
     return MRE_OK;
 }
 
+int mre_ctx::fork_aux(cudaStream_t st, cudaStream_t *aux_out) {
+    if (!aux) {
+        MRE_CUDA(cudaStreamCreateWithFlags(&aux, cudaStreamNonBlocking));
+        MRE_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+        MRE_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+    }
+    MRE_CUDA(cudaEventRecord(ev_fork, st));
+    MRE_CUDA(cudaStreamWaitEvent(aux, ev_fork, 0));
+    *aux_out = aux;
+    return MRE_OK;
+}
+int mre_ctx::join_aux(cudaStream_t st) {
+    MRE_CUDA(cudaEventRecord(ev_join, aux));
+    MRE_CUDA(cudaStreamWaitEvent(st, ev_join, 0));
+    return MRE_OK;
+}
+
 namespace mre {
 
 static int check_job(const mre_rank_job *job) {

@@ -699,10 +699,19 @@ static int bil_prepass(mre_ctx *ctx, const mre_rank_job *job, cudaStream_t st, B
 
 static int run_bilinear(mre_ctx *ctx, const mre_index *ix, const mre_rank_job *job, float *store, cudaStream_t st) {
     BilScratch sc{};
-    MRE_TRY(bil_prepass(ctx, job, st, sc));
     BilParams bp{};
     RankParams &p = bp.r;
     MRE_TRY(fill_rank_params(ctx, ix, job, BM, BN, st, p));
+    // the known-true tile filter needs only the job's descriptors: it runs on the context's second stream beside the table
+    // split, query-vector and threshold kernels, joined before the rank kernel
+    if (job->Q > 0) {
+        cudaStream_t aux = nullptr;
+        MRE_TRY(ctx->fork_aux(st, &aux));
+        init_counts_kernel<<<grid_for(4 * job->Q, 256), 256, 0, aux>>>(job->counts, 4 * job->Q);
+        ctx->launches += 1;
+        MRE_TRY(build_tile_filter(ctx, job, p, BM, BN, aux));
+    }
+    MRE_TRY(bil_prepass(ctx, job, st, sc));
     p.ent = sc.ent_full;
     p.D = sc.Kp;
     bp.k8 = sc.K8;
@@ -739,9 +748,6 @@ static int run_bilinear(mre_ctx *ctx, const mre_index *ix, const mre_rank_job *j
         b_hi = g_hi;
         b_lo = g_lo;
     }
-    init_counts_kernel<<<grid_for(4 * job->Q, 256), 256, 0, st>>>(job->counts, 4 * job->Q);
-    ctx->launches += 1;
-    MRE_TRY(build_tile_filter(ctx, job, p, BM, BN, st));
     const size_t qhalf = ((size_t)job->Q * sc.K8 * sizeof(__nv_bfloat16) + 255) & ~(size_t)255;
     const __nv_bfloat16 *q_hi = ctx->qvec2.as<__nv_bfloat16>();
     const __nv_bfloat16 *q_lo = reinterpret_cast<const __nv_bfloat16 *>(ctx->qvec2.as<char>() + qhalf);
@@ -765,6 +771,7 @@ static int run_bilinear(mre_ctx *ctx, const mre_index *ix, const mre_rank_job *j
                           : (int)std::max<int64_t>(1, std::min<int64_t>(p.total_items, ctx->sm_count));
     bp.store = store;
     bp.store_ld = cand_rows;
+    MRE_TRY(ctx->join_aux(st));
     MRE_TRY(ctx->time_begin(st));
     if (pair) {
         cudaLaunchConfig_t cfg = {};

@@ -114,6 +114,12 @@ struct mre_ctx {
     size_t ev_used = 0;
     int time_begin(cudaStream_t st);
     int time_end(cudaStream_t st);
+    // second stream for work that does not depend on the query vectors (the known-true tile filter): forked after the
+    // caller's stream has the job's descriptors in flight, joined before the rank kernel
+    cudaStream_t aux = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    int fork_aux(cudaStream_t st, cudaStream_t *aux_out);
+    int join_aux(cudaStream_t st);
 };
 
 namespace mre {

@@ -623,6 +623,13 @@ int rank_transe(mre_ctx *ctx, const mre_index *ix, const mre_rank_job *job, cuda
     p.ent = ent;
     p.D = Dp;
     if (job->Q == 0) return MRE_OK;
+    // the known-true tile filter (count / scan / fill) needs only the job's descriptors: it runs on the context's second
+    // stream beside the query-vector and threshold kernels, joined before the rank kernel
+    cudaStream_t aux = nullptr;
+    MRE_TRY(ctx->fork_aux(st, &aux));
+    init_counts_kernel<<<grid_for(4 * job->Q, 256), 256, 0, aux>>>(job->counts, 4 * job->Q);
+    ctx->launches += 1;
+    MRE_TRY(build_tile_filter(ctx, job, p, TQ, TILE_E, aux));
     if (job->p_norm == 1) MRE_TRY(transe_queries<1>(ctx, p, rel, st));
     else MRE_TRY(transe_queries<2>(ctx, p, rel, st));
     p.qvec = ctx->qvec.as<float>();
@@ -641,13 +648,11 @@ int rank_transe(mre_ctx *ctx, const mre_index *ix, const mre_rank_job *job, cuda
         }
         cand_table = ctx->ent_aux.as<float>();
     }
-    init_counts_kernel<<<grid_for(4 * job->Q, 256), 256, 0, st>>>(job->counts, 4 * job->Q);
-    ctx->launches += 1;
-    MRE_TRY(build_tile_filter(ctx, job, p, TQ, TILE_E, st));
     CUtensorMap tm_q, tm_e;
     // query vectors: [slots / 2 pair-rows][2 Dp floats], box = 64 pair-rows x 32 floats (16 d-values of two queries)
     MRE_TRY(make_tmap_f32_2d(&tm_q, p.qvec, std::max<int64_t>(p.total_slots / 2, 1), 2 * Dp, 2 * Dp, TQ / 2, CHUNK));
     MRE_TRY(make_tmap_f32_2d(&tm_e, cand_table, std::max<int64_t>(cand_rows, 1), Dp, Dp, TILE_E, CHUNK));
+    MRE_TRY(ctx->join_aux(st));
     MRE_TRY(ctx->time_begin(st));
     // the tie count is always on: one extra compare per score, in the epilogue only
     if (job->p_norm == 1) MRE_TRY((launch_rank<1, true>(ctx, p, tm_q, tm_e, st)));
