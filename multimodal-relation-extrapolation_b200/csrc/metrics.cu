@@ -23,25 +23,42 @@ __global__ void __launch_bounds__(MET_THREADS) metrics_kernel(const int32_t *__r
     const int32_t *eq = counts + (raw ? 1 : 3) * Q;
     long long acc[2][6] = {{0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0}};
     double rr[2] = {0.0, 0.0};
-    for (int64_t q = threadIdx.x; q < Q; q += MET_THREADS) {
-        const int s = q_side ? (int)q_side[q] : side;
-        long long a = max(lt[q], 0), e = max(eq[q], 0);
-        long long rank = a + 1;
-        if (rank_mode == MRE_RANK_TIES_HALF) rank += e / 2;
-        else if (rank_mode == MRE_RANK_PESSIMISTIC) rank += e;
-        const double inv = 1.0 / (double)rank;
+    // four queries of this thread's stride are fetched together (one exposed load latency per four instead of per one); they
+    // are accumulated in the same order as a plain strided loop would, so the float64 sum does not depend on the batching
+    constexpr int MB = 4;
+    for (int64_t q0 = threadIdx.x; q0 < Q; q0 += (int64_t)MB * MET_THREADS) {
+        int32_t va[MB], ve[MB];
+        int vs[MB];
 #pragma unroll
-        for (int ss = 0; ss < 2; ss++) {               // static indices: the accumulators stay in registers
-            const long long on = s == ss ? 1 : 0;
-            acc[ss][0] += on;
-            acc[ss][1] += on * rank;
-            acc[ss][2] += on & (rank <= 1);
-            acc[ss][3] += on & (rank <= 3);
-            acc[ss][4] += on & (rank <= 5);
-            acc[ss][5] += on & (rank <= 10);
-            rr[ss] += on ? inv : 0.0;
+        for (int k = 0; k < MB; k++) {
+            const int64_t q = q0 + (int64_t)k * MET_THREADS;
+            const bool ok = q < Q;
+            va[k] = ok ? lt[q] : 0;
+            ve[k] = ok ? eq[q] : 0;
+            vs[k] = ok ? (q_side ? (int)q_side[q] : side) : -1;
         }
-        if (hist) atomicAdd(hist + min((long long)hist_len - 1, rank), 1ull);
+#pragma unroll
+        for (int k = 0; k < MB; k++) {
+            if (vs[k] < 0) continue;
+            const int s = vs[k];
+            long long a = max(va[k], 0), e = max(ve[k], 0);
+            long long rank = a + 1;
+            if (rank_mode == MRE_RANK_TIES_HALF) rank += e / 2;
+            else if (rank_mode == MRE_RANK_PESSIMISTIC) rank += e;
+            const double inv = 1.0 / (double)rank;
+#pragma unroll
+            for (int ss = 0; ss < 2; ss++) {           // static indices: the accumulators stay in registers
+                const long long on = s == ss ? 1 : 0;
+                acc[ss][0] += on;
+                acc[ss][1] += on * rank;
+                acc[ss][2] += on & (rank <= 1);
+                acc[ss][3] += on & (rank <= 3);
+                acc[ss][4] += on & (rank <= 5);
+                acc[ss][5] += on & (rank <= 10);
+                rr[ss] += on ? inv : 0.0;
+            }
+            if (hist) atomicAdd(hist + min((long long)hist_len - 1, rank), 1ull);
+        }
     }
     // all 14 quantities together, in a FIXED order: butterfly inside each warp, then the 32 warp partials summed by warp 0
     // in lane order -- deterministic, two block barriers in total
