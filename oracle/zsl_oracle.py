@@ -94,3 +94,51 @@ def separable_scores(w, A, B, head, cands, rel_vecs):
     r = rel_vecs.astype(np.float64)
     cos = (g @ r.T) / (np.linalg.norm(g, axis=1)[:, None] * np.linalg.norm(r, axis=1)[None, :])
     return cos.mean(1)
+
+
+def tf32_split(x):
+    """hi + lo as the tensor-core kernel splits an FP32 operand: hi = round-to-nearest (ties away) to 11 significand bits, lo =
+    the exact FP32 remainder cut to its leading 11 bits (what kind::tf32 reads of it)"""
+    x = np.ascontiguousarray(x, np.float32)
+    hi = ((x.view(np.uint32) + np.uint32(0x1000)) & np.uint32(0xFFFFE000)).view(np.float32)
+    lo = ((x - hi).astype(np.float32).view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
+    return hi, lo
+
+
+def tensor_core_scores(w, A, B, head, cands, rel_vecs, split=True):
+    """csrc/zsl_rank.cu:zsl_tc_kernel restated: hidden layer split per entity (A1 = W1 A + b1, B1 = W1 B, FP32), the 400 -> 200
+    contraction as hi*hi + hi*lo + lo*hi of TF32-split operands (products and sums in float64 here: the tensor core adds FP32
+    rounding on top), the LayerNorm mean from the column-sum row of W2, and the one-pass centred sums
+        var = sum d^2 / D,  z . rsum = rstd sum (d g) rsum + be . rsum,  |z|^2 = rstd^2 sum (d g)^2 + 2 rstd sum (d g) be + |be|^2
+    with rsum = sum_k r_k / |r_k| (the cosine mean is linear in the normalised relation vectors)."""
+    f32 = np.float32
+    W1, b1 = w["support_encoder.proj1.weight"].astype(f32), w["support_encoder.proj1.bias"].astype(f32)
+    W2, b2 = w["support_encoder.proj2.weight"].astype(f32), w["support_encoder.proj2.bias"].astype(f32)
+    g, be = w["support_encoder.layer_norm.weight"].astype(f32), w["support_encoder.layer_norm.bias"].astype(f32)
+    D = W2.shape[0]
+    a1 = (A[head].astype(np.float64) @ W1.T.astype(np.float64) + b1).astype(f32)
+    b1c = (B[cands].astype(np.float64) @ W1.T.astype(np.float64)).astype(f32)
+    hid = np.maximum(a1[None, :] + b1c, f32(0))                                        # FP32 add, as the gather warps do
+    wsum = W2.sum(0, dtype=np.float32)                                                  # the extra output row: column sums
+    W2x = np.concatenate([W2, wsum[None, :]], 0)
+    if split:
+        hh, hl = tf32_split(hid)
+        wh = ((W2x.view(np.uint32) + np.uint32(0x1000)) & np.uint32(0xFFFFE000)).view(f32)
+        r = (W2x - wh).astype(f32)
+        wl = ((r.view(np.uint32) + np.uint32(0x1000)) & np.uint32(0xFFFFE000)).view(f32)
+        acc = (hl.astype(np.float64) @ wh.T.astype(np.float64) + hh.astype(np.float64) @ wl.T.astype(np.float64)
+               + hh.astype(np.float64) @ wh.T.astype(np.float64))
+    else:
+        acc = hid.astype(np.float64) @ W2x.T.astype(np.float64)
+    acc = acc.astype(f32)
+    x = A[head][None, :].astype(f32) + B[cands].astype(f32)
+    mu = ((acc[:, D] + b2.sum(dtype=f32)) + (A[head].sum(dtype=f32) + B[cands].sum(1, dtype=f32))) / f32(D)
+    u = (acc[:, :D] + b2[None, :]) + x
+    d = (u - mu[:, None]).astype(np.float64)
+    e = d * g
+    rn = np.linalg.norm(rel_vecs.astype(np.float64), axis=1)
+    rsum = (rel_vecs.astype(np.float64) / np.where(rn > 0, rn, 1.0)[:, None] * (rn > 0)[:, None]).sum(0)
+    rstd = 1.0 / np.sqrt((d * d).sum(1) / D + 1e-5)
+    dot = rstd * (e @ rsum) + float(be.astype(np.float64) @ rsum)
+    nn = rstd * rstd * (e * e).sum(1) + 2.0 * rstd * (e @ be.astype(np.float64)) + float((be.astype(np.float64) ** 2).sum())
+    return np.where(nn > 0, dot / np.sqrt(np.where(nn > 0, nn, 1.0)), 0.0) / rel_vecs.shape[0]

@@ -41,6 +41,30 @@ def test_separable_form_matches_reference_scores(setup):
     assert hi == lo + 1
 
 
+def test_tensor_core_restatement_matches_reference_scores(setup):
+    """oracle/zsl_oracle.py:tensor_core_scores restates what zsl_tc_kernel computes -- per-entity hidden halves, the TF32
+    hi/lo split with the lo*lo product dropped, the LayerNorm mean from a column-sum row of W2, one-pass centred sums, the
+    cosine mean folded into one normalised relation sum -- and must land on the reference's own scores"""
+    g, w, conn, deg, heads, rels, cands, rel_vecs = setup
+    n_ent = int(g["n_ent"])
+    A, B = zo.entity_halves(w, np.arange(n_ent), conn[:, :, 1], deg)
+    worst = 0.0
+    for t in range(len(cands)):
+        ref = g["scores"][g["ptr"][t]:g["ptr"][t + 1]]
+        mine = zo.tensor_core_scores(w, A, B, int(heads[t]), cands[t], rel_vecs[rels[t]])
+        worst = max(worst, float(np.abs(mine - ref).max()))
+        # the split costs nothing measurable: the same algebra with unsplit FP32 operands is no closer
+        full = zo.tensor_core_scores(w, A, B, int(heads[t]), cands[t], rel_vecs[rels[t]], split=False)
+        assert np.abs(mine - full).max() < 2e-7
+    assert worst < 2e-7, worst
+    # the split itself: hi + lo reproduces an FP32 value to 2^-21 relative, hi has 11 significand bits
+    x = np.random.default_rng(0).standard_normal(4096).astype(np.float32)
+    x = np.abs(x)
+    hi, lo = zo.tf32_split(x)
+    assert (hi.view(np.uint32) & 0x1FFF).max() == 0 and (lo.view(np.uint32) & 0x1FFF).max() == 0
+    assert (np.abs((hi.astype(np.float64) + lo) - x) <= np.abs(x) * 2.0 ** -21).all()
+
+
 def rank_bounds(ref_scores, tol):
     """ranks the reference scores allow when every score may move by tol"""
     s0 = ref_scores[0]
@@ -61,6 +85,9 @@ def test_zsl_kernels_vs_reference(mre, setup):
     err = float(np.abs(s - g["scores"]).max())
     print(f"max |score - reference score| = {err:.3e}")
     assert err < TOL                                                 # against the reference's own scores
+    for t in (2, 9):                                                 # and against the oracle's restatement of the tensor-core algebra
+        want = zo.tensor_core_scores(w, A, B, int(heads[t]), cands[t], rel_vecs[rels[t]])
+        assert np.abs(s[g["ptr"][t]:g["ptr"][t + 1]] - want).max() < TOL
     exact = 0
     for t in range(len(cands)):
         ref = g["scores"][g["ptr"][t]:g["ptr"][t + 1]]
