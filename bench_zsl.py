@@ -103,7 +103,6 @@ def main(args, rank, world, local):
     ev = mre_b200.paper.ZSLEvaluator(wl["w"], wl["conn"], wl["deg"], np.arange(wl["E"]), device=local)
     ctx, L = ev.ctx, mre_b200._lib
     rk = mre_b200.engine.Ranker(ctx)
-    fp32_peak = ctx.probe_fp32_peak()
     # device-resident inputs for `value`; pinned host inputs for `e2e`
     ptr = np.concatenate([[0], np.cumsum([len(c) for c in wl["cands"]])]).astype(np.int64)
     flat = np.concatenate(wl["cands"])

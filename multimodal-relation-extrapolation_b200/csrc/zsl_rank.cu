@@ -9,10 +9,13 @@
 //                                            cosine_similarity(cand_vecs, relation_vecs).mean(1), argsort, rank of index 0
 // The reference runs one Extractor forward per test triple, re-encoding the head's and every candidate's 50 neighbours each
 // time.  Here the encoder is SPLIT where it is linear: reshape_layer([N_h | tanh fc1(h) | tanh fc2(c) | N_c]) = A_h + B_c with
-// per-ENTITY halves A (its contribution as a pair's head) and B (as the candidate), computed once per entity; what remains
-// per (head, candidate) pair is the 200 -> 400 -> 200 support encoder, LayerNorm and the cosine mean -- two FP32 tile GEMMs
-// over all pairs of the sweep, the second with LayerNorm + cosine-mean fused in its epilogue (whole rows stay in one warp),
-// and a per-triple compare/count.  FP32 throughout (the reference's arithmetic); scores agree to rounding.
+// per-ENTITY halves A (its contribution as a pair's head) and B (as the candidate), computed once per entity; proj1 splits the
+// same way (A1 = W1 A + b1, B1 = W1 B), and the cosine mean is one dot product with sum_k r_k / ||r_k||.  What remains per
+// (head, candidate) pair -- relu(A1_h + B1_c) W2^T, the residual, LayerNorm, that dot product -- is zsl_tc_kernel below: a
+// 3 x TF32 tcgen05 contraction over CTA pairs with the epilogue read out of TMEM (FP32-level accuracy: scores within 5e-8 of
+// the reference's), then a per-triple compare/count.  The FP32 CUDA-core kernels the scorer started as (zsl_layer1_kernel in
+// pair mode + zsl_layer2_kernel: two tile GEMMs over all pairs) serve model widths the tensor-core tiles do not fit and, behind
+// MRE_DEV_ZSL_FP32=1, as the full-size cross-check of tests/test_zsl.py.
 #include <math.h>
 #include <stdlib.h>
 
