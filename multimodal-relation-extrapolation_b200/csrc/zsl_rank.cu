@@ -799,6 +799,7 @@ int zsl_rank(mre_ctx *ctx, const mre_zsl_model *m, const float *A, const float *
     MRE_CHECK_ARG(P == 0 || cand_idx, "cand_idx is NULL");
     MRE_CHECK_ARG(P == 0 || n_ent > 0, "pairs given but the entity table is empty");
     MRE_CHECK_ARG(P < (1LL << 31), "too many (head, candidate) pairs for one call");
+    MRE_CHECK_ARG(n_ent < (1LL << 31), "entity ids must fit 31 bits");
     const int D = (int)m->D, K = 2 * D, NP = (D + 16) / 16 * 16;   // >= D + 1: one spare output row for the column sums
     const char *dev_fp32 = getenv("MRE_DEV_ZSL_FP32");                     // developer switch: the CUDA-core FP32 tile GEMMs
     const bool fp32_path = (dev_fp32 && dev_fp32[0] == '1') || NP > 224;  // (three operand stages of wider tiles do not fit the SM's shared memory)
