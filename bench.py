@@ -500,8 +500,9 @@ def main():
                 run(rng.integers(0, n_test, 8))
                 n_s = 256
                 s, q = run(rng.integers(0, n_test, n_s))
-                if s < 5:
-                    s2, q2 = run(rng.integers(0, n_test, 4 * n_s))
+                if s < 10:                               # about 10 s of CPU work in all, sized from the first sample's rate
+                    more = int(min(max((10.0 - s) * q / max(s, 1e-3), n_s), 64 * n_s))
+                    s2, q2 = run(rng.integers(0, n_test, more))
                     s, q = s + s2, q + q2
             cpu_base = {"value": q / s, "unit": "queries/s", "cores": threads, "kind": kind,
                         "sample": f"{q} queries of the same workload in {s:.1f} s: torch-CPU scoring (reference tensor expression) + "

@@ -188,7 +188,7 @@ def main(args, rank, world, local):
     if rank == 0 and not args.no_extra:
         rng = np.random.default_rng(0)
         cpu_reference(wl, threads, rng.integers(0, T, 2))
-        n_s = 48
+        n_s = 96
         s = cpu_reference(wl, threads, rng.integers(0, T, n_s))
         cpu_base = {"value": n_s / s, "unit": "triples/s", "cores": threads, "kind": "port",
                     "sample": f"{n_s} test triples of the same workload in {s:.1f} s: one torch-CPU Extractor forward per triple (the reference's loop)"}
