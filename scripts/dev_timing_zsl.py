@@ -1,13 +1,14 @@
 """Developer timing probe: ZSL candidate scorer (entity halves + pair MLP + cosine mean + rank) at FB15K-237-ZS scale."""
 import sys, os, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, root); sys.path.insert(0, os.path.join(root, "tests", "golden"))
 import numpy as np, torch
 import mre_b200
-from oracle import zsl_oracle as zo
+import golden_util as gu
 E, R, D, NB, T, C = 14208, 29, 200, 50, int(sys.argv[1]) if len(sys.argv) > 1 else 17596, 1000
 rng = np.random.default_rng(0)
 n_symbols = E + R
-w = zo.seeded_extractor_weights(1, n_symbols, D)
+w = gu.seeded_extractor_weights(1, n_symbols, D)
 conn = rng.integers(0, E, (E, NB)).astype(np.int64)
 deg = rng.integers(1, NB + 1, E).astype(np.float32)
 t0 = time.time()
