@@ -286,6 +286,9 @@ int mre_zsl_entity_features(mre_ctx *ctx, const mre_zsl_model *model, const int6
  * counts[0] + counts[1] + 1 (MRE_RANK_PESSIMISTIC); the reference's argsort leaves exact ties unpinned.
  * A, B: the [n_ent, D] halves mre_zsl_entity_features wrote (n_ent rows: the hidden layer of the support encoder is
  * split per entity the same way, W1 A + b1 and W1 B, before the per-pair tensor-core contraction with W2).
+ * Arithmetic: FP32 everywhere except that contraction, which runs as hi*hi + hi*lo + lo*hi of TF32-split FP32 operands
+ * with FP32 accumulation (relative error 2^-21 per product; scores within 1e-7 of an all-FP32 evaluation, 5e-8 of the
+ * reference's on tests/golden/golden_zsl.npz).  D up to 216 takes that path, wider models all-FP32 CUDA-core kernels.
  */
 int mre_zsl_rank(mre_ctx *ctx, const mre_zsl_model *model, const float *A, const float *B, int64_t n_ent,
                  const int64_t *q_head, const int64_t *q_rel, const int64_t *cand_ptr, const int64_t *cand_idx, int64_t T,
