@@ -90,3 +90,8 @@ def test_compute_fails_loudly_without_a_gpu(mre):
     ix = eng.KGIndex.from_arrays(5, 2, (np.array([1]), np.array([2]), np.array([0])))
     with pytest.raises(mre.MreError):
         ix.to_device(0)
+    # the paper-side entry points too: the ZSL evaluator and the candidate-list evaluate have no host path to fall back to
+    import golden_util as gu
+    n_symbols, conn, deg, heads, rels, cands, rel_vecs = gu.synthetic_zsl_setup(D=16, max_nb=4)
+    with pytest.raises(mre.MreError, match="CUDA|device"):
+        mre.paper.ZSLEvaluator(gu.seeded_extractor_weights(1, n_symbols, 16), conn, deg, np.arange(300), device=0)
