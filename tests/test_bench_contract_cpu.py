@@ -1,0 +1,33 @@
+"""bench.py's reference arm (the one leg that runs without a GPU): ONE JSON line on stdout, carrying the contract's keys.
+It times the reference's own CPU path (torch-CPU scorer + the compiled Base.so rank loop, or the oracle port when the
+reference library was not built) on a bounded sample of the default workload."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_reference_arm_prints_one_contract_line():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                         cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, lines                                   # nothing but the JSON line reaches stdout
+    j = json.loads(lines[0])
+    assert j["impl"] == "reference" and j["metric"] == "filtered-rank eval queries/sec" and j["unit"] == "queries/s"
+    assert j["higher_is_better"] is True and j["n_gpus"] == 1 and j["steps"] == 1 and j["value"] > 0
+    assert j["config"]["workload"] == "db15k_zs"
+    cb = j["cpu_baseline"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == j["value"] and cb["sample"]
+    assert j["e2e"] == {"value": j["value"], "unit": j["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_reference_arm_other_ranks_exit_quietly():
+    """under torchrun only rank 0 runs the reference arm; the others exit 0 without output"""
+    env = dict(os.environ, RANK="1", LOCAL_RANK="1", WORLD_SIZE="2")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1"],
+                         cwd=ROOT, capture_output=True, text=True, timeout=300, env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert out.stdout.strip() == ""
