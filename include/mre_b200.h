@@ -61,6 +61,11 @@ extern "C" {
 #define MRE_RANK_TIES_HALF   1   /* 1 + #(s_j <  s_true) + #(s_j == s_true)/2   main.py:245-250 */
 #define MRE_RANK_PESSIMISTIC 2   /* 1 + #(s_j <= s_true), upper end of module/zsl_module.py:705-706's unpinned argsort */
 
+/* negative-sampling losses (mre_ns_loss) */
+#define MRE_LOSS_MARGIN   0   /* OpenKE/openke/module/loss/MarginLoss.py:24-28, module/loss.py:20-24 */
+#define MRE_LOSS_SIGMOID  1   /* OpenKE/openke/module/loss/SigmoidLoss.py:22-26 */
+#define MRE_LOSS_SOFTPLUS 2   /* OpenKE/openke/module/loss/SoftplusLoss.py:22-26 */
+
 /* index totals */
 #define MRE_TOTAL_ENTITY   0   /* getEntityTotal   Setting.h:107-110 */
 #define MRE_TOTAL_RELATION 1   /* getRelationTotal */
@@ -318,6 +323,32 @@ int mre_score_triples(mre_ctx *ctx, int32_t scorer, const float *ent, const floa
 int mre_transe_backward(mre_ctx *ctx, const float *ent, const float *rel, int64_t D, const int64_t *h, const int64_t *t,
                         const int64_t *r, int64_t n, int32_t p_norm, int32_t normalize, const float *score, const float *dscore,
                         float *grad_ent, float *grad_rel, void *stream);
+/*
+ * dLoss/d(tables) of the similarity models given dLoss/dscore of n explicit triples: autograd through DistMult._calc
+ * (DistMult.py:34-44; s = sum h*r*t) and ComplEx._calc (ComplEx.py:20-27), accumulated with float atomics into dense gradient
+ * tables of the tables' shapes (caller zeroes them; g_ent_im / g_rel_im only for ComplEx).
+ */
+int mre_bilinear_backward(mre_ctx *ctx, int32_t scorer, const float *ent, const float *ent_im, const float *rel, const float *rel_im,
+                          int64_t D, const int64_t *h, const int64_t *t, const int64_t *r, int64_t n, const float *dscore,
+                          float *g_ent, float *g_ent_im, float *g_rel, float *g_rel_im, void *stream);
+/*
+ * The losses of the negative-sampling strategy on its score layout (strategy/NegativeSampling.py:13-21: p_b = score[b],
+ * n_bk = score[B + k*B + b]), value and gradient in one launch: kind = MRE_LOSS_* ; adv != 0 applies the detached
+ * self-adversarial weights softmax_k(-T n_bk) (margin, MarginLoss.py:21-26) / softmax_k(+T n_bk) (sigmoid, softplus;
+ * SigmoidLoss.py:19-24, SoftplusLoss.py:19-24) with T = adv_temperature.  loss_out: device float32 [1];
+ * dscore (nullable): device float32 [B*(1+neg)] = dLoss/dscore.
+ */
+int mre_ns_loss(mre_ctx *ctx, int32_t kind, const float *score, int64_t B, int64_t neg, float margin, int32_t adv,
+                float adv_temperature, float *loss_out, float *dscore, void *stream);
+/*
+ * One fused forward + loss + backward step of the strategy for ANY scorer and loss (Trainer.train_one_step, Trainer.py:43-54,
+ * without the optimizer): mre_score_triples -> mre_ns_loss -> mre_transe_backward / mre_bilinear_backward, three launches.
+ * mre_transe_margin_step is the (MRE_TRANSE, MRE_LOSS_MARGIN, adv = 0) case.
+ */
+int mre_ns_train_step(mre_ctx *ctx, int32_t scorer, const float *ent, const float *ent_im, const float *rel, const float *rel_im,
+                      int64_t D, const int64_t *h, const int64_t *t, const int64_t *r, int64_t B, int64_t neg, int32_t loss_kind,
+                      float margin, int32_t adv, float adv_temperature, int32_t p_norm, int32_t normalize,
+                      float *g_ent, float *g_ent_im, float *g_rel, float *g_rel_im, float *loss_out, float *scores_out, void *stream);
 /* w -= lr * g (torch.optim.SGD as Trainer.py:73-78 configures it), then g = 0; device arrays of n floats */
 int mre_sgd_update(mre_ctx *ctx, float *w, float *g, int64_t n, float lr, void *stream);
 

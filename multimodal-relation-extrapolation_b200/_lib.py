@@ -25,6 +25,7 @@ FILTER_NONE, FILTER_INDEX, FILTER_CSR = 0, 1, 2
 RANK_STRICT, RANK_TIES_HALF, RANK_PESSIMISTIC = 0, 1, 2
 TOTAL_ENTITY, TOTAL_RELATION, TOTAL_TRAIN, TOTAL_VALID, TOTAL_TEST, TOTAL_TRIPLE = range(6)
 SPLIT_TRAIN, SPLIT_VALID, SPLIT_TEST = 0, 1, 2
+LOSS_MARGIN, LOSS_SIGMOID, LOSS_SOFTPLUS = 0, 1, 2
 
 
 class MreError(RuntimeError):
@@ -131,6 +132,9 @@ def lib():
     L.mre_sgd_update.argtypes = [vp, vp, vp, i64, f32, vp]
     L.mre_score_triples.argtypes = [vp, i32, vp, vp, vp, vp, i64, vp, vp, vp, i64, i32, i32, vp, vp]
     L.mre_transe_backward.argtypes = [vp, vp, vp, i64, vp, vp, vp, i64, i32, i32, vp, vp, vp, vp, vp]
+    L.mre_bilinear_backward.argtypes = [vp, i32, vp, vp, vp, vp, i64, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp]
+    L.mre_ns_loss.argtypes = [vp, i32, vp, i64, i64, f32, i32, f32, vp, vp, vp]
+    L.mre_ns_train_step.argtypes = [vp, i32, vp, vp, vp, vp, i64, vp, vp, vp, i64, i64, i32, f32, i32, f32, i32, i32, vp, vp, vp, vp, vp, vp, vp]
     L.mre_probe_fp32_peak.argtypes = [vp, P(C.c_double)]
     L.mre_probe_tf32_peak.argtypes = [vp, P(C.c_double)]
     L.mre_probe_bf16_peak.argtypes = [vp, P(C.c_double)]

@@ -265,6 +265,32 @@ int mre_transe_backward(mre_ctx *ctx, const float *ent, const float *rel, int64_
     return transe_backward(ctx, ent, rel, D, h, t, r, n, p_norm, normalize, score, dscore, grad_ent, grad_rel, (cudaStream_t)stream);
 }
 
+int mre_bilinear_backward(mre_ctx *ctx, int32_t scorer, const float *ent, const float *ent_im, const float *rel, const float *rel_im,
+                          int64_t D, const int64_t *h, const int64_t *t, const int64_t *r, int64_t n, const float *dscore,
+                          float *g_ent, float *g_ent_im, float *g_rel, float *g_rel_im, void *stream) {
+    MRE_CHECK_ARG(ctx != nullptr, "ctx is NULL");
+    MRE_CUDA(cudaSetDevice(ctx->device));
+    return bilinear_backward(ctx, scorer, ent, ent_im, rel, rel_im, D, h, t, r, n, dscore, g_ent, g_ent_im, g_rel, g_rel_im,
+                             (cudaStream_t)stream);
+}
+
+int mre_ns_loss(mre_ctx *ctx, int32_t kind, const float *score, int64_t B, int64_t neg, float margin, int32_t adv,
+                float adv_temperature, float *loss_out, float *dscore, void *stream) {
+    MRE_CHECK_ARG(ctx != nullptr, "ctx is NULL");
+    MRE_CUDA(cudaSetDevice(ctx->device));
+    return ns_loss(ctx, kind, score, B, neg, margin, adv, adv_temperature, loss_out, dscore, (cudaStream_t)stream);
+}
+
+int mre_ns_train_step(mre_ctx *ctx, int32_t scorer, const float *ent, const float *ent_im, const float *rel, const float *rel_im,
+                      int64_t D, const int64_t *h, const int64_t *t, const int64_t *r, int64_t B, int64_t neg, int32_t loss_kind,
+                      float margin, int32_t adv, float adv_temperature, int32_t p_norm, int32_t normalize,
+                      float *g_ent, float *g_ent_im, float *g_rel, float *g_rel_im, float *loss_out, float *scores_out, void *stream) {
+    MRE_CHECK_ARG(ctx != nullptr, "ctx is NULL");
+    MRE_CUDA(cudaSetDevice(ctx->device));
+    return ns_train_step(ctx, scorer, ent, ent_im, rel, rel_im, D, h, t, r, B, neg, loss_kind, margin, adv, adv_temperature, p_norm,
+                         normalize, g_ent, g_ent_im, g_rel, g_rel_im, loss_out, scores_out, (cudaStream_t)stream);
+}
+
 int mre_sgd_update(mre_ctx *ctx, float *w, float *g, int64_t n, float lr, void *stream) {
     MRE_CHECK_ARG(ctx != nullptr, "ctx is NULL");
     MRE_CUDA(cudaSetDevice(ctx->device));

@@ -105,6 +105,7 @@ struct mre_ctx {
     mre::DevBuf counters;            // raw/corr counters, work counters
     mre::DevBuf misc;                // loss partials etc.
     mre::DevBuf misc2;               // known-true pair list of the tile filter
+    mre::DevBuf loss_acc;            // float64 loss accumulator + finished-block counter of ns_loss (self re-arming)
     mre::DevBuf stage_dev;           // device staging for *_host entry points
     mre::PinnedBuf stage_pin;        // pinned host staging
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -148,6 +149,15 @@ int score_triples(mre_ctx *ctx, int scorer, const float *ent, const float *ent_i
 int transe_backward(mre_ctx *ctx, const float *ent, const float *rel, int64_t D, const int64_t *h, const int64_t *t, const int64_t *r,
                     int64_t n, int32_t p_norm, int32_t normalize, const float *score, const float *dscore, float *grad_ent,
                     float *grad_rel, cudaStream_t st);
+int ns_loss(mre_ctx *ctx, int32_t kind, const float *score, int64_t B, int64_t neg, float margin, int32_t adv, float temperature,
+            float *loss_out, float *dscore, cudaStream_t st);
+int bilinear_backward(mre_ctx *ctx, int scorer, const float *ent, const float *ent_im, const float *rel, const float *rel_im, int64_t D,
+                      const int64_t *h, const int64_t *t, const int64_t *r, int64_t n, const float *dscore, float *g_ent,
+                      float *g_ent_im, float *g_rel, float *g_rel_im, cudaStream_t st);
+int ns_train_step(mre_ctx *ctx, int32_t scorer, const float *ent, const float *ent_im, const float *rel, const float *rel_im,
+                  int64_t D, const int64_t *h, const int64_t *t, const int64_t *r, int64_t B, int64_t neg, int32_t loss_kind,
+                  float margin, int32_t adv, float temperature, int32_t p_norm, int32_t normalize, float *g_ent, float *g_ent_im,
+                  float *g_rel, float *g_rel_im, float *loss_out, float *scores_out, cudaStream_t st);
 int zsl_entity_features(mre_ctx *ctx, const mre_zsl_model *m, const int64_t *ent_symbol, const int64_t *conn, const float *deg,
                         int64_t n_ent, int32_t max_nb, float *A, float *B, cudaStream_t st);
 int zsl_rank(mre_ctx *ctx, const mre_zsl_model *m, const float *A, const float *B, int64_t n_ent, const int64_t *q_head,

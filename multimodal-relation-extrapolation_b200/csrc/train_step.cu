@@ -66,50 +66,86 @@ __global__ void __launch_bounds__(256) transe_fwd_kernel(const float *__restrict
     }
 }
 
-// loss = mean_{b,k} max(p_b - n_bk, -m) + m, float64 accumulation; one thread per (b, k)
-__global__ void __launch_bounds__(256) margin_loss_kernel(const float *__restrict__ score, int64_t B, int64_t neg, float margin,
-                                                          double *__restrict__ acc) {
+// Negative-sampling losses on the strategy's score layout (p_b = score[b], n_bk = score[B + k*B + b],
+// strategy/NegativeSampling.py:13-21), forward value and dLoss/dscore in ONE launch -- one thread per positive row b:
+//   MARGIN    mean_b sum_k w_bk max(p_b - n_bk, -m) + m                     MarginLoss.py:24-28 (module/loss.py:20-24)
+//   SIGMOID   -(mean_b logsig(p_b) + mean_b sum_k w_bk logsig(-n_bk)) / 2   SigmoidLoss.py:22-26
+//   SOFTPLUS   (mean_b softplus(-p_b) + mean_b sum_k w_bk softplus(n_bk)) / 2   SoftplusLoss.py:22-26
+// w_bk = 1/neg, or the detached self-adversarial weights softmax_k(-T n_bk) (margin, MarginLoss.py:21-22) /
+// softmax_k(+T n_bk) (sigmoid, softplus; SigmoidLoss.py:19-20) when adv != 0.  The loss is accumulated in float64; the
+// last block to finish writes loss_out and re-arms the accumulator, so a step needs no memset and no finishing launch.
+__device__ __forceinline__ float log_sigmoid(float x) {          // nn.LogSigmoid: min(x, 0) - log1p(exp(-|x|))
+    return fminf(x, 0.f) - log1pf(expf(-fabsf(x)));
+}
+__device__ __forceinline__ float softplus20(float x) {           // nn.Softplus(beta = 1, threshold = 20)
+    return x > 20.f ? x : log1pf(expf(x));
+}
+__device__ __forceinline__ float sigmoidf(float x) { return 1.f / (1.f + expf(-x)); }
+
+template <int KIND>
+__global__ void __launch_bounds__(256) ns_loss_kernel(const float *__restrict__ score, int64_t B, int64_t neg, float margin,
+                                                       int adv, float temperature, float *__restrict__ dscore,
+                                                       double *__restrict__ acc, unsigned int *__restrict__ done,
+                                                       float *__restrict__ loss_out) {
     __shared__ double part[8];
-    double s = 0.0;
-    const int64_t total = B * neg;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t b = i % B;
-        const float v = score[b] - score[B + i];
-        s += (double)(v > -margin ? v : -margin);
+    double local = 0.0;
+    const float invB = 1.0f / (float)B;
+    const float sgn = KIND == MRE_LOSS_MARGIN ? -temperature : temperature;
+    for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < B; b += (int64_t)gridDim.x * blockDim.x) {
+        const float p = score[b];
+        const float *nrow = score + B + b;
+        float zmax = -INFINITY, zsum = 0.f;
+        if (adv) {                                   // softmax over the row's negatives, two passes (max, then sum)
+            for (int64_t k = 0; k < neg; k++) zmax = fmaxf(zmax, sgn * nrow[k * B]);
+            for (int64_t k = 0; k < neg; k++) zsum += expf(sgn * nrow[k * B] - zmax);
+        }
+        const float wu = 1.0f / (float)neg;
+        float row = 0.f, dp = 0.f;
+        for (int64_t k = 0; k < neg; k++) {
+            const float nk = nrow[k * B];
+            const float w = adv ? expf(sgn * nk - zmax) / zsum : wu;
+            float term, dn;
+            if (KIND == MRE_LOSS_MARGIN) {
+                const float v = p - nk;
+                const bool active = v > -margin;
+                term = active ? v : -margin;
+                dn = active ? -w * invB : 0.f;
+                dp += active ? w * invB : 0.f;
+            } else if (KIND == MRE_LOSS_SIGMOID) {
+                term = -0.5f * log_sigmoid(-nk);
+                dn = 0.5f * w * invB * sigmoidf(nk);
+            } else {
+                term = 0.5f * softplus20(nk);
+                dn = 0.5f * w * invB * (nk > 20.f ? 1.f : sigmoidf(nk));
+            }
+            row += w * term;
+            if (dscore) dscore[B + k * B + b] = dn;
+        }
+        if (KIND == MRE_LOSS_SIGMOID) {
+            row += -0.5f * log_sigmoid(p);
+            dp = -0.5f * invB * sigmoidf(-p);
+        } else if (KIND == MRE_LOSS_SOFTPLUS) {
+            row += 0.5f * softplus20(-p);
+            dp = -0.5f * invB * (-p > 20.f ? 1.f : sigmoidf(-p));
+        }
+        if (dscore) dscore[b] = dp;
+        local += (double)row;
     }
 #pragma unroll
-    for (int m = 16; m > 0; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
-    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+    for (int m = 16; m > 0; m >>= 1) local += __shfl_xor_sync(0xffffffffu, local, m);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = local;
     __syncthreads();
     if (threadIdx.x == 0) {
         double t = 0.0;
         for (int w = 0; w < 8; w++) t += part[w];
         atomicAdd(acc, t);
-    }
-}
-
-__global__ void finish_loss_kernel(const double *acc, int64_t B, int64_t neg, float margin, float *loss_out) {
-    loss_out[0] = (float)(acc[0] / (double)(B * neg) + (double)margin);
-}
-
-// dLoss/dscore for the margin loss on the strategy's layout: positives collect one term per active negative of their
-// row, negatives get -1/(B*neg) when active (MarginLoss.py:24-28 through strategy/NegativeSampling.py:13-21)
-__global__ void __launch_bounds__(256) margin_grad_kernel(const float *__restrict__ score, int64_t B, int64_t neg, float margin,
-                                                          float *__restrict__ dscore) {
-    const int64_t n = B * (1 + neg);
-    const float inv = 1.0f / (float)(B * neg);
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        float c;
-        if (i < B) {
-            const float p = score[i];
-            int active = 0;
-            for (int64_t k = 0; k < neg; k++) active += (p - score[B + k * B + i] > -margin) ? 1 : 0;
-            c = (float)active * inv;
-        } else {
-            const int64_t b = (i - B) % B;
-            c = (score[b] - score[i] > -margin) ? -inv : 0.f;
+        __threadfence();
+        if (atomicAdd(done, 1u) == gridDim.x - 1) {          // last block: publish the loss, re-arm for the next call
+            const double total = atomicAdd(acc, 0.0);
+            loss_out[0] = (float)(total / (double)B + (KIND == MRE_LOSS_MARGIN ? (double)margin : 0.0));
+            *acc = 0.0;
+            *done = 0u;
         }
-        dscore[i] = c;
     }
 }
 
@@ -187,6 +223,39 @@ __global__ void __launch_bounds__(256) bilinear_fwd_kernel(int scorer, const flo
     }
 }
 
+// backward of the similarity models (autograd through DistMult.py:34-44 / ComplEx.py:20-27): one warp per triple,
+// c = dLoss/dscore_i, scattered with float atomics into the dense gradient tables
+__global__ void __launch_bounds__(256) bilinear_bwd_kernel(int scorer, const float *__restrict__ ent, const float *__restrict__ ent_im,
+                                                           const float *__restrict__ rel, const float *__restrict__ rel_im, int D,
+                                                           const int64_t *__restrict__ bh, const int64_t *__restrict__ bt,
+                                                           const int64_t *__restrict__ br, int64_t n, const float *__restrict__ dscore,
+                                                           float *__restrict__ g_ent, float *__restrict__ g_ent_im,
+                                                           float *__restrict__ g_rel, float *__restrict__ g_rel_im) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n; i += warps) {
+        const float c = dscore[i];
+        if (c == 0.f) continue;
+        const int64_t h = bh[i] * D, t = bt[i] * D, r = br[i] * D;
+        for (int d = lane; d < D; d += 32) {
+            if (scorer == MRE_DISTMULT) {
+                const float vh = ent[h + d], vt = ent[t + d], vr = rel[r + d];
+                atomicAdd(g_ent + h + d, c * (vr * vt));
+                atomicAdd(g_ent + t + d, c * (vh * vr));
+                atomicAdd(g_rel + r + d, c * (vh * vt));
+            } else {
+                const float hr = ent[h + d], hi = ent_im[h + d], tr = ent[t + d], ti = ent_im[t + d], rr = rel[r + d], ri = rel_im[r + d];
+                atomicAdd(g_ent + h + d, c * (tr * rr + ti * ri));
+                atomicAdd(g_ent_im + h + d, c * (ti * rr - tr * ri));
+                atomicAdd(g_ent + t + d, c * (hr * rr - hi * ri));
+                atomicAdd(g_ent_im + t + d, c * (hi * rr + hr * ri));
+                atomicAdd(g_rel + r + d, c * (hr * tr + hi * ti));
+                atomicAdd(g_rel_im + r + d, c * (hr * ti - hi * tr));
+            }
+        }
+    }
+}
+
 __global__ void sgd_kernel(float *__restrict__ w, float *__restrict__ g, int64_t n, float lr) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         w[i] = w[i] - lr * g[i];
@@ -230,6 +299,41 @@ int transe_backward(mre_ctx *ctx, const float *ent, const float *rel, int64_t D,
     return MRE_OK;
 }
 
+int ns_loss(mre_ctx *ctx, int32_t kind, const float *score, int64_t B, int64_t neg, float margin, int32_t adv, float temperature,
+            float *loss_out, float *dscore, cudaStream_t st) {
+    MRE_CHECK_ARG(score && loss_out, "NULL argument");
+    MRE_CHECK_ARG(B > 0 && neg > 0, "B and neg must be positive");
+    MRE_CHECK_ARG(kind >= MRE_LOSS_MARGIN && kind <= MRE_LOSS_SOFTPLUS, "unknown loss kind %d", kind);
+    if (!ctx->loss_acc.p) {                               // accumulator + finished-block counter, re-armed by the kernel itself
+        MRE_TRY(ctx->loss_acc.reserve(64));
+        MRE_CUDA(cudaMemset(ctx->loss_acc.p, 0, 64));
+    }
+    double *acc = ctx->loss_acc.as<double>();
+    unsigned int *done = (unsigned int *)(acc + 1);
+    const int grid = (int)std::min<int64_t>((B + 255) / 256, (int64_t)ctx->sm_count * 4);
+    if (kind == MRE_LOSS_MARGIN) ns_loss_kernel<MRE_LOSS_MARGIN><<<grid, 256, 0, st>>>(score, B, neg, margin, adv, temperature, dscore, acc, done, loss_out);
+    else if (kind == MRE_LOSS_SIGMOID) ns_loss_kernel<MRE_LOSS_SIGMOID><<<grid, 256, 0, st>>>(score, B, neg, margin, adv, temperature, dscore, acc, done, loss_out);
+    else ns_loss_kernel<MRE_LOSS_SOFTPLUS><<<grid, 256, 0, st>>>(score, B, neg, margin, adv, temperature, dscore, acc, done, loss_out);
+    ctx->launches += 1;
+    MRE_CUDA(cudaGetLastError());
+    return MRE_OK;
+}
+
+int bilinear_backward(mre_ctx *ctx, int scorer, const float *ent, const float *ent_im, const float *rel, const float *rel_im, int64_t D,
+                      const int64_t *h, const int64_t *t, const int64_t *r, int64_t n, const float *dscore, float *g_ent,
+                      float *g_ent_im, float *g_rel, float *g_rel_im, cudaStream_t st) {
+    MRE_CHECK_ARG(ent && rel && h && t && r && dscore && g_ent && g_rel, "NULL argument");
+    MRE_CHECK_ARG(scorer == MRE_DISTMULT || (scorer == MRE_COMPLEX && ent_im && rel_im && g_ent_im && g_rel_im),
+                  "bad scorer / missing ComplEx tables");
+    MRE_CHECK_ARG(D > 0 && D < (1 << 30) && n >= 0, "bad shape");
+    if (n == 0) return MRE_OK;
+    bilinear_bwd_kernel<<<launch_grid(ctx, n), 256, 0, st>>>(scorer, ent, ent_im, rel, rel_im, (int)D, h, t, r, n, dscore, g_ent, g_ent_im,
+                                                             g_rel, g_rel_im);
+    ctx->launches += 1;
+    MRE_CUDA(cudaGetLastError());
+    return MRE_OK;
+}
+
 int transe_margin_step(mre_ctx *ctx, const float *ent, const float *rel, int64_t E, int64_t R, int64_t D, const int64_t *h,
                        const int64_t *t, const int64_t *r, int64_t B, int64_t neg, float margin, int32_t p_norm,
                        int32_t normalize, float *grad_ent, float *grad_rel, float *loss_out, float *scores_out,
@@ -242,19 +346,33 @@ int transe_margin_step(mre_ctx *ctx, const float *ent, const float *rel, int64_t
     MRE_TRY(ctx->qvec.reserve((size_t)2 * n * sizeof(float)));
     float *dscore = ctx->qvec.as<float>();
     float *score = scores_out ? scores_out : dscore + n;
-    MRE_TRY(ctx->misc.reserve(256));
-    double *acc = ctx->misc.as<double>();
-    MRE_CUDA(cudaMemsetAsync(acc, 0, sizeof(double), st));
     MRE_TRY(ctx->time_begin(st));
     MRE_TRY(score_triples(ctx, MRE_TRANSE, ent, nullptr, rel, nullptr, D, h, t, r, n, p_norm, normalize, score, st));
-    const int lgrid = (int)std::min<int64_t>((B * neg + 255) / 256, (int64_t)ctx->sm_count * 4);
-    margin_loss_kernel<<<lgrid, 256, 0, st>>>(score, B, neg, margin, acc);
-    finish_loss_kernel<<<1, 1, 0, st>>>(acc, B, neg, margin, loss_out);
-    margin_grad_kernel<<<(int)std::min<int64_t>((n + 255) / 256, (int64_t)ctx->sm_count * 8), 256, 0, st>>>(score, B, neg, margin, dscore);
-    ctx->launches += 3;
+    MRE_TRY(ns_loss(ctx, MRE_LOSS_MARGIN, score, B, neg, margin, 0, 0.f, loss_out, dscore, st));
     MRE_TRY(transe_backward(ctx, ent, rel, D, h, t, r, n, p_norm, normalize, score, dscore, grad_ent, grad_rel, st));
     MRE_TRY(ctx->time_end(st));
     MRE_CUDA(cudaGetLastError());
+    return MRE_OK;
+}
+
+int ns_train_step(mre_ctx *ctx, int32_t scorer, const float *ent, const float *ent_im, const float *rel, const float *rel_im,
+                  int64_t D, const int64_t *h, const int64_t *t, const int64_t *r, int64_t B, int64_t neg, int32_t loss_kind,
+                  float margin, int32_t adv, float temperature, int32_t p_norm, int32_t normalize, float *g_ent, float *g_ent_im,
+                  float *g_rel, float *g_rel_im, float *loss_out, float *scores_out, cudaStream_t st) {
+    MRE_CHECK_ARG(ent && rel && h && t && r && g_ent && g_rel && loss_out, "NULL argument");
+    MRE_CHECK_ARG(B > 0 && neg > 0 && D > 0 && D < (1 << 30), "bad shape");
+    const int64_t n = B * (1 + neg);
+    MRE_TRY(ctx->qvec.reserve((size_t)2 * n * sizeof(float)));
+    float *dscore = ctx->qvec.as<float>();
+    float *score = scores_out ? scores_out : dscore + n;
+    MRE_TRY(ctx->time_begin(st));
+    MRE_TRY(score_triples(ctx, scorer, ent, ent_im, rel, rel_im, D, h, t, r, n, p_norm, normalize, score, st));
+    MRE_TRY(ns_loss(ctx, loss_kind, score, B, neg, margin, adv, temperature, loss_out, dscore, st));
+    if (scorer == MRE_TRANSE)
+        MRE_TRY(transe_backward(ctx, ent, rel, D, h, t, r, n, p_norm, normalize, score, dscore, g_ent, g_rel, st));
+    else
+        MRE_TRY(bilinear_backward(ctx, scorer, ent, ent_im, rel, rel_im, D, h, t, r, n, dscore, g_ent, g_ent_im, g_rel, g_rel_im, st));
+    MRE_TRY(ctx->time_end(st));
     return MRE_OK;
 }
 

@@ -365,5 +365,24 @@ def transe_margin_step(ctx, ent, rel, h, t, r, B, neg, margin, p_norm=1, normali
     return loss, grad_ent, grad_rel, scores
 
 
+def ns_train_step(ctx, scorer, tables, grads, h, t, r, B, neg, loss_kind, margin=0.0, adv=0, temperature=0.0, p_norm=1,
+                  normalize=False, want_scores=False):
+    """mre_ns_train_step: fused score + negative-sampling loss + backward for any scorer; `grads` are accumulated into.
+    tables / grads: (ent, rel) or, for ComplEx, (ent_re, ent_im, rel_re, rel_im).  -> loss[1] (and the n scores if asked)."""
+    if scorer == "complex":
+        ent, ent_im, rel, rel_im = tables
+        g_ent, g_ent_im, g_rel, g_rel_im = grads
+    else:
+        (ent, rel), ent_im, rel_im = tables, None, None
+        (g_ent, g_rel), g_ent_im, g_rel_im = grads, None, None
+    loss = torch.empty(1, dtype=torch.float32, device=ent.device)
+    scores = torch.empty(B * (1 + neg), dtype=torch.float32, device=ent.device) if want_scores else None
+    L.check(L.lib().mre_ns_train_step(ctx._h, SCORERS[scorer], _ptr(ent), _ptr(ent_im), _ptr(rel), _ptr(rel_im), ent.shape[1],
+                                      _ptr(h), _ptr(t), _ptr(r), B, neg, int(loss_kind), float(margin), int(adv), float(temperature),
+                                      int(p_norm), int(bool(normalize)), _ptr(g_ent), _ptr(g_ent_im), _ptr(g_rel), _ptr(g_rel_im),
+                                      _ptr(loss), _ptr(scores), _stream()))
+    return (loss, scores) if want_scores else loss
+
+
 def sgd_update(ctx, w, g, lr):
     L.check(L.lib().mre_sgd_update(ctx._h, _ptr(w), _ptr(g), w.numel(), float(lr), _stream()))

@@ -1,32 +1,14 @@
-"""MarginLoss (OpenKE/openke/module/loss/MarginLoss.py:10-32; the paper's copy module/loss.py:5-28).  The plain form
-is fused into mre_transe_margin_step by the NegativeSampling strategy; this module is the general (torch, [B, neg]
-elementwise) form used when a caller combines it with other scorers or the self-adversarial weights."""
-import numpy as np
-import torch
-import torch.nn as nn
-import torch.nn.functional as F
+"""MarginLoss (OpenKE/openke/module/loss/MarginLoss.py:10-32; the paper's copy module/loss.py:5-28):
+mean_b sum_k w_bk max(p_b - n_bk, -margin) + margin, w = 1/neg or softmax_k(-T n_bk) -- kind MRE_LOSS_MARGIN of mre_ns_loss."""
+from .... import _lib as L
+from ._ns_loss import NegativeSamplingLoss
 
 
-class MarginLoss(nn.Module):
+class MarginLoss(NegativeSamplingLoss):
+    kind = L.LOSS_MARGIN
+
     def __init__(self, adv_temperature=None, margin=6.0):
-        super().__init__()
-        self.margin = nn.Parameter(torch.Tensor([margin]))
-        self.margin.requires_grad = False
-        if adv_temperature is not None:
-            self.adv_temperature = nn.Parameter(torch.Tensor([adv_temperature]))
-            self.adv_temperature.requires_grad = False
-            self.adv_flag = True
-        else:
-            self.adv_flag = False
+        super().__init__(adv_temperature=adv_temperature, margin=margin)
 
-    def get_weights(self, n_score):
-        return F.softmax(-n_score * self.adv_temperature, dim=-1).detach()
-
-    def forward(self, p_score, n_score):
-        if self.adv_flag:
-            return (self.get_weights(n_score) * torch.max(p_score - n_score, -self.margin)).sum(dim=-1).mean() + self.margin
-        return (torch.max(p_score - n_score, -self.margin)).mean() + self.margin
-
-    def predict(self, p_score, n_score):
-        score = self.forward(p_score, n_score)
-        return score.cpu().data.numpy()
+    def adv_sign(self):
+        return -1.0           # lower distance = harder negative (MarginLoss.py:21-22)

@@ -1,28 +1,11 @@
-"""SoftplusLoss (OpenKE/openke/module/loss/SoftplusLoss.py:7-33): (mean softplus(-p) + mean softplus(n)) / 2, with the
-optional self-adversarial weights softmax(n * T) over a row's negatives."""
-import torch
-import torch.nn as nn
-import torch.nn.functional as F
+"""SoftplusLoss (OpenKE/openke/module/loss/SoftplusLoss.py:7-33): (mean softplus(-p) + mean_b sum_k w_bk softplus(n_bk)) / 2,
+w = 1/neg or softmax_k(T n_bk) -- kind MRE_LOSS_SOFTPLUS of mre_ns_loss."""
+from .... import _lib as L
+from ._ns_loss import NegativeSamplingLoss
 
 
-class SoftplusLoss(nn.Module):
+class SoftplusLoss(NegativeSamplingLoss):
+    kind = L.LOSS_SOFTPLUS
+
     def __init__(self, adv_temperature=None):
-        super().__init__()
-        self.criterion = nn.Softplus()
-        if adv_temperature is not None:
-            self.adv_temperature = nn.Parameter(torch.Tensor([adv_temperature]))
-            self.adv_temperature.requires_grad = False
-            self.adv_flag = True
-        else:
-            self.adv_flag = False
-
-    def get_weights(self, n_score):
-        return F.softmax(n_score * self.adv_temperature, dim=-1).detach()
-
-    def forward(self, p_score, n_score):
-        if self.adv_flag:
-            return (self.criterion(-p_score).mean() + (self.get_weights(n_score) * self.criterion(n_score)).sum(dim=-1).mean()) / 2
-        return (self.criterion(-p_score).mean() + self.criterion(n_score).mean()) / 2
-
-    def predict(self, p_score, n_score):
-        return self.forward(p_score, n_score).cpu().data.numpy()
+        super().__init__(adv_temperature=adv_temperature)

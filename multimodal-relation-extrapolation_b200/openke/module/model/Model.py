@@ -31,30 +31,52 @@ def expand_batch(data, device):
     return grow(h), grow(t), grow(r)
 
 
+def _check_ids(h, t, r, E, R):
+    """torch's embedding lookup raises on an out-of-range id; the kernels would read (and atomically add) out of bounds"""
+    if h.numel() == 0:
+        return
+    bad = ((h < 0) | (h >= E)).any() | ((t < 0) | (t >= E)).any() | ((r < 0) | (r >= R)).any()
+    if bool(bad):                                                               # one small device read per call
+        raise IndexError(f"triple ids out of range for {E} entities / {R} relations")
+
+
 class _ScoreFn(torch.autograd.Function):
-    """raw model score of explicit triples with gradients to the two TransE tables (mre_score_triples /
-    mre_transe_backward)"""
+    """raw model score of explicit triples with gradients to every embedding table of the model: mre_score_triples forward,
+    mre_transe_backward (TransE) / mre_bilinear_backward (DistMult, SimplE, ComplEx) backward"""
 
     @staticmethod
-    def forward(ctx, ent, rel, model, h, t, r):
-        score = model._score(h, t, r)
+    def forward(ctx, model, h, t, r, *tabs):
+        score = model._score(h, t, r, tabs)
         ctx.model, ctx.idx = model, (h, t, r)
-        ctx.save_for_backward(ent, rel, score)
+        ctx.save_for_backward(score, *tabs)
         return score
 
     @staticmethod
     def backward(ctx, dscore):
-        ent, rel, score = ctx.saved_tensors
+        score, *tabs = ctx.saved_tensors
         m = ctx.model
         h, t, r = ctx.idx
-        if m.scorer != "transe":
-            raise NotImplementedError("training through DistMult/ComplEx is outside the round-1 hot path (BASELINE configs[3] is TransE)")
-        ge, gr = torch.zeros_like(ent), torch.zeros_like(rel)
-        L.check(L.lib().mre_transe_backward(m.ctx()._h, ent.data_ptr(), rel.data_ptr(), ent.shape[1], h.data_ptr(), t.data_ptr(),
-                                            r.data_ptr(), h.numel(), m.p_norm, int(m.norm_flag), score.data_ptr(),
-                                            dscore.contiguous().data_ptr(), ge.data_ptr(), gr.data_ptr(),
-                                            torch.cuda.current_stream().cuda_stream))
-        return ge, gr, None, None, None, None
+        lib, st = L.lib(), torch.cuda.current_stream().cuda_stream
+        grads = [torch.zeros_like(w) for w in tabs]
+        dscore = dscore.contiguous()
+        D = tabs[0].shape[1]
+        if m.scorer == "transe":
+            ent, rel = tabs
+            L.check(lib.mre_transe_backward(m.ctx()._h, ent.data_ptr(), rel.data_ptr(), D, h.data_ptr(), t.data_ptr(), r.data_ptr(),
+                                            h.numel(), m.p_norm, int(m.norm_flag), score.data_ptr(), dscore.data_ptr(),
+                                            grads[0].data_ptr(), grads[1].data_ptr(), st))
+        else:
+            if m.scorer == "complex":
+                ent, ent_im, rel, rel_im = tabs
+                g_ent, g_ent_im, g_rel, g_rel_im = grads
+            else:
+                (ent, rel), ent_im, rel_im = tabs, None, None
+                (g_ent, g_rel), g_ent_im, g_rel_im = grads, None, None
+            ptr = lambda x: x.data_ptr() if x is not None else None
+            L.check(lib.mre_bilinear_backward(m.ctx()._h, engine.SCORERS[m.scorer], ent.data_ptr(), ptr(ent_im), rel.data_ptr(), ptr(rel_im),
+                                              D, h.data_ptr(), t.data_ptr(), r.data_ptr(), h.numel(), dscore.data_ptr(),
+                                              g_ent.data_ptr(), ptr(g_ent_im), g_rel.data_ptr(), ptr(g_rel_im), st))
+        return (None, None, None, None, *grads)
 
 
 class Model(nn.Module):
@@ -92,8 +114,8 @@ class Model(nn.Module):
     def rank_kwargs(self):
         return {}
 
-    def _score(self, h, t, r):
-        tabs = self.tables()
+    def _score(self, h, t, r, tabs=None):
+        tabs = tabs if tabs is not None else self.tables()
         if self.scorer == "complex":
             ent, ent_im, rel, rel_im = tabs
         else:
@@ -107,13 +129,15 @@ class Model(nn.Module):
                                           torch.cuda.current_stream().cuda_stream))
         return out
 
-    def raw_score(self, data):
-        """the model's raw score (distance for TransE, similarity for DistMult/ComplEx) of the batch's triples"""
+    def raw_score(self, data, tables=None):
+        """the model's raw score (distance for TransE, similarity for DistMult/ComplEx) of the batch's triples, differentiable
+        with respect to the embedding tables (`tables` overrides the model's own, e.g. SimplE's inverse-relation pass)"""
         h, t, r = expand_batch(data, self.device())
-        tabs = self.tables()
-        if self.scorer == "transe" and torch.is_grad_enabled() and any(p.requires_grad for p in tabs):
-            return _ScoreFn.apply(tabs[0], tabs[1], self, h, t, r)
-        return self._score(h, t, r)
+        tabs = tuple(tables) if tables is not None else tuple(self.tables())
+        _check_ids(h, t, r, tabs[0].shape[0], tabs[-1].shape[0])
+        if torch.is_grad_enabled() and any(p.requires_grad for p in tabs):
+            return _ScoreFn.apply(self, h, t, r, *tabs)
+        return self._score(h, t, r, tabs)
 
     # ---- BaseModule.py:16-55
     def load_checkpoint(self, path):

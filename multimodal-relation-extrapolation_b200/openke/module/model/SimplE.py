@@ -24,11 +24,9 @@ class SimplE(Model):
         return self.ent_embeddings.weight, self.rel_embeddings.weight
 
     def forward(self, data):                                                    # SimplE.py:25-34: (<h,r,t> + <h,r_inv,t>) / 2
-        h = self.ent_embeddings(data["batch_h"])
-        t = self.ent_embeddings(data["batch_t"])
-        r = self.rel_embeddings(data["batch_r"])
-        r_inv = self.rel_inv_embeddings(data["batch_r"])
-        return (torch.sum(h * r * t, -1) + torch.sum(h * r_inv * t, -1)) / 2
+        fwd = self.raw_score(data)
+        inv = self.raw_score(data, tables=(self.ent_embeddings.weight, self.rel_inv_embeddings.weight))
+        return (fwd + inv) / 2
 
     def regularization(self, data):                                             # SimplE.py:36-45
         h = self.ent_embeddings(data["batch_h"])

@@ -1,14 +1,13 @@
 """NegativeSampling strategy (OpenKE/openke/module/strategy/NegativeSampling.py:5-32): splits the flat score vector
-into p_score [B, 1] and n_score [B, neg] and applies the loss.  For TransE + plain MarginLoss with no regulariser
-(the configuration of OpenKE/examples/train_transe_FB15K237.py:23-39, BASELINE configs[3]) `fused_step` runs the whole
-forward + backward in mre_transe_margin_step and leaves the gradients in .grad, so Trainer skips autograd."""
+into p_score [B, 1] and n_score [B, neg] and applies the loss.  When nothing but the loss feeds the gradient (no regulariser:
+the configuration of OpenKE/examples/train_transe_FB15K237.py:23-39, BASELINE configs[3]) `fused_step` runs the whole
+forward + loss + backward in mre_ns_train_step and leaves the gradients in .grad, so Trainer skips autograd; otherwise
+forward() is differentiable end to end (library score and loss kernels behind autograd nodes)."""
 import torch
 import torch.nn as nn
 
 from .... import engine
-from ..loss.MarginLoss import MarginLoss
 from ..model.Model import expand_batch
-from ..model.TransE import TransE
 
 
 class NegativeSampling(nn.Module):
@@ -41,20 +40,26 @@ class NegativeSampling(nn.Module):
 
     # ---- fused path
     def can_fuse(self):
-        return (isinstance(self.model, TransE) and isinstance(self.loss, MarginLoss) and not self.loss.adv_flag
-                and not self.model.margin_flag and self.regul_rate == 0 and self.l3_regul_rate == 0)
+        """one mre_ns_train_step (score -> loss -> backward, three launches) replaces forward + autograd when the loss is one of
+        the library's and nothing else feeds the gradient (no regulariser, no margin-shifted score, single-pass scorer)"""
+        from ..loss._ns_loss import NegativeSamplingLoss
+        from ..model.SimplE import SimplE
+        return (isinstance(self.loss, NegativeSamplingLoss) and getattr(self.model, "scorer", None) in engine.SCORERS
+                and not isinstance(self.model, SimplE) and not getattr(self.model, "margin_flag", False)
+                and self.regul_rate == 0 and self.l3_regul_rate == 0)
 
     def fused_step(self, data):
         """loss [1] of one batch with d loss / d tables ACCUMULATED into the embeddings' .grad (as backward() would)"""
         m = self.model
-        ent, rel = m.tables()
-        h, t, r = expand_batch(data, ent.device)
+        tabs = m.tables()
+        h, t, r = expand_batch(data, tabs[0].device)
         n = h.numel()
         B = self.batch_size
         assert n % B == 0 and n > B
-        for w in (ent, rel):
+        for w in tabs:
             if w.grad is None:
                 w.grad = torch.zeros_like(w)
-        loss, _, _, _ = engine.transe_margin_step(m.ctx(), ent.data, rel.data, h, t, r, B, n // B - 1, float(self.loss.margin.item()),
-                                                  m.p_norm, m.norm_flag, grad_ent=ent.grad, grad_rel=rel.grad)
-        return loss
+        margin, adv, temp = self.loss.hyper()
+        kw = m.rank_kwargs()
+        return engine.ns_train_step(m.ctx(), m.scorer, [w.data for w in tabs], [w.grad for w in tabs], h, t, r, B, n // B - 1,
+                                    self.loss.kind, margin, adv, temp, kw.get("p_norm", 1), kw.get("normalize", False))

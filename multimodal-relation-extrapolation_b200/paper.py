@@ -16,29 +16,71 @@ from . import _lib as L
 from . import engine
 
 
+class _TripleScoreFn(torch.autograd.Function):
+    """score of n explicit (h, t, r) index triples into a row table `ent` [rows, D] and a relation-row table `rel`, differentiable
+    with respect to both tables: mre_score_triples forward, mre_transe_backward / mre_bilinear_backward backward (float atomics
+    into dense gradients of the tables' shapes)"""
+
+    @staticmethod
+    def forward(ctx, ent, rel, h, t, r, scorer, p_norm, norm_flag, lib_ctx):
+        n = h.numel()
+        out = torch.empty(n, dtype=torch.float32, device=ent.device)
+        L.check(L.lib().mre_score_triples(lib_ctx._h, scorer, ent.data_ptr(), None, rel.data_ptr(), None, ent.shape[1], h.data_ptr(),
+                                          t.data_ptr(), r.data_ptr(), n, p_norm, int(norm_flag), out.data_ptr(),
+                                          torch.cuda.current_stream().cuda_stream))
+        ctx.save_for_backward(ent, rel, h, t, r, out)
+        ctx.cfg = (scorer, p_norm, norm_flag, lib_ctx)
+        return out
+
+    @staticmethod
+    def backward(ctx, dscore):
+        ent, rel, h, t, r, score = ctx.saved_tensors
+        scorer, p_norm, norm_flag, lib_ctx = ctx.cfg
+        ge, gr = torch.zeros_like(ent), torch.zeros_like(rel)
+        dscore = dscore.contiguous()
+        st = torch.cuda.current_stream().cuda_stream
+        if scorer == L.TRANSE:
+            L.check(L.lib().mre_transe_backward(lib_ctx._h, ent.data_ptr(), rel.data_ptr(), ent.shape[1], h.data_ptr(), t.data_ptr(),
+                                                r.data_ptr(), h.numel(), p_norm, int(norm_flag), score.data_ptr(), dscore.data_ptr(),
+                                                ge.data_ptr(), gr.data_ptr(), st))
+        else:
+            L.check(L.lib().mre_bilinear_backward(lib_ctx._h, scorer, ent.data_ptr(), None, rel.data_ptr(), None, ent.shape[1],
+                                                  h.data_ptr(), t.data_ptr(), r.data_ptr(), h.numel(), dscore.data_ptr(),
+                                                  ge.data_ptr(), None, gr.data_ptr(), None, st))
+        return ge, gr, None, None, None, None, None, None, None
+
+
 class PaperScorer:
     """score_model 'transe': ||(h + r) - t||_1 without normalisation (score_norm_flag False :31, p_norm 1 :47);
-    'distmult': sum h*r*t.  Inputs are embedding ROWS ([n, D] tensors) as in the reference's _calc(h, t, r)."""
+    'distmult': sum h*r*t.  Inputs are embedding ROWS ([n, D] tensors) as in the reference's _calc(h, t, r); the result is
+    differentiable with respect to them (the reference trains the RGCN / M3AE outputs through this score)."""
+
+    SCORERS = {"transe": L.TRANSE, "distmult": L.DISTMULT}
 
     def __init__(self, p_norm=1, score_norm_flag=False, device=0):
         self.p_norm, self.norm_flag = p_norm, score_norm_flag
         self.ctx = engine.Context(device)
         self.device = torch.device("cuda", device)
 
+    def score_indexed(self, ent, rel, h, t, r, score_model="transe"):
+        """scores of the triples (ent[h], rel[r], ent[t]) without gathering the rows: ent [rows, D], rel [rows', D] float32,
+        h / t / r int64 index vectors of equal length, all on the scorer's device"""
+        ent, rel = ent.to(self.device, torch.float32).contiguous(), rel.to(self.device, torch.float32).contiguous()
+        h, t, r = (x.to(self.device, torch.int64).contiguous() for x in (h, t, r))
+        if h.numel() and (int(torch.stack([h.min(), t.min(), r.min()]).min()) < 0 or int(torch.stack([h.max(), t.max()]).max()) >= ent.shape[0]
+                          or int(r.max()) >= rel.shape[0]):
+            raise IndexError("triple index out of range of the row tables")
+        return _TripleScoreFn.apply(ent, rel, h, t, r, self.SCORERS[score_model], self.p_norm, self.norm_flag, self.ctx)
+
     def _calc(self, h, t, r, mode="normal", score_model="transe"):
         n = max(h.shape[0], t.shape[0], r.shape[0])
         D = h.shape[-1]
         rows = [x.reshape(-1, D).to(self.device, torch.float32) for x in (h, t, r)]
-        rows = [x if x.shape[0] == n else x.repeat(n // x.shape[0], 1) for x in rows]
-        ent = torch.cat(rows[:2]).contiguous()          # [2n, D]: heads then tails
-        rel = rows[2].contiguous()
+        rows = [x if x.shape[0] == n else x.repeat(n // x.shape[0], 1) for x in rows]      # the view(-1, B, D) broadcast (:148-151)
+        ent = torch.cat(rows[:2])                        # [2n, D]: heads then tails
         idx = torch.arange(n, device=self.device)
-        out = torch.empty(n, dtype=torch.float32, device=self.device)
-        scorer = {"transe": L.TRANSE, "distmult": L.DISTMULT}[score_model]
-        L.check(L.lib().mre_score_triples(self.ctx._h, scorer, ent.data_ptr(), None, rel.data_ptr(), None, D, idx.data_ptr(),
-                                          (idx + n).data_ptr(), idx.data_ptr(), n, self.p_norm, int(self.norm_flag), out.data_ptr(),
-                                          torch.cuda.current_stream().cuda_stream))
-        return out
+        tails = idx + n                                  # kept alive until the call returns
+        return self.score_indexed(ent, rows[2], idx, tails, idx, score_model)
 
     def evaluate(self, h, r, t, score_model="transe"):
         if score_model != "transe":
@@ -111,7 +153,10 @@ class NegativeSampling(PaperScorer):
         return self.neg_sample_fn(local_global_id, mapped_node_list, edge_index, edge_type)
 
     def scoring_fn(self, local_global_id, x, relations, edge_index, edge_type):
-        return self._calc(h=x[edge_index[0].long()], t=x[edge_index[1].long()], r=relations)
+        """:102-109 -- _calc(h = x[edge_index[0]], t = x[edge_index[1]], r = relations) without materialising the gathered rows;
+        differentiable with respect to x and relations"""
+        ei = torch.as_tensor(edge_index)
+        return self.score_indexed(x, relations, ei[0].long(), ei[1].long(), torch.arange(relations.shape[0], device=self.device))
 
     def _get_positive_score(self, score, num_pos_samples):
         return score[:num_pos_samples].view(-1, num_pos_samples).permute(1, 0)
@@ -227,9 +272,10 @@ def _plan_candidates(test_candidates, e2id, r2id):
     return (np.asarray(q_h, np.int64), np.asarray(q_t, np.int64), np.asarray(q_r, np.int64)), excl, groups, counts, names
 
 
-def evaluate(ent_embs, rel_embs, e2id, r2id, test_candidates, hits_at_k=(1, 3, 10), ranker=None, verbose=True):
+def evaluate(ent_embs, rel_embs, e2id, r2id, test_candidates, hits_at_k=(1, 3, 10), ranker=None, verbose=True, return_ranks=False):
     """main.evaluate: ranks the true tail of every test triple among its candidate list with the TransE-L1 scorer,
-    rank = #(n < p) + #(n == p) // 2 + 1.  Returns (mrr, hits@k...) over all triples; prints the reference's lines."""
+    rank = #(n < p) + #(n == p) // 2 + 1.  Returns (mrr, hits@k...) over all triples (the reference prints them and returns
+    nothing, main.py:263-272); prints the reference's lines.  return_ranks=True appends the int64 ranks in file order."""
     ranker = ranker or engine.Ranker(device=ent_embs.device.index or 0 if ent_embs.is_cuda else 0)
     dev = ranker.device
     ent = ent_embs.detach().to(dev, torch.float32).contiguous()
@@ -254,6 +300,8 @@ def evaluate(ent_embs, rel_embs, e2id, r2id, test_candidates, hits_at_k=(1, 3, 1
     hits = [float((rk <= k).mean()) for k in hits_at_k]
     if verbose:
         print(f"[Final Scores] MRR: {mrr} \t" + " \t".join(f"Hits@{k}: {h}" for k, h in zip(hits_at_k, hits)))
+    if return_ranks:
+        return (mrr, *hits, ranks)
     return (mrr, *hits)
 
 

@@ -1,10 +1,11 @@
-"""numpy restatement of the paper-side (main.py / module/ / utils/) ranking code -- TEST INFRASTRUCTURE ONLY.
+"""CPU restatement of the paper-side (main.py / module/ / utils/) scorer, ranker and sampler -- TEST INFRASTRUCTURE ONLY.
 
-The paper half of the reference cannot be imported here or anywhere offline (module.vqgan is absent,
-torch_geometric / ml_collections / skimage are not installed, the data blobs are missing), and
-the reference holds no test or golden vector for it: PARITY UNPINNED for this file beyond the checks
-tests/ run between it and oracle/openke_torch.py (whose tensor expressions ARE pinned to the reference's
-OpenKE modules, and main.py's scorer is the same expression).  Pure-python loops: small cases only.
+Pinned to the reference's own class: tests/golden/make_golden_paper.py imports /root/reference/module/NegativeSampling.py
+(with the two modules it cannot import here, module.model and module.vqgan, stubbed), runs its _calc / evaluate /
+neg_sample_fn and main.py's evaluate() on seeded inputs, and asserts that THIS file reproduces every output bit for bit
+(scores: same torch CPU expressions; sampler: same control flow on the same Mersenne-Twister stream under random.seed(k);
+main.evaluate: same ranks, same printed summary).  The outputs are committed as tests/golden/golden_paper.npz, and
+tests/test_paper_golden.py re-checks this file against them on any box.  Pure-python loops: small cases only.
 """
 import numpy as np
 
@@ -35,6 +36,64 @@ def paper_transe_scores(ent, rel, h, r, cands):
     return np.abs(u).sum(-1, dtype=np.float32)
 
 
+def torch_calc(h, t, r, mode="normal", score_model="transe", score_norm_flag=False, p_norm=1):
+    """NegativeSampling._calc (module/NegativeSampling.py:142-168) on torch CPU tensors: the reference's expression, hence
+    its bits (F.normalize rows when score_norm_flag :144-147, the view for 1-vs-all modes :148-151, h + (r - t) for
+    head_batch else (h + r) - t :152-155, torch.norm(p) :156; distmult h * (r * t) / (h * r) * t, torch.sum :158-168)."""
+    import torch
+    import torch.nn.functional as F
+    h, t, r = (torch.as_tensor(x) for x in (h, t, r))
+    if score_model == "transe" and score_norm_flag:
+        h, r, t = F.normalize(h, 2, -1), F.normalize(r, 2, -1), F.normalize(t, 2, -1)
+    if mode != "normal":
+        B, D = r.shape[0], r.shape[-1]
+        h, t, r = h.view(-1, B, D), t.view(-1, B, D), r.view(-1, B, D)
+    if score_model == "transe":
+        u = h + (r - t) if mode == "head_batch" else (h + r) - t
+        return torch.norm(u, p_norm, -1).flatten()
+    u = h * (r * t) if mode == "head_batch" else (h * r) * t
+    return torch.sum(u, -1).flatten()
+
+
+def torch_evaluate(h, r, t, score_norm_flag=False, p_norm=1):
+    """NegativeSampling.evaluate (module/NegativeSampling.py:294-305): ||(h + r) - t||_p on rows"""
+    return torch_calc(h, t, r, "normal", "transe", score_norm_flag, p_norm)
+
+
+def _mrr_f32(ranks):
+    """sum([1.0 / rank ...]) / len(ranks) as main.py:252,263 evaluate it: `rank` is a 0-dim torch LONG tensor there, so
+    1.0 / rank is a float32 tensor and Python's sum() accumulates sequentially in float32"""
+    acc = np.float32(0.0)
+    for x in ranks:
+        acc = np.float32(acc + np.float32(1.0) / np.float32(x))
+    return float(np.float32(acc / np.float32(len(ranks))))
+
+
+def evaluate_candidates(ent, rel, e2id, r2id, test_candidates, hits_at_k=(1, 3, 10)):
+    """main.evaluate (main.py:217-272) on a {mode}_candidates.json dict: per test triple the head / relation rows repeated
+    against the candidates' rows (:236-244), model.evaluate (:245), rank = #(n < p) + #(n == p) // 2 + 1 (:246-250).
+    Returns (ranks in file order, per-query score vectors, per-relation (name, n, mrr, hit1, hit3, hit10), (mrr, hits...))."""
+    import torch
+    ent, rel = torch.as_tensor(ent), torch.as_tensor(rel)
+    ranks, scores, per_rel = [], [], []
+    for query, items in test_candidates.items():
+        tmp = []
+        for key, cands in items.items():
+            head, rela, _ = key.split("\t")
+            hrow = ent[e2id[head]].repeat(len(cands), 1)
+            rrow = rel[r2id[rela]].repeat(len(cands), 1)
+            trow = torch.stack([ent[e2id[c]] for c in cands])
+            s = torch_evaluate(hrow, rrow, trow).numpy()
+            scores.append(s)
+            tmp.append(rank_ties_half(s))
+        ranks.extend(tmp)
+        per_rel.append((query, len(items), _mrr_f32(tmp)) + tuple(
+            sum(1.0 if x <= k else 0.0 for x in tmp) / len(tmp) for k in hits_at_k))
+    mrr = _mrr_f32(ranks)
+    hits = [sum(1.0 if x <= k else 0.0 for x in ranks) / len(ranks) for k in hits_at_k]
+    return ranks, scores, per_rel, (mrr, *hits)
+
+
 def rank_ties_half(scores):
     """main.py:245-250: p = scores[0]; rank = #(n < p) + #(n == p) // 2 + 1."""
     p, n = scores[0], scores[1:]
@@ -56,8 +115,10 @@ def summarize(ranks, ks):
 class ReferenceSubgraphSampler:
     """Restatement of module/NegativeSampling.py's sampler with the reference's own control flow and Python `random`
     (neg_sample_fn :114-140, __normal_batch :321-349, __corrupt_head/__corrupt_tail :351-375, __count_htr :59-93), ids as
-    ints.  The reference's RNG is unseeded Python `random`, so its output is a DISTRIBUTION, not a vector: tests compare
-    the product's sampler with this one statistically (head/tail split, uniformity over the admissible nodes, no leaks)."""
+    ints.  With rng = random.Random(k) it reproduces the reference class under random.seed(k) bit for bit
+    (tests/golden/make_golden_paper.py asserts it; golden_paper.npz holds the reference's vectors).  The product's sampler
+    draws from Philox instead of Python's Mersenne Twister, so IT is compared with this one statistically (head/tail split,
+    uniformity over the admissible nodes, layout, no leaks) and bit for bit with its own Philox CPU replay."""
 
     def __init__(self, whole_triples, neg_ent=1, filter_flag=True, rng=None):
         import random

@@ -104,3 +104,88 @@ def synthetic_zsl_setup(seed=192, n_ent=300, n_rel=3, D=200, max_nb=50, T=14):
     cands[3][5] = cands[3][0]                                                           # an exact tie with the true candidate
     rel_vecs = rng.standard_normal((n_rel, 20, D)).astype(np.float32)
     return n_symbols, conn, deg.astype(np.float32), heads, rels, cands, rel_vecs
+
+
+# ---- paper half (tests/golden/make_golden_paper.py, tests/test_paper_golden.py): seeded inputs of golden_paper.npz
+PAPER_CALC_CASES = (
+    # name, score_model, mode, score_norm_flag, B (relation rows), k (candidate blocks; 1 for 'normal')
+    ("transe_normal", "transe", "normal", False, 96, 1),
+    ("transe_normal_norm", "transe", "normal", True, 96, 1),
+    ("transe_head_batch", "transe", "head_batch", False, 8, 40),
+    ("transe_tail_batch", "transe", "tail_batch", False, 8, 40),
+    ("distmult_normal", "distmult", "normal", False, 96, 1),
+    ("distmult_head_batch", "distmult", "head_batch", False, 8, 40),
+    ("distmult_tail_batch", "distmult", "tail_batch", False, 8, 40),
+)
+
+
+def paper_calc_inputs(seed, name, D=200):
+    """(h, t, r) float32 row tensors of one _calc case, shaped as module/NegativeSampling.py:142-168 expects them:
+    normal: all [B, D]; head_batch: h [k*B, D], t and r [B, D]; tail_batch: t [k*B, D], h and r [B, D]."""
+    case = next(c for c in PAPER_CALC_CASES if c[0] == name)
+    _, _, mode, _, B, k = case
+    rng = np.random.default_rng([seed, PAPER_CALC_CASES.index(case)])
+    draw = lambda n: (rng.standard_normal((n, D)) * 0.3).astype(np.float32)
+    h = draw(k * B if mode == "head_batch" else B)
+    t = draw(k * B if mode == "tail_batch" else B)
+    r = draw(B)
+    return h, t, r
+
+
+def paper_subgraph_cases(seed=SEED, n_cases=4):
+    """Seeded sampled subgraphs for neg_sample_fn (module/NegativeSampling.py:114-140): a global train graph (E = 120,
+    R = 4, dense enough that the filter rejects often), then per case a node subset in LOCAL ids and the train edges inside it.
+    Returns (whole_triples (h, r, t) lists of GLOBAL ids, [case dicts: l2g, edge_h, edge_t, edge_r, neg_ent, py_seed])."""
+    rng = np.random.default_rng([seed, 77])
+    E, R, n_train = 120, 4, 2600
+    th, tt, tr = rng.integers(0, E, n_train), rng.integers(0, E, n_train), rng.integers(0, R, n_train)
+    cases = []
+    for c in range(n_cases):
+        n_local = (30, 48, 64, 90)[c % 4]
+        l2g = rng.choice(E, n_local, replace=False).astype(np.int64)
+        g2l = {int(g): i for i, g in enumerate(l2g)}
+        inside = np.array([i for i in range(n_train) if int(th[i]) in g2l and int(tt[i]) in g2l], np.int64)
+        pick = rng.choice(inside, min((25, 60, 90, 120)[c % 4], len(inside)), replace=False)
+        cases.append(dict(l2g=l2g, edge_h=np.array([g2l[int(th[i])] for i in pick], np.int64),
+                          edge_t=np.array([g2l[int(tt[i])] for i in pick], np.int64), edge_r=tr[pick].astype(np.int64),
+                          neg_ent=(1, 4, 8, 16)[c % 4], py_seed=1000 + c))
+    return (th.tolist(), tr.tolist(), tt.tolist()), E, R, cases
+
+
+def paper_eval_setup(seed=SEED, E=400, R=6, D=200, per_rel=15):
+    """Seeded inputs of main.evaluate (main.py:217-272): entity / relation symbols and ids, embeddings, and a
+    {mode}_candidates.json-shaped dict {relation: {"head\\trel\\ttail": [true tail, candidates...]}} with ragged candidate
+    lists (1 ... 300) and planted EXACT ties (clones of the true tail's embedding row among the candidates)."""
+    rng = np.random.default_rng([seed, 99])
+    ents = [f"/m/e{i:03d}" for i in range(E)]
+    rels = [f"/r/rel{i}" for i in range(R)]
+    e2id = {e: i for i, e in enumerate(ents)}
+    r2id = {r: i for i, r in enumerate(rels)}
+    ent = (rng.standard_normal((E, D)) * 0.25).astype(np.float32)
+    rel = (rng.standard_normal((R, D)) * 0.25).astype(np.float32)
+    # entities 380..399 are clones in groups of five: rows identical -> exactly equal scores for any query
+    for g in range(4):
+        ent[380 + 5 * g: 385 + 5 * g] = ent[380 + 5 * g]
+    sizes = [1, 2, 3, 17, 64, 65, 128, 129, 200, 257, 300, 33, 90, 150, 7]
+    cand = {}
+    for ri, rname in enumerate(rels):
+        items = {}
+        for k in range(per_rel):
+            head = int(rng.integers(0, 380))
+            n = sizes[(k + ri) % len(sizes)]
+            if k % 5 == 0 and n >= 5:      # planted ties: the true tail is a clone, 1..4 of its siblings are candidates
+                g = int(rng.integers(0, 4))
+                true = 380 + 5 * g
+                sib = [true + 1 + j for j in range(1 + (k // 5 + ri) % 4)]
+                rest = rng.choice(380, n - 1 - len(sib), replace=False).tolist()
+                lst = [true] + sib + rest
+            else:
+                lst = rng.choice(380, n, replace=False).tolist()
+            if head in lst[1:]:
+                lst = [x for x in lst if x != head] if lst[0] != head else lst
+            key = "\t".join((ents[head], rname, ents[lst[0]]))
+            if key in items:
+                continue
+            items[key] = [ents[i] for i in lst]
+        cand[rname] = items
+    return ents, rels, e2id, r2id, ent, rel, cand
