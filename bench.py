@@ -1,21 +1,27 @@
 #!/usr/bin/env python
 """bench.py -- filtered-rank eval queries/sec on B200 (BASELINE.json metric), one JSON line on rank 0.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--queries Q] [--impl ours|reference]
 
-A "step" is one pass of the hot path (pre-pass -> fused score+rank kernel -> metric sums) over one batch of
-queries.  Workloads (synthetic seeded tables of the reference's shapes -- trained features cannot be had offline):
-  db15k_zs        BASELINE configs[1]: DB15K-ZS test triples (5 653 tail queries x 12 741 entities, D = 200),
-                  TransE L1 un-normalised (the paper's evaluate), strict filtered rank, known tails from the bundled
-                  test tasks.  DEFAULT at every N.
+A "step" is one pass of the hot path over ONE GLOBAL query set: pre-pass -> fused score+rank kernel -> metric sums ->
+(N > 1) the integer all-reduce of the metric sums, all inside the timed region.  Multi-GPU is STRONG scaling: the global
+query set is cut into contiguous blocks (DistContext.shard, the reference's relation-sorted order, Reader.h:227), every
+rank ranks its block against the replicated tables, and one NCCL all-reduce of the int64 [2, 8] sums per step combines
+them -- `result.n` is the global query count at every N and the metric tuple is bit-identical to N = 1.
+
+Workloads (synthetic seeded tables of the reference's shapes -- trained features cannot be had offline):
+  synthetic2m     BASELINE configs[4] -- DEFAULT at every N: 2 M entities x 256, TransE L1, 131 072 tail queries per step
+                  (--queries 1000000 runs the north_star's full 1 M), known-true lists ~ 1 + Geom(2.5) from a synthetic train
+                  split; tables (2 GB) exceed the 126 MB L2, so no flush is needed between steps
+  db15k_zs        configs[1]: DB15K-ZS test triples (5 653 tail queries x 12 741 entities, D = 200), TransE L1 un-normalised
+                  (the paper's evaluate), strict filtered rank -- reported in `extra.db15k_zs` of the default line at every N
   fb15k237_zs     configs[0]: FB15K-237-ZS, rel2candidates (1 000 per relation), ties//2 rank (main.evaluate)
   fb15k237        OpenKE Tester protocol: head + tail queries of the 20 466 test triples, TransE L1 normalised
   distmult|complex configs[2]: FB15K-237-ZS all-entity filtered ranking on the tcgen05 contraction path
-  synthetic2m     configs[4]: 2 M entities x 256, 8 192 queries per rank per step
-  train           configs[3]: OpenKE TransE training step, B = 4096 x 25 Bernoulli negatives + margin loss
-Multi-GPU (torchrun, one rank per GPU): queries shard with no data-path collective; every rank ranks its own shard
-against the replicated tables and the integer metric sums are combined by one NCCL all-reduce (weak scaling: the
-per-rank batch is fixed).  `value` = queries of all ranks / max-over-ranks device time.
+  train           configs[3]: OpenKE TransE training step, B = 4096 x 25 Bernoulli negatives + margin loss (bench_train.py)
+  zsl             ZSLmodule.eval at FB15K-237-ZS size (bench_zsl.py)
+The default line carries every other workload under `extra` (each with its own value / roofline / parity), so the
+tcgen05 paths, the candidate-list path, the ZSL scorer and the training step are all measured under the driver's clock.
 """
 import argparse
 import json
@@ -31,6 +37,8 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
 
 SEED = 192  # the reference's default seed (args.py:8)
+DEFAULT_WORKLOAD = "synthetic2m"
+DEFAULT_QUERIES = 131072
 
 
 # ------------------------------------------------------------------------------------------------- workloads
@@ -45,13 +53,21 @@ def csr_from_lists(lists):
     return ptr, idx
 
 
-def known_tail_csr(h, r, t):
-    """per-query sorted known tails of (h, r) over the given triples (e1rel_e2, utils/gen_e1r_e2_all.py:14-19)"""
-    d = {}
-    for a, b, c in zip(h.tolist(), r.tolist(), t.tolist()):
-        d.setdefault((a, b), set()).add(c)
-    d = {k: np.fromiter(sorted(v), np.int64, len(v)) for k, v in d.items()}
-    return csr_from_lists([d[(a, b)] for a, b in zip(h.tolist(), r.tolist())])
+def known_tail_csr(q_h, q_r, all_h, all_r, all_t, R):
+    """per-query sorted, de-duplicated known tails of (h, r) over the given triples (e1rel_e2, utils/gen_e1r_e2_all.py:14-19;
+    what _find answers for a tail query, Corrupt.h:166-177) -- vectorised: one sort of the triples, one search per query"""
+    key = all_h.astype(np.int64) * R + all_r
+    order = np.lexsort((all_t, key))
+    key, val = key[order], all_t[order].astype(np.int64)
+    keep = np.ones(len(key), bool)
+    keep[1:] = (key[1:] != key[:-1]) | (val[1:] != val[:-1])
+    key, val = key[keep], val[keep]
+    qk = q_h.astype(np.int64) * R + q_r
+    lo, hi = np.searchsorted(key, qk, "left"), np.searchsorted(key, qk, "right")
+    n = hi - lo
+    ptr = np.concatenate([[0], np.cumsum(n)]).astype(np.int64)
+    idx = val[np.repeat(lo - ptr[:-1], n) + np.arange(int(ptr[-1]))] if ptr[-1] else np.zeros(0, np.int64)
+    return ptr, idx
 
 
 class Workload:
@@ -63,10 +79,11 @@ class Workload:
     side = 1
     index_splits = None    # (train, valid, test) for MRE_FILTER_INDEX
     filt_csr = None        # host (ptr, idx)
-    dim_k = None
+    known = None           # (h, t, r) triples whose tails are "known" besides the test triples themselves (synthetic train split)
+    flush_l2 = True
 
 
-def load_workload(name, rank=0):
+def load_workload(name, queries=None):
     import golden_util as gu
     w = Workload()
     w.name = name
@@ -75,7 +92,7 @@ def load_workload(name, rank=0):
         z = gu.load("db15k_zs.npz")
         w.E, w.R, w.D = int(z["E"]), int(z["R"]), 200
         w.q_h, w.q_r, w.q_t = (z[k].astype(np.int64) for k in ("test_h", "test_r", "test_t"))
-        w.filt_csr = known_tail_csr(w.q_h, w.q_r, w.q_t)
+        w.filt_csr = known_tail_csr(w.q_h, w.q_r, w.q_h, w.q_r, w.q_t, w.R)
         w.desc = "DB15K-ZS test tasks, TransE L1 (paper evaluate), all-entity strict filtered rank"
     elif name in ("fb15k237_zs", "distmult", "complex"):
         z = gu.load("fb15k237_zs.npz")
@@ -83,7 +100,7 @@ def load_workload(name, rank=0):
         h, r, t = (z[k].astype(np.int64) for k in ("test_h", "test_r", "test_t"))
         order = np.argsort(r, kind="stable")
         w.q_h, w.q_r, w.q_t = h[order], r[order], t[order]
-        w.filt_csr = known_tail_csr(w.q_h, w.q_r, w.q_t)
+        w.filt_csr = known_tail_csr(w.q_h, w.q_r, w.q_h, w.q_r, w.q_t, w.R)
         if name == "fb15k237_zs":
             rel2cand = {int(rr): z["cand_ent"][i].astype(np.int64) for i, rr in enumerate(z["cand_rel"])}
             rels, counts = np.unique(w.q_r, return_counts=True)
@@ -100,23 +117,49 @@ def load_workload(name, rank=0):
         w.normalize = True
         w.desc = "OpenKE FB15K237 Tester protocol: head+tail queries of all test triples, TransE L1 normalised"
     elif name == "synthetic2m":
+        # BASELINE configs[4] / SURVEY 8d cfg 5: E = 2 M, D = 256, R = 1 000, tables ~ N(0, 1) / sqrt(D); queries uniform; every
+        # query's known-true set = its own tail + k - 1 synthetic TRAIN triples (h, r, x), k ~ min(1 + Geom(mean 2.5), 1024)
         w.E, w.R, w.D = 2_000_000, 1000, 256
-        Q = 8192
-        qrng = np.random.default_rng(SEED + 1 + rank)
+        Q = int(queries or DEFAULT_QUERIES)
+        qrng = np.random.default_rng(SEED + 1)
         w.q_h, w.q_t, w.q_r = qrng.integers(0, w.E, Q), qrng.integers(0, w.E, Q), qrng.integers(0, w.R, Q)
-        k = np.minimum(1 + qrng.geometric(1 / 2.5, Q), 1024)
-        lists = [np.unique(np.concatenate([[tt], qrng.integers(0, w.E, kk - 1)])) for tt, kk in zip(w.q_t.tolist(), k.tolist())]
-        w.filt_csr = csr_from_lists(lists)
-        w.desc = "synthetic 2M entities x 256, 8192 tail queries per rank per step, TransE L1, known-true lists ~1+Geom(2.5)"
+        order = np.lexsort((w.q_t, w.q_h, w.q_r))                 # the order the reference iterates test triples (Reader.h:227)
+        w.q_h, w.q_t, w.q_r = w.q_h[order], w.q_t[order], w.q_r[order]
+        k = np.minimum(qrng.geometric(1 / 2.5, Q), 1024) - 1      # extra known tails per query
+        rep = np.repeat(np.arange(Q), k)
+        w.known = (w.q_h[rep], qrng.integers(0, w.E, len(rep)), w.q_r[rep])
+        w.filt_csr = known_tail_csr(w.q_h, w.q_r, np.concatenate([w.q_h, w.known[0]]), np.concatenate([w.q_r, w.known[2]]),
+                                    np.concatenate([w.q_t, w.known[1]]), w.R)
+        w.flush_l2 = False
+        w.desc = f"synthetic 2M entities x 256, {Q} tail queries per step (global, sharded across ranks), TransE L1, known-true lists ~1+Geom(2.5)"
     else:
         raise SystemExit(f"unknown workload {name}")
     if name == "synthetic2m":
-        w.tables = None  # generated on the device (2 GB)
+        w.tables = None            # 2 GB: drawn lazily (host_tables) so that rank > 0 of the reference arm never pays for them
     else:
         n_tab = 4 if w.scorer == "complex" else 2
         shapes = [(w.E, w.D), (w.R, w.D)] if n_tab == 2 else [(w.E, w.D), (w.E, w.D), (w.R, w.D), (w.R, w.D)]
         w.tables = [xavier(rng, a, b) for a, b in shapes]
     return w
+
+
+def host_tables(w):
+    """the workload's float32 tables in host memory (the same bits in both arms: numpy PCG64, SEED)"""
+    if w.tables is None:
+        rng = np.random.default_rng(SEED)
+        s = np.float32(1.0 / np.sqrt(w.D))
+        w.tables = [rng.standard_normal((w.E, w.D), dtype=np.float32) * s, rng.standard_normal((w.R, w.D), dtype=np.float32) * s]
+    return w.tables
+
+
+def config_of(w, world):
+    """identical in both arms (the driver compares the two dicts)"""
+    Q = len(w.q_h) if w.index_splits is None else 2 * len(w.index_splits[2][0])
+    return {"workload": w.name, "desc": w.desc, "E": w.E, "R": w.R, "D": w.D, "queries_per_step": int(Q), "scorer": w.scorer,
+            "rank_mode": w.rank_mode,
+            "l2": "256 MiB buffer written between timed steps (L2 flush)" if w.flush_l2 else "inputs (2 GB of tables) exceed the 126 MB L2; no flush",
+            "sharding": "one global query set per step, contiguous blocks per rank (strong scaling), tables replicated, "
+                        "ONE int64 all-reduce of the metric sums per step inside the timed region"}
 
 
 # ------------------------------------------------------------------------------------------------- clocks
@@ -191,17 +234,22 @@ class stdout_to_stderr:
 def reference_eval_setup(w, threads):
     """The reference's CPU path for this workload: torch-CPU scoring with the reference's tensor expression
     (oracle/openke_torch.py, asserted bit-identical to OpenKE's modules) + the UNMODIFIED Base.so testTail/testHead
-    when oracle/_ref/Base.so exists (else the C restatement of Test.h).  Returns run(sample_indices) -> seconds."""
+    when oracle/_ref/Base.so exists (else the C restatement of Test.h).
+    Returns run(sample_indices, record=None) -> (seconds, queries), the test-set size, the kind, and the test triples in the
+    order the sample indices refer to.  With `record` (a list) every query appends (index, side, raw, filt, lo, hi): the
+    counts Test.h produces from the reference's scores and their 1e-5 tie-band interval (the parity block's ground truth)."""
     import tempfile
     import torch
+    import golden_util as gu
     from oracle import kge_oracle as ko, openke_torch as ot, ref_driver as rd
     torch.set_num_threads(threads)
-    tables = [torch.from_numpy(t) for t in w.tables]
+    tables = [torch.from_numpy(t) for t in host_tables(w)]
     if w.index_splits is not None:
         train, valid, test = w.index_splits
-    else:  # the ZS train blobs are missing from the reference: the known set is the bundled test tasks
+    else:  # the ZS train blobs are missing from the reference: the known set is the test tasks (+ the synthetic train split)
         trip = (w.q_h, w.q_t, w.q_r)
-        train, valid, test = trip, tuple(x[:1] for x in trip), trip
+        train = trip if w.known is None else tuple(np.concatenate([a, b]) for a, b in zip(trip, w.known))
+        valid, test = tuple(x[:1] for x in trip), trip
     kind = "port"
     ref = None
     if rd.available() and w.groups is None:
@@ -209,18 +257,23 @@ def reference_eval_setup(w, threads):
         rd.write_benchmark_dir(d, w.E, w.R, train, valid, test)
         ref = rd.RefOpenKE(d + "/", threads=threads)
         ref.load_test()
-        th, tt, tr = (np.zeros(ref.test_tot, np.int64) for _ in range(3))
         kind = "reference"
     ix = ko.OracleIndex(w.E, w.R, train, valid, test)
     th, tt, tr = ix.test_triples()
     ar = torch.arange(w.E)
     sides = (0, 1) if w.index_splits is not None else (1,)
+    csr_pos = None
+    if w.filt_csr is not None:
+        csr_pos = {}
+        for p, key in enumerate(zip(w.q_h.tolist(), w.q_r.tolist())):
+            csr_pos.setdefault(key, p)
 
-    def run(sample):
+    def run(sample, record=None):
         t0 = time.perf_counter()
         n = 0
         with torch.no_grad():
             for i in sample:
+                i = int(i)
                 h, t, r = int(th[i]), int(tt[i]), int(tr[i])
                 for side in sides:
                     if side == 0:
@@ -235,9 +288,23 @@ def reference_eval_setup(w, threads):
                     else:
                         ix.rank_from_scores(s, side, h, t, r)
                     n += 1
+                    if record is not None and side == 1 and csr_pos is not None:
+                        t1 = time.perf_counter()
+                        raw, filt = ix.rank_from_scores(s, side, h, t, r)
+                        p = csr_pos[(h, r)]
+                        known = w.filt_csr[1][w.filt_csr[0][p]:w.filt_csr[0][p + 1]]
+                        band = gu.TIE_BAND * max(abs(float(s[t])), float(np.abs(s).mean()))
+                        lo, hi = gu.band_counts(s, t, known, band)
+                        record.append((h, r, t, raw, filt, lo, hi))
+                        t0 += time.perf_counter() - t1            # bookkeeping is not part of the reference's path
         return time.perf_counter() - t0, n
 
     return run, len(th), kind
+
+
+def reference_sample_size(w):
+    """test triples per reference step, sized so that K = 20 steps stay within a few minutes of CPU time"""
+    return 4 if w.name == "synthetic2m" else 512
 
 
 def run_reference(args, w):
@@ -245,12 +312,12 @@ def run_reference(args, w):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    per_step = 512
+    per_step = reference_sample_size(w)
     rng = np.random.default_rng(0)
     with stdout_to_stderr():
         run, n_test, kind = reference_eval_setup(w, threads)
         for _ in range(min(args.warmup, 2)):
-            run(rng.integers(0, n_test, 16))
+            run(rng.integers(0, n_test, max(1, per_step // 32)))
         tot_s, tot_q = 0.0, 0
         for _ in range(args.steps):
             s, q = run(rng.integers(0, n_test, per_step))
@@ -262,8 +329,8 @@ def run_reference(args, w):
     emit(({
         "impl": "reference", "metric": "filtered-rank eval queries/sec", "value": v, "unit": "queries/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": w.name, "desc": w.desc, "E": w.E, "D": w.D},
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config_of(w, 1),
         "cpu_baseline": {"value": v, "unit": "queries/s", "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": v, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
@@ -291,14 +358,322 @@ def emit(obj):
         os.write(_JSON_FD, line)
 
 
-# ------------------------------------------------------------------------------------------------- our arm
 def measured_peaks():
     """driver-written MEASURED_PEAKS.json at the repo root (HBM GB/s, dense BF16 TFLOP/s), or None"""
     try:
-        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "MEASURED_PEAKS.json")) as f:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
             return json.load(f)
     except Exception:  # noqa: BLE001
         return None
+
+
+def committed_traffic(name):
+    """DRAM bytes of the dominant kernel per launch from the committed `ncu --set full` captures (profiles/*_traffic.json)"""
+    for fn in ("r2_traffic.json", "r1_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", fn)) as f:
+                tr = json.load(f).get(name)
+            if tr and tr.get("dram_bytes_read") is not None:
+                return tr
+        except Exception:  # noqa: BLE001
+            pass
+    return None
+
+
+# ------------------------------------------------------------------------------------------------- our arm
+class Runner:
+    """Everything one process needs to time workloads on its GPU: context, ranker, the L2-flush buffer, the process group."""
+
+    def __init__(self, rank, world, local):
+        import torch
+        import mre_b200
+        mre_b200.build()
+        self.torch, self.mre, self.eng = torch, mre_b200, mre_b200.engine
+        self.rank, self.world, self.local = rank, world, local
+        torch.cuda.set_device(local)
+        self.dev = torch.device("cuda", local)
+        self.dctx = mre_b200.dist.DistContext() if world > 1 else None
+        self.ctx = self.eng.Context(local)
+        self.rk = self.eng.Ranker(self.ctx)
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)  # > 126 MB L2
+        self._peaks = {}
+
+    # ---- plumbing
+    def barrier(self):
+        if self.world > 1:
+            self.torch.distributed.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, x):
+        if self.world == 1:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        self.torch.distributed.all_reduce(t, op=self.torch.distributed.ReduceOp.MAX)
+        return t.item()
+
+    def fp32_peak(self):
+        if "fp32" not in self._peaks:
+            self._peaks["fp32"] = self.ctx.probe_fp32_peak()
+        return self._peaks["fp32"]
+
+    def mma_peak(self):
+        """dense BF16 tensor peak: the driver-measured cuBLAS figure when present, else the in-process tcgen05 kind::f16 probe"""
+        if "mma" not in self._peaks:
+            probe = self.ctx.probe_bf16_peak()
+            mp = measured_peaks()
+            if mp and mp.get("bf16_tflops"):
+                self._peaks["mma"] = (float(mp["bf16_tflops"]) * 1e12,
+                                      f"MEASURED_PEAKS.json bf16_tflops (burst, cuBLAS); in-process tcgen05 kind::f16 probe: {probe / 1e12:.0f} TFLOP/s")
+            else:
+                self._peaks["mma"] = (probe, "tcgen05 kind::f16 (BF16) dense MMA microbenchmark run in this process (mre_probe_bf16_peak); MEASURED_PEAKS.json absent")
+        return self._peaks["mma"]
+
+    # ---- one workload, sharded over the ranks
+    def prepare(self, w):
+        """device-resident inputs of this rank's block of the workload's global query set + the two step functions"""
+        torch, eng, dev = self.torch, self.eng, self.dev
+        tables = [torch.from_numpy(t).to(dev) for t in host_tables(w)]
+        kw = dict(p_norm=w.p_norm, normalize=w.normalize)
+        index = None
+        if w.index_splits is not None:
+            index = eng.KGIndex.from_arrays(w.E, w.R, *w.index_splits).to_device(self.local)
+            th, tt, tr = index.test_triples()
+            q_h, q_t, q_r = np.repeat(th, 2), np.repeat(tt, 2), np.repeat(tr, 2)
+            side_all = np.tile(np.array([0, 1], np.uint8), len(th))
+        else:
+            q_h, q_t, q_r, side_all = w.q_h, w.q_t, w.q_r, None
+        Q_global = len(q_h)
+        lo, hi = eng_shard(self.mre, Q_global, self.rank, self.world)
+        if w.groups is not None and self.world > 1:
+            raise SystemExit("candidate-group workloads run on one GPU (bench extras); shard the relation groups to scale them")
+        host = [torch.from_numpy(np.ascontiguousarray(a[lo:hi])).pin_memory() for a in (q_h, q_t, q_r)]
+        devq = [a.to(dev) for a in host]
+        if side_all is not None:
+            side_host = torch.from_numpy(np.ascontiguousarray(side_all[lo:hi])).pin_memory()
+            side_d = side_host.to(dev)
+        else:
+            side_host = side_d = w.side
+        if w.groups is not None:
+            kw["groups"] = eng.CandidateGroups.from_lists(w.groups[0], w.groups[1], dev)
+        if w.filt_csr is not None:
+            ptr, idx = w.filt_csr
+            kw["filt_csr"] = (torch.from_numpy(ptr[lo:hi + 1] - ptr[lo]).to(dev), torch.from_numpy(np.ascontiguousarray(idx[ptr[lo]:ptr[hi]])).to(dev))
+        if index is not None:
+            kw["index"] = index
+        Q = hi - lo
+        counts_d = torch.empty((4, Q), dtype=torch.int32, device=dev)
+        counts_h = torch.empty((4, Q), dtype=torch.int32).pin_memory()
+        rk, dctx, rank_mode = self.rk, self.dctx, w.rank_mode
+        dist = torch.distributed if self.world > 1 else None
+
+        def rank_dev():
+            return rk.rank(w.scorer, tables, devq[0], devq[1], devq[2], side_d, out=counts_d, **kw)
+
+        def step_dev():
+            c = rank_dev()
+            sums = rk.metrics(c, side_d, rank_mode)["sums"]
+            if dist is not None:
+                dist.all_reduce(sums)                       # ONE int64 [2, 8] collective per step, timed
+            return sums
+
+        def step_e2e():
+            """host query ids in -> host counts out through mre_rank_host, metric sums on the host, all-reduced when N > 1"""
+            c = rk.rank_host(w.scorer, tables, host[0], host[1], host[2], side_host, out=counts_h, **kw)
+            sums = host_metric_sums(c.numpy(), side_host if side_all is not None else w.side, rank_mode)
+            if dist is not None:
+                t = torch.from_numpy(sums).to(dev)
+                dist.all_reduce(t)
+                sums = t.cpu().numpy()
+            return sums
+
+        h2d = sum(a.numel() * a.element_size() for a in host) + (side_host.numel() if side_all is not None else 0)
+        d2h = counts_h.numel() * 4
+        return dict(step_dev=step_dev, step_e2e=step_e2e, rank_dev=rank_dev, side=side_d, Q=Q, Q_global=Q_global, lo=lo, hi=hi, h2d=h2d, d2h=d2h, counts_d=counts_d,
+                    q=(q_h, q_t, q_r), tables=tables)
+
+    def timed(self, step, steps, warmup, flush_l2):
+        """W warm-up steps, then K steps each bracketed by its own CUDA event pair on the launching stream; the dominant
+        kernel is bracketed by its own pairs inside the library (mre_ctx_timing).  -> (sum ms max over ranks, last result,
+        kernel ms per launch, launches of the library inside the timed region)"""
+        torch, ctx = self.torch, self.ctx
+        for _ in range(warmup):
+            step()
+        self.barrier()
+        ctx.timing(True)
+        ctx.timing_read()
+        l0 = ctx.launches
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        out = None
+        for a, b in ev:
+            if flush_l2:
+                self.flush.zero_()
+            a.record()
+            out = step()
+            b.record()
+        self.barrier()
+        ms = self.max_over_ranks(sum(a.elapsed_time(b) for a, b in ev))
+        launches = ctx.launches - l0
+        kern_ms, kern_n = ctx.timing_read()
+        ctx.timing(False)
+        return ms, out, kern_ms / max(kern_n, 1), kern_n, launches
+
+    def e2e_timed(self, step, steps, warmup):
+        for _ in range(warmup):
+            step()
+        self.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step()
+        self.torch.cuda.synchronize()
+        return self.max_over_ranks(time.perf_counter() - t0)
+
+    def roofline(self, w, Q, kern_ms, kern_n):
+        K = w.D * (2 if w.scorer == "complex" else 1)
+        n_cand = w.E if w.groups is None else float(np.mean([len(np.unique(c)) for c in w.groups[1]]))
+        alg_ops = 2.0 * Q * n_cand * K   # lane-ops (TransE) or flops (bilinear) of THIS rank's launch
+        achieved = alg_ops / (kern_ms * 1e-3) / 1e12
+        if w.scorer == "transe":
+            peak = self.fp32_peak()
+            roof = {"bound": "fp32", "achieved": achieved, "peak": peak / 1e12, "unit": "TFLOP/s", "frac": achieved / (peak / 1e12),
+                    "traffic": None, "kernel": "transe_rank_kernel", "kernel_ms": kern_ms, "launches_timed": kern_n,
+                    "peak_source": "FP32 add-rate microbenchmark run in this process (mre_probe_fp32_peak: the better of the scalar FADD and the packed FADD2 stream; 148 SM x 128 lanes x SM clock); MEASURED_PEAKS.json holds no FP32 figure",
+                    "algorithmic": "2*Q*E*D FP32 lane-ops per launch, Q = this rank's queries (one subtract + one add-abs per element; issued as packed sub.f32x2 / add.f32x2)",
+                    "hbm_floor_gbs": (4.0 * (n_cand + Q) * w.D + 16.0 * Q) / (kern_ms * 1e-3) / 1e9}
+        else:
+            peak, src = self.mma_peak()
+            roof = {"bound": "tensor", "achieved": achieved, "peak": peak / 1e12, "unit": "TFLOP/s", "frac": achieved / (peak / 1e12),
+                    "traffic": None, "kernel": "bilinear_rank_kernel", "kernel_ms": kern_ms, "launches_timed": kern_n,
+                    "peak_source": src, "pipe_frac": BIL_PRODUCTS * achieved / (peak / 1e12),
+                    "algorithmic": "2*Q*E*K flops counted ONCE; the kernel issues %d BF16 MMA(s) per product, pipe_frac = executed flops / peak" % BIL_PRODUCTS}
+        tr = committed_traffic(w.name)
+        if tr:
+            roof["traffic"] = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+            roof["traffic_source"] = tr["source"]
+            roof["algorithmic_bytes"] = 4.0 * (w.E + Q) * w.D
+        return roof
+
+    def measure(self, w, steps, warmup, e2e_steps=None, clocks=False):
+        """full sub-line of one workload at this world size"""
+        p = self.prepare(w)
+        sampler = ClockSampler(self.local) if clocks else None
+        if sampler:
+            sampler.__enter__()
+        try:
+            ms, sums, kern_ms, kern_n, launches = self.timed(p["step_dev"], steps, warmup, w.flush_l2)
+            es = e2e_steps or steps
+            e2e_s = self.e2e_timed(p["step_e2e"], es, 1 if e2e_steps else warmup)
+        finally:
+            if sampler:
+                sampler.__exit__()
+        sums = sums.cpu().numpy()
+        summ = self.eng.summarize(sums)
+        Qg = p["Q_global"]
+        out = {"value": Qg * steps / (ms * 1e-3), "unit": "queries/s", "ms_per_step": ms / steps, "steps": steps, "warmup": warmup,
+               "config": config_of(w, self.world), "roofline": self.roofline(w, p["Q"], kern_ms, kern_n),
+               "e2e": {"value": Qg * es / e2e_s, "unit": "queries/s", "steps": es, "h2d_bytes_per_step": p["h2d"], "d2h_bytes_per_step": p["d2h"],
+                       "api": "mre_rank_host through Ranker.rank_host: pinned host query ids in, int32 rank counts out, metric sums (+ all-reduce)"},
+               "gpu_launches": int(launches), "result": {"tail": summ[1], "head": summ[0]}}
+        if sampler:
+            out["clocks"] = sampler.summary()
+        return out, p
+
+
+def eng_shard(mre, n, rank, world):
+    return mre.dist.DistContext.shard_of(n, rank, world)
+
+
+BIL_PRODUCTS = 3   # BF16 MMAs the bilinear kernel issues per FP32 product (hi*hi + lo*hi + hi*lo)
+
+
+def host_metric_sums(counts, side, rank_mode):
+    """mre_metrics' int64 [2, 8] sums from HOST counts [4, Q] (the e2e leg: what a caller of mre_rank_host does next)"""
+    lt, eq = counts[2].astype(np.int64), counts[3].astype(np.int64)
+    rank = lt + 1 + (eq // 2 if rank_mode == "ties_half" else (eq if rank_mode == "pessimistic" else 0))
+    sums = np.zeros((2, 8), np.int64)
+    sides = np.full(len(rank), int(side), np.int64) if isinstance(side, (int, np.integer)) else side.numpy().astype(np.int64)
+    for s in (0, 1):
+        r = rank[sides == s]
+        sums[s, :7] = [len(r), r.sum(), (r <= 1).sum(), (r <= 3).sum(), (r <= 5).sum(), (r <= 10).sum(), ((1 << 32) // r).sum()]
+    return sums
+
+
+# ------------------------------------------------------------------------------------------------- parity
+def parity_vs_golden(name, p, w):
+    """GPU counts of the run's own queries vs tests/golden/golden_bench.npz (the real reference's counts for 512 sampled
+    queries of THIS workload: reference torch modules -> Base.so, or the reference's main.evaluate for the candidate path)"""
+    import golden_util as gu
+    try:
+        g = gu.load("golden_bench.npz")
+    except Exception as e:  # noqa: BLE001
+        return {"checked": 0, "error": str(e)}
+    if f"{name}_q" not in g:
+        return None
+    c = p["counts_d"].cpu().numpy()
+    q_h, q_t, q_r = p["q"]
+    pos = {}
+    for i, key in enumerate(zip(q_h[p["lo"]:p["hi"]].tolist(), q_r[p["lo"]:p["hi"]].tolist(), q_t[p["lo"]:p["hi"]].tolist())):
+        pos.setdefault(key, i)
+    rows = [(k, pos[tuple(q)]) for k, q in enumerate(g[f"{name}_q"].tolist()) if tuple(q) in pos]
+    if not rows:
+        return {"checked": 0}
+    k, i = np.array(rows).T
+    if f"{name}_rank" in g:        # candidate path: ties//2 rank; exact wherever the reference's own 1e-5 band is empty
+        mine = c[2][i].astype(np.int64) + c[3][i] // 2 + 1
+        ref, band = g[f"{name}_rank"][k], g[f"{name}_band"][k]
+        bad = int(((np.abs(mine - ref) > band)).sum())
+        return {"checked": int(len(k)), "mismatches": bad, "equal": int((mine == ref).sum()), "band_open": int((band > 0).sum()),
+                "against": "reference NegativeSampling.evaluate + main.evaluate (tests/golden/golden_bench.npz); a rank may move by at most the number of candidates inside the reference's 1e-5 relative tie band"}
+    filt = c[2][i]
+    lo, hi, ref = g[f"{name}_lo"][k], g[f"{name}_hi"][k], g[f"{name}_filt"][k]
+    return {"checked": int(len(k)), "mismatches": int(((filt < lo) | (filt > hi)).sum()), "equal": int((filt == ref).sum()),
+            "band_open": int((lo != hi).sum()),
+            "against": "reference OpenKE modules -> unmodified Base.so testTail (tests/golden/golden_bench.npz): filtered counts inside the 1e-5 relative tie band, equal where it is empty"}
+
+
+def parity_vs_cpu_sample(record, p, w):
+    """GPU counts vs the counts Test.h gives the reference's own scores for the queries the cpu_baseline leg just ranked,
+    plus a few queries bit for bit against the sequential-FP32 C oracle"""
+    from oracle import kge_oracle as ko
+    c = p["counts_d"].cpu().numpy()
+    q_h, q_t, q_r = (a[p["lo"]:p["hi"]] for a in p["q"])
+    pos = {}
+    for i, key in enumerate(zip(q_h.tolist(), q_r.tolist(), q_t.tolist())):
+        pos.setdefault(key, i)
+    checked = bad = equal = open_ = 0
+    for h, r, t, raw, filt, lo, hi in record:
+        i = pos.get((h, r, t))
+        if i is None:
+            continue
+        checked += 1
+        equal += int(c[2][i] == filt and c[0][i] == raw)
+        open_ += int(lo != hi)
+        bad += int(not (lo <= c[2][i] <= hi))
+    ent, rel = host_tables(w)[:2]
+    seq_n = seq_bad = 0
+    if w.scorer == "transe" and not w.normalize:
+        ptr, idx = w.filt_csr
+        for i in np.linspace(0, len(q_h) - 1, 6).astype(np.int64).tolist():
+            s = ko.transe_scores(ent, rel, w.p_norm, 1, int(q_h[i]), int(q_t[i]), int(q_r[i]))
+            t = int(q_t[i])
+            known = idx[ptr[p["lo"] + i]:ptr[p["lo"] + i + 1]]
+            raw = int((s < s[t]).sum())
+            filt = raw - int((s[known[known != t]] < s[t]).sum())
+            seq_n += 1
+            seq_bad += int(not (c[0][i] == raw and c[2][i] == filt))
+    return {"checked": checked, "mismatches": bad + seq_bad, "equal": equal, "band_open": open_, "sequential_oracle_checked": seq_n,
+            "sequential_oracle_mismatches": seq_bad,
+            "against": "the cpu_baseline sample (reference torch scoring -> Test.h counts, pinned to the unmodified Base.so): filtered counts inside "
+                       "the 1e-5 relative tie band; plus raw + filtered counts bit for bit against oracle/kge_oracle.c (sequential FP32)"}
+
+
+# ------------------------------------------------------------------------------------------------- main
+def sub_bench(module, rank, world, local, steps, warmup, gpus):
+    """run bench_train / bench_zsl inside this process and capture its line"""
+    box = {}
+    ns = argparse.Namespace(steps=steps, warmup=warmup, impl="ours", no_extra=False, gpus=gpus, emit=lambda o: box.update(o), nested=True)
+    module.main(ns, rank, world, local)
+    keep = ("metric", "value", "unit", "ms_per_step", "steps", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks", "result", "scaling")
+    return {k: box[k] for k in keep if k in box}
 
 
 def main():
@@ -306,13 +681,15 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--workload", default="db15k_zs")
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD)
+    ap.add_argument("--queries", type=int, default=None, help="synthetic2m: global queries per step (default 131072; the north_star's full size is 1000000)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--no-extra", action="store_true", help="skip the extra (synthetic2m, cpu_baseline) legs")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra legs (other workloads, cpu_baseline, parity)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     claim_stdout()
     args.emit = emit
+    args.nested = False
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -324,221 +701,79 @@ def main():
         import bench_zsl
         return bench_zsl.main(args, rank, world, local)
 
-    w = load_workload(args.workload, rank)
+    w = load_workload(args.workload, args.queries)
     if args.impl == "reference":
         return run_reference(args, w)
 
-    import torch
-    import torch.distributed as dist
-    import mre_b200
-    mre_b200.build()
-    eng = mre_b200.engine
-    torch.cuda.set_device(local)
-    dctx = mre_b200.dist.DistContext() if world > 1 else None
-    ctx = eng.Context(local)
-    rk = eng.Ranker(ctx)
-    dev = torch.device("cuda", local)
-
-    def build(w):
-        if w.tables is None:
-            g = torch.Generator(device=dev).manual_seed(SEED)
-            tables = [torch.randn(w.E, w.D, device=dev, generator=g) / w.D ** 0.5, torch.randn(w.R, w.D, device=dev, generator=g) / w.D ** 0.5]
-        else:
-            tables = [torch.from_numpy(t).to(dev) for t in w.tables]
-        kw = dict(p_norm=w.p_norm, normalize=w.normalize)
-        index = None
-        if w.index_splits is not None:
-            index = eng.KGIndex.from_arrays(w.E, w.R, *w.index_splits).to_device(local)
-            th, tt, tr = index.test_triples()
-            w.q_h, w.q_t, w.q_r = np.repeat(th, 2), np.repeat(tt, 2), np.repeat(tr, 2)
-            side_h = np.tile(np.array([0, 1], np.uint8), len(th))
-        else:
-            side_h = None
-        host = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in (w.q_h, w.q_t, w.q_r)]
-        devq = [a.to(dev) for a in host]
-        side_d = torch.from_numpy(side_h).to(dev) if side_h is not None else w.side
-        side_host = torch.from_numpy(side_h).pin_memory() if side_h is not None else w.side
-        if w.groups is not None:
-            kw["groups"] = eng.CandidateGroups.from_lists(w.groups[0], w.groups[1], dev)
-        if w.filt_csr is not None:
-            kw["filt_csr"] = tuple(torch.from_numpy(a).to(dev) for a in w.filt_csr)
-        if index is not None:
-            kw["index"] = index
-        Q = len(w.q_h)
-        counts_d = torch.empty((4, Q), dtype=torch.int32, device=dev)
-        counts_h = torch.empty((4, Q), dtype=torch.int32).pin_memory()
-
-        def step_dev():
-            c = rk.rank(w.scorer, tables, devq[0], devq[1], devq[2], side_d, out=counts_d, **kw)
-            return rk.metrics(c, side_d, w.rank_mode)
-
-        def step_e2e():
-            c = rk.rank_host(w.scorer, tables, host[0], host[1], host[2], side_host, out=counts_h, **kw)
-            return c
-
-        h2d = sum(a.numel() * a.element_size() for a in host) + (side_host.numel() if side_h is not None else 0)
-        d2h = counts_h.numel() * 4
-        return step_dev, step_e2e, Q, h2d, d2h
-
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(step, steps, warmup, flush_l2):
-        for _ in range(warmup):
-            step()
-        barrier()
-        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-        out = None
-        for a, b in ev:
-            if flush_l2:
-                flush.zero_()
-            a.record()
-            out = step()
-            b.record()
-        barrier()
-        ms = sum(a.elapsed_time(b) for a, b in ev)
-        if world > 1:
-            t = torch.tensor([ms], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = t.item()
-        return ms, out
-
-    def e2e_timed(step, steps, warmup):
-        for _ in range(warmup):
-            step()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(steps):
-            step()
-        torch.cuda.synchronize()
-        s = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([s], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            s = t.item()
-        return s
-
-    step_dev, step_e2e, Q, h2d, d2h = build(w)
-    fp32_peak = ctx.probe_fp32_peak()
-    mma_peak = mma_peak_src = None
-    if w.scorer != "transe":
-        # dense BF16 tensor peak: the driver-measured cuBLAS figure when present, else the in-process tcgen05 kind::f16 probe
-        probe = ctx.probe_bf16_peak()
-        mp = measured_peaks()
-        if mp and mp.get("bf16_tflops"):
-            mma_peak, mma_peak_src = float(mp["bf16_tflops"]) * 1e12, f"MEASURED_PEAKS.json bf16_tflops (burst, cuBLAS); in-process tcgen05 kind::f16 probe: {probe / 1e12:.0f} TFLOP/s"
-        else:
-            mma_peak, mma_peak_src = probe, "tcgen05 kind::f16 (BF16) dense MMA microbenchmark run in this process (mre_probe_bf16_peak); MEASURED_PEAKS.json absent"
-
-
-    def measure(step, steps, warmup, flush_l2):
-        """warm-up, then `steps` timed steps with the dominant kernel bracketed by its own event pairs"""
-        for _ in range(warmup):
-            step()
-        torch.cuda.synchronize()
-        ctx.timing(True)
-        ctx.timing_read()
-        l0 = ctx.launches
-        ms, out = timed(step, steps, 0, flush_l2)
-        launches = ctx.launches - l0
-        kern_ms, kern_n = ctx.timing_read()
-        ctx.timing(False)
-        return ms, out, kern_ms / max(kern_n, 1), kern_n, launches
-
-    with ClockSampler(local) as clocks:
-        ms, out, kern_ms_avg, kern_n, launches = measure(step_dev, args.steps, args.warmup, True)
-        e2e_s = e2e_timed(step_e2e, args.steps, args.warmup)
-    # metric tuple of this rank's shard, combined across ranks by one integer all-reduce
-    sums, rr = out["sums"].clone(), out["rr"].clone()
-    if dctx is not None:
-        sums, rr = dctx.all_reduce_metrics(sums, rr)
-    summ = eng.summarize(sums.cpu().numpy(), rr.cpu().numpy())
-
-    value = world * Q * args.steps / (ms * 1e-3)
-    e2e_v = world * Q * args.steps / e2e_s
-    K = w.D * (2 if w.scorer == "complex" else 1)
-    n_cand = w.E if w.groups is None else float(np.mean([len(np.unique(c)) for c in w.groups[1]]))
-    alg_ops = 2.0 * Q * n_cand * K   # lane-ops (TransE) or flops (bilinear) per launch
-    achieved = alg_ops / (kern_ms_avg * 1e-3) / 1e12
-    if w.scorer == "transe":
-        roof = {"bound": "fp32", "achieved": achieved, "peak": fp32_peak / 1e12, "unit": "TFLOP/s", "frac": achieved / (fp32_peak / 1e12),
-                "traffic": None, "kernel": "transe_rank_kernel", "kernel_ms": kern_ms_avg, "launches_timed": kern_n,
-                "peak_source": "FP32 add-rate microbenchmark run in this process (mre_probe_fp32_peak: the better of the scalar FADD and the packed FADD2 stream; 148 SM x 128 lanes x SM clock); MEASURED_PEAKS.json holds no FP32 figure",
-                "algorithmic": "2*Q*E*D FP32 lane-ops (one subtract + one add-abs per element; issued as packed sub.f32x2 / add.f32x2)",
-                "hbm_floor_gbs": (4.0 * (w.E + Q) * w.D + 16.0 * Q) / (kern_ms_avg * 1e-3) / 1e9}
-    else:
-        roof = {"bound": "tensor", "achieved": achieved, "peak": mma_peak / 1e12, "unit": "TFLOP/s", "frac": achieved / (mma_peak / 1e12),
-                "traffic": None, "kernel": "bilinear_rank_kernel", "kernel_ms": kern_ms_avg, "launches_timed": kern_n,
-                "peak_source": mma_peak_src, "pipe_frac": 3 * achieved / (mma_peak / 1e12),
-                "algorithmic": "2*Q*E*K flops counted ONCE; to stay FP32-faithful the kernel issues 3 BF16 MMAs per product "
-                               "(hi*hi + lo*hi + hi*lo), so frac <= 1/3 by construction; pipe_frac = executed flops / peak"}
-
-    # DRAM traffic of the dominant kernel per launch, from the committed `ncu --set full` capture of this workload's shape
-    try:
-        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_traffic.json")) as f:
-            tr = json.load(f).get(w.name)
-        if tr and tr.get("dram_bytes_read") is not None:
-            roof["traffic"] = tr["dram_bytes_read"] + tr["dram_bytes_write"]
-            roof["traffic_source"] = tr["source"]
-            roof["algorithmic_bytes"] = 4.0 * (w.E + Q) * w.D
-    except Exception:  # noqa: BLE001
-        pass
+    R = Runner(rank, world, local)
+    heavy = w.name == "synthetic2m"
+    line, p = R.measure(w, args.steps, args.warmup, e2e_steps=max(3, args.steps // 4) if heavy else None, clocks=True)
 
     extra = {}
-    cpu_base = None
-    if rank == 0 and not args.no_extra:
-        # bounded CPU sample of the same workload on the host cores (reference path)
-        try:
-            threads = os.cpu_count() or 1
-            with stdout_to_stderr():
-                run, n_test, kind = reference_eval_setup(w, threads)
-                rng = np.random.default_rng(0)
-                run(rng.integers(0, n_test, 8))
-                n_s = 256
-                s, q = run(rng.integers(0, n_test, n_s))
-                if s < 10:                               # about 10 s of CPU work in all, sized from the first sample's rate
-                    more = int(min(max((10.0 - s) * q / max(s, 1e-3), n_s), 64 * n_s))
-                    s2, q2 = run(rng.integers(0, n_test, more))
-                    s, q = s + s2, q + q2
-            cpu_base = {"value": q / s, "unit": "queries/s", "cores": threads, "kind": kind,
-                        "sample": f"{q} queries of the same workload in {s:.1f} s: torch-CPU scoring (reference tensor expression) + "
-                                  + ("unmodified Base.so testHead/testTail" if kind == "reference" else "C restatement of Test.h")}
-        except Exception as e:  # noqa: BLE001
-            cpu_base = {"value": None, "unit": "queries/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
-    if not args.no_extra and args.workload == "db15k_zs":
-        # BASELINE configs[4] at this N: same weak-scaling protocol on the 2M-entity synthetic table
-        try:
-            w2 = load_workload("synthetic2m", rank)
-            sd, se, Q2, _, _ = build(w2)
-            ms2, _, kms, _, _ = measure(sd, 3, 3, False)
-            ops2 = 2.0 * Q2 * w2.E * w2.D
-            extra["synthetic2m"] = {"value": world * Q2 * 3 / (ms2 * 1e-3), "unit": "queries/s", "ms_per_step": ms2 / 3,
-                                    "kernel_ms": kms, "roofline_frac_fp32": ops2 / (kms * 1e-3) / fp32_peak,
-                                    "config": w2.desc, "l2": "tables (2 GB) exceed L2"}
-        except Exception as e:  # noqa: BLE001
-            extra["synthetic2m"] = {"error": str(e)}
+    cpu_base = parity = None
+    if not args.no_extra:
+        # ---- bounded CPU sample of the same workload on the host cores (reference path) + the parity block on its queries
+        if rank == 0 and world == 1:
+            try:
+                threads = os.cpu_count() or 1
+                record = []
+                with stdout_to_stderr():
+                    run, n_test, kind = reference_eval_setup(w, threads)
+                    rng = np.random.default_rng(0)
+                    n_s = 4 if heavy else 256
+                    run(rng.integers(0, n_test, 2 if heavy else 8))
+                    s, q = run(rng.integers(0, n_test, n_s), record)
+                    if s < 10:                               # about 10-20 s of CPU work in all, sized from the first sample's rate
+                        more = int(min(max((12.0 - s) * q / max(s, 1e-3), n_s), 64 * n_s))
+                        s2, q2 = run(rng.integers(0, n_test, more), record)
+                        s, q = s + s2, q + q2
+                cpu_base = {"value": q / s, "unit": "queries/s", "cores": threads, "kind": kind,
+                            "sample": f"{q} queries of the same workload in {s:.1f} s: torch-CPU scoring (reference tensor expression) + "
+                                      + ("unmodified Base.so testHead/testTail" if kind == "reference" else "C restatement of Test.h")}
+                parity = parity_vs_cpu_sample(record, p, w) if record else parity_vs_golden(w.name, p, w)
+            except Exception as e:  # noqa: BLE001
+                cpu_base = {"value": None, "unit": "queries/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {type(e).__name__}: {e}"}
+        del p
+        R.torch.cuda.empty_cache()
+        # ---- the other BASELINE configs under the same clock (each strong-scaled over the same ranks where it shards)
+        if args.workload == DEFAULT_WORKLOAD:
+            names = ["db15k_zs", "distmult", "complex"] + (["fb15k237_zs", "fb15k237"] if world == 1 else [])
+            for name in names:
+                try:
+                    w2 = load_workload(name)
+                    sub, p2 = R.measure(w2, 20, 3)
+                    par = parity_vs_golden(name, p2, w2)
+                    if par is not None and world > 1:    # every rank checks its own block; the line reports the sum
+                        t = R.torch.tensor([par.get("checked", 0), par.get("mismatches", 0), par.get("equal", 0), par.get("band_open", 0)], device=R.dev)
+                        R.torch.distributed.all_reduce(t)
+                        par.update(checked=int(t[0]), mismatches=int(t[1]), equal=int(t[2]), band_open=int(t[3]))
+                    if par is not None:
+                        sub["parity"] = par
+                    extra[name] = sub
+                    del p2
+                except Exception as e:  # noqa: BLE001
+                    extra[name] = {"error": f"{type(e).__name__}: {e}"}
+            try:
+                import bench_train
+                extra["train"] = sub_bench(bench_train, rank, world, local, 20, 3, args.gpus)
+            except Exception as e:  # noqa: BLE001
+                extra["train"] = {"error": f"{type(e).__name__}: {e}"}
+            if world == 1:
+                try:
+                    import bench_zsl
+                    extra["zsl"] = sub_bench(bench_zsl, rank, world, local, 10, 3, args.gpus)
+                except Exception as e:  # noqa: BLE001
+                    extra["zsl"] = {"error": f"{type(e).__name__}: {e}"}
 
     if rank == 0:
-        line = {
-            "metric": "filtered-rank eval queries/sec", "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": w.name, "desc": w.desc, "E": w.E, "R": w.R, "D": w.D, "queries_per_rank_per_step": Q,
-                       "scorer": w.scorer, "rank_mode": w.rank_mode, "l2": "256 MiB buffer written between timed steps (L2 flush)",
-                       "sharding": "queries sharded across ranks, tables replicated, integer metric sums all-reduced"},
-            "roofline": roof, "cpu_baseline": cpu_base,
-            "e2e": {"value": e2e_v, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "api": "mre_rank_host through Ranker.rank_host: pinned host query ids in, int32 rank counts out"},
-            "gpu_launches": int(launches), "clocks": clocks.summary(),
-            "result": {"tail": summ[1], "head": summ[0]}, "extra": extra,
-        }
-        emit(line)
+        out = {"metric": "filtered-rank eval queries/sec", "value": line["value"], "unit": "queries/s", "n_gpus": world, "steps": args.steps,
+               "warmup": args.warmup, "ms_per_step": line["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+               "dtype": "f32", "data": "synthetic", "config": line["config"], "roofline": line["roofline"], "cpu_baseline": cpu_base,
+               "e2e": line["e2e"], "gpu_launches": line["gpu_launches"], "clocks": line.get("clocks"), "parity": parity,
+               "result": line["result"], "extra": extra}
+        emit(out)
     if world > 1:
-        dist.destroy_process_group()
+        R.torch.distributed.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -178,5 +178,5 @@ def main(args, rank, world, local):
             "e2e": {"value": world * n * args.steps / e2e_s, "unit": "triples/s", "h2d_bytes_per_step": 3 * n * 8, "d2h_bytes_per_step": 3 * n * 8 + n * 4 + 4,
                     "api": "sample_host (reference loader contract: numpy batch on the host) -> pinned H2D -> margin step -> loss.item()"},
             "gpu_launches": int(launches), "clocks": clocks.summary(), "result": {"last_loss": float(loss.item())}})
-    if world > 1:
+    if world > 1 and not getattr(args, "nested", False):
         dist.destroy_process_group()

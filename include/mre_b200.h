@@ -206,8 +206,10 @@ int mre_bilinear_scores(mre_ctx *ctx, const mre_rank_job *job, float *scores_out
 /*
  * Metric sums from counts (test_link_prediction, Test.h:232-277, without the printf table; the paper's
  * main.py:263-272 and zsl_module.py:707-745 summaries).  counts: device int32 [4][Q]; q_side as in the job.
- * sums_out: device int64 [2][8] per side s: {n, sum_rank, hits@1, hits@3, hits@5, hits@10, 0, 0} for the
- * FILTERED rank and rr_out: device double [2] sum of 1/rank, reduced in a fixed order (deterministic).
+ * sums_out: device int64 [2][8] per side s: {n, sum_rank, hits@1, hits@3, hits@5, hits@10, rr_fx, 0} for the
+ * FILTERED rank, rr_fx = sum floor(2^32 / rank), the reciprocal-rank sum in 32.32 fixed point (an integer: shards of a query
+ * set add up exactly, in any order and on any number of GPUs; MRR = rr_fx / 2^32 / n to within 2^-32), and
+ * rr_out: device double [2] sum of 1/rank, reduced in a fixed order (deterministic on one device).
  * raw != 0 => use the raw counts instead of the filtered ones.  hist (nullable): device int64 [hist_len],
  * hist[k] += #queries with rank k (k clipped to hist_len-1): the integer form combined across GPUs by allreduce.
  */

@@ -6,7 +6,9 @@
 //   main.py:263-272, module/zsl_module.py:707-745  the paper's Hits@1/3/10 and Hits@10/5/1 + MRR summaries
 // The reference accumulates in float32 globals (Test.h:13-20), which loses integer exactness past 2^24; here every
 // sum is an int64 and the reciprocal-rank sum is a float64 reduced in a FIXED order by a single CTA, so the result
-// is deterministic.  The optional rank histogram is the all-integer form that is summed across GPUs.
+// is deterministic.  Slot 6 of every side's sums is the reciprocal-rank sum in 32.32 FIXED POINT (sum floor(2^32 / rank)):
+// an integer, so shards of a query set add up to exactly the whole set's value in any order -- the form all-reduced across
+// GPUs (MRR error <= 2^-32).  The optional rank histogram is the other all-integer form.
 #include "common.h"
 
 namespace mre {
@@ -17,11 +19,11 @@ __global__ void __launch_bounds__(MET_THREADS) metrics_kernel(const int32_t *__r
                                                               int side, int64_t Q, int rank_mode, int raw,
                                                               int64_t *__restrict__ sums_out, double *__restrict__ rr_out,
                                                               unsigned long long *__restrict__ hist, int64_t hist_len) {
-    __shared__ long long s_int[MET_THREADS / 32][12];
+    __shared__ long long s_int[MET_THREADS / 32][14];
     __shared__ double s_rr[MET_THREADS / 32][2];
     const int32_t *lt = counts + (raw ? 0 : 2) * Q;
     const int32_t *eq = counts + (raw ? 1 : 3) * Q;
-    long long acc[2][6] = {{0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0}};
+    long long acc[2][7] = {{0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0}};
     double rr[2] = {0.0, 0.0};
     // four queries of this thread's stride are fetched together (one exposed load latency per four instead of per one); they
     // are accumulated in the same order as a plain strided loop would, so the float64 sum does not depend on the batching
@@ -46,6 +48,7 @@ __global__ void __launch_bounds__(MET_THREADS) metrics_kernel(const int32_t *__r
             if (rank_mode == MRE_RANK_TIES_HALF) rank += e / 2;
             else if (rank_mode == MRE_RANK_PESSIMISTIC) rank += e;
             const double inv = 1.0 / (double)rank;
+            const long long inv_fx = (long long)((1ull << 32) / (unsigned long long)rank);
 #pragma unroll
             for (int ss = 0; ss < 2; ss++) {           // static indices: the accumulators stay in registers
                 const long long on = s == ss ? 1 : 0;
@@ -55,6 +58,7 @@ __global__ void __launch_bounds__(MET_THREADS) metrics_kernel(const int32_t *__r
                 acc[ss][3] += on & (rank <= 3);
                 acc[ss][4] += on & (rank <= 5);
                 acc[ss][5] += on & (rank <= 10);
+                acc[ss][6] += on * inv_fx;
                 rr[ss] += on ? inv : 0.0;
             }
             if (hist) atomicAdd(hist + min((long long)hist_len - 1, rank), 1ull);
@@ -66,7 +70,7 @@ __global__ void __launch_bounds__(MET_THREADS) metrics_kernel(const int32_t *__r
 #pragma unroll
     for (int s = 0; s < 2; s++) {
 #pragma unroll
-        for (int k = 0; k < 6; k++)
+        for (int k = 0; k < 7; k++)
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) acc[s][k] += __shfl_xor_sync(0xffffffffu, acc[s][k], o);
 #pragma unroll
@@ -76,25 +80,25 @@ __global__ void __launch_bounds__(MET_THREADS) metrics_kernel(const int32_t *__r
 #pragma unroll
         for (int s = 0; s < 2; s++) {
 #pragma unroll
-            for (int k = 0; k < 6; k++) s_int[warp][s * 6 + k] = acc[s][k];
+            for (int k = 0; k < 7; k++) s_int[warp][s * 7 + k] = acc[s][k];
             s_rr[warp][s] = rr[s];
         }
     }
     __syncthreads();
     if (warp == 0) {
 #pragma unroll
-        for (int k = 0; k < 12; k++) {
+        for (int k = 0; k < 14; k++) {
             long long v = s_int[lane][k];
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if (lane == 0) sums_out[(k / 6) * 8 + (k % 6)] = v;
+            if (lane == 0) sums_out[(k / 7) * 8 + (k % 7)] = v;
         }
 #pragma unroll
         for (int s = 0; s < 2; s++) {
             double v = s_rr[lane][s];
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if (lane == 0) { rr_out[s] = v; sums_out[s * 8 + 6] = 0; sums_out[s * 8 + 7] = 0; }
+            if (lane == 0) { rr_out[s] = v; sums_out[s * 8 + 7] = 0; }
         }
     }
 }

@@ -1,9 +1,11 @@
 """Multi-GPU plumbing for the hot path: one process per GPU, torch.distributed (NCCL over NVLink 5 / NVSwitch on the
 B200 box; gloo in the CPU tests).  The path shards by QUERY: every rank ranks a contiguous block of queries against
 the replicated entity table, so there is no data-path collective; the only exchanges are
-  * one all-reduce of the integer metric sums / the integer rank histogram (eval), and
-  * one all-reduce of the two dense gradient tables per step (data-parallel training).
-MRR is computed from the all-reduced INTEGER rank histogram in float64, so it is bit-identical for any number of GPUs.
+  * ONE all-reduce of the int64 [2, 8] metric sums (eval) -- counts, rank sums, Hits@k and the reciprocal-rank sum in 32.32
+    fixed point (mre_metrics slot 6), all integers, so the reduced tuple is bit-identical for any number of GPUs and any
+    sharding (MRR to within 2^-32 of the float64 sum); the integer rank histogram is the alternative exact form
+    (metrics_from_hist; it needs hist_len > the largest possible rank, i.e. E + 2, or ranks are clipped into the last bin);
+  * one all-reduce of the dense gradient buffer per step (data-parallel training).
 """
 import os
 
@@ -38,12 +40,13 @@ class DistContext:
         lo = rank * base + min(rank, rem)
         return lo, lo + base + (1 if rank < rem else 0)
 
-    def all_reduce_metrics(self, sums, rr):
-        """sums: int64 [2, 8]; rr: float64 [2] -> summed over ranks (in place on copies)"""
-        sums, rr = sums.clone(), rr.clone()
+    def all_reduce_metrics(self, sums, rr=None):
+        """sums: int64 [2, 8] of mre_metrics -> summed over ranks with ONE collective; returns (sums, rr) where rr (float64 [2])
+        is rebuilt from the all-reduced fixed-point slot, so every rank -- and every world size -- sees the same bits.
+        `rr` (the local float64 sums) is accepted for the old call shape and ignored."""
+        sums = sums.clone()
         dist.all_reduce(sums)
-        dist.all_reduce(rr)
-        return sums, rr
+        return sums, sums[:, 6].to(torch.float64) / float(1 << 32)
 
     def all_reduce_hist(self, hist):
         hist = hist.clone()

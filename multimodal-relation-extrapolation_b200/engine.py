@@ -306,15 +306,21 @@ class Ranker:
         return {"sums": sums, "rr": rr, "hist": hist}
 
 
-def summarize(sums, rr):
-    """per-side integer sums + rr sums (host numpy) -> dict of means per side: mrr, mr, hits@1/3/5/10"""
+RR_FIXED_ONE = float(1 << 32)     # sums[s][6] is the reciprocal-rank sum in 32.32 fixed point (metrics.cu)
+
+
+def summarize(sums, rr=None):
+    """per-side integer sums (host numpy [2, 8]) -> dict of means per side: mrr, mr, hits@1/3/5/10.  MRR comes from the
+    INTEGER fixed-point reciprocal-rank sum (slot 6), so the tuple is bit-identical however the queries were sharded; pass
+    the float64 `rr` sums to use those instead (one device, <= 2^-32 apart)."""
     out = []
     for s in range(2):
         n = int(sums[s][0])
         if n == 0:
             out.append(None)
             continue
-        out.append({"n": n, "mr": float(sums[s][1]) / n, "mrr": float(rr[s]) / n, "hits1": float(sums[s][2]) / n,
+        rr_s = float(rr[s]) if rr is not None else float(int(sums[s][6])) / RR_FIXED_ONE
+        out.append({"n": n, "mr": float(sums[s][1]) / n, "mrr": rr_s / n, "hits1": float(sums[s][2]) / n,
                     "hits3": float(sums[s][3]) / n, "hits5": float(sums[s][4]) / n, "hits10": float(sums[s][5]) / n})
     return out
 

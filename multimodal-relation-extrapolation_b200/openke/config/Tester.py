@@ -94,9 +94,10 @@ class Tester(object):
             out = self.model.ranker().metrics(counts, side_d, "strict")
             sums, rr = out["sums"], out["rr"]
         if dist is not None:
-            sums, rr = dist.all_reduce_metrics(sums, rr)
-        sums, rr = sums.cpu().numpy(), rr.cpu().numpy()
-        self.last = engine.summarize(sums, rr)
+            sums, _ = dist.all_reduce_metrics(sums)
+        sums = sums.cpu().numpy()
+        rr = sums[:, 6].astype(np.float64) / engine.RR_FIXED_ONE    # integer fixed-point sums: the same bits for any sharding
+        self.last = engine.summarize(sums)
         # test_link_prediction (Test.h:232-277): each side divided by testTotal, then (head + tail) / 2 of the filtered values
         T = float(self.data_loader.get_triple_tot())
         mrr = (rr[0] + rr[1]) / T / 2

@@ -521,6 +521,30 @@ void orc_complex_scores(const float *ent_re, const float *ent_im, const float *r
     }
 }
 
+/* The same ComplEx score in CONTRACTION form: tail query => -[a;b].[t_re;t_im] with a = h_re r_re - h_im r_im,
+   b = h_im r_re + h_re r_im; head query => -[a';b'].[h_re;h_im] with a' = t_re r_re + t_im r_im, b' = t_im r_re - t_re r_im.
+   Algebraically ComplEx.py:20-27; the roundings are those of a K = 2D dot product of a pre-multiplied query vector with the
+   [re|im] entity rows, accumulated sequentially in float32 -- the association the tcgen05 path's exact re-score uses, so its
+   COUNTS can be asserted bit for bit (the 4-term form above differs from it, and from torch's own reduction, by ~1e-7 relative). */
+void orc_complex_scores_contracted(const float *ent_re, const float *ent_im, const float *rel_re, const float *rel_im,
+                                   int64_t E, int64_t D, int side, int64_t h, int64_t t, int64_t r, float *out) {
+    const int64_t f = side == 0 ? t : h;   /* the entity that stays fixed */
+    const float *fr = ent_re + f * D, *fi = ent_im + f * D, *rr = rel_re + r * D, *ri = rel_im + r * D;
+    float *v = (float *)malloc((size_t)(2 * D) * sizeof(float));
+    for (int64_t d = 0; d < D; d++) {
+        if (side) { v[d] = fr[d] * rr[d] - fi[d] * ri[d]; v[D + d] = fi[d] * rr[d] + fr[d] * ri[d]; }
+        else      { v[d] = fr[d] * rr[d] + fi[d] * ri[d]; v[D + d] = fi[d] * rr[d] - fr[d] * ri[d]; }
+    }
+    for (int64_t j = 0; j < E; j++) {
+        const float *er = ent_re + j * D, *ei = ent_im + j * D;
+        float acc = 0.f;
+        for (int64_t d = 0; d < D; d++) acc = acc + v[d] * er[d];
+        for (int64_t d = 0; d < D; d++) acc = acc + v[D + d] * ei[d];
+        out[j] = -acc;
+    }
+    free(v);
+}
+
 /* Paper candidate rank, true candidate at index 0: main.py:245-250
    rank = #(n < p) + floor(#(n == p) / 2) + 1 over candidates 1..C-1. */
 int64_t orc_rank_ties_half(const float *scores, int64_t C) {

@@ -70,6 +70,7 @@ def lib():
                                       C.c_int64, C.c_int64, C.c_int64, _f32p]
     L.orc_complex_scores.argtypes = [_f32p, _f32p, _f32p, _f32p, C.c_int64, C.c_int64, C.c_int,
                                      C.c_int64, C.c_int64, C.c_int64, _f32p]
+    L.orc_complex_scores_contracted.argtypes = L.orc_complex_scores.argtypes
     L.orc_rank_ties_half.restype = C.c_int64
     L.orc_rank_ties_half.argtypes = [_f32p, C.c_int64]
     L.orc_margin_loss.restype = C.c_double
@@ -232,6 +233,14 @@ def complex_scores(ent_re, ent_im, rel_re, rel_im, side, h, t, r):
     ent_re, ent_im, rel_re, rel_im = _f32(ent_re), _f32(ent_im), _f32(rel_re), _f32(rel_im)
     out = np.empty(ent_re.shape[0], np.float32)
     lib().orc_complex_scores(ent_re, ent_im, rel_re, rel_im, ent_re.shape[0], ent_re.shape[1], side, h, t, r, out)
+    return out
+
+
+def complex_scores_contracted(ent_re, ent_im, rel_re, rel_im, side, h, t, r):
+    """ComplEx in contraction form ([a;b] . [e_re;e_im], K = 2D, sequential float32): the tcgen05 path's association"""
+    ent_re, ent_im, rel_re, rel_im = _f32(ent_re), _f32(ent_im), _f32(rel_re), _f32(rel_im)
+    out = np.empty(ent_re.shape[0], np.float32)
+    lib().orc_complex_scores_contracted(ent_re, ent_im, rel_re, rel_im, ent_re.shape[0], ent_re.shape[1], side, h, t, r, out)
     return out
 
 

@@ -18,7 +18,7 @@ def test_reference_arm_prints_one_contract_line():
     j = json.loads(lines[0])
     assert j["impl"] == "reference" and j["metric"] == "filtered-rank eval queries/sec" and j["unit"] == "queries/s"
     assert j["higher_is_better"] is True and j["n_gpus"] == 1 and j["steps"] == 1 and j["value"] > 0
-    assert j["config"]["workload"] == "db15k_zs"
+    assert j["config"]["workload"] == "synthetic2m" and j["scaling"] == "strong"
     cb = j["cpu_baseline"]
     assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == j["value"] and cb["sample"]
     assert j["e2e"] == {"value": j["value"], "unit": j["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}

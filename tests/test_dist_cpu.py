@@ -26,6 +26,7 @@ def _worker(rank, world, port, ranks_all, out_dir):
     sums[1, 0] = len(mine); sums[1, 1] = int(mine.sum())
     for col, k in ((2, 1), (3, 3), (4, 5), (5, 10)):
         sums[1, col] = int((mine <= k).sum())
+    sums[1, 6] = int(((1 << 32) // mine).sum())                   # mre_metrics slot 6: sum floor(2^32 / rank), 32.32 fixed point
     rr = torch.tensor([0.0, float((1.0 / mine).sum())], dtype=torch.float64)
     hist = torch.from_numpy(np.bincount(mine, minlength=64).astype(np.int64))
     sums2, rr2 = d.all_reduce_metrics(sums, rr)
@@ -65,7 +66,12 @@ def test_two_rank_gloo_metrics_equal_single_process(tmp_path):
     sums, rr, hist = out["sums"].numpy(), out["rr"].numpy(), out["hist"].numpy()
     assert sums[1][0] == len(ranks_all) and sums[1][1] == ranks_all.sum()
     assert [sums[1][2], sums[1][3], sums[1][4], sums[1][5]] == [(ranks_all <= k).sum() for k in (1, 3, 5, 10)]
-    assert np.isclose(rr[1], (1.0 / ranks_all).sum(), rtol=1e-13)
+    # ONE integer collective: the reciprocal-rank sum comes back from the fixed-point slot -- exactly the single-process
+    # integer, hence the same MRR bits for any world size; within 2^-32 per query of the float64 sum
+    assert sums[1][6] == ((1 << 32) // ranks_all).sum() and rr[1] == float(sums[1][6]) / float(1 << 32)
+    assert abs(rr[1] - (1.0 / ranks_all).sum()) <= len(ranks_all) * 2.0 ** -32
+    s1 = mre_b200.engine.summarize(sums)[1]
+    assert s1["n"] == len(ranks_all) and abs(s1["mrr"] - (1.0 / ranks_all).mean()) <= 2.0 ** -32
     assert np.array_equal(hist, np.bincount(ranks_all, minlength=64))
     # the histogram route: float64 from integers only => identical for any world size
     m = mre_b200.dist.metrics_from_hist(hist)

@@ -1,7 +1,8 @@
-"""Size-independent properties at BASELINE.json's full sizes (no CPU oracle finishes 2 M x 256 in seconds):
+"""BASELINE.json's full sizes (2 M entities x 256):
+  * counts of sampled queries BIT-EXACT against the C oracle's sequential-FP32 scores of the same tables (oracle/kge_oracle.c:
+    orc_transe_scores / orc_distmult_scores; ~0.7 s per query on one host core): raw = #(s_j < s_true), ties, and
+    raw - filtered = #known entities scoring below s_true; Model.predict's materialised float32[E] equals the oracle's vector;
   * additivity over a partition of the candidate set: counts(all entities) = sum of the counts over disjoint candidate groups;
-  * agreement with the kernel family's own materialised scores (Model.predict's float32[E]) for a sample of queries:
-    raw = #(s_j < s_true), raw - filtered = #known entities scoring below s_true;
   * a planted duplicate of the true entity is an exact tie, never a strict win;
   * shard additivity of the integer metric sums (what the N-GPU all-reduce relies on) on the full FB15K237 protocol.
 """
@@ -10,6 +11,7 @@ import pytest
 import torch
 
 import golden_util as gu
+from oracle import kge_oracle as ko
 
 pytestmark = pytest.mark.gpu
 
@@ -29,7 +31,7 @@ def big(mre):
     fidx = np.concatenate(lists)
     d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
     return dict(ent=ent, rel=rel, q=(d(q_h), d(q_t), d(q_r)), q_host=(q_h, q_t, q_r), lists=lists, csr=(d(fptr), d(fidx)),
-                rk=mre.engine.Ranker(device=0), eng=mre.engine)
+                rk=mre.engine.Ranker(device=0), eng=mre.engine, ent_host=ent.cpu().numpy(), rel_host=rel.cpu().numpy())
 
 
 @pytest.mark.parametrize("scorer", ["transe", "distmult"])
@@ -39,19 +41,20 @@ def test_full_size_counts_match_own_scores_and_partition(big, scorer):
     q_h, q_t, q_r = big["q"]
     c = rk.rank(scorer, tabs, q_h, q_t, q_r, 1, filt_csr=big["csr"]).cpu().numpy()
     assert np.all(c[2] <= c[0]) and np.all(c[3] < c[1])
-    # (1) the kernel's own materialised scores for a sample of queries
+    # (1) the C oracle's sequential-FP32 scores of the same tables for a sample of queries
+    score_fn = ko.transe_scores if scorer == "transe" else ko.distmult_scores
     for q in (0, 1, Q2M // 2, Q2M - 1):
-        s = rk.predict(scorer, tabs, q_h, q_t, q_r, 1, query=q)
-        t = int(big["q_host"][1][q])
+        h, t, r = (int(a[q]) for a in big["q_host"])
+        s = score_fn(big["ent_host"], big["rel_host"], 1, 1, h, t, r) if scorer == "transe" else score_fn(big["ent_host"], big["rel_host"], 1, h, t, r)
         st = s[t]
-        lt = int((s < st).sum().item())
-        eq = int((s == st).sum().item())                 # raw_eq counts every candidate at the true score, the true one included
+        lt, eq = int((s < st).sum()), int((s == st).sum())    # raw_eq counts every candidate at the true score, the true one included
         assert (c[0][q], c[1][q]) == (lt, eq), (scorer, q)
-        known = torch.from_numpy(big["lists"][q]).cuda()
+        known = big["lists"][q]
         known = known[known != t]
-        k_lt = int((s[known] < st).sum().item())
-        k_eq = int((s[known] == st).sum().item())
+        k_lt, k_eq = int((s[known] < st).sum()), int((s[known] == st).sum())
         assert (c[2][q], c[3][q]) == (lt - k_lt, eq - 1 - k_eq), (scorer, q)     # filtered: minus the known ones, minus itself
+        if q in (0, Q2M - 1):                                                    # Model.predict's vector is the oracle's, bit for bit
+            assert np.array_equal(rk.predict(scorer, tabs, q_h, q_t, q_r, 1, query=q).cpu().numpy(), s)
     # (2) the planted duplicate of query 0's true tail ties exactly
     assert c[3][0] >= 1
     # (3) additivity over a partition of the candidates into three ragged groups (every query ranks against each part)

@@ -213,6 +213,7 @@ def test_metrics_histogram(mre):
         assert sums[s][0] == len(ranks) and sums[s][1] == ranks.sum()
         assert [sums[s][2], sums[s][3], sums[s][4], sums[s][5]] == [(ranks <= k).sum() for k in (1, 3, 5, 10)]
         assert np.isclose(rr[s], (1.0 / ranks).sum(), rtol=1e-12)
+        assert sums[s][6] == int(((1 << 32) // ranks.astype(np.int64)).sum())       # 32.32 fixed-point reciprocal-rank sum
     assert np.array_equal(hist, np.bincount(c[2] + 1, minlength=400))
     raw = rk.metrics(dev(c), dev(side), "strict", raw=True)["sums"].cpu().numpy()
     assert raw[0][1] + raw[1][1] == (c[0] + 1).sum()

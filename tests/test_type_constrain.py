@@ -111,6 +111,7 @@ def test_type_constrained_counts_gpu(env, fb15k237, name, wname):
         score = lambda s, h, t, r: ko.transe_scores(eo, ro, 1, s, h, t, r)
     sums_all = np.zeros((2, 8), np.int64)
     rr_all = np.zeros(2)
+    bands = gu.load("golden_bands.npz")
     for side in (0, 1):
         c = rk.rank(scorer, (dev(ent), dev(rel)), dev(q_h), dev(q_t), dev(q_r), side, index=ix,
                     groups=groups_for(eng, ix, side, q_r), **kw)
@@ -121,12 +122,12 @@ def test_type_constrained_counts_gpu(env, fb15k237, name, wname):
             raw, filt = fb15k237.oracle.rank_from_scores_constrained(score(side, h, t, r), side, h, t, r,
                                                                       heads[r] if side == 0 else tails[r])
             assert (cn[0][k], cn[2][k]) == (raw, filt), (side, k)
-        # against the compiled reference's counts: equal outside the (rare) near-ties of the torch-CPU summation order
-        ref_raw, ref_filt = z[f"{wname}_{name}_raw"][:, side], z[f"{wname}_{name}_filt"][:, side]
-        if name == "distmult" and wname == "xavier":
-            assert np.array_equal(cn[0], ref_raw) and np.array_equal(cn[2], ref_filt)
-        else:
-            assert np.mean(cn[2] == ref_filt) >= 0.9 and np.abs(cn[2] - ref_filt).max() <= 4
+        # against the compiled reference's counts: inside the 1e-5 relative tie band of the reference's own scores
+        # (tests/golden/golden_bands.npz), equal wherever that band is empty
+        ref_filt = z[f"{wname}_{name}_filt"][:, side]
+        lo, hi = bands[f"tc_{wname}_{name}_lo"][:, side], bands[f"tc_{wname}_{name}_hi"][:, side]
+        assert np.all((cn[2] >= lo) & (cn[2] <= hi)), (side, int(((cn[2] < lo) | (cn[2] > hi)).sum()))
+        assert np.array_equal(cn[2][lo == hi], ref_filt[lo == hi])
         m = rk.metrics(c, side, "strict")
         sums_all += m["sums"].cpu().numpy()
         rr_all += m["rr"].cpu().numpy()
