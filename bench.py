@@ -501,6 +501,7 @@ class Runner:
         self.barrier()
         ctx.timing(True)
         ctx.timing_read()
+        ctx.stat("bil_rescored")
         l0 = ctx.launches
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         out = None
@@ -515,6 +516,7 @@ class Runner:
         launches = ctx.launches - l0
         kern_ms, kern_n = ctx.timing_read()
         ctx.timing(False)
+        self.last_rescored = ctx.stat("bil_rescored")
         return ms, out, kern_ms / max(kern_n, 1), kern_n, launches
 
     def e2e_timed(self, step, steps, warmup):
@@ -545,6 +547,9 @@ class Runner:
                     "traffic": None, "kernel": "bilinear_rank_kernel", "kernel_ms": kern_ms, "launches_timed": kern_n,
                     "peak_source": src, "pipe_frac": BIL_PRODUCTS * achieved / (peak / 1e12),
                     "algorithmic": "2*Q*E*K flops counted ONCE; the kernel issues %d BF16 MMA(s) per product, pipe_frac = executed flops / peak" % BIL_PRODUCTS}
+        if w.scorer != "transe":
+            n_re = getattr(self, "last_rescored", 0)
+            roof["rescored_fraction"] = n_re / max(1.0, float(kern_n) * Q * n_cand) if kern_n else None
         tr = committed_traffic(w.name)
         if tr:
             roof["traffic"] = tr["dram_bytes_read"] + tr["dram_bytes_write"]
@@ -684,6 +689,7 @@ def main():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD)
     ap.add_argument("--queries", type=int, default=None, help="synthetic2m: global queries per step (default 131072; the north_star's full size is 1000000)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--opt", action="append", default=[], help="mre_ctx_option key=value (e.g. bil_products=1); repeatable")
     ap.add_argument("--no-extra", action="store_true", help="skip the extra legs (other workloads, cpu_baseline, parity)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -706,6 +712,12 @@ def main():
         return run_reference(args, w)
 
     R = Runner(rank, world, local)
+    for kv in args.opt:
+        k, v = kv.split("=")
+        R.ctx.option(k, int(v))
+        if k == "bil_products":
+            global BIL_PRODUCTS
+            BIL_PRODUCTS = int(v)
     heavy = w.name == "synthetic2m"
     line, p = R.measure(w, args.steps, args.warmup, e2e_steps=max(3, args.steps // 4) if heavy else None, clocks=True)
 

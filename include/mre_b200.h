@@ -134,6 +134,18 @@ int  mre_ctx_sm_count(const mre_ctx *ctx);
 /* number of kernels this library has launched through `ctx` since creation (bench.py gpu_launches) */
 int64_t mre_ctx_launch_count(const mre_ctx *ctx);
 
+/*
+ * Tunables of one workspace (defaults in brackets): "bil_products" [3] = tensor-core products per FP32 product of the
+ * DistMult / ComplEx path (3: BF16 hi/lo split, hi*hi + lo*hi + hi*lo; 1: one FP16 product with a wider -- still rigorous --
+ * near-tie guard and more exact re-scores; the COUNTS are those of the sequential FP32 scorer either way);
+ * "bil_pair" [1] = CTA pairs (cta_group::2) on that path; "transe_ctas_per_sm" [0 = built-in]; "zsl_fp32" [0] = run the ZSL
+ * pair contraction on the FP32 CUDA-core kernels instead of 3xTF32 tcgen05.  Unknown keys fail with MRE_ERR_INVALID.
+ */
+int mre_ctx_option(mre_ctx *ctx, const char *key, int64_t value);
+/* Read-and-reset a device-side statistic (synchronises the device): "bil_rescored" = columns of the DistMult / ComplEx path that
+ * fell inside the near-tie guard and were re-scored exactly since the last read (bench.py reports the fraction). */
+int mre_ctx_stat(mre_ctx *ctx, const char *key, int64_t *value);
+
 /* ------------------------------------------------------------------------------------------- ranking */
 /*
  * One ranking job: Q queries, each ranked against a candidate set, fused score + compare + count.

@@ -117,6 +117,8 @@ def lib():
     L.mre_ctx_sm_count.argtypes = [vp]
     L.mre_ctx_launch_count.argtypes = [vp]
     L.mre_ctx_launch_count.restype = i64
+    L.mre_ctx_option.argtypes = [vp, C.c_char_p, i64]
+    L.mre_ctx_stat.argtypes = [vp, C.c_char_p, P(i64)]
     L.mre_rank.argtypes = [vp, vp, P(RankJob), vp]
     L.mre_rank_host.argtypes = [vp, vp, P(RankJob), vp]
     L.mre_predict.argtypes = [vp, P(RankJob), i64, vp, vp]

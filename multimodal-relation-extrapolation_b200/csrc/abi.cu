@@ -23,6 +23,14 @@ int mre_ctx::time_end(cudaStream_t st) {
     return MRE_OK;
 }
 
+int mre_ctx::allow_smem(const void *func, size_t bytes) {
+    for (const void *f : smem_ready)
+        if (f == func) return MRE_OK;
+    MRE_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    smem_ready.push_back(func);
+    return MRE_OK;
+}
+
 int mre_ctx::fork_aux(cudaStream_t st, cudaStream_t *aux_out) {
     if (!aux) {
         MRE_CUDA(cudaStreamCreateWithFlags(&aux, cudaStreamNonBlocking));
@@ -328,6 +336,36 @@ int mre_probe_bf16_peak(mre_ctx *ctx, double *flops_per_s) {
     MRE_CHECK_ARG(ctx != nullptr, "ctx is NULL");
     MRE_CUDA(cudaSetDevice(ctx->device));
     return probe_bf16_peak(ctx, flops_per_s);
+}
+
+int mre_ctx_option(mre_ctx *ctx, const char *key, int64_t value) {
+    MRE_CHECK_ARG(ctx != nullptr && key != nullptr, "NULL argument");
+    const std::string k(key);
+    if (k == "bil_products") {
+        MRE_CHECK_ARG(value == 1 || value == 3, "bil_products must be 1 (FP16 single product) or 3 (BF16 hi/lo split)");
+        ctx->opt_bil_products = (int)value;
+    } else if (k == "bil_pair") ctx->opt_bil_pair = value != 0;
+    else if (k == "transe_ctas_per_sm") ctx->opt_transe_ctas = (int)std::max<int64_t>(0, value);
+    else if (k == "zsl_fp32") ctx->opt_zsl_fp32 = value != 0;
+    else {
+        set_error("unknown option '%s'", key);
+        return MRE_ERR_INVALID;
+    }
+    return MRE_OK;
+}
+
+int mre_ctx_stat(mre_ctx *ctx, const char *key, int64_t *value) {
+    MRE_CHECK_ARG(ctx != nullptr && key != nullptr && value != nullptr, "NULL argument");
+    MRE_CHECK_ARG(std::string(key) == "bil_rescored", "unknown statistic '%s'", key);
+    *value = 0;
+    if (!ctx->stats.p) return MRE_OK;
+    MRE_CUDA(cudaSetDevice(ctx->device));
+    unsigned long long v = 0;
+    MRE_CUDA(cudaDeviceSynchronize());
+    MRE_CUDA(cudaMemcpy(&v, ctx->stats.p, sizeof(v), cudaMemcpyDeviceToHost));
+    MRE_CUDA(cudaMemset(ctx->stats.p, 0, sizeof(v)));
+    *value = (int64_t)v;
+    return MRE_OK;
 }
 
 int mre_ctx_timing(mre_ctx *ctx, int32_t enable) {

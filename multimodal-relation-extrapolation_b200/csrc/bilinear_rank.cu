@@ -26,6 +26,7 @@
 // warps 2..9 = epilogue (TMEM lane quarter = warp % 4, two warps per quarter: one per 128-column half of the tile).  Shared memory: 2 stages x {A_hi, A_lo: 128 x 128 B;
 // B_hi, B_lo: 256 x 128 B} (64 BF16 of K per row), 128-byte swizzle, K-major, fed by TMA tensor tiles.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <math.h>
 #include <stdlib.h>
 
@@ -56,12 +57,15 @@ constexpr uint32_t B_BYTES = BN * BK * 2;   // 32 KiB
 // one CTA per tile: a stage holds A_hi, A_lo (128 rows) and B_hi, B_lo (256 rows) = 96 KiB, 2 stages.
 // CTA pair (cta_group::2): M = 256 over two CTAs, each CTA stages its own 128 query rows and HALF of the candidate tile
 // (128 rows) -- 64 KiB per stage, 3 stages -- and the pair's MMA reads both halves: a third less L2 -> SM traffic per flop.
-template <bool PAIR> struct StageCfg {
-    static constexpr int STAGES = (PAIR ? 3 : 2) * (64 / BK);
+// NPROD = 3: BF16 hi / lo operands, three MMAs per product.  NPROD = 1: ONE FP16 operand per side and one MMA per product --
+// half the bytes per stage, so twice the stages in the same 192 KiB.
+template <bool PAIR, int NPROD> struct StageCfg {
+    static constexpr int STAGES = (PAIR ? 3 : 2) * (64 / BK) * (NPROD == 1 ? 2 : 1);
     static constexpr uint32_t B_HALF = PAIR ? B_BYTES / 2 : B_BYTES;
-    static constexpr uint32_t BYTES = 2 * A_BYTES + 2 * B_HALF;
+    static constexpr uint32_t BYTES = (NPROD == 1 ? 1 : 2) * (A_BYTES + B_HALF);
+    static constexpr uint32_t B_OFF = (NPROD == 1 ? 1 : 2) * A_BYTES;      // first B operand inside a stage
 };
-constexpr int MAX_STAGES = 3 * (64 / BK);
+constexpr int MAX_STAGES = 6 * (64 / BK);
 __device__ __forceinline__ uint64_t umma_desc_op(uint32_t addr) { return BK == 64 ? umma_desc_k128(addr) : umma_desc_k64(addr); }
 #ifndef MRE_EPI_WARPS
 #define MRE_EPI_WARPS 4
@@ -70,15 +74,16 @@ constexpr int EPI_WARPS = MRE_EPI_WARPS;     // 4: one per TMEM lane quarter; 8:
 constexpr int RESCORE_WARPS = 4;             // one per epilogue warp of the first column slice
 constexpr int BIL_THREADS = (2 + EPI_WARPS + RESCORE_WARPS) * 32;
 constexpr int EPI_WARP0 = 2;
-constexpr int PEND_CAP = 128;                // per epilogue warp: ring of near-ties handed to its re-score warp through shared memory
+constexpr int PEND_CAP = 512;                // per epilogue warp: ring of near-ties handed to its re-score warp through shared memory
 constexpr int MASK_STRIDE = 9;               // words per row of the per-warp known-true mask (8 + 1 pad: conflict-free)
-constexpr size_t BIL_SMEM = 1024 + (size_t)2 * (64 / BK) * (2 * A_BYTES + 2 * B_BYTES) + 32 * sizeof(uint64_t) + EPI_WARPS * 32 * MASK_STRIDE * 4 + RESCORE_WARPS * (PEND_CAP * sizeof(uint2) + 16) + 64;   // both configurations: 192 KiB of stages
+constexpr size_t BIL_SMEM = 1024 + (size_t)2 * (64 / BK) * (2 * A_BYTES + 2 * B_BYTES) + 48 * sizeof(uint64_t) + EPI_WARPS * 32 * MASK_STRIDE * 4 + RESCORE_WARPS * (PEND_CAP * sizeof(uint2) + 16) + 64;   // both configurations: 192 KiB of stages
 constexpr uint32_t TMEM_COLS = 512;     // two 256-column accumulator buffers
 
 struct BilParams {
     RankParams r;            // r.ent = full-precision [E, K] table (scalar scorer), r.qvec = full-precision query vectors
     const float *delta;      // [Q] near-tie guard: |s_mma - s_true| <= delta => the column is re-scored in scalar FP32
     int64_t k8;              // K padded to a multiple of 8: row pitch (elements) of the BF16 hi / lo tables
+    unsigned long long *rescored;   // running total of exact re-scores (mre_ctx_stat "bil_rescored")
     float *store;            // STORE mode only: [Q, store_ld] tensor-core similarities are written instead of counted
     int64_t store_ld;
 };
@@ -90,45 +95,136 @@ __device__ __forceinline__ void bf16_split(float x, __nv_bfloat16 &hi, __nv_bflo
     lo = __float2bfloat16_rn(x - __bfloat162float(hi));
 }
 
-// entity table -> BF16 hi / lo splits [rows, K8] (ComplEx: [re | im]; zero padded) + optional full-precision copy [rows, Kp]
-__global__ void bil_split_table_kernel(const float *__restrict__ re, const float *__restrict__ im, int64_t rows, int64_t D,
-                                       int64_t K, int64_t Kp, int64_t K8, float *__restrict__ full, __nv_bfloat16 *__restrict__ hi,
-                                       __nv_bfloat16 *__restrict__ lo) {
-    const int64_t total = rows * K8;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t row = i / K8, d = i - row * K8;
-        float x = 0.f;
-        if (d < K) x = d < D ? re[row * D + d] : im[row * D + (d - D)];
-        if (full && d < Kp) full[row * Kp + d] = x;
-        bf16_split(x, hi[i], lo[i]);
-    }
-}
-
-// per-query vector (see the header comment), full precision [Q, Kp] + BF16 hi / lo [Q, K8]
-__global__ void bil_qvec_kernel(int scorer, const float *__restrict__ ent, const float *__restrict__ ent_im,
-                                const float *__restrict__ rel, const float *__restrict__ rel_im, int64_t D, int64_t K, int64_t Kp,
-                                int64_t K8, const int64_t *__restrict__ q_h, const int64_t *__restrict__ q_t,
-                                const int64_t *__restrict__ q_r, const uint8_t *__restrict__ q_side, int side, int64_t Q,
-                                float *__restrict__ qv, __nv_bfloat16 *__restrict__ qhi, __nv_bfloat16 *__restrict__ qlo) {
-    const int64_t total = Q * K8;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t q = i / K8, d = i - q * K8;
-        const int s = q_side ? (int)q_side[q] : side;
-        const int64_t e = s ? q_h[q] : q_t[q];   // the entity that stays fixed in the query
-        const int64_t r = q_r[q];
-        float v = 0.f;
-        if (d < K) {
-            if (scorer == MRE_DISTMULT) {
-                v = s ? ent[e * D + d] * rel[r * D + d] : rel[r * D + d] * ent[e * D + d];
+// entity table -> tensor-core operands [rows, K8] (ComplEx: [re | im]; zero padded) + optional full-precision copy [rows, Kp]
+// + the largest row norm (atomicMax on the bit pattern: positive floats order like their bits), ONE pass, one warp per row.
+// NPROD = 3: BF16 hi / lo split.  NPROD = 1: hi = rn_fp16(x), lo untouched.
+template <int NPROD>
+__global__ void __launch_bounds__(256) bil_table_kernel(const float *__restrict__ re, const float *__restrict__ im, int64_t rows, int64_t D,
+                                                        int64_t K, int64_t Kp, int64_t K8, float *__restrict__ full,
+                                                        uint16_t *__restrict__ hi, uint16_t *__restrict__ lo, unsigned int *__restrict__ max_norm) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    float best = 0.f;
+    for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += warps) {
+        float ss = 0.f;
+        for (int64_t d = lane; d < K8; d += 32) {
+            float x = 0.f;
+            if (d < K) x = d < D ? re[row * D + d] : im[row * D + (d - D)];
+            if (full && d < Kp) full[row * Kp + d] = x;
+            ss = fmaf(x, x, ss);
+            if (NPROD == 3) {
+                __nv_bfloat16 h, l;
+                bf16_split(x, h, l);
+                hi[row * K8 + d] = __bfloat16_as_ushort(h);
+                lo[row * K8 + d] = __bfloat16_as_ushort(l);
             } else {
-                const int64_t dd = d < D ? d : d - D;
-                const float ere = ent[e * D + dd], eim = ent_im[e * D + dd], rre = rel[r * D + dd], rim = rel_im[r * D + dd];
-                if (s) v = d < D ? ere * rre - eim * rim : eim * rre + ere * rim;
-                else v = d < D ? ere * rre + eim * rim : eim * rre - ere * rim;
+                hi[row * K8 + d] = __half_as_ushort(__float2half_rn(x));
             }
         }
-        if (d < Kp) qv[q * Kp + d] = v;
-        bf16_split(v, qhi[i], qlo[i]);
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, m);
+        best = fmaxf(best, ss);
+    }
+    if (lane == 0 && best > 0.f) atomicMax(max_norm, __float_as_uint(sqrtf(best) * 1.0001f));
+}
+
+// sequential FP32 dot product from SHARED memory, same roundings and order as bil_dot below
+__device__ __forceinline__ float bil_dot_smem(const float *v, const float *e, int K) {
+    float acc = 0.f;
+    for (int d = 0; d < K; d++) acc = acc + v[d] * e[d];
+    return acc;
+}
+
+// Everything per query in ONE launch, one warp per query: the query vector (full precision [Q, Kp] + tensor-core operands
+// [Q, K8]), the threshold pair on the predict scale (p = -sim: lower is better; s_true from the SAME sequential FP32 dot the
+// exact re-score uses, taken by lane 0 from shared-memory copies of the two rows), the near-tie guard, and the zeroing of the
+// query's four counters.
+// Guard (rigorous, relative to sum_d |v_d e_d| <= ||v|| * max_j ||e_j||): the tensor-core value differs from the sequential
+// FP32 value by
+//   NPROD = 3  the split: x - hi - lo <= 2^-18 |x| per operand and the dropped lo*lo <= 2^-18  ->  <= 3 * 2^-18 = 1.15e-5
+//   NPROD = 1  one FP16 rounding per operand: |x - rn(x)| <= 2^-11 |x| + 2^-25 (subnormals) -> (2^-10 + 2^-22) of the scale
+//              plus 2^-25 (||v||_1 + ||e||_1) <= 2^-25 sqrt(K) (||v|| + max||e||); operands beyond the FP16 range make the
+//              guard infinite (every column of that query is re-scored exactly)
+//   both       the FP32 accumulation of the K/16 (x3) MMAs and the scalar scorer's own K roundings  ->  < K * 1.2e-7
+// Every column closer than the guard to s_true is re-scored with the scalar scorer, so the COUNTS are exactly those of the
+// FP32 scorer for ANY table.
+constexpr int QK_WARPS = 4;
+constexpr int QK_MAX = 1024;      // K up to this is staged in shared memory; wider models take the row pointers (slower, same bits)
+template <int NPROD>
+__global__ void __launch_bounds__(QK_WARPS * 32) bil_query_kernel(int scorer, const float *__restrict__ ent, const float *__restrict__ ent_im,
+        const float *__restrict__ rel, const float *__restrict__ rel_im, const float *__restrict__ ent_full, int64_t D, int64_t K, int64_t Kp,
+        int64_t K8, const int64_t *__restrict__ q_h, const int64_t *__restrict__ q_t, const int64_t *__restrict__ q_r,
+        const uint8_t *__restrict__ q_side, int side, int64_t Q, const unsigned int *__restrict__ max_norm, float *__restrict__ qv,
+        uint16_t *__restrict__ qhi, uint16_t *__restrict__ qlo, float2 *__restrict__ thr, float *__restrict__ delta,
+        int32_t *__restrict__ counts) {
+    extern __shared__ float qk_smem[];                   // [QK_WARPS][2][Kp] when Kp <= QK_MAX
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool staged = Kp <= QK_MAX;
+    float *sv = qk_smem + (size_t)warp * 2 * Kp, *se = sv + Kp;
+    for (int64_t q = (int64_t)blockIdx.x * QK_WARPS + warp; q < Q; q += (int64_t)gridDim.x * QK_WARPS) {
+        const int s = q_side ? (int)q_side[q] : side;
+        const int64_t e = s ? q_h[q] : q_t[q];          // the entity that stays fixed in the query
+        const int64_t truth = s ? q_t[q] : q_h[q];
+        const int64_t r = q_r[q];
+        float ss = 0.f, vmax = 0.f;
+        for (int64_t d = lane; d < K8; d += 32) {
+            float v = 0.f;
+            if (d < K) {
+                if (scorer == MRE_DISTMULT) {
+                    v = s ? ent[e * D + d] * rel[r * D + d] : rel[r * D + d] * ent[e * D + d];
+                } else {
+                    const int64_t dd = d < D ? d : d - D;
+                    const float ere = ent[e * D + dd], eim = ent_im[e * D + dd], rre = rel[r * D + dd], rim = rel_im[r * D + dd];
+                    if (s) v = d < D ? ere * rre - eim * rim : eim * rre + ere * rim;
+                    else v = d < D ? ere * rre + eim * rim : eim * rre - ere * rim;
+                }
+            }
+            if (d < Kp) {
+                qv[q * Kp + d] = v;
+                if (staged) { sv[d] = v; se[d] = ent_full[truth * Kp + d]; }
+            }
+            ss = fmaf(v, v, ss);
+            vmax = fmaxf(vmax, fabsf(v));
+            if (NPROD == 3) {
+                __nv_bfloat16 h, l;
+                bf16_split(v, h, l);
+                qhi[q * K8 + d] = __bfloat16_as_ushort(h);
+                qlo[q * K8 + d] = __bfloat16_as_ushort(l);
+            } else {
+                qhi[q * K8 + d] = __half_as_ushort(__float2half_rn(v));
+            }
+        }
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) {
+            ss += __shfl_xor_sync(0xffffffffu, ss, m);
+            vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, m));
+        }
+        if (lane < 4) counts[(int64_t)lane * Q + q] = 0;
+        __syncwarp();
+        if (lane == 0) {
+            float dot;
+            if (staged) {
+                dot = bil_dot_smem(sv, se, (int)Kp);
+            } else {                                     // the rows this warp just wrote / the table row, sequentially from global
+                dot = 0.f;
+                __threadfence_block();
+                for (int64_t d = 0; d < Kp; d++) dot = dot + qv[q * Kp + d] * ent_full[truth * Kp + d];
+            }
+            const float pt = -dot;
+            float hi = pt;
+            if (pt == pt && fabsf(pt) < INFINITY) hi = nextafterf(pt, INFINITY);
+            thr[q] = make_float2(pt, hi);
+            const float vn = sqrtf(ss), en = __uint_as_float(*max_norm);
+            float g;
+            if (NPROD == 3) {
+                g = (1.3e-5f + 1.2e-7f * (float)Kp) * vn * en;
+            } else {
+                g = (9.77e-4f + 1.2e-7f * (float)Kp) * vn * en + 3.1e-8f * sqrtf((float)Kp) * (vn + en);
+                if (!(vmax < 6.0e4f) || !(en < 6.0e4f)) g = INFINITY;
+            }
+            delta[q] = g;
+        }
+        __syncwarp();
     }
 }
 
@@ -147,45 +243,6 @@ __device__ __forceinline__ float bil_dot(const float *__restrict__ v, const floa
         acc = acc + a.w * b.w;
     }
     return acc;
-}
-
-// largest row norm of the entity table (positive floats order like their bit patterns)
-__global__ void bil_max_rownorm_kernel(const float *__restrict__ ent, int64_t E, int64_t K, unsigned int *__restrict__ out) {
-    const int lane = threadIdx.x & 31;
-    const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
-    float best = 0.f;
-    for (int64_t j = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); j < E; j += warps) {
-        float ss = 0.f;
-        for (int64_t d = lane; d < K; d += 32) ss = fmaf(ent[j * K + d], ent[j * K + d], ss);
-#pragma unroll
-        for (int m = 16; m > 0; m >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, m);
-        best = fmaxf(best, ss);
-    }
-    if (lane == 0) atomicMax(out, __float_as_uint(sqrtf(best) * 1.0001f));
-}
-
-// per query: threshold pair on the predict scale (p = -sim: lower is better) and the near-tie guard.
-// Guard (rigorous, relative to sum_d |v_d e_d| <= ||v|| * max_j ||e_j||): the tensor-core value differs from the
-// sequential FP32 value by
-//   the split: x - hi - lo <= 2^-18 |x| per operand and the dropped lo*lo <= 2^-18  ->  <= 3 * 2^-18 = 1.15e-5,
-//   the FP32 accumulation of the 3K/16 MMAs and the scalar scorer's own K roundings  ->  <= (K + 3K/16) * 2^-24 < K * 0.72e-7,
-// so guard = (1.3e-5 + 1.2e-7 K) ||v|| max||e|| (4.4e-5 at K = 256) bounds it with margin for ANY table; the measured
-// discrepancy is ~50x smaller (tests/test_bilinear_gpu.py).  Every column closer than the guard to s_true is re-scored
-// with the scalar scorer, so the COUNTS are exactly those of the FP32 scorer; on Gaussian tables ~5e-4 of the columns.
-__global__ void bil_threshold_kernel(const RankParams p, const unsigned int *__restrict__ max_norm, float2 *__restrict__ thr,
-                                     float *__restrict__ delta) {
-    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= p.Q) return;
-    const int s = p.q_side ? (int)p.q_side[q] : p.side;
-    const int64_t truth = s ? p.q_t[q] : p.q_h[q];
-    const float *v = p.qvec + q * p.D;
-    const float pt = -bil_dot(v, p.ent + truth * p.D, p.D);
-    float hi = pt;
-    if (pt == pt && fabsf(pt) < INFINITY) hi = nextafterf(pt, INFINITY);
-    thr[q] = make_float2(pt, hi);
-    float ss = 0.f;
-    for (int64_t d = 0; d < p.D; d++) ss = fmaf(v[d], v[d], ss);
-    delta[q] = (1.3e-5f + 1.2e-7f * (float)p.D) * sqrtf(ss) * __uint_as_float(*max_norm);
 }
 
 __global__ void bil_predict_kernel(const float *__restrict__ ent, int64_t E, int64_t K, const float *__restrict__ qv,
@@ -209,13 +266,13 @@ __device__ __forceinline__ void decode_pitem(const RankParams &p, int64_t item, 
     et = (int)(local / n_qp);
 }
 
-template <bool STORE, bool PAIR>
+template <bool STORE, bool PAIR, int NPROD>
 __global__ void __launch_bounds__(BIL_THREADS, 1)
 bilinear_rank_kernel(const BilParams bp, const __grid_constant__ CUtensorMap tm_ahi, const __grid_constant__ CUtensorMap tm_alo,
                      const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ CUtensorMap tm_blo) {
-    using Cfg = StageCfg<PAIR>;
+    using Cfg = StageCfg<PAIR, NPROD>;
     constexpr int B_STAGES = Cfg::STAGES;
-    constexpr uint32_t BSTAGE_BYTES = Cfg::BYTES, B_HALF = Cfg::B_HALF;
+    constexpr uint32_t BSTAGE_BYTES = Cfg::BYTES, B_HALF = Cfg::B_HALF, B_OFF = Cfg::B_OFF;
     const RankParams &p = bp.r;
     extern __shared__ unsigned char smem_raw[];
     const uint32_t ring_u32 = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -225,7 +282,7 @@ bilinear_rank_kernel(const BilParams bp, const __grid_constant__ CUtensorMap tm_
     const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + MAX_STAGES), tfull0 = smem_u32(bars + 2 * MAX_STAGES),
                    tempty0 = smem_u32(bars + 2 * MAX_STAGES + 2);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * MAX_STAGES + 4);
-    uint32_t *mask_all = reinterpret_cast<uint32_t *>(bars + 32);      // per epilogue warp: [32 rows][MASK_STRIDE] known-true bits
+    uint32_t *mask_all = reinterpret_cast<uint32_t *>(bars + 48);      // per epilogue warp: [32 rows][MASK_STRIDE] known-true bits
     uint2 *pend_all = reinterpret_cast<uint2 *>(mask_all + EPI_WARPS * 32 * MASK_STRIDE);   // per epilogue warp: [PEND_CAP] ring of near-ties
     volatile uint32_t *pend_ctl = reinterpret_cast<volatile uint32_t *>(pend_all + RESCORE_WARPS * PEND_CAP);   // per ring: published, consumed, done
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -284,16 +341,16 @@ bilinear_rank_kernel(const BilParams bp, const __grid_constant__ CUtensorMap tm_
                         const uint32_t full = full_leader0 + 8 * s;
                         if (rank == 0) mbar_arrive_expect_tx(full0 + 8 * s, 2 * BSTAGE_BYTES);
                         tma_load_2d_pair(base, &tm_ahi, kb * BK, qrow, full, L2_EVICT_LAST);
-                        tma_load_2d_pair(base + A_BYTES, &tm_alo, kb * BK, qrow, full, L2_EVICT_LAST);
-                        tma_load_2d_pair(base + 2 * A_BYTES, &tm_bhi, kb * BK, erow, full, L2_EVICT_NORMAL);
-                        tma_load_2d_pair(base + 2 * A_BYTES + B_HALF, &tm_blo, kb * BK, erow, full, L2_EVICT_NORMAL);
+                        if (NPROD == 3) tma_load_2d_pair(base + A_BYTES, &tm_alo, kb * BK, qrow, full, L2_EVICT_LAST);
+                        tma_load_2d_pair(base + B_OFF, &tm_bhi, kb * BK, erow, full, L2_EVICT_NORMAL);
+                        if (NPROD == 3) tma_load_2d_pair(base + B_OFF + B_HALF, &tm_blo, kb * BK, erow, full, L2_EVICT_NORMAL);
                     } else {
                         const uint32_t full = full0 + 8 * s;
                         mbar_arrive_expect_tx(full, BSTAGE_BYTES);
                         tma_load_2d_hint(base, &tm_ahi, kb * BK, qrow, full, L2_EVICT_LAST);
-                        tma_load_2d_hint(base + A_BYTES, &tm_alo, kb * BK, qrow, full, L2_EVICT_LAST);
-                        tma_load_2d_hint(base + 2 * A_BYTES, &tm_bhi, kb * BK, erow, full, L2_EVICT_NORMAL);
-                        tma_load_2d_hint(base + 2 * A_BYTES + B_HALF, &tm_blo, kb * BK, erow, full, L2_EVICT_NORMAL);
+                        if (NPROD == 3) tma_load_2d_hint(base + A_BYTES, &tm_alo, kb * BK, qrow, full, L2_EVICT_LAST);
+                        tma_load_2d_hint(base + B_OFF, &tm_bhi, kb * BK, erow, full, L2_EVICT_NORMAL);
+                        if (NPROD == 3) tma_load_2d_hint(base + B_OFF + B_HALF, &tm_blo, kb * BK, erow, full, L2_EVICT_NORMAL);
                     }
                 }
             }
@@ -302,7 +359,7 @@ bilinear_rank_kernel(const BilParams bp, const __grid_constant__ CUtensorMap tm_
     } else if (warp == 1) {
         // ================================================= MMA issuer ===================================================
         if (lane == 0 && rank == 0) {      // in a pair only the leader CTA issues: one instruction drives both SMs' tensor cores
-            constexpr uint32_t idesc = umma_idesc_bf16(PAIR ? 2 * BM : BM, BN);
+            constexpr uint32_t idesc = NPROD == 3 ? umma_idesc_bf16(PAIR ? 2 * BM : BM, BN) : umma_idesc_f16(PAIR ? 2 * BM : BM, BN);
             uint32_t it = 0, tile = 0;
             for (int64_t item = worker; item < n_items; item += n_workers, tile++) {
                 const uint32_t buf = tile & 1;
@@ -317,17 +374,18 @@ bilinear_rank_kernel(const BilParams bp, const __grid_constant__ CUtensorMap tm_
                     const int n_ks = (int)min((int64_t)(BK / UK), (bp.k8 - (int64_t)kb * BK + UK - 1) / UK);
                     for (int ks = 0; ks < n_ks; ks++) {
                         const uint32_t koff = ks * UK * 2;   // bytes along K inside the 128-byte swizzle atom
-                        const uint64_t ahi = umma_desc_op(base + koff), alo = umma_desc_op(base + A_BYTES + koff);
-                        const uint64_t bhi = umma_desc_op(base + 2 * A_BYTES + koff);
-                        const uint64_t blo = umma_desc_op(base + 2 * A_BYTES + B_HALF + koff);
-                        if (PAIR) {
-                            umma_bf16_pair(d_tmem, ahi, bhi, idesc, (kb | ks) != 0);
-                            umma_bf16_pair(d_tmem, alo, bhi, idesc, 1);
-                            umma_bf16_pair(d_tmem, ahi, blo, idesc, 1);
-                        } else {
-                            umma_bf16(d_tmem, ahi, bhi, idesc, (kb | ks) != 0);
-                            umma_bf16(d_tmem, alo, bhi, idesc, 1);
-                            umma_bf16(d_tmem, ahi, blo, idesc, 1);
+                        const uint64_t ahi = umma_desc_op(base + koff), bhi = umma_desc_op(base + B_OFF + koff);
+                        if (PAIR) umma_bf16_pair(d_tmem, ahi, bhi, idesc, (kb | ks) != 0);       // kind::f16: BF16 or FP16 per idesc
+                        else umma_bf16(d_tmem, ahi, bhi, idesc, (kb | ks) != 0);
+                        if (NPROD == 3) {
+                            const uint64_t alo = umma_desc_op(base + A_BYTES + koff), blo = umma_desc_op(base + B_OFF + B_HALF + koff);
+                            if (PAIR) {
+                                umma_bf16_pair(d_tmem, alo, bhi, idesc, 1);
+                                umma_bf16_pair(d_tmem, ahi, blo, idesc, 1);
+                            } else {
+                                umma_bf16(d_tmem, alo, bhi, idesc, 1);
+                                umma_bf16(d_tmem, ahi, blo, idesc, 1);
+                            }
                         }
                     }
                     // shared-memory stage reusable (in both CTAs of a pair) once these MMAs retire
@@ -562,32 +620,66 @@ bilinear_rank_kernel(const BilParams bp, const __grid_constant__ CUtensorMap tm_
         if (lane == 0) ctl[2] = 1u;                       // no more entries will be published
     } else {
         // ================================================= re-score warps ===============================================
+        // Entries are drained in batches (the ring nearly half full, or the epilogue warp finished) so that all 32 lanes work,
+        // and every lane interleaves up to four sequential dot products: a single FP32 chain issues one add every ~4 cycles,
+        // four independent chains keep the lane's issue slot busy.
         const int ring_id = warp - EPI_WARP0 - EPI_WARPS;
         const uint2 *pend = pend_all + ring_id * PEND_CAP;
         volatile uint32_t *ctl = pend_ctl + ring_id * 4;
         uint32_t cons = 0;
+        const int n4 = (int)(p.D >> 2);
         for (;;) {
             const uint32_t done = ctl[2];               // read BEFORE the counter: done => the counter is final
             const uint32_t pub = ctl[0];
-            if (pub == cons) {
-                if (done) break;
-                __nanosleep(200);
+            if (pub - cons < (uint32_t)(PEND_CAP / 4) && !(done && pub != cons)) {
+                if (done && pub == cons) break;
+                __nanosleep(100);
                 continue;
             }
             __threadfence_block();                      // the counter before the entries
             const uint32_t n_new = pub - cons;          // <= PEND_CAP
-            for (uint32_t k = lane; k < n_new; k += 32) {
-                const uint2 it2 = pend[(cons + k) & (PEND_CAP - 1)];
-                const int64_t q2 = it2.x, ent_id = it2.y & 0x7fffffffu;
-                const bool kn = (it2.y >> 31) != 0u;
-                const float s2 = bil_dot(p.qvec + q2 * p.D, p.ent + ent_id * p.D, p.D);
-                const float st = -__ldg(&p.thr[q2].x);
-                if (s2 > st) { atomicAdd(p.counts + q2, 1); if (!kn) atomicAdd(p.counts + 2 * p.Q + q2, 1); }
-                if (s2 == st) { atomicAdd(p.counts + p.Q + q2, 1); if (!kn) atomicAdd(p.counts + 3 * p.Q + q2, 1); }
+            for (uint32_t k0 = 0; k0 < n_new; k0 += 128) {
+                int64_t q2[4], ent_id[4];
+                bool kn[4], live[4];
+                const float4 *v4[4], *e4[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const uint32_t k = k0 + 32 * u + lane;
+                    live[u] = k < n_new;
+                    const uint2 it2 = live[u] ? pend[(cons + k) & (PEND_CAP - 1)] : make_uint2(0u, 0u);
+                    q2[u] = it2.x; ent_id[u] = it2.y & 0x7fffffffu; kn[u] = (it2.y >> 31) != 0u;
+                    v4[u] = reinterpret_cast<const float4 *>(p.qvec + q2[u] * p.D);
+                    e4[u] = reinterpret_cast<const float4 *>(p.ent + ent_id[u] * p.D);
+                }
+                float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 2
+                for (int d = 0; d < n4; d++) {
+                    float4 a[4], b[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) { a[u] = __ldg(v4[u] + d); b[u] = __ldg(e4[u] + d); }
+#pragma unroll
+                    for (int u = 0; u < 4; u++) acc[u] = acc[u] + a[u].x * b[u].x;
+#pragma unroll
+                    for (int u = 0; u < 4; u++) acc[u] = acc[u] + a[u].y * b[u].y;
+#pragma unroll
+                    for (int u = 0; u < 4; u++) acc[u] = acc[u] + a[u].z * b[u].z;
+#pragma unroll
+                    for (int u = 0; u < 4; u++) acc[u] = acc[u] + a[u].w * b[u].w;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    if (!live[u]) continue;
+                    const float st = -__ldg(&p.thr[q2[u]].x);
+                    if (acc[u] > st) { atomicAdd(p.counts + q2[u], 1); if (!kn[u]) atomicAdd(p.counts + 2 * p.Q + q2[u], 1); }
+                    if (acc[u] == st) { atomicAdd(p.counts + p.Q + q2[u], 1); if (!kn[u]) atomicAdd(p.counts + 3 * p.Q + q2[u], 1); }
+                }
             }
             __syncwarp();
             cons = pub;
-            if (lane == 0) ctl[1] = cons;               // the ring slots may be reused
+            if (lane == 0) {
+                ctl[1] = cons;                          // the ring slots may be reused
+                atomicAdd(bp.rescored, (unsigned long long)n_new);
+            }
         }
     }
 
@@ -662,118 +754,68 @@ int probe_bf16_peak(mre_ctx *ctx, double *flops_per_s) { return probe_mma_peak<t
 // ------------------------------------------------------------------------------------------ host side
 struct BilScratch {
     const float *ent_full;   // [E, Kp] full precision (the scalar scorer's table)
-    const __nv_bfloat16 *ent_hi, *ent_lo;   // [E, K8]
+    const uint16_t *ent_hi, *ent_lo;   // [E, K8] BF16 hi / lo (NPROD = 3) or FP16 (NPROD = 1; lo unused)
+    const uint16_t *q_hi, *q_lo;       // [Q, K8]
+    float2 *thr;
+    float *delta;
     int64_t K, Kp, K8;
 };
 
-static int bil_prepass(mre_ctx *ctx, const mre_rank_job *job, cudaStream_t st, BilScratch &sc) {
-    const int64_t D = job->D;
+// the two pre-pass launches: table operands + largest row norm, then everything per query (vector, operands, threshold, guard,
+// counter zeroing).  `counts` may be NULL for callers that only want the query vectors (predict).
+static int bil_prepass(mre_ctx *ctx, const mre_rank_job *job, int nprod, int32_t *counts, cudaStream_t st, BilScratch &sc) {
+    const int64_t D = job->D, Q = std::max<int64_t>(job->Q, 1);
     sc.K = job->scorer == MRE_COMPLEX ? 2 * D : D;
     sc.Kp = (sc.K + 3) & ~(int64_t)3;
     sc.K8 = (sc.K + 7) & ~(int64_t)7;
-    const size_t half = ((size_t)job->E * sc.K8 * sizeof(__nv_bfloat16) + 255) & ~(size_t)255;
+    const size_t half = ((size_t)job->E * sc.K8 * sizeof(uint16_t) + 255) & ~(size_t)255;
     // layout of ctx->ent_n: [hi | lo | full (only when a repacked full-precision copy is needed)]
     const bool need_full = job->scorer == MRE_COMPLEX || sc.Kp != D;
     MRE_TRY(ctx->ent_n.reserve(2 * half + (need_full ? (size_t)job->E * sc.Kp * sizeof(float) : 0)));
     char *base = ctx->ent_n.as<char>();
-    __nv_bfloat16 *hi = reinterpret_cast<__nv_bfloat16 *>(base), *lo = reinterpret_cast<__nv_bfloat16 *>(base + half);
+    uint16_t *hi = reinterpret_cast<uint16_t *>(base), *lo = reinterpret_cast<uint16_t *>(base + half);
     float *full = need_full ? reinterpret_cast<float *>(base + 2 * half) : nullptr;
-    bil_split_table_kernel<<<grid_for(job->E * sc.K8, 256), 256, 0, st>>>(job->ent, job->ent_im, job->E, D, sc.K, sc.Kp, sc.K8, full, hi, lo);
-    ctx->launches += 1;
+    const size_t qhalf = ((size_t)Q * sc.K8 * sizeof(uint16_t) + 255) & ~(size_t)255;
+    MRE_TRY(ctx->qvec.reserve((size_t)Q * sc.Kp * sizeof(float)));
+    MRE_TRY(ctx->qvec2.reserve(2 * qhalf));
+    MRE_TRY(ctx->thr.reserve((size_t)Q * (sizeof(float2) + sizeof(float)) + (counts ? 0 : (size_t)4 * Q * sizeof(int32_t)) + 16));
+    sc.thr = ctx->thr.as<float2>();
+    sc.delta = reinterpret_cast<float *>(sc.thr + Q);
+    unsigned int *max_norm = reinterpret_cast<unsigned int *>(sc.delta + Q);
+    if (!counts) counts = reinterpret_cast<int32_t *>(max_norm + 4);
     sc.ent_full = need_full ? full : job->ent;
-    sc.ent_hi = hi;
-    sc.ent_lo = lo;
+    sc.ent_hi = hi; sc.ent_lo = lo;
+    sc.q_hi = ctx->qvec2.as<uint16_t>();
+    sc.q_lo = reinterpret_cast<const uint16_t *>(ctx->qvec2.as<char>() + qhalf);
+    MRE_CUDA(cudaMemsetAsync(max_norm, 0, sizeof(unsigned int), st));
+    const int tgrid = (int)std::max<int64_t>(1, std::min<int64_t>((job->E + 7) / 8, (int64_t)ctx->sm_count * 8));
+    if (nprod == 3) bil_table_kernel<3><<<tgrid, 256, 0, st>>>(job->ent, job->ent_im, job->E, D, sc.K, sc.Kp, sc.K8, full, hi, lo, max_norm);
+    else bil_table_kernel<1><<<tgrid, 256, 0, st>>>(job->ent, job->ent_im, job->E, D, sc.K, sc.Kp, sc.K8, full, hi, lo, max_norm);
+    ctx->launches += 1;
     if (job->Q > 0) {
-        const size_t qhalf = ((size_t)job->Q * sc.K8 * sizeof(__nv_bfloat16) + 255) & ~(size_t)255;
-        MRE_TRY(ctx->qvec.reserve((size_t)job->Q * sc.Kp * sizeof(float)));
-        MRE_TRY(ctx->qvec2.reserve(2 * qhalf));
-        __nv_bfloat16 *qhi = ctx->qvec2.as<__nv_bfloat16>(), *qlo = reinterpret_cast<__nv_bfloat16 *>(ctx->qvec2.as<char>() + qhalf);
-        bil_qvec_kernel<<<grid_for(job->Q * sc.K8, 256), 256, 0, st>>>(job->scorer, job->ent, job->ent_im, job->rel, job->rel_im, D, sc.K,
-                                                                     sc.Kp, sc.K8, job->q_h, job->q_t, job->q_r, job->q_side, job->side,
-                                                                     job->Q, ctx->qvec.as<float>(), qhi, qlo);
+        const size_t smem = sc.Kp <= QK_MAX ? (size_t)QK_WARPS * 2 * sc.Kp * sizeof(float) : 0;
+        const int qgrid = (int)std::max<int64_t>(1, std::min<int64_t>((job->Q + QK_WARPS - 1) / QK_WARPS, (int64_t)ctx->sm_count * 16));
+        uint16_t *qhi = const_cast<uint16_t *>(sc.q_hi), *qlo = const_cast<uint16_t *>(sc.q_lo);
+        if (nprod == 3)
+            bil_query_kernel<3><<<qgrid, QK_WARPS * 32, smem, st>>>(job->scorer, job->ent, job->ent_im, job->rel, job->rel_im, sc.ent_full, D, sc.K,
+                                                                  sc.Kp, sc.K8, job->q_h, job->q_t, job->q_r, job->q_side, job->side, job->Q,
+                                                                  max_norm, ctx->qvec.as<float>(), qhi, qlo, sc.thr, sc.delta, counts);
+        else
+            bil_query_kernel<1><<<qgrid, QK_WARPS * 32, smem, st>>>(job->scorer, job->ent, job->ent_im, job->rel, job->rel_im, sc.ent_full, D, sc.K,
+                                                                  sc.Kp, sc.K8, job->q_h, job->q_t, job->q_r, job->q_side, job->side, job->Q,
+                                                                  max_norm, ctx->qvec.as<float>(), qhi, qlo, sc.thr, sc.delta, counts);
         ctx->launches += 1;
     }
     MRE_CUDA(cudaGetLastError());
     return MRE_OK;
 }
 
-static int run_bilinear(mre_ctx *ctx, const mre_index *ix, const mre_rank_job *job, float *store, cudaStream_t st) {
-    BilScratch sc{};
-    BilParams bp{};
-    RankParams &p = bp.r;
-    MRE_TRY(fill_rank_params(ctx, ix, job, BM, BN, st, p));
-    // the known-true tile filter needs only the job's descriptors: it runs on the context's second stream beside the table
-    // split, query-vector and threshold kernels, joined before the rank kernel
-    if (job->Q > 0) {
-        cudaStream_t aux = nullptr;
-        MRE_TRY(ctx->fork_aux(st, &aux));
-        init_counts_kernel<<<grid_for(4 * job->Q, 256), 256, 0, aux>>>(job->counts, 4 * job->Q);
-        ctx->launches += 1;
-        MRE_TRY(build_tile_filter(ctx, job, p, BM, BN, aux));
-    }
-    MRE_TRY(bil_prepass(ctx, job, st, sc));
-    p.ent = sc.ent_full;
-    p.D = sc.Kp;
-    bp.k8 = sc.K8;
-    p.qvec = ctx->qvec.as<float>();
-    if (job->Q == 0) return MRE_OK;
-    MRE_TRY(ctx->thr.reserve((size_t)job->Q * (sizeof(float2) + sizeof(float)) + 16));
-    float2 *thr = ctx->thr.as<float2>();
-    float *delta = reinterpret_cast<float *>(thr + job->Q);
-    unsigned int *max_norm = reinterpret_cast<unsigned int *>(delta + job->Q);
-    p.thr = thr;
-    bp.delta = delta;
-    MRE_CUDA(cudaMemsetAsync(max_norm, 0, sizeof(unsigned int), st));
-    bil_max_rownorm_kernel<<<grid_for(job->E * 32, 256), 256, 0, st>>>(sc.ent_full, job->E, sc.Kp, max_norm);
-    bil_threshold_kernel<<<(unsigned)((job->Q + 127) / 128), 128, 0, st>>>(p, max_norm, thr, delta);
-    ctx->launches += 2;
-    // candidate tables the B tiles stream from
-    const __nv_bfloat16 *b_hi = sc.ent_hi, *b_lo = sc.ent_lo;
-    int64_t cand_rows = job->E;
-    if (!p.all_entities) {
-        cand_rows = job->group_cptr[job->n_groups];
-        MRE_CHECK_ARG(cand_rows < (1LL << 31), "too many candidate rows");
-        const size_t cb = ((size_t)std::max<int64_t>(cand_rows, 1) * sc.K8 * sizeof(__nv_bfloat16) + 255) & ~(size_t)255;
-        MRE_TRY(ctx->ent_aux.reserve(2 * cb));
-        __nv_bfloat16 *g_hi = ctx->ent_aux.as<__nv_bfloat16>(), *g_lo = reinterpret_cast<__nv_bfloat16 *>(ctx->ent_aux.as<char>() + cb);
-        if (cand_rows > 0) {
-            // a BF16 row of K8 elements is K8 / 2 floats (a multiple of 4): the float4 row gather serves it unchanged
-            const int64_t row_f = sc.K8 >> 1;
-            gather_rows_kernel<<<grid_for(cand_rows * (row_f >> 2), 256), 256, 0, st>>>(reinterpret_cast<const float *>(sc.ent_hi), row_f,
-                                                                                        job->cand_idx, cand_rows, reinterpret_cast<float *>(g_hi));
-            gather_rows_kernel<<<grid_for(cand_rows * (row_f >> 2), 256), 256, 0, st>>>(reinterpret_cast<const float *>(sc.ent_lo), row_f,
-                                                                                        job->cand_idx, cand_rows, reinterpret_cast<float *>(g_lo));
-            ctx->launches += 2;
-        }
-        b_hi = g_hi;
-        b_lo = g_lo;
-    }
-    const size_t qhalf = ((size_t)job->Q * sc.K8 * sizeof(__nv_bfloat16) + 255) & ~(size_t)255;
-    const __nv_bfloat16 *q_hi = ctx->qvec2.as<__nv_bfloat16>();
-    const __nv_bfloat16 *q_lo = reinterpret_cast<const __nv_bfloat16 *>(ctx->qvec2.as<char>() + qhalf);
-    // CTA pairs (cta_group::2) whenever there is more than one query tile; a lone CTA per tile otherwise
-    bool pair = p.total_items > p.total_pitems && ctx->sm_count >= 2;
-    if (const char *e = getenv("MRE_DEV_BIL_PAIR")) pair = pair && atoi(e) != 0;     // developer A/B switch
-    CUtensorMap tm_ahi, tm_alo, tm_bhi, tm_blo;
-    MRE_TRY(make_tmap_bf16_2d(&tm_ahi, q_hi, job->Q, sc.K8, sc.K8, BM, BK));
-    MRE_TRY(make_tmap_bf16_2d(&tm_alo, q_lo, job->Q, sc.K8, sc.K8, BM, BK));
-    MRE_TRY(make_tmap_bf16_2d(&tm_bhi, b_hi, std::max<int64_t>(cand_rows, 1), sc.K8, sc.K8, pair ? BN / 2 : BN, BK));
-    MRE_TRY(make_tmap_bf16_2d(&tm_blo, b_lo, std::max<int64_t>(cand_rows, 1), sc.K8, sc.K8, pair ? BN / 2 : BN, BK));
-    static bool configured = false;
-    if (!configured) {
-        MRE_CUDA(cudaFuncSetAttribute(bilinear_rank_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BIL_SMEM));
-        MRE_CUDA(cudaFuncSetAttribute(bilinear_rank_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BIL_SMEM));
-        MRE_CUDA(cudaFuncSetAttribute(bilinear_rank_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BIL_SMEM));
-        MRE_CUDA(cudaFuncSetAttribute(bilinear_rank_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BIL_SMEM));
-        configured = true;
-    }
-    const int grid = pair ? 2 * (int)std::max<int64_t>(1, std::min<int64_t>(p.total_pitems, ctx->sm_count / 2))
-                          : (int)std::max<int64_t>(1, std::min<int64_t>(p.total_items, ctx->sm_count));
-    bp.store = store;
-    bp.store_ld = cand_rows;
-    MRE_TRY(ctx->join_aux(st));
-    MRE_TRY(ctx->time_begin(st));
-    if (pair) {
+template <bool STORE, bool PAIR, int NPROD>
+static int launch_bilinear(mre_ctx *ctx, int grid, const BilParams &bp, const CUtensorMap &tm_ahi, const CUtensorMap &tm_alo,
+                           const CUtensorMap &tm_bhi, const CUtensorMap &tm_blo, cudaStream_t st) {
+    auto kern = bilinear_rank_kernel<STORE, PAIR, NPROD>;
+    MRE_TRY(ctx->allow_smem(reinterpret_cast<const void *>(kern), BIL_SMEM));
+    if (PAIR) {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)grid);
         cfg.blockDim = dim3(BIL_THREADS);
@@ -786,12 +828,89 @@ static int run_bilinear(mre_ctx *ctx, const mre_index *ix, const mre_rank_job *j
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        if (store) MRE_CUDA(cudaLaunchKernelEx(&cfg, bilinear_rank_kernel<true, true>, bp, tm_ahi, tm_alo, tm_bhi, tm_blo));
-        else MRE_CUDA(cudaLaunchKernelEx(&cfg, bilinear_rank_kernel<false, true>, bp, tm_ahi, tm_alo, tm_bhi, tm_blo));
+        MRE_CUDA(cudaLaunchKernelEx(&cfg, kern, bp, tm_ahi, tm_alo, tm_bhi, tm_blo));
     } else {
-        if (store) bilinear_rank_kernel<true, false><<<grid, BIL_THREADS, BIL_SMEM, st>>>(bp, tm_ahi, tm_alo, tm_bhi, tm_blo);
-        else bilinear_rank_kernel<false, false><<<grid, BIL_THREADS, BIL_SMEM, st>>>(bp, tm_ahi, tm_alo, tm_bhi, tm_blo);
+        kern<<<grid, BIL_THREADS, BIL_SMEM, st>>>(bp, tm_ahi, tm_alo, tm_bhi, tm_blo);
     }
+    return MRE_OK;
+}
+
+static int run_bilinear(mre_ctx *ctx, const mre_index *ix, const mre_rank_job *job, float *store, cudaStream_t st) {
+    BilScratch sc{};
+    BilParams bp{};
+    RankParams &p = bp.r;
+    const int nprod = ctx->opt_bil_products == 1 ? 1 : 3;
+    MRE_TRY(fill_rank_params(ctx, ix, job, BM, BN, st, p));
+    // the known-true tile filter needs only the job's descriptors: it runs on the context's second stream beside the table
+    // and query pre-pass kernels, joined before the rank kernel
+    if (job->Q > 0) {
+        cudaStream_t aux = nullptr;
+        MRE_TRY(ctx->fork_aux(st, &aux));
+        MRE_TRY(build_tile_filter(ctx, job, p, BM, BN, aux));
+    }
+    MRE_TRY(bil_prepass(ctx, job, nprod, job->counts, st, sc));
+    p.ent = sc.ent_full;
+    p.D = sc.Kp;
+    bp.k8 = sc.K8;
+    p.qvec = ctx->qvec.as<float>();
+    if (job->Q == 0) return MRE_OK;
+    p.thr = sc.thr;
+    bp.delta = sc.delta;
+    // candidate tables the B tiles stream from
+    const uint16_t *b_hi = sc.ent_hi, *b_lo = sc.ent_lo;
+    int64_t cand_rows = job->E;
+    if (!p.all_entities) {
+        cand_rows = job->group_cptr[job->n_groups];
+        MRE_CHECK_ARG(cand_rows < (1LL << 31), "too many candidate rows");
+        const size_t cb = ((size_t)std::max<int64_t>(cand_rows, 1) * sc.K8 * sizeof(uint16_t) + 255) & ~(size_t)255;
+        MRE_TRY(ctx->ent_aux.reserve(2 * cb));
+        uint16_t *g_hi = ctx->ent_aux.as<uint16_t>(), *g_lo = reinterpret_cast<uint16_t *>(ctx->ent_aux.as<char>() + cb);
+        if (cand_rows > 0) {
+            // a 16-bit row of K8 elements is K8 / 2 floats (a multiple of 4): the float4 row gather serves it unchanged
+            const int64_t row_f = sc.K8 >> 1;
+            gather_rows_kernel<<<grid_for(cand_rows * (row_f >> 2), 256), 256, 0, st>>>(reinterpret_cast<const float *>(sc.ent_hi), row_f,
+                                                                                        job->cand_idx, cand_rows, reinterpret_cast<float *>(g_hi));
+            ctx->launches += 1;
+            if (nprod == 3) {
+                gather_rows_kernel<<<grid_for(cand_rows * (row_f >> 2), 256), 256, 0, st>>>(reinterpret_cast<const float *>(sc.ent_lo), row_f,
+                                                                                            job->cand_idx, cand_rows, reinterpret_cast<float *>(g_lo));
+                ctx->launches += 1;
+            }
+        }
+        b_hi = g_hi;
+        b_lo = g_lo;
+    }
+    // CTA pairs (cta_group::2) whenever there is more than one query tile; a lone CTA per tile otherwise
+    const bool pair = p.total_items > p.total_pitems && ctx->sm_count >= 2 && ctx->opt_bil_pair;
+    CUtensorMap tm_ahi, tm_alo, tm_bhi, tm_blo;
+    MRE_TRY(make_tmap_bf16_2d(&tm_ahi, sc.q_hi, job->Q, sc.K8, sc.K8, BM, BK));
+    MRE_TRY(make_tmap_bf16_2d(&tm_alo, sc.q_lo, job->Q, sc.K8, sc.K8, BM, BK));
+    MRE_TRY(make_tmap_bf16_2d(&tm_bhi, b_hi, std::max<int64_t>(cand_rows, 1), sc.K8, sc.K8, pair ? BN / 2 : BN, BK));
+    MRE_TRY(make_tmap_bf16_2d(&tm_blo, b_lo, std::max<int64_t>(cand_rows, 1), sc.K8, sc.K8, pair ? BN / 2 : BN, BK));
+    const int grid = pair ? 2 * (int)std::max<int64_t>(1, std::min<int64_t>(p.total_pitems, ctx->sm_count / 2))
+                          : (int)std::max<int64_t>(1, std::min<int64_t>(p.total_items, ctx->sm_count));
+    bp.store = store;
+    bp.store_ld = cand_rows;
+    if (!ctx->stats.p) {
+        MRE_TRY(ctx->stats.reserve(64));
+        MRE_CUDA(cudaMemset(ctx->stats.p, 0, 64));
+    }
+    bp.rescored = ctx->stats.as<unsigned long long>();
+    MRE_TRY(ctx->join_aux(st));
+    MRE_TRY(ctx->time_begin(st));
+    int rc;
+    if (nprod == 3) {
+        if (pair) rc = store ? launch_bilinear<true, true, 3>(ctx, grid, bp, tm_ahi, tm_alo, tm_bhi, tm_blo, st)
+                             : launch_bilinear<false, true, 3>(ctx, grid, bp, tm_ahi, tm_alo, tm_bhi, tm_blo, st);
+        else rc = store ? launch_bilinear<true, false, 3>(ctx, grid, bp, tm_ahi, tm_alo, tm_bhi, tm_blo, st)
+                        : launch_bilinear<false, false, 3>(ctx, grid, bp, tm_ahi, tm_alo, tm_bhi, tm_blo, st);
+    } else {
+        if (pair) rc = store ? launch_bilinear<true, true, 1>(ctx, grid, bp, tm_ahi, tm_alo, tm_bhi, tm_blo, st)
+                             : launch_bilinear<false, true, 1>(ctx, grid, bp, tm_ahi, tm_alo, tm_bhi, tm_blo, st);
+        else rc = store ? launch_bilinear<true, false, 1>(ctx, grid, bp, tm_ahi, tm_alo, tm_bhi, tm_blo, st)
+                        : launch_bilinear<false, false, 1>(ctx, grid, bp, tm_ahi, tm_alo, tm_bhi, tm_blo, st);
+    }
+    MRE_TRY(rc);
     MRE_TRY(ctx->time_end(st));
     ctx->launches += 1;
     MRE_CUDA(cudaGetLastError());
@@ -817,7 +936,7 @@ int predict_bilinear(mre_ctx *ctx, const mre_rank_job *job, int64_t query, float
     one.q_side = job->q_side ? job->q_side + query : nullptr;
     one.Q = 1;
     BilScratch sc{};
-    MRE_TRY(bil_prepass(ctx, &one, st, sc));
+    MRE_TRY(bil_prepass(ctx, &one, 3, nullptr, st, sc));
     bil_predict_kernel<<<(unsigned)((job->E + 127) / 128), 128, 0, st>>>(sc.ent_full, job->E, sc.Kp, ctx->qvec.as<float>(), scores_out);
     ctx->launches += 1;
     MRE_CUDA(cudaGetLastError());

@@ -235,6 +235,11 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// kind::f16 with C = F32, A = B = FP16 (format 0), both K-major
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
 // first index in [lo, hi) with a[i] >= key
 __device__ __forceinline__ int64_t lower_bound_i64(const int64_t *__restrict__ a, int64_t lo, int64_t hi, int64_t key) {
     while (lo < hi) {

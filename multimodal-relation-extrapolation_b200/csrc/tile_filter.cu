@@ -178,9 +178,13 @@ int build_tile_filter(mre_ctx *ctx, const mre_rank_job *job, RankParams &p, int 
     MRE_CHECK_ARG(n < (1LL << 31), "too many work items (%lld); rank the queries in smaller batches", (long long)n);
     const int64_t nb = (n + SCAN_CHUNK - 1) / SCAN_CHUNK;
     // layout of ctx->counters: cnt[n] | ptr[n + 1] | block_sums[nb] | total[1]
+    const void *before = ctx->counters.p;
     MRE_TRY(ctx->counters.reserve((size_t)(2 * n + nb + 8) * sizeof(uint32_t)));
     uint32_t *cnt = ctx->counters.as<uint32_t>(), *ptr = cnt + n, *bsum = ptr + n + 1, *total = bsum + nb;
-    MRE_CUDA(cudaMemsetAsync(cnt, 0, (size_t)n * sizeof(uint32_t), st));
+    // tf_fill_kernel runs every counter it filled back down to zero, so the first `counters_armed` words are already zero when
+    // the previous job on this context had at least as many work items: no memset node in the steady state
+    if (ctx->counters.p != before || ctx->counters_armed < n) MRE_CUDA(cudaMemsetAsync(cnt, 0, (size_t)n * sizeof(uint32_t), st));
+    ctx->counters_armed = 0;
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((p.Q + 7) / 8, (int64_t)ctx->sm_count * 8));
     tf_count_kernel<<<grid, 256, 0, st>>>(p, tile_q, tile_e, cnt);
     if (n <= SMALL_SCAN_MAX) {
@@ -206,6 +210,7 @@ int build_tile_filter(mre_ctx *ctx, const mre_rank_job *job, RankParams &p, int 
     MRE_TRY(ctx->misc2.reserve((size_t)std::max<int64_t>(cap, 1) * sizeof(uint32_t)));
     tf_fill_kernel<<<grid, 256, 0, st>>>(p, tile_q, tile_e, cnt, ptr, ctx->misc2.as<uint32_t>());
     ctx->launches += 1;
+    ctx->counters_armed = n;
     MRE_CUDA(cudaGetLastError());
     p.tf_ptr = ptr;
     p.tf_pairs = ctx->misc2.as<uint32_t>();

@@ -113,58 +113,72 @@ __global__ void normalize_rows_kernel(const float *__restrict__ x, int64_t n, in
     for (int64_t d = D; d < Dp; d++) o[d] = 0.f;
 }
 
-// v_q = h + r (tail query) or -(r - t) (head query), written PAIR-INTERLEAVED by slot: a query's slot is its position in
-// its candidate group counted from the group's (even) first slot, element d of slot s lives at [s / 2][d][s & 1].
-// Queries of dropped (empty) groups own no slot.  Grid-stride over Q * D elements.
-__global__ void transe_qvec_kernel(const RankParams p, const float *__restrict__ rel, float *__restrict__ qvec) {
-    const int64_t D = p.D, total = p.Q * D;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t q = i / D, d = i - q * D;
+// Everything per query in ONE launch, one warp per query:
+//   * v_q = h + r (tail query) or -(r - t) (head query), written PAIR-INTERLEAVED by slot: a query's slot is its position in
+//     its candidate group counted from the group's (even) first slot, element d of slot s lives at [s / 2][d][s & 1];
+//     queries of dropped (empty) groups own no slot;
+//   * the thresholds from the true entity's accumulator: the lanes compute u_d = v_d - e_true,d (the same single rounding as
+//     transe_acc) into shared memory, lane 0 accumulates them SEQUENTIALLY over d -- the order of the tile kernel and of the
+//     oracle.  p = 1: score = acc.  p = 2: score = sqrt(acc) and the reference compares the square roots, so
+//     lo = min{x : sqrt(x) >= s_true}, hi = min{x : sqrt(x) > s_true} (sqrt is monotone), which lets the tile kernel compare raw
+//     accumulators and still agree with sqrtf(acc_j) < sqrtf(acc_true) exactly;
+//   * the zeroing of the query's four counters.
+constexpr int TQ_WARPS = 8;
+constexpr int TQ_MAX_D = 1024;    // D up to this is staged in shared memory; wider rows are accumulated straight from global
+template <int P>
+__global__ void __launch_bounds__(TQ_WARPS * 32) transe_query_kernel(const RankParams p, const float *__restrict__ rel,
+                                                                      float *__restrict__ qvec, float2 *__restrict__ thr) {
+    extern __shared__ float tq_smem[];                   // [TQ_WARPS][D]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t D = p.D;
+    const bool staged = D <= TQ_MAX_D;
+    float *su = tq_smem + (size_t)warp * D;
+    for (int64_t q = (int64_t)blockIdx.x * TQ_WARPS + warp; q < p.Q; q += (int64_t)gridDim.x * TQ_WARPS) {
         const GroupDesc &gd = p.groups[p.n_groups > 1 ? group_of_query(p, q) : 0];
-        if (q < gd.q0 || q - gd.q0 >= gd.nq) continue;
+        const bool owns_slot = q >= gd.q0 && q - gd.q0 < gd.nq;
         const int64_t slot = gd.s0 + (q - gd.q0);
         const int s = query_side(p, q);
-        const float rv = rel[p.q_r[q] * D + d];
-        float v;
-        if (s) v = p.ent[p.q_h[q] * D + d] + rv;
-        else v = -(rv - p.ent[p.q_t[q] * D + d]);
-        qvec[(slot >> 1) * (2 * D) + 2 * d + (slot & 1)] = v;
-    }
-}
-
-// thresholds from the true entity's accumulator.  p = 1: score = acc.  p = 2: score = sqrt(acc) and the reference
-// compares the square roots, so lo = min{x : sqrt(x) >= s_true}, hi = min{x : sqrt(x) > s_true} (sqrt is monotone),
-// which lets the tile kernel compare raw accumulators and still agree with sqrtf(acc_j) < sqrtf(acc_true) exactly.
-template <int P>
-__global__ void transe_threshold_kernel(const float *__restrict__ ent, const float *__restrict__ rel, int64_t D,
-                                        const int64_t *__restrict__ q_h, const int64_t *__restrict__ q_t,
-                                        const int64_t *__restrict__ q_r, const uint8_t *__restrict__ q_side, int side,
-                                        int64_t Q, float2 *__restrict__ thr) {
-    int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= Q) return;
-    int s = q_side ? (int)q_side[q] : side;
-    int64_t truth = s ? q_t[q] : q_h[q], fixed = s ? q_h[q] : q_t[q];
-    float acc = transe_acc<P>(ent + fixed * D, rel + q_r[q] * D, s, ent + truth * D, D);
-    float lo = acc, hi = acc;
-    if (acc >= 0.f && acc < INFINITY) {
-        if (P == 1) {
-            hi = __int_as_float(__float_as_int(acc) + 1);
-        } else {
-            float st = __fsqrt_rn(acc);
-            float x = acc;
-            while (x > 0.f) {
-                float y = __int_as_float(__float_as_int(x) - 1);
-                if (__fsqrt_rn(y) >= st) x = y; else break;
-            }
-            lo = x;
-            x = acc;
-            for (;;) {
-                float y = __int_as_float(__float_as_int(x) + 1);
-                if (y < INFINITY && __fsqrt_rn(y) <= st) x = y; else { hi = y; break; }
-            }
+        const int64_t fixed = s ? p.q_h[q] : p.q_t[q], truth = s ? p.q_t[q] : p.q_h[q];
+        const float *a = p.ent + fixed * D, *rr = rel + p.q_r[q] * D, *e = p.ent + truth * D;
+        float *qrow = qvec + (slot >> 1) * (2 * D) + (slot & 1);
+        for (int64_t d = lane; d < D; d += 32) {
+            const float rv = rr[d];
+            const float v = s ? a[d] + rv : -(rv - a[d]);
+            if (owns_slot) qrow[2 * d] = v;
+            if (staged) su[d] = v - e[d];
         }
+        if (lane < 4) p.counts[(int64_t)lane * p.Q + q] = 0;
+        __syncwarp();
+        if (lane == 0) {
+            float acc = 0.f;
+            if (staged) {
+                for (int d = 0; d < (int)D; d++) acc = P == 1 ? acc + fabsf(su[d]) : fmaf(su[d], su[d], acc);
+            } else {
+                acc = transe_acc<P>(a, rr, s, e, D);
+            }
+            float lo = acc, hi = acc;
+            if (acc >= 0.f && acc < INFINITY) {
+                if (P == 1) {
+                    hi = __int_as_float(__float_as_int(acc) + 1);
+                } else {
+                    float st = __fsqrt_rn(acc);
+                    float x = acc;
+                    while (x > 0.f) {
+                        float y = __int_as_float(__float_as_int(x) - 1);
+                        if (__fsqrt_rn(y) >= st) x = y; else break;
+                    }
+                    lo = x;
+                    x = acc;
+                    for (;;) {
+                        float y = __int_as_float(__float_as_int(x) + 1);
+                        if (y < INFINITY && __fsqrt_rn(y) <= st) x = y; else { hi = y; break; }
+                    }
+                }
+            }
+            thr[q] = make_float2(lo, hi);
+        }
+        __syncwarp();
     }
-    thr[q] = make_float2(lo, hi);
 }
 
 // Model.predict for one query: the materialised float32[E] score vector (tests / drop-in callers only)
@@ -581,17 +595,17 @@ static int transe_tables(mre_ctx *ctx, const mre_rank_job *job, cudaStream_t st,
     return MRE_OK;
 }
 
-// per-query thresholds + the pair-interleaved query vectors (p.ent, p.D, p.groups, p.total_slots already set)
+// per-query thresholds + the pair-interleaved query vectors + zeroed counters (p.ent, p.D, p.groups, p.total_slots, p.counts set)
 template <int P>
 static int transe_queries(mre_ctx *ctx, const RankParams &p, const float *rel, cudaStream_t st) {
     const size_t qbytes = (size_t)std::max<int64_t>(p.total_slots, 2) * p.D * sizeof(float);
     MRE_TRY(ctx->qvec.reserve(qbytes));
     MRE_TRY(ctx->thr.reserve((size_t)p.Q * sizeof(float2)));
     if (p.total_slots != p.Q) MRE_CUDA(cudaMemsetAsync(ctx->qvec.p, 0, qbytes, st));   // the odd halves no query owns
-    transe_qvec_kernel<<<grid_for(p.Q * p.D, 256), 256, 0, st>>>(p, rel, ctx->qvec.as<float>());
-    transe_threshold_kernel<P><<<(unsigned)((p.Q + 127) / 128), 128, 0, st>>>(p.ent, rel, p.D, p.q_h, p.q_t, p.q_r, p.q_side, p.side,
-                                                                               p.Q, ctx->thr.as<float2>());
-    ctx->launches += 2;
+    const size_t smem = p.D <= TQ_MAX_D ? (size_t)TQ_WARPS * p.D * sizeof(float) : 0;
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((p.Q + TQ_WARPS - 1) / TQ_WARPS, (int64_t)ctx->sm_count * 8));
+    transe_query_kernel<P><<<grid, TQ_WARPS * 32, smem, st>>>(p, rel, ctx->qvec.as<float>(), ctx->thr.as<float2>());
+    ctx->launches += 1;
     MRE_CUDA(cudaGetLastError());
     return MRE_OK;
 }
@@ -599,13 +613,8 @@ static int transe_queries(mre_ctx *ctx, const RankParams &p, const float *rel, c
 template <int P, bool NEED_EQ>
 static int launch_rank(mre_ctx *ctx, const RankParams &p, const CUtensorMap &tm_q, const CUtensorMap &tm_e, cudaStream_t st) {
     auto kern = transe_rank_kernel<P, NEED_EQ>;
-    static bool configured = false;
-    if (!configured) {
-        MRE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RANK_SMEM));
-        configured = true;
-    }
-    int per_sm = CTAS_PER_SM;
-    if (const char *e = getenv("MRE_DEV_CTAS_PER_SM")) per_sm = atoi(e) > 0 ? atoi(e) : CTAS_PER_SM;   // developer experiments only
+    MRE_TRY(ctx->allow_smem(reinterpret_cast<const void *>(kern), RANK_SMEM));     // per device: function attributes are
+    const int per_sm = ctx->opt_transe_ctas > 0 ? ctx->opt_transe_ctas : CTAS_PER_SM;
     int grid = (int)std::max<int64_t>(1, std::min<int64_t>(p.total_items, (int64_t)ctx->sm_count * per_sm));
     kern<<<grid, RANK_THREADS, RANK_SMEM, st>>>(p, tm_q, tm_e);
     ctx->launches += 1;
@@ -627,8 +636,6 @@ int rank_transe(mre_ctx *ctx, const mre_index *ix, const mre_rank_job *job, cuda
     // stream beside the query-vector and threshold kernels, joined before the rank kernel
     cudaStream_t aux = nullptr;
     MRE_TRY(ctx->fork_aux(st, &aux));
-    init_counts_kernel<<<grid_for(4 * job->Q, 256), 256, 0, aux>>>(job->counts, 4 * job->Q);
-    ctx->launches += 1;
     MRE_TRY(build_tile_filter(ctx, job, p, TQ, TILE_E, aux));
     if (job->p_norm == 1) MRE_TRY(transe_queries<1>(ctx, p, rel, st));
     else MRE_TRY(transe_queries<2>(ctx, p, rel, st));

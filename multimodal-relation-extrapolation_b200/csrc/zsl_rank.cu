@@ -801,8 +801,9 @@ int zsl_rank(mre_ctx *ctx, const mre_zsl_model *m, const float *A, const float *
     MRE_CHECK_ARG(P < (1LL << 31), "too many (head, candidate) pairs for one call");
     MRE_CHECK_ARG(n_ent < (1LL << 31), "entity ids must fit 31 bits");
     const int D = (int)m->D, K = 2 * D, NP = (D + 16) / 16 * 16;   // >= D + 1: one spare output row for the column sums
-    const char *dev_fp32 = getenv("MRE_DEV_ZSL_FP32");                     // developer switch: the CUDA-core FP32 tile GEMMs
-    const bool fp32_path = (dev_fp32 && dev_fp32[0] == '1') || NP > 224;  // (three operand stages of wider tiles do not fit the SM's shared memory)
+    // mre_ctx_option "zsl_fp32": the CUDA-core FP32 tile GEMMs (also taken by wide models: three operand stages of wider tiles
+    // do not fit the SM's shared memory)
+    const bool fp32_path = ctx->opt_zsl_fp32 != 0 || NP > 224;
     const int64_t P1 = (std::max<int64_t>(P, 1) + 3) / 4 * 4;                // keeps the float4-read relation sums 16-byte aligned
     // scratch: pair -> triple map, scores (when the caller does not want them), relation-vector norms / normalised sums
     MRE_TRY(ctx->misc2.reserve((size_t)P1 * (sizeof(int32_t) + sizeof(float)) + (size_t)n_rel * std::max(n_vec, D + 1) * sizeof(float) + 64));

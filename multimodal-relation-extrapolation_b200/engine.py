@@ -149,6 +149,17 @@ class Context:
     def launches(self):
         return L.lib().mre_ctx_launch_count(self._h)
 
+    def option(self, key, value):
+        """mre_ctx_option: 'bil_products' (1 | 3), 'bil_pair', 'transe_ctas_per_sm', 'zsl_fp32'"""
+        L.check(L.lib().mre_ctx_option(self._h, key.encode(), int(value)))
+        return self
+
+    def stat(self, key):
+        """mre_ctx_stat: read-and-reset a device-side counter ('bil_rescored')"""
+        v = C.c_int64()
+        L.check(L.lib().mre_ctx_stat(self._h, key.encode(), C.byref(v)))
+        return v.value
+
     def timing(self, enable):
         L.check(L.lib().mre_ctx_timing(self._h, 1 if enable else 0))
 

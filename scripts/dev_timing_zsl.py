@@ -18,9 +18,9 @@ heads = rng.integers(0, E, T); rels = rng.integers(0, R, T)
 cands = [rng.choice(E, C, replace=False) for _ in range(min(T, 64))]
 cands = [cands[i % len(cands)] for i in range(T)]
 rel_vecs = rng.standard_normal((R, 20, D)).astype(np.float32)
-os.environ["MRE_DEV_ZSL_FP32"] = "1"
+ev.ctx.option("zsl_fp32", 1)
 c32, s32 = ev.rank(heads, rels, cands, rel_vecs, want_scores=True)
-os.environ["MRE_DEV_ZSL_FP32"] = "0"
+ev.ctx.option("zsl_fp32", 0)
 ctc, stc = ev.rank(heads, rels, cands, rel_vecs, want_scores=True)
 d = (s32 - stc).abs()
 print(f"tensor-core vs FP32 CUDA-core scores: max |diff| {d.max().item():.3e} mean {d.mean().item():.3e}; rank counts differing: {(c32[0] != ctc[0]).sum().item()} of {T}")

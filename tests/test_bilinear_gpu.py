@@ -207,3 +207,43 @@ def test_tensor_core_discrepancy_stays_far_under_the_guard(env, fb15k237, kind):
     K = D * (2 if kind == "complex" else 1)
     assert worst < (1.3e-5 + 1.2e-7 * K) / 4, worst
     print(f"{kind}: worst tensor-core discrepancy {worst:.3e} of ||v|| max||e|| (guard {(1.3e-5 + 1.2e-7 * K):.3e})")
+
+
+@pytest.mark.parametrize("kind", ["distmult", "complex"])
+def test_single_fp16_product_mode_counts_bit_exact(mre, fb15k237, kind):
+    """mre_ctx_option bil_products = 1: ONE FP16 MMA per product with the wider (still rigorous) guard and ~25x more exact
+    re-scores.  The COUNTS must not move: bit for bit those of the sequential FP32 oracle, on both weight sets, both sides, with
+    the index filter; on ragged shapes; and equal to the 3-product mode's on candidate groups."""
+    eng = mre.engine
+    rk = eng.Ranker(device=0)
+    rk.ctx.option("bil_products", 1)
+    ix = eng.KGIndex.from_arrays(fb15k237.E, fb15k237.R, fb15k237.train, fb15k237.valid, fb15k237.test).to_device(0)
+    E, R, D = fb15k237.E, fb15k237.R, 200
+    th, tt, tr = fb15k237.oracle.test_triples()
+    sel = np.linspace(0, len(th) - 1, 100).astype(np.int64)
+    q_h, q_t, q_r = np.repeat(th[sel], 2), np.repeat(tt[sel], 2), np.repeat(tr[sel], 2)
+    side = np.tile(np.array([0, 1], np.uint8), len(sel))
+    for wname in gu.WEIGHT_SETS:
+        tabs = tables_for(kind, wname, E, R, D)
+        fn = (lambda s, h, t, r: ko.distmult_scores(tabs[0], tabs[1], s, h, t, r)) if kind == "distmult" else \
+             (lambda s, h, t, r: ko.complex_scores_contracted(*tabs, s, h, t, r))
+        raw_o, filt_o = helpers.oracle_counts(fb15k237, fn, q_h, q_t, q_r, side)
+        c = rk.rank(kind, tuple(dev(t) for t in tabs), dev(q_h), dev(q_t), dev(q_r), dev(side), index=ix).cpu().numpy()
+        assert np.array_equal(c[0], raw_o) and np.array_equal(c[2], filt_o), wname
+    # huge values overflow FP16: the guard turns infinite and every column is re-scored -- still the oracle's counts
+    rng = np.random.default_rng(3)
+    E2, R2, D2, Q2 = 300, 4, 24, 70
+    ds = helpers.synthetic_graph(9, E2, R2, 1500, 50, Q2)
+    ix2 = eng.KGIndex.from_arrays(E2, R2, ds.train, ds.valid, ds.test).to_device(0)
+    for scale in (1.0, 1.0e5, 1.0e-6):
+        tabs = [(rng.standard_normal(s) * scale).astype(np.float32) for s in ([(E2, D2), (R2, D2)] if kind == "distmult" else [(E2, D2), (E2, D2), (R2, D2), (R2, D2)])]
+        if scale > 1:
+            for t in tabs[-2:] if kind == "complex" else tabs[-1:]:
+                t /= scale                                   # keep the products finite in FP32: only the entity rows are huge
+        th2, tt2, tr2 = ds.oracle.test_triples()
+        side2 = (np.arange(Q2) % 2).astype(np.uint8)
+        c = rk.rank(kind, tuple(dev(t) for t in tabs), dev(th2), dev(tt2), dev(tr2), dev(side2), index=ix2).cpu().numpy()
+        for q in range(Q2):
+            h, t, r, s = int(th2[q]), int(tt2[q]), int(tr2[q]), int(side2[q])
+            sc = ko.distmult_scores(tabs[0], tabs[1], s, h, t, r) if kind == "distmult" else ko.complex_scores_contracted(*tabs, s, h, t, r)
+            assert (int(c[0][q]), int(c[2][q])) == ds.oracle.rank_from_scores(sc, s, h, t, r), (scale, q)
