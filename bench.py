@@ -690,6 +690,7 @@ def main():
     ap.add_argument("--queries", type=int, default=None, help="synthetic2m: global queries per step (default 131072; the north_star's full size is 1000000)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--opt", action="append", default=[], help="mre_ctx_option key=value (e.g. bil_products=1); repeatable")
+    ap.add_argument("--no-flush", action="store_true", help="developer: skip the L2 flush between timed steps (the line then says so and is not a bench value)")
     ap.add_argument("--no-extra", action="store_true", help="skip the extra legs (other workloads, cpu_baseline, parity)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -708,6 +709,9 @@ def main():
         return bench_zsl.main(args, rank, world, local)
 
     w = load_workload(args.workload, args.queries)
+    if args.no_flush:
+        w.flush_l2 = False
+        w.desc += " [developer run: NO L2 flush between steps]"
     if args.impl == "reference":
         return run_reference(args, w)
 

@@ -139,7 +139,9 @@ int64_t mre_ctx_launch_count(const mre_ctx *ctx);
  * DistMult / ComplEx path (3: BF16 hi/lo split, hi*hi + lo*hi + hi*lo; 1: one FP16 product with a wider -- still rigorous --
  * near-tie guard and more exact re-scores; the COUNTS are those of the sequential FP32 scorer either way);
  * "bil_pair" [1] = CTA pairs (cta_group::2) on that path; "transe_ctas_per_sm" [0 = built-in]; "zsl_fp32" [0] = run the ZSL
- * pair contraction on the FP32 CUDA-core kernels instead of 3xTF32 tcgen05.  Unknown keys fail with MRE_ERR_INVALID.
+ * pair contraction on the FP32 CUDA-core kernels instead of 3xTF32 tcgen05; "tf_fused" [0] = the known-true tile filter as
+ * one cooperative launch instead of three plain ones (it then cannot overlap the other pre-pass kernels).  Unknown keys fail
+ * with MRE_ERR_INVALID.
  */
 int mre_ctx_option(mre_ctx *ctx, const char *key, int64_t value);
 /* Read-and-reset a device-side statistic (synchronises the device): "bil_rescored" = columns of the DistMult / ComplEx path that

@@ -96,12 +96,13 @@ __device__ __forceinline__ void bf16_split(float x, __nv_bfloat16 &hi, __nv_bflo
 }
 
 // entity table -> tensor-core operands [rows, K8] (ComplEx: [re | im]; zero padded) + optional full-precision copy [rows, Kp]
-// + the largest row norm (atomicMax on the bit pattern: positive floats order like their bits), ONE pass, one warp per row.
+// + the largest row norm (atomicMax on (generation << 32 | bit pattern): positive floats order like their bits), ONE pass, one warp per row.
 // NPROD = 3: BF16 hi / lo split.  NPROD = 1: hi = rn_fp16(x), lo untouched.
 template <int NPROD>
 __global__ void __launch_bounds__(256) bil_table_kernel(const float *__restrict__ re, const float *__restrict__ im, int64_t rows, int64_t D,
                                                         int64_t K, int64_t Kp, int64_t K8, float *__restrict__ full,
-                                                        uint16_t *__restrict__ hi, uint16_t *__restrict__ lo, unsigned int *__restrict__ max_norm) {
+                                                        uint16_t *__restrict__ hi, uint16_t *__restrict__ lo,
+                                                        unsigned long long *__restrict__ max_norm, unsigned int epoch) {
     const int lane = threadIdx.x & 31;
     const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
     float best = 0.f;
@@ -125,20 +126,18 @@ __global__ void __launch_bounds__(256) bil_table_kernel(const float *__restrict_
         for (int m = 16; m > 0; m >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, m);
         best = fmaxf(best, ss);
     }
-    if (lane == 0 && best > 0.f) atomicMax(max_norm, __float_as_uint(sqrtf(best) * 1.0001f));
+    // the slot is tagged with the call's generation in its high word: a newer call always wins, so nothing resets it
+    if (lane == 0 && best > 0.f)
+        atomicMax(max_norm, ((unsigned long long)epoch << 32) | (unsigned long long)__float_as_uint(sqrtf(best) * 1.0001f));
 }
 
-// sequential FP32 dot product from SHARED memory, same roundings and order as bil_dot below
-__device__ __forceinline__ float bil_dot_smem(const float *v, const float *e, int K) {
-    float acc = 0.f;
-    for (int d = 0; d < K; d++) acc = acc + v[d] * e[d];
-    return acc;
-}
-
-// Everything per query in ONE launch, one warp per query: the query vector (full precision [Q, Kp] + tensor-core operands
-// [Q, K8]), the threshold pair on the predict scale (p = -sim: lower is better; s_true from the SAME sequential FP32 dot the
-// exact re-score uses, taken by lane 0 from shared-memory copies of the two rows), the near-tie guard, and the zeroing of the
-// query's four counters.
+// Everything per query in ONE launch: the query vector (full precision [Q, Kp] + tensor-core operands [Q, K8]), the threshold
+// pair on the predict scale (p = -sim: lower is better), the near-tie guard, and the zeroing of the query's four counters.
+// s_true must carry the roundings and the ORDER of the exact re-score (bil_dot: acc = acc + v_d * e_d, d ascending), and a
+// sequential sum by one lane of a warp costs a whole issue slot per instruction.  So a warp takes 8 queries at a time: for
+// every 128-wide chunk of d the lanes first work ACROSS d (query by query: coalesced row reads, the vector and its operands
+// written out, the rounded products v_d * e_true,d parked in shared memory), then ALONG d (lane l < 8 adds query l's products
+// to its accumulator in order) -- 8 sequential sums advance side by side, bit-identical to the scalar scorer.
 // Guard (rigorous, relative to sum_d |v_d e_d| <= ||v|| * max_j ||e_j||): the tensor-core value differs from the sequential
 // FP32 value by
 //   NPROD = 3  the split: x - hi - lo <= 2^-18 |x| per operand and the dropped lo*lo <= 2^-18  ->  <= 3 * 2^-18 = 1.15e-5
@@ -148,83 +147,142 @@ __device__ __forceinline__ float bil_dot_smem(const float *v, const float *e, in
 //   both       the FP32 accumulation of the K/16 (x3) MMAs and the scalar scorer's own K roundings  ->  < K * 1.2e-7
 // Every column closer than the guard to s_true is re-scored with the scalar scorer, so the COUNTS are exactly those of the
 // FP32 scorer for ANY table.
-constexpr int QK_WARPS = 4;
-constexpr int QK_MAX = 1024;      // K up to this is staged in shared memory; wider models take the row pointers (slower, same bits)
+constexpr int QK_WARPS = 8;      // warps per block
+constexpr int QK_G = 8;          // queries a warp works on together (lanes 0..7 run their sequential sums side by side)
+constexpr int QK_CH = 64;        // elements of d per round: two per lane; a round requests all of its row elements up front
 template <int NPROD>
 __global__ void __launch_bounds__(QK_WARPS * 32) bil_query_kernel(int scorer, const float *__restrict__ ent, const float *__restrict__ ent_im,
         const float *__restrict__ rel, const float *__restrict__ rel_im, const float *__restrict__ ent_full, int64_t D, int64_t K, int64_t Kp,
         int64_t K8, const int64_t *__restrict__ q_h, const int64_t *__restrict__ q_t, const int64_t *__restrict__ q_r,
-        const uint8_t *__restrict__ q_side, int side, int64_t Q, const unsigned int *__restrict__ max_norm, float *__restrict__ qv,
-        uint16_t *__restrict__ qhi, uint16_t *__restrict__ qlo, float2 *__restrict__ thr, float *__restrict__ delta,
+        const uint8_t *__restrict__ q_side, int side, int64_t Q, const unsigned long long *__restrict__ max_norm, unsigned int epoch,
+        float *__restrict__ qv, uint16_t *__restrict__ qhi, uint16_t *__restrict__ qlo, float2 *__restrict__ thr, float *__restrict__ delta,
         int32_t *__restrict__ counts) {
-    extern __shared__ float qk_smem[];                   // [QK_WARPS][2][Kp] when Kp <= QK_MAX
+    __shared__ float sP[QK_WARPS][QK_G][QK_CH + 1];     // rounded products v_d * e_true,d; +1: conflict-free both ways
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const bool staged = Kp <= QK_MAX;
-    float *sv = qk_smem + (size_t)warp * 2 * Kp, *se = sv + Kp;
-    for (int64_t q = (int64_t)blockIdx.x * QK_WARPS + warp; q < Q; q += (int64_t)gridDim.x * QK_WARPS) {
-        const int s = q_side ? (int)q_side[q] : side;
-        const int64_t e = s ? q_h[q] : q_t[q];          // the entity that stays fixed in the query
-        const int64_t truth = s ? q_t[q] : q_h[q];
-        const int64_t r = q_r[q];
-        float ss = 0.f, vmax = 0.f;
-        for (int64_t d = lane; d < K8; d += 32) {
-            float v = 0.f;
-            if (d < K) {
-                if (scorer == MRE_DISTMULT) {
-                    v = s ? ent[e * D + d] * rel[r * D + d] : rel[r * D + d] * ent[e * D + d];
-                } else {
-                    const int64_t dd = d < D ? d : d - D;
-                    const float ere = ent[e * D + dd], eim = ent_im[e * D + dd], rre = rel[r * D + dd], rim = rel_im[r * D + dd];
-                    if (s) v = d < D ? ere * rre - eim * rim : eim * rre + ere * rim;
-                    else v = d < D ? ere * rre + eim * rim : eim * rre - ere * rim;
+    const int64_t n_groups = (Q + QK_G - 1) / QK_G;
+    for (int64_t grp = (int64_t)blockIdx.x * QK_WARPS + warp; grp < n_groups; grp += (int64_t)gridDim.x * QK_WARPS) {
+        const int64_t q0 = grp * QK_G;
+        const int nq = (int)min((int64_t)QK_G, Q - q0);
+        // lane l < nq holds the ids of query q0 + l
+        int my_s = 0, my_fixed = 0, my_truth = 0, my_r = 0;
+        if (lane < nq) {
+            const int64_t q = q0 + lane;
+            my_s = q_side ? (int)q_side[q] : side;
+            my_fixed = (int)(my_s ? q_h[q] : q_t[q]);          // the entity that stays fixed in the query
+            my_truth = (int)(my_s ? q_t[q] : q_h[q]);
+            my_r = (int)q_r[q];
+        }
+        float acc = 0.f;                          // lane l: the sequential sum of query q0 + l
+        float ss[QK_G], vmax[QK_G];               // per-lane partials of ||v||^2 and max |v| of the group's queries
+#pragma unroll
+        for (int qi = 0; qi < QK_G; qi++) { ss[qi] = 0.f; vmax[qi] = 0.f; }
+        for (int64_t c0 = 0; c0 < K8; c0 += QK_CH) {
+            // every row element this chunk needs, for all the group's queries, is requested BEFORE anything is used: one memory
+            // round trip per chunk instead of one per query (the pre-pass runs on cold caches: the chain of trips is its cost)
+            constexpr int J = QK_CH / 32;
+            float x0[QK_G][J], x1[QK_G][J], x2[QK_G][J], x3[QK_G][J], xt[QK_G][J];
+            int sq[QK_G];
+            const int dbase = (int)c0 + lane, Di = (int)D, Ki = (int)K, Kpi = (int)Kp, K8i = (int)K8;     // K8 < 2^31: 32-bit column math
+#pragma unroll
+            for (int qi = 0; qi < QK_G; qi++) {
+                sq[qi] = __shfl_sync(0xffffffffu, my_s, qi);
+                const int64_t e = __shfl_sync(0xffffffffu, my_fixed, qi), truth = __shfl_sync(0xffffffffu, my_truth, qi);
+                const int64_t r = __shfl_sync(0xffffffffu, my_r, qi);
+                const float *pe = ent + e * D, *pr = rel + r * D, *pt = ent_full + truth * Kp;        // row bases: one 64-bit multiply each
+                const float *pei = scorer != MRE_DISTMULT ? ent_im + e * D : pe, *pri = scorer != MRE_DISTMULT ? rel_im + r * D : pr;
+#pragma unroll
+                for (int j = 0; j < J; j++) {
+                    const int d = dbase + 32 * j;
+                    const bool live = qi < nq && d < Ki;
+                    const int dd = d < Di ? d : d - Di;
+                    x0[qi][j] = live ? pe[dd] : 0.f;
+                    x1[qi][j] = live ? pr[dd] : 0.f;
+                    if (scorer != MRE_DISTMULT) {
+                        x2[qi][j] = live ? pei[dd] : 0.f;
+                        x3[qi][j] = live ? pri[dd] : 0.f;
+                    }
+                    xt[qi][j] = (qi < nq && d < Kpi) ? pt[d] : 0.f;
                 }
             }
-            if (d < Kp) {
-                qv[q * Kp + d] = v;
-                if (staged) { sv[d] = v; se[d] = ent_full[truth * Kp + d]; }
-            }
-            ss = fmaf(v, v, ss);
-            vmax = fmaxf(vmax, fabsf(v));
-            if (NPROD == 3) {
-                __nv_bfloat16 h, l;
-                bf16_split(v, h, l);
-                qhi[q * K8 + d] = __bfloat16_as_ushort(h);
-                qlo[q * K8 + d] = __bfloat16_as_ushort(l);
-            } else {
-                qhi[q * K8 + d] = __half_as_ushort(__float2half_rn(v));
-            }
-        }
 #pragma unroll
-        for (int m = 16; m > 0; m >>= 1) {
-            ss += __shfl_xor_sync(0xffffffffu, ss, m);
-            vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, m));
-        }
-        if (lane < 4) counts[(int64_t)lane * Q + q] = 0;
-        __syncwarp();
-        if (lane == 0) {
-            float dot;
-            if (staged) {
-                dot = bil_dot_smem(sv, se, (int)Kp);
-            } else {                                     // the rows this warp just wrote / the table row, sequentially from global
-                dot = 0.f;
-                __threadfence_block();
-                for (int64_t d = 0; d < Kp; d++) dot = dot + qv[q * Kp + d] * ent_full[truth * Kp + d];
+            for (int qi = 0; qi < QK_G; qi++) {
+                if (qi >= nq) break;                                            // warp-uniform
+                const int s = sq[qi];
+                const int64_t q = q0 + qi;
+                float *oq = qv + q * Kp;
+                uint16_t *ohi = qhi + q * K8, *olo = qlo + q * K8;
+#pragma unroll
+                for (int j = 0; j < J; j++) {
+                    const int d = dbase + 32 * j;
+                    float v = 0.f;
+                    if (d < Ki) {
+                        if (scorer == MRE_DISTMULT) {
+                            v = s ? x0[qi][j] * x1[qi][j] : x1[qi][j] * x0[qi][j];
+                        } else {
+                            const float ere = x0[qi][j], eim = x2[qi][j], rre = x1[qi][j], rim = x3[qi][j];
+                            if (s) v = d < Di ? ere * rre - eim * rim : eim * rre + ere * rim;
+                            else v = d < Di ? ere * rre + eim * rim : eim * rre - ere * rim;
+                        }
+                    }
+                    float prod = 0.f;
+                    if (d < Kpi) {
+                        oq[d] = v;
+                        prod = v * xt[qi][j];
+                    }
+                    if (d < K8i) {
+                        if (NPROD == 3) {
+                            __nv_bfloat16 h, l;
+                            bf16_split(v, h, l);
+                            ohi[d] = __bfloat16_as_ushort(h);
+                            olo[d] = __bfloat16_as_ushort(l);
+                        } else {
+                            ohi[d] = __half_as_ushort(__float2half_rn(v));
+                        }
+                    }
+                    sP[warp][qi][lane + 32 * j] = prod;
+                    ss[qi] = fmaf(v, v, ss[qi]);
+                    vmax[qi] = fmaxf(vmax[qi], fabsf(v));
+                }
             }
-            const float pt = -dot;
+            __syncwarp();
+            if (lane < nq) {                       // lane l adds query l's products in order: the scalar scorer's sum, 8 at a time
+                const int nd = (int)min((int64_t)QK_CH, Kp - c0);
+#pragma unroll 8
+                for (int dd = 0; dd < nd; dd++) acc = acc + sP[warp][lane][dd];
+            }
+            __syncwarp();
+        }
+        // ||v||^2 and max |v| of every query of the group (any order will do: they only size the guard), handed to the query's lane
+        float my_ss = 0.f, my_vmax = 0.f;
+#pragma unroll
+        for (int qi = 0; qi < QK_G; qi++) {
+            float a = ss[qi], m = vmax[qi];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                a += __shfl_xor_sync(0xffffffffu, a, o);
+                m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+            }
+            if (lane == qi) { my_ss = a; my_vmax = m; }
+        }
+        if (lane < nq) {
+            const int64_t q = q0 + lane;
+            const float pt = -acc;
             float hi = pt;
             if (pt == pt && fabsf(pt) < INFINITY) hi = nextafterf(pt, INFINITY);
             thr[q] = make_float2(pt, hi);
-            const float vn = sqrtf(ss), en = __uint_as_float(*max_norm);
+            const unsigned long long mn = *max_norm;
+            const float vn = sqrtf(my_ss), en = (unsigned int)(mn >> 32) == epoch ? __uint_as_float((unsigned int)mn) : 0.f;
             float g;
             if (NPROD == 3) {
                 g = (1.3e-5f + 1.2e-7f * (float)Kp) * vn * en;
             } else {
                 g = (9.77e-4f + 1.2e-7f * (float)Kp) * vn * en + 3.1e-8f * sqrtf((float)Kp) * (vn + en);
-                if (!(vmax < 6.0e4f) || !(en < 6.0e4f)) g = INFINITY;
+                if (!(my_vmax < 6.0e4f) || !(en < 6.0e4f)) g = INFINITY;
             }
             delta[q] = g;
+#pragma unroll
+            for (int c = 0; c < 4; c++) counts[(int64_t)c * Q + q] = 0;
         }
-        __syncwarp();
     }
 }
 
@@ -620,9 +678,10 @@ bilinear_rank_kernel(const BilParams bp, const __grid_constant__ CUtensorMap tm_
         if (lane == 0) ctl[2] = 1u;                       // no more entries will be published
     } else {
         // ================================================= re-score warps ===============================================
-        // Entries are drained in batches (the ring nearly half full, or the epilogue warp finished) so that all 32 lanes work,
-        // and every lane interleaves up to four sequential dot products: a single FP32 chain issues one add every ~4 cycles,
-        // four independent chains keep the lane's issue slot busy.
+        // NPROD = 3 (near-ties are rare, ~5e-4 of the columns): entries are re-scored as soon as they are published, one per lane,
+        // spread over the kernel's whole run.  NPROD = 1 (~1e-2 of the columns): drained in batches so that all 32 lanes work,
+        // every lane interleaving four sequential dot products (a single FP32 chain issues one add every ~4 cycles).
+        constexpr uint32_t BATCH = NPROD == 3 ? 1u : (uint32_t)(PEND_CAP / 4);
         const int ring_id = warp - EPI_WARP0 - EPI_WARPS;
         const uint2 *pend = pend_all + ring_id * PEND_CAP;
         volatile uint32_t *ctl = pend_ctl + ring_id * 4;
@@ -631,13 +690,24 @@ bilinear_rank_kernel(const BilParams bp, const __grid_constant__ CUtensorMap tm_
         for (;;) {
             const uint32_t done = ctl[2];               // read BEFORE the counter: done => the counter is final
             const uint32_t pub = ctl[0];
-            if (pub - cons < (uint32_t)(PEND_CAP / 4) && !(done && pub != cons)) {
+            if (pub - cons < BATCH && !(done && pub != cons)) {
                 if (done && pub == cons) break;
-                __nanosleep(100);
+                __nanosleep(NPROD == 3 ? 200 : 100);
                 continue;
             }
             __threadfence_block();                      // the counter before the entries
             const uint32_t n_new = pub - cons;          // <= PEND_CAP
+            if (NPROD == 3) {
+                for (uint32_t k = lane; k < n_new; k += 32) {
+                    const uint2 it2 = pend[(cons + k) & (PEND_CAP - 1)];
+                    const int64_t q2 = it2.x, ent_id = it2.y & 0x7fffffffu;
+                    const bool kn = (it2.y >> 31) != 0u;
+                    const float s2 = bil_dot(p.qvec + q2 * p.D, p.ent + ent_id * p.D, p.D);
+                    const float st = -__ldg(&p.thr[q2].x);
+                    if (s2 > st) { atomicAdd(p.counts + q2, 1); if (!kn) atomicAdd(p.counts + 2 * p.Q + q2, 1); }
+                    if (s2 == st) { atomicAdd(p.counts + p.Q + q2, 1); if (!kn) atomicAdd(p.counts + 3 * p.Q + q2, 1); }
+                }
+            } else
             for (uint32_t k0 = 0; k0 < n_new; k0 += 128) {
                 int64_t q2[4], ent_id[4];
                 bool kn[4], live[4];
@@ -781,29 +851,37 @@ static int bil_prepass(mre_ctx *ctx, const mre_rank_job *job, int nprod, int32_t
     MRE_TRY(ctx->thr.reserve((size_t)Q * (sizeof(float2) + sizeof(float)) + (counts ? 0 : (size_t)4 * Q * sizeof(int32_t)) + 16));
     sc.thr = ctx->thr.as<float2>();
     sc.delta = reinterpret_cast<float *>(sc.thr + Q);
-    unsigned int *max_norm = reinterpret_cast<unsigned int *>(sc.delta + Q);
-    if (!counts) counts = reinterpret_cast<int32_t *>(max_norm + 4);
+    if (!counts) counts = reinterpret_cast<int32_t *>(sc.delta + Q);
+    if (!ctx->stats.p) {
+        MRE_TRY(ctx->stats.reserve(64));
+        MRE_CUDA(cudaMemset(ctx->stats.p, 0, 64));
+    }
+    unsigned long long *max_norm = ctx->stats.as<unsigned long long>() + 1;     // slot 1; slot 0 counts the exact re-scores
+    if (++ctx->bil_epoch == 0xffffffffu) {            // generation tags are exhausted once in 4 billion calls
+        MRE_CUDA(cudaMemsetAsync(max_norm, 0, sizeof(*max_norm), st));
+        ctx->bil_epoch = 1;
+    }
+    const unsigned int epoch = ctx->bil_epoch;
     sc.ent_full = need_full ? full : job->ent;
     sc.ent_hi = hi; sc.ent_lo = lo;
     sc.q_hi = ctx->qvec2.as<uint16_t>();
     sc.q_lo = reinterpret_cast<const uint16_t *>(ctx->qvec2.as<char>() + qhalf);
-    MRE_CUDA(cudaMemsetAsync(max_norm, 0, sizeof(unsigned int), st));
     const int tgrid = (int)std::max<int64_t>(1, std::min<int64_t>((job->E + 7) / 8, (int64_t)ctx->sm_count * 8));
-    if (nprod == 3) bil_table_kernel<3><<<tgrid, 256, 0, st>>>(job->ent, job->ent_im, job->E, D, sc.K, sc.Kp, sc.K8, full, hi, lo, max_norm);
-    else bil_table_kernel<1><<<tgrid, 256, 0, st>>>(job->ent, job->ent_im, job->E, D, sc.K, sc.Kp, sc.K8, full, hi, lo, max_norm);
+    if (nprod == 3) bil_table_kernel<3><<<tgrid, 256, 0, st>>>(job->ent, job->ent_im, job->E, D, sc.K, sc.Kp, sc.K8, full, hi, lo, max_norm, epoch);
+    else bil_table_kernel<1><<<tgrid, 256, 0, st>>>(job->ent, job->ent_im, job->E, D, sc.K, sc.Kp, sc.K8, full, hi, lo, max_norm, epoch);
     ctx->launches += 1;
     if (job->Q > 0) {
-        const size_t smem = sc.Kp <= QK_MAX ? (size_t)QK_WARPS * 2 * sc.Kp * sizeof(float) : 0;
-        const int qgrid = (int)std::max<int64_t>(1, std::min<int64_t>((job->Q + QK_WARPS - 1) / QK_WARPS, (int64_t)ctx->sm_count * 16));
+        const size_t smem = 0;
+        const int qgrid = (int)std::max<int64_t>(1, std::min<int64_t>((job->Q + QK_G * QK_WARPS - 1) / (QK_G * QK_WARPS), (int64_t)ctx->sm_count * 8));
         uint16_t *qhi = const_cast<uint16_t *>(sc.q_hi), *qlo = const_cast<uint16_t *>(sc.q_lo);
         if (nprod == 3)
             bil_query_kernel<3><<<qgrid, QK_WARPS * 32, smem, st>>>(job->scorer, job->ent, job->ent_im, job->rel, job->rel_im, sc.ent_full, D, sc.K,
                                                                   sc.Kp, sc.K8, job->q_h, job->q_t, job->q_r, job->q_side, job->side, job->Q,
-                                                                  max_norm, ctx->qvec.as<float>(), qhi, qlo, sc.thr, sc.delta, counts);
+                                                                  max_norm, epoch, ctx->qvec.as<float>(), qhi, qlo, sc.thr, sc.delta, counts);
         else
             bil_query_kernel<1><<<qgrid, QK_WARPS * 32, smem, st>>>(job->scorer, job->ent, job->ent_im, job->rel, job->rel_im, sc.ent_full, D, sc.K,
                                                                   sc.Kp, sc.K8, job->q_h, job->q_t, job->q_r, job->q_side, job->side, job->Q,
-                                                                  max_norm, ctx->qvec.as<float>(), qhi, qlo, sc.thr, sc.delta, counts);
+                                                                  max_norm, epoch, ctx->qvec.as<float>(), qhi, qlo, sc.thr, sc.delta, counts);
         ctx->launches += 1;
     }
     MRE_CUDA(cudaGetLastError());
@@ -891,10 +969,6 @@ static int run_bilinear(mre_ctx *ctx, const mre_index *ix, const mre_rank_job *j
                           : (int)std::max<int64_t>(1, std::min<int64_t>(p.total_items, ctx->sm_count));
     bp.store = store;
     bp.store_ld = cand_rows;
-    if (!ctx->stats.p) {
-        MRE_TRY(ctx->stats.reserve(64));
-        MRE_CUDA(cudaMemset(ctx->stats.p, 0, 64));
-    }
     bp.rescored = ctx->stats.as<unsigned long long>();
     MRE_TRY(ctx->join_aux(st));
     MRE_TRY(ctx->time_begin(st));

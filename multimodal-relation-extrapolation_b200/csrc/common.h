@@ -105,6 +105,7 @@ struct mre_ctx {
     mre::DevBuf counters;            // raw/corr counters, work counters
     mre::DevBuf misc;                // loss partials etc.
     mre::DevBuf misc2;               // known-true pair list of the tile filter
+    mre::DevBuf met_scratch;         // mre_metrics: per-CTA float64 partials + ticket counter
     mre::DevBuf stats;               // device-side statistics counters (mre_ctx_stat)
     mre::DevBuf loss_acc;            // float64 loss accumulator + finished-block counter of ns_loss (self re-arming)
     mre::DevBuf stage_dev;           // device staging for *_host entry points
@@ -114,7 +115,9 @@ struct mre_ctx {
     int allow_smem(const void *func, size_t bytes);
     // tunables (mre_ctx_option): BF16/FP16 MMAs per product of the bilinear path, CTA pairs on/off, persistent CTAs per SM of the
     // TransE kernel, FP32 fallback of the ZSL scorer -- developer A/B switches, read from the context, never from the environment
-    int opt_bil_products = 3, opt_bil_pair = 1, opt_transe_ctas = 0, opt_zsl_fp32 = 0;
+    int opt_bil_products = 3, opt_bil_pair = 1, opt_transe_ctas = 0, opt_zsl_fp32 = 0, opt_tf_fused = 0;
+    int tf_fused_blocks_per_sm = 0;  // occupancy of the cooperative tile-filter kernel on this device (queried once)
+    unsigned int bil_epoch = 0;      // generation tag of the bilinear path's max-row-norm slot (no reset launch per call)
     int64_t counters_armed = 0;      // leading uint32 counters of `counters` known to be zero (tf_fill runs them back down)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // optional per-launch timing of the dominant (rank) kernel: event pairs recorded on the launching stream

@@ -527,7 +527,7 @@ void mre_ctx_destroy(mre_ctx *c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     mre::DevBuf *bufs[] = {&c->ent_n, &c->rel_n, &c->ent_aux, &c->ent_aux2, &c->qvec, &c->qvec2, &c->thr,
-                           &c->tiles, &c->counters, &c->misc, &c->misc2, &c->stage_dev, &c->loss_acc, &c->stats};
+                           &c->tiles, &c->counters, &c->misc, &c->misc2, &c->stage_dev, &c->loss_acc, &c->stats, &c->met_scratch};
     for (auto *b : bufs) b->release();
     c->stage_pin.release();
     if (c->ev0) cudaEventDestroy(c->ev0);

@@ -11,6 +11,8 @@
 // slots in a bit mask.  The filtered count is then taken from the very registers the raw count is taken from -- no second
 // scoring pass, no inconsistency between two arithmetic paths.  The true entity of each query is routed the same way, so
 // it never counts against itself.
+#include <cooperative_groups.h>
+
 #include <algorithm>
 
 #include "common.h"
@@ -40,8 +42,10 @@ __device__ __forceinline__ void for_each_known(const RankParams &p, int tile_q, 
     }
     const GroupDesc &gd = p.groups[p.all_entities ? 0 : group_of_query(p, q)];
     if (q < gd.q0 || q - gd.q0 >= gd.nq) return;                       // the query's own group was empty (dropped): nothing is scored for it
-    const int64_t qt = (q - gd.q0) / tile_q;
-    const int row = (int)((q - gd.q0) - qt * tile_q);
+    // tile sizes are powers of two (checked on the host): shifts, not 64-bit divisions
+    const int sh_q = 31 - __clz(tile_q), sh_e = 31 - __clz(tile_e);
+    const int64_t qt = (q - gd.q0) >> sh_q;
+    const int row = (int)((q - gd.q0) & (tile_q - 1));
     for (int64_t i = lo + lane; i <= hi; i += 32) {        // index hi stands for the true entity itself
         const int64_t x = i < hi ? __ldg(list + i) : truth;
         if (i < hi && x == truth) continue;                 // listed once, as the last entry
@@ -52,8 +56,8 @@ __device__ __forceinline__ void for_each_known(const RankParams &p, int tile_q, 
             if (k >= gd.c0 + gd.nc || __ldg(p.cand_idx + k) != x) continue;
             pos = k - gd.c0;
         }
-        const int64_t et = pos / tile_e;
-        fn(gd.item0 + et * gd.n_qt + qt, row, (int)(pos - et * tile_e));
+        const int64_t et = pos >> sh_e;
+        fn(gd.item0 + et * gd.n_qt + qt, row, (int)(pos & (tile_e - 1)));
     }
 }
 
@@ -170,6 +174,54 @@ __global__ void __launch_bounds__(1024) scan_small_kernel(const uint32_t *__rest
     }
 }
 
+// count -> scan -> fill in ONE cooperative launch (grid-wide barriers between the phases) for jobs whose counters fit one
+// block's scan (n <= 16 384 work items: every real dataset of the reference) and whose pair-list capacity is known up front.
+// Three dependent launches of a few microseconds of work each cost more in launch gaps and cold-cache round trips than in
+// work; here the phases share one launch and the query descriptors stay in L1/L2 between them.
+constexpr int TF_FUSED_THREADS = 512;
+__global__ void __launch_bounds__(TF_FUSED_THREADS) tf_fused_kernel(const RankParams p, int tile_q, int tile_e, uint32_t *__restrict__ cnt,
+                                                                    uint32_t *__restrict__ ptr, uint32_t *__restrict__ total,
+                                                                    uint32_t *__restrict__ pairs, int n) {
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5), w0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    for (int64_t q = w0; q < p.Q; q += warps)
+        for_each_known(p, tile_q, tile_e, q, lane, [&](int64_t item, int, int) { atomicAdd(cnt + item, 1u); });
+    grid.sync();
+    if (blockIdx.x == 0) {                                  // exclusive scan of the n counters by one block
+        __shared__ uint32_t sh[TF_FUSED_THREADS];
+        const int per = (n + TF_FUSED_THREADS - 1) / TF_FUSED_THREADS, base = threadIdx.x * per;    // per <= 32
+        uint32_t v[32], sum = 0;                            // all of a thread's loads are issued together: one latency, not 32
+#pragma unroll
+        for (int k = 0; k < 32; k++) {
+            v[k] = (k < per && base + k < n) ? cnt[base + k] : 0u;
+            sum += v[k];
+        }
+        sh[threadIdx.x] = sum;
+        __syncthreads();
+        for (int off = 1; off < TF_FUSED_THREADS; off <<= 1) {
+            const uint32_t add = threadIdx.x >= off ? sh[threadIdx.x - off] : 0u;
+            __syncthreads();
+            sh[threadIdx.x] += add;
+            __syncthreads();
+        }
+        uint32_t run = sh[threadIdx.x] - sum;
+#pragma unroll
+        for (int k = 0; k < 32; k++) {
+            if (k < per && base + k < n) ptr[base + k] = run;
+            run += v[k];
+        }
+        if (threadIdx.x == TF_FUSED_THREADS - 1) { ptr[n] = sh[TF_FUSED_THREADS - 1]; *total = sh[TF_FUSED_THREADS - 1]; }
+    }
+    grid.sync();
+    for (int64_t q = w0; q < p.Q; q += warps)
+        for_each_known(p, tile_q, tile_e, q, lane, [&](int64_t item, int row, int col) {
+            const uint32_t slot = atomicSub(cnt + item, 1u) - 1u;    // counts run back down to zero
+            pairs[ptr[item] + slot] = ((uint32_t)row << 16) | (uint32_t)col;
+        });
+}
+
 int build_tile_filter(mre_ctx *ctx, const mre_rank_job *job, RankParams &p, int tile_q, int tile_e, cudaStream_t st) {
     p.tf_ptr = nullptr;
     p.tf_pairs = nullptr;
@@ -185,7 +237,34 @@ int build_tile_filter(mre_ctx *ctx, const mre_rank_job *job, RankParams &p, int 
     // the previous job on this context had at least as many work items: no memset node in the steady state
     if (ctx->counters.p != before || ctx->counters_armed < n) MRE_CUDA(cudaMemsetAsync(cnt, 0, (size_t)n * sizeof(uint32_t), st));
     ctx->counters_armed = 0;
-    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((p.Q + 7) / 8, (int64_t)ctx->sm_count * 8));
+    int64_t known_cap = -1;
+    if (job->filter == MRE_FILTER_NONE) known_cap = p.Q;
+    else if (job->filt_nnz > 0) known_cap = job->filt_nnz + p.Q;
+    // The cooperative single-launch form is kept behind mre_ctx_option "tf_fused": a cooperative launch does not run beside the
+    // main stream's table / query kernels (the two pre-pass chains serialise: measured 64 + 56 us instead of max(55, 56) us on
+    // FB15K-237-ZS DistMult), so the three plain launches on the second stream are the default.
+    if (ctx->opt_tf_fused && n <= SMALL_SCAN_MAX && known_cap >= 0 && known_cap < (1LL << 31)) {
+        MRE_TRY(ctx->misc2.reserve((size_t)std::max<int64_t>(known_cap, 1) * sizeof(uint32_t)));
+        if (ctx->tf_fused_blocks_per_sm == 0) {
+            int per_sm = 0;
+            MRE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tf_fused_kernel, TF_FUSED_THREADS, 0));
+            ctx->tf_fused_blocks_per_sm = std::max(per_sm, 1);
+        }
+        // cooperative launch: every block must be resident; one block per SM is plenty for the real datasets
+        const int cgrid = (int)std::max<int64_t>(1, std::min<int64_t>((p.Q + 15) / 16, (int64_t)ctx->sm_count * std::min(ctx->tf_fused_blocks_per_sm, 2)));
+        uint32_t *pairs = ctx->misc2.as<uint32_t>();
+        int n32 = (int)n;
+        void *args[] = {(void *)&p, (void *)&tile_q, (void *)&tile_e, (void *)&cnt, (void *)&ptr, (void *)&total, (void *)&pairs, (void *)&n32};
+        MRE_CUDA(cudaLaunchCooperativeKernel((const void *)tf_fused_kernel, dim3((unsigned)cgrid), dim3(TF_FUSED_THREADS), args, 0, st));
+        ctx->launches += 1;
+        ctx->counters_armed = n;
+        p.tf_ptr = ptr;
+        p.tf_pairs = pairs;
+        return MRE_OK;
+    }
+    MRE_CHECK_ARG((tile_q & (tile_q - 1)) == 0 && (tile_e & (tile_e - 1)) == 0, "tile sizes must be powers of two");
+    // one warp per query while that stays within a few waves: the per-query chain of dependent loads runs once per warp
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((p.Q + 7) / 8, (int64_t)ctx->sm_count * 32));
     tf_count_kernel<<<grid, 256, 0, st>>>(p, tile_q, tile_e, cnt);
     if (n <= SMALL_SCAN_MAX) {
         scan_small_kernel<<<1, 1024, 0, st>>>(cnt, (int)n, ptr, total);

@@ -113,49 +113,99 @@ __global__ void normalize_rows_kernel(const float *__restrict__ x, int64_t n, in
     for (int64_t d = D; d < Dp; d++) o[d] = 0.f;
 }
 
-// Everything per query in ONE launch, one warp per query:
+// Everything per query in ONE launch:
 //   * v_q = h + r (tail query) or -(r - t) (head query), written PAIR-INTERLEAVED by slot: a query's slot is its position in
 //     its candidate group counted from the group's (even) first slot, element d of slot s lives at [s / 2][d][s & 1];
 //     queries of dropped (empty) groups own no slot;
-//   * the thresholds from the true entity's accumulator: the lanes compute u_d = v_d - e_true,d (the same single rounding as
-//     transe_acc) into shared memory, lane 0 accumulates them SEQUENTIALLY over d -- the order of the tile kernel and of the
-//     oracle.  p = 1: score = acc.  p = 2: score = sqrt(acc) and the reference compares the square roots, so
-//     lo = min{x : sqrt(x) >= s_true}, hi = min{x : sqrt(x) > s_true} (sqrt is monotone), which lets the tile kernel compare raw
-//     accumulators and still agree with sqrtf(acc_j) < sqrtf(acc_true) exactly;
+//   * the thresholds from the true entity's accumulator, which must carry the tile kernel's (and the oracle's) SEQUENTIAL order
+//     over d.  A warp takes 8 queries at a time: for every 64-wide chunk of d the lanes first work ACROSS d (query by query:
+//     coalesced row reads, v written out, u_d = v_d - e_true,d -- the same single rounding as transe_acc -- parked in shared
+//     memory), then ALONG d (lane l < 8 accumulates query l's u_d in order): 8 sequential sums side by side instead of one
+//     lane of a warp paying a whole issue slot per instruction.  p = 1: score = acc.  p = 2: score = sqrt(acc) and the
+//     reference compares the square roots, so lo = min{x : sqrt(x) >= s_true}, hi = min{x : sqrt(x) > s_true} (sqrt is
+//     monotone), which lets the tile kernel compare raw accumulators and still agree with sqrtf(acc_j) < sqrtf(acc_true) exactly;
 //   * the zeroing of the query's four counters.
 constexpr int TQ_WARPS = 8;
-constexpr int TQ_MAX_D = 1024;    // D up to this is staged in shared memory; wider rows are accumulated straight from global
+constexpr int TQ_G = 8;
+constexpr int TQ_CH = 64;
 template <int P>
 __global__ void __launch_bounds__(TQ_WARPS * 32) transe_query_kernel(const RankParams p, const float *__restrict__ rel,
                                                                       float *__restrict__ qvec, float2 *__restrict__ thr) {
-    extern __shared__ float tq_smem[];                   // [TQ_WARPS][D]
+    __shared__ float sU[TQ_WARPS][TQ_G][TQ_CH + 1];      // +1: conflict-free both ways
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t D = p.D;
-    const bool staged = D <= TQ_MAX_D;
-    float *su = tq_smem + (size_t)warp * D;
-    for (int64_t q = (int64_t)blockIdx.x * TQ_WARPS + warp; q < p.Q; q += (int64_t)gridDim.x * TQ_WARPS) {
-        const GroupDesc &gd = p.groups[p.n_groups > 1 ? group_of_query(p, q) : 0];
-        const bool owns_slot = q >= gd.q0 && q - gd.q0 < gd.nq;
-        const int64_t slot = gd.s0 + (q - gd.q0);
-        const int s = query_side(p, q);
-        const int64_t fixed = s ? p.q_h[q] : p.q_t[q], truth = s ? p.q_t[q] : p.q_h[q];
-        const float *a = p.ent + fixed * D, *rr = rel + p.q_r[q] * D, *e = p.ent + truth * D;
-        float *qrow = qvec + (slot >> 1) * (2 * D) + (slot & 1);
-        for (int64_t d = lane; d < D; d += 32) {
-            const float rv = rr[d];
-            const float v = s ? a[d] + rv : -(rv - a[d]);
-            if (owns_slot) qrow[2 * d] = v;
-            if (staged) su[d] = v - e[d];
+    const int64_t n_groups = (p.Q + TQ_G - 1) / TQ_G;
+    for (int64_t grp = (int64_t)blockIdx.x * TQ_WARPS + warp; grp < n_groups; grp += (int64_t)gridDim.x * TQ_WARPS) {
+        const int64_t q0 = grp * TQ_G;
+        const int nq = (int)min((int64_t)TQ_G, p.Q - q0);
+        // lane l < nq holds the descriptors of query q0 + l
+        int my_s = 0, my_fixed = 0, my_truth = 0, my_r = 0;
+        long long my_slot = -1;                                      // -1: the query owns no slot (its group was dropped)
+        if (lane < nq) {
+            const int64_t q = q0 + lane;
+            const GroupDesc &gd = p.groups[p.n_groups > 1 ? group_of_query(p, q) : 0];
+            if (q >= gd.q0 && q - gd.q0 < gd.nq) my_slot = gd.s0 + (q - gd.q0);
+            my_s = query_side(p, q);
+            my_fixed = (int)(my_s ? p.q_h[q] : p.q_t[q]);
+            my_truth = (int)(my_s ? p.q_t[q] : p.q_h[q]);
+            my_r = (int)p.q_r[q];
         }
-        if (lane < 4) p.counts[(int64_t)lane * p.Q + q] = 0;
-        __syncwarp();
-        if (lane == 0) {
-            float acc = 0.f;
-            if (staged) {
-                for (int d = 0; d < (int)D; d++) acc = P == 1 ? acc + fabsf(su[d]) : fmaf(su[d], su[d], acc);
-            } else {
-                acc = transe_acc<P>(a, rr, s, e, D);
+        float acc = 0.f;
+        for (int64_t c0 = 0; c0 < D; c0 += TQ_CH) {
+            // every row element this chunk needs, for all the group's queries, is requested BEFORE anything is used: one memory
+            // round trip per chunk instead of one per query (the pre-pass runs on cold caches: the chain of trips is its cost)
+            constexpr int J = TQ_CH / 32;
+            float xa[TQ_G][J], xr[TQ_G][J], xe[TQ_G][J];
+            int sq[TQ_G];
+            long long sl[TQ_G];
+#pragma unroll
+            for (int qi = 0; qi < TQ_G; qi++) {
+                sq[qi] = __shfl_sync(0xffffffffu, my_s, qi);
+                sl[qi] = __shfl_sync(0xffffffffu, my_slot, qi);
+                const float *a = p.ent + (int64_t)__shfl_sync(0xffffffffu, my_fixed, qi) * D;
+                const float *e = p.ent + (int64_t)__shfl_sync(0xffffffffu, my_truth, qi) * D;
+                const float *rr = rel + (int64_t)__shfl_sync(0xffffffffu, my_r, qi) * D;
+#pragma unroll
+                for (int j = 0; j < J; j++) {
+                    const int64_t d = c0 + lane + 32 * j;
+                    const bool live = qi < nq && d < D;
+                    xa[qi][j] = live ? a[d] : 0.f;
+                    xr[qi][j] = live ? rr[d] : 0.f;
+                    xe[qi][j] = live ? e[d] : 0.f;
+                }
             }
+#pragma unroll
+            for (int qi = 0; qi < TQ_G; qi++) {
+                if (qi >= nq) break;                                            // warp-uniform
+                const int s = sq[qi];
+                const long long slot = sl[qi];
+                float *qrow = qvec + (slot >> 1) * (2 * D) + (slot & 1);
+#pragma unroll
+                for (int j = 0; j < J; j++) {
+                    const int64_t d = c0 + lane + 32 * j;
+                    float u = 0.f;
+                    if (d < D) {
+                        const float rv = xr[qi][j];
+                        const float v = s ? xa[qi][j] + rv : -(rv - xa[qi][j]);
+                        if (slot >= 0) qrow[2 * d] = v;
+                        u = v - xe[qi][j];
+                    }
+                    sU[warp][qi][lane + 32 * j] = u;
+                }
+            }
+            __syncwarp();
+            if (lane < nq) {
+                const int nd = (int)min((int64_t)TQ_CH, D - c0);
+#pragma unroll 8
+                for (int dd = 0; dd < nd; dd++) {
+                    const float u = sU[warp][lane][dd];
+                    acc = P == 1 ? acc + fabsf(u) : fmaf(u, u, acc);
+                }
+            }
+            __syncwarp();
+        }
+        if (lane < nq) {
+            const int64_t q = q0 + lane;
             float lo = acc, hi = acc;
             if (acc >= 0.f && acc < INFINITY) {
                 if (P == 1) {
@@ -176,8 +226,9 @@ __global__ void __launch_bounds__(TQ_WARPS * 32) transe_query_kernel(const RankP
                 }
             }
             thr[q] = make_float2(lo, hi);
+#pragma unroll
+            for (int c = 0; c < 4; c++) p.counts[(int64_t)c * p.Q + q] = 0;
         }
-        __syncwarp();
     }
 }
 
@@ -602,9 +653,8 @@ static int transe_queries(mre_ctx *ctx, const RankParams &p, const float *rel, c
     MRE_TRY(ctx->qvec.reserve(qbytes));
     MRE_TRY(ctx->thr.reserve((size_t)p.Q * sizeof(float2)));
     if (p.total_slots != p.Q) MRE_CUDA(cudaMemsetAsync(ctx->qvec.p, 0, qbytes, st));   // the odd halves no query owns
-    const size_t smem = p.D <= TQ_MAX_D ? (size_t)TQ_WARPS * p.D * sizeof(float) : 0;
-    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((p.Q + TQ_WARPS - 1) / TQ_WARPS, (int64_t)ctx->sm_count * 8));
-    transe_query_kernel<P><<<grid, TQ_WARPS * 32, smem, st>>>(p, rel, ctx->qvec.as<float>(), ctx->thr.as<float2>());
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((p.Q + TQ_G * TQ_WARPS - 1) / (TQ_G * TQ_WARPS), (int64_t)ctx->sm_count * 8));
+    transe_query_kernel<P><<<grid, TQ_WARPS * 32, 0, st>>>(p, rel, ctx->qvec.as<float>(), ctx->thr.as<float2>());
     ctx->launches += 1;
     MRE_CUDA(cudaGetLastError());
     return MRE_OK;
@@ -637,11 +687,8 @@ int rank_transe(mre_ctx *ctx, const mre_index *ix, const mre_rank_job *job, cuda
     cudaStream_t aux = nullptr;
     MRE_TRY(ctx->fork_aux(st, &aux));
     MRE_TRY(build_tile_filter(ctx, job, p, TQ, TILE_E, aux));
-    if (job->p_norm == 1) MRE_TRY(transe_queries<1>(ctx, p, rel, st));
-    else MRE_TRY(transe_queries<2>(ctx, p, rel, st));
-    p.qvec = ctx->qvec.as<float>();
-    p.thr = ctx->thr.as<float2>();
-    // the table the candidate tiles stream from: the entity table itself, or the gathered candidate rows
+    // the table the candidate tiles stream from: the entity table itself, or the gathered candidate rows (gathered on the second
+    // stream too: it depends on the tables and the candidate lists only)
     const float *cand_table = ent;
     int64_t cand_rows = job->E;
     if (!p.all_entities) {
@@ -649,12 +696,16 @@ int rank_transe(mre_ctx *ctx, const mre_index *ix, const mre_rank_job *job, cuda
         MRE_CHECK_ARG(cand_rows < (1LL << 31), "too many candidate rows");
         MRE_TRY(ctx->ent_aux.reserve((size_t)std::max<int64_t>(cand_rows, 1) * Dp * sizeof(float)));
         if (cand_rows > 0) {
-            gather_rows_kernel<<<grid_for(cand_rows * (Dp >> 2), 256), 256, 0, st>>>(ent, Dp, job->cand_idx, cand_rows,
-                                                                                     ctx->ent_aux.as<float>());
+            gather_rows_kernel<<<grid_for(cand_rows * (Dp >> 2), 256), 256, 0, aux>>>(ent, Dp, job->cand_idx, cand_rows,
+                                                                                      ctx->ent_aux.as<float>());
             ctx->launches += 1;
         }
         cand_table = ctx->ent_aux.as<float>();
     }
+    if (job->p_norm == 1) MRE_TRY(transe_queries<1>(ctx, p, rel, st));
+    else MRE_TRY(transe_queries<2>(ctx, p, rel, st));
+    p.qvec = ctx->qvec.as<float>();
+    p.thr = ctx->thr.as<float2>();
     CUtensorMap tm_q, tm_e;
     // query vectors: [slots / 2 pair-rows][2 Dp floats], box = 64 pair-rows x 32 floats (16 d-values of two queries)
     MRE_TRY(make_tmap_f32_2d(&tm_q, p.qvec, std::max<int64_t>(p.total_slots / 2, 1), 2 * Dp, 2 * Dp, TQ / 2, CHUNK));

@@ -305,8 +305,8 @@ class Ranker:
     def metrics(self, counts, side, rank_mode="strict", raw=False, hist_len=0):
         """counts [4, Q] (device) -> dict of per-side integer sums + float64 reciprocal-rank sums (+ histogram)."""
         Q = counts.shape[1]
-        sums = torch.zeros((2, 8), dtype=torch.int64, device=self.device)
-        rr = torch.zeros(2, dtype=torch.float64, device=self.device)
+        sums = torch.empty((2, 8), dtype=torch.int64, device=self.device)     # mre_metrics writes all 16 + 2 slots
+        rr = torch.empty(2, dtype=torch.float64, device=self.device)
         hist = torch.zeros(hist_len, dtype=torch.int64, device=self.device) if hist_len else None
         if isinstance(side, (int, np.integer)):
             side_ptr, side_val = None, int(side)
