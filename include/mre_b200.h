@@ -271,6 +271,19 @@ int mre_sample_subgraph(mre_ctx *ctx, const mre_index *ix, uint64_t seed, uint64
                         int64_t neg_ent, int32_t bern, int32_t filter,
                         int32_t *out_h, int32_t *out_t, int32_t *out_r, void *stream);
 
+/*
+ * Type-constrained negative tails: corrupt(h, r), Corrupt.h:179-195 -- a tail drawn uniformly from the relation's tail-type
+ * list (type_constrain.txt, importTypeFiles, Reader.h:267-317), redrawn while (h, r, tail) is a known triple of ANY split
+ * (_find, Corrupt.h:166-177); after 1000 failed draws (or for an empty list) the exact-uniform corrupt_head over the train
+ * set (Corrupt.h:7-44).  The reference draws with libc rand(); here
+ *   key = (seed_lo, seed_hi); ctr = (pair i lo, attempt | (i hi) << 16, step_lo, (step_hi & 0xffff) | stream_id << 16)
+ *   attempt 0..999: list position (x1:x0) % length;  attempt 1000: the draw word of the corrupt_head fallback.
+ * The index's type lists are sorted and de-duplicated (the reference keeps repeated ids of the file, which then weigh
+ * more).  h, r: device int64 [n]; t_out: device int64 [n].  The index must hold type constraints and be on ctx's device.
+ */
+int mre_corrupt_typed(mre_ctx *ctx, const mre_index *ix, uint64_t seed, uint64_t step, uint32_t stream_id,
+                      const int64_t *h, const int64_t *r, int64_t n, int64_t *t_out, void *stream);
+
 /* ------------------------------------------------------------------------------------------ ZSL scorer */
 /*
  * The ZSL candidate scorer of ZSLmodule.eval (module/zsl_module.py:662-745): Extractor.forward (zsl_module.py:46-106, with

@@ -128,6 +128,7 @@ def lib():
     L.mre_sample.argtypes = samp
     L.mre_sample_host.argtypes = samp
     L.mre_sample_subgraph.argtypes = [vp, vp, u64, u64, u32, vp, vp, vp, i64, vp, i64, vp, i64, i64, i32, i32, vp, vp, vp, vp]
+    L.mre_corrupt_typed.argtypes = [vp, vp, u64, u64, u32, vp, vp, i64, vp, vp]
     L.mre_zsl_entity_features.argtypes = [vp, P(ZslModel), vp, vp, vp, i64, i32, vp, vp, vp]
     L.mre_zsl_rank.argtypes = [vp, P(ZslModel), vp, vp, i64, vp, vp, vp, vp, i64, i64, vp, i64, i32, vp, vp, vp]
     L.mre_transe_margin_step.argtypes = [vp, vp, vp, i64, i64, i64, vp, vp, vp, i64, i64, f32, i32, i32, vp, vp, vp, vp, vp]

@@ -247,6 +247,13 @@ int mre_sample_subgraph(mre_ctx *ctx, const mre_index *ix, uint64_t seed, uint64
                            n_local, neg_ent, bern, filter, out_h, out_t, out_r, (cudaStream_t)stream);
 }
 
+int mre_corrupt_typed(mre_ctx *ctx, const mre_index *ix, uint64_t seed, uint64_t step, uint32_t stream_id, const int64_t *h,
+                      const int64_t *r, int64_t n, int64_t *t_out, void *stream) {
+    MRE_CHECK_ARG(ctx != nullptr, "ctx is NULL");
+    MRE_CUDA(cudaSetDevice(ctx->device));
+    return corrupt_typed(ctx, ix, seed, step, stream_id, h, r, n, t_out, (cudaStream_t)stream);
+}
+
 int mre_transe_margin_step(mre_ctx *ctx, const float *ent, const float *rel, int64_t E, int64_t R, int64_t D, const int64_t *h,
                            const int64_t *t, const int64_t *r, int64_t B, int64_t neg, float margin, int32_t p_norm,
                            int32_t normalize, float *grad_ent, float *grad_rel, float *loss_out, float *scores_out,

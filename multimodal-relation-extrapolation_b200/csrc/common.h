@@ -90,6 +90,7 @@ struct mre_index {
     int64_t *d_tr_hr_key = nullptr;                                   // h*R+r of trainList (sorted); payload = d_tr_t
     int64_t *d_tr_tr_key = nullptr, *d_tr_tr_val = nullptr;           // (t,r,h) order: key t*R+r, val = h
     float *d_bern_prob = nullptr;
+    int64_t *d_type_ptr[2] = {nullptr, nullptr}, *d_type_idx[2] = {nullptr, nullptr};   // type-constraint lists (when loaded)
 };
 
 struct mre_ctx {
@@ -149,6 +150,8 @@ int sample_subgraph(mre_ctx *ctx, const mre_index *ix, uint64_t seed, uint64_t s
                     const int64_t *edge_t, const int64_t *edge_r, int64_t n_edges, const int64_t *node_list, int64_t n_nodes,
                     const int64_t *local_to_global, int64_t n_local, int64_t neg, int32_t bern, int32_t filter, int32_t *out_h,
                     int32_t *out_t, int32_t *out_r, cudaStream_t st);
+int corrupt_typed(mre_ctx *ctx, const mre_index *ix, uint64_t seed, uint64_t step, uint32_t stream_id, const int64_t *h,
+                  const int64_t *r, int64_t n, int64_t *t_out, cudaStream_t st);
 int transe_margin_step(mre_ctx *ctx, const float *ent, const float *rel, int64_t E, int64_t R, int64_t D,
                        const int64_t *h, const int64_t *t, const int64_t *r, int64_t B, int64_t neg, float margin,
                        int32_t p_norm, int32_t normalize, float *grad_ent, float *grad_rel, float *loss_out,

@@ -379,9 +379,25 @@ void mre_index_destroy(mre_index *ix) {
         cudaFree(ix->d_all_hr_key); cudaFree(ix->d_all_hr_val); cudaFree(ix->d_all_tr_key); cudaFree(ix->d_all_tr_val);
         cudaFree(ix->d_tr_h); cudaFree(ix->d_tr_r); cudaFree(ix->d_tr_t); cudaFree(ix->d_tr_hr_key);
         cudaFree(ix->d_tr_tr_key); cudaFree(ix->d_tr_tr_val); cudaFree(ix->d_bern_prob);
+        for (int side = 0; side < 2; side++) { cudaFree(ix->d_type_ptr[side]); cudaFree(ix->d_type_idx[side]); }
         cudaSetDevice(cur);
     }
     delete ix;
+}
+
+// the type-constraint lists follow the index onto its device (corrupt(), Corrupt.h:179-195, draws from them there)
+static int upload_type_lists(mre_index *ix) {
+    if (ix->device < 0 || !ix->has_type) return MRE_OK;
+    MRE_CUDA(cudaSetDevice(ix->device));
+    for (int side = 0; side < 2; side++) {
+        if (ix->d_type_ptr[side]) { cudaFree(ix->d_type_ptr[side]); ix->d_type_ptr[side] = nullptr; }
+        if (ix->d_type_idx[side]) { cudaFree(ix->d_type_idx[side]); ix->d_type_idx[side] = nullptr; }
+        std::vector<int64_t> idx = ix->type_idx[side];
+        if (idx.empty()) idx.push_back(0);               // keep the pointer non-NULL
+        MRE_TRY(upload(ix->type_ptr[side], &ix->d_type_ptr[side]));
+        MRE_TRY(upload(idx, &ix->d_type_idx[side]));
+    }
+    return MRE_OK;
 }
 
 int mre_index_to_device(mre_index *ix, int device) {
@@ -421,7 +437,7 @@ int mre_index_to_device(mre_index *ix, int device) {
     MRE_TRY(upload(ix->bern_prob, &ix->d_bern_prob));
     ix->n_train = (int64_t)n;
     ix->device = device;
-    return MRE_OK;
+    return upload_type_lists(ix);
 }
 
 int64_t mre_index_total(const mre_index *ix, int which) {
@@ -454,9 +470,12 @@ int mre_index_get_means(const mre_index *ix, float *tph, float *hpt) {
     return MRE_OK;
 }
 
+static int upload_type_lists(mre_index *ix);
+
 int mre_index_load_type_constrain(mre_index *ix, const char *path) {
     MRE_CHECK_ARG(ix && path, "NULL argument");
-    return read_type_constrain(path, ix);
+    MRE_TRY(read_type_constrain(path, ix));
+    return upload_type_lists(ix);                       // no-op while the index is host-only
 }
 
 int mre_index_set_type_constrain(mre_index *ix, const int64_t *head_ptr, const int64_t *head_idx, const int64_t *tail_ptr,
@@ -484,7 +503,7 @@ int mre_index_set_type_constrain(mre_index *ix, const int64_t *head_ptr, const i
         ix->type_idx[side].swap(new_idx[side]);
     }
     ix->has_type = true;
-    return MRE_OK;
+    return upload_type_lists(ix);
 }
 
 int64_t mre_index_type_total(const mre_index *ix, int side) {

@@ -94,6 +94,61 @@ int sample(mre_ctx *ctx, const mre_index *ix, uint64_t seed, uint64_t step, uint
     return MRE_OK;
 }
 
+// ------------------------------------------------------------------------------------ type-constrained corruption
+// corrupt(h, r), Corrupt.h:179-195: a tail drawn uniformly from the relation's tail-type list (type_constrain.txt), redrawn while
+// (h, r, tail) is a known triple of ANY split (_find), and after 1000 failed draws the exact-uniform corrupt_head over the train
+// set.  The reference draws with libc rand(); here attempt a of pair i takes Philox counter (i_lo, a | i_hi << 16, step words),
+// key = seed: bit-reproducible, one thread per (h, r) pair, no shared state.  The type lists of the index are sorted and
+// de-duplicated (the reference keeps repeated ids of the file, which then weigh more); an empty list goes straight to the fallback.
+constexpr int TYPED_MAX_LOOP = 1000;
+__global__ void __launch_bounds__(256) corrupt_typed_kernel(const SamplerTables T, const int64_t *__restrict__ all_key,
+                                                            const int64_t *__restrict__ all_val, int64_t n_all,
+                                                            const int64_t *__restrict__ tail_ptr, const int64_t *__restrict__ tail_idx,
+                                                            uint32_t k0, uint32_t k1, uint32_t c2, uint32_t c3,
+                                                            const int64_t *__restrict__ qh, const int64_t *__restrict__ qr, int64_t n,
+                                                            int64_t *__restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t h = qh[i], r = qr[i];
+        const int64_t ll = __ldg(tail_ptr + r), cnt = __ldg(tail_ptr + r + 1) - ll;
+        const int64_t key = h * T.R + r;
+        const int64_t lo = lower_bound_i64(all_key, 0, n_all, key), hi = lower_bound_i64(all_key, lo, n_all, key + 1);
+        const uint32_t c0 = (uint32_t)i, hi16 = (uint32_t)((uint64_t)i >> 32) << 16;
+        int64_t res = -1;
+        for (int loop = 0; loop < TYPED_MAX_LOOP && cnt > 0; loop++) {
+            const Philox4 x = philox4x32_10(c0, (uint32_t)loop | hi16, c2, c3, k0, k1);
+            const int64_t t = __ldg(tail_idx + ll + (int64_t)((((uint64_t)x.x[1] << 32) | x.x[0]) % (uint64_t)cnt));
+            if (!contains_i64(all_val, lo, hi, t)) { res = t; break; }
+        }
+        if (res < 0) {                                    // corrupt_head(0, h, r), Corrupt.h:7-44
+            const Philox4 x = philox4x32_10(c0, (uint32_t)TYPED_MAX_LOOP | hi16, c2, c3, k0, k1);
+            const int64_t tl = lower_bound_i64(T.hr_key, 0, T.n_train, key);
+            const int64_t tr = lower_bound_i64(T.hr_key, tl, T.n_train, key + 1) - 1;
+            res = tr >= tl ? skip_draw(T.tr_t, tl, tr, T.E, ((uint64_t)x.x[1] << 32) | x.x[0], h)
+                           : (int64_t)((((uint64_t)x.x[1] << 32) | x.x[0]) % (uint64_t)T.E);    // no train tail to skip: any entity
+        }
+        out[i] = res;
+    }
+}
+
+int corrupt_typed(mre_ctx *ctx, const mre_index *ix, uint64_t seed, uint64_t step, uint32_t stream_id, const int64_t *h,
+                  const int64_t *r, int64_t n, int64_t *t_out, cudaStream_t st) {
+    MRE_CHECK_ARG(ix != nullptr, "index is NULL");
+    MRE_CHECK_ARG(ix->device == ctx->device, "index is not on device %d (call mre_index_to_device)", ctx->device);
+    MRE_CHECK_ARG(ix->has_type && ix->d_type_ptr[1], "the index holds no type constraints on the device (load them before mre_index_to_device)");
+    MRE_CHECK_ARG(n >= 0 && (n == 0 || (h && r && t_out)), "bad argument");
+    MRE_CHECK_ARG(stream_id < 65536u, "stream_id must be < 65536");
+    if (n == 0) return MRE_OK;
+    SamplerTables T{ix->d_tr_h, ix->d_tr_r, ix->d_tr_t, ix->d_tr_hr_key, ix->d_tr_tr_key, ix->d_tr_tr_val, ix->d_bern_prob,
+                    ix->n_train, ix->E, ix->R};
+    const uint32_t c2 = (uint32_t)step, c3 = ((uint32_t)(step >> 32) & 0xffffu) | (stream_id << 16);
+    const int grid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)ctx->sm_count * 8);
+    corrupt_typed_kernel<<<grid, 256, 0, st>>>(T, ix->d_all_hr_key, ix->d_all_hr_val, ix->n_all, ix->d_type_ptr[1], ix->d_type_idx[1],
+                                               (uint32_t)seed, (uint32_t)(seed >> 32), c2, c3, h, r, n, t_out);
+    ctx->launches += 1;
+    MRE_CUDA(cudaGetLastError());
+    return MRE_OK;
+}
+
 // ------------------------------------------------------------------------------------ subgraph sampler (paper side)
 // module/NegativeSampling.py:114-140 (neg_sample_fn), :321-375 (__normal_batch, __corrupt_head, __corrupt_tail): per edge
 // of a sampled subgraph, neg_ent corruptions drawn from the subgraph's node list (LOCAL ids), split into head- and

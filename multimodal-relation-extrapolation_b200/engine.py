@@ -364,6 +364,13 @@ class Sampler:
                                         _ptr(h), _ptr(t), _ptr(r), _ptr(y), _stream()))
         return h, t, r, y
 
+    def corrupt_typed(self, step, h, r):
+        """mre_corrupt_typed: corrupt(h, r) of Corrupt.h:179-195 for device int64 arrays h, r -> device int64 tails"""
+        out = torch.empty_like(h)
+        L.check(L.lib().mre_corrupt_typed(self.ctx._h, self.index._h, self.seed, int(step), self.stream_id, _ptr(h), _ptr(r),
+                                          h.numel(), _ptr(out), _stream()))
+        return out
+
 
 def transe_margin_step(ctx, ent, rel, h, t, r, B, neg, margin, p_norm=1, normalize=True, grad_ent=None, grad_rel=None,
                        want_scores=False):

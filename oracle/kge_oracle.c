@@ -444,6 +444,69 @@ void orc_sample_subgraph_philox(const orc_index *ix, uint64_t seed, uint64_t ste
     }
 }
 
+/*
+ * corrupt(h, r), OpenKE/openke/base/Corrupt.h:179-195, as a function of the random words it consumes: a tail drawn from the
+ * relation's tail-type list [ll, rr) (importTypeFiles, Reader.h:267-317; `rand(ll, rr)` = word % (rr - ll) + ll,
+ * Random.h:32-34), redrawn while _find says (h, r, tail) is a triple of any split; after 1000 failed draws
+ * corrupt_head(0, h, r) (Corrupt.h:7-44) with one more word.  words[0..999] = the attempts, words[1000] = the fallback's
+ * draw word; *used = attempts consumed.  Returns -1 when the fallback is needed and `fallback_word` is NULL.
+ * Pinned to the compiled reference's own corrupt() through the libc rand() stream (tests/golden/make_golden_corrupt.py).
+ */
+typedef uint64_t (*orc_word_fn)(void *state, int attempt);
+static int64_t corrupt_typed_core(const orc_index *ix, const int64_t *tail_ptr, const int64_t *tail_idx, int64_t h, int64_t r,
+                                  orc_word_fn next, void *state, int64_t *used) {
+    int64_t ll = tail_ptr[r], cnt = tail_ptr[r + 1] - ll;
+    int loop = 0;
+    for (; loop < 1000 && cnt > 0; loop++) {
+        int64_t t = tail_idx[ll + (int64_t)(next(state, loop) % (uint64_t)cnt)];
+        if (!orc_find(ix, h, t, r)) { if (used) *used = loop + 1; return t; }
+    }
+    if (used) *used = loop;
+    uint64_t word = next(state, 1000);
+    int64_t ll2, rr2;
+    run_of(ix->train_head, 1, ix->lef_head[h], ix->rig_head[h], r, &ll2, &rr2);   /* empty run: rr2 < ll2 */
+    return rr2 >= ll2 ? orc_corrupt_head(ix, h, r, word) : (int64_t)(word % (uint64_t)ix->E);
+}
+
+/* the reference's streams: a caller-provided array of libc rand() values consumed in order for the list draws, and thread 0's
+   LCG (randd(0), Random.h:18-21; *lcg_state = next_random[0]) for the corrupt_head fallback */
+typedef struct { const int64_t *w; int64_t pos, n; uint64_t *lcg_state; } word_array;
+static uint64_t next_from_array(void *state, int attempt) {
+    word_array *a = state;
+    if (attempt == 1000) return lcg(a->lcg_state);
+    return a->pos < a->n ? (uint64_t)a->w[a->pos++] : 0;
+}
+int64_t orc_corrupt_typed_words(const orc_index *ix, const int64_t *tail_ptr, const int64_t *tail_idx, const int64_t *qh,
+                                const int64_t *qr, int64_t n, const int64_t *words, int64_t n_words, uint64_t *lcg_state,
+                                int64_t *out) {
+    word_array a = { words, 0, n_words, lcg_state };
+    for (int64_t i = 0; i < n; i++) out[i] = corrupt_typed_core(ix, tail_ptr, tail_idx, qh[i], qr[i], next_from_array, &a, NULL);
+    return a.pos;                                   /* words consumed */
+}
+
+/*
+ * CPU replay of mre_corrupt_typed: the same function on the product's Philox stream
+ *   ctr = (pair i lo, attempt | (i hi) << 16, step_lo, (step_hi & 0xffff) | stream << 16), key = seed, word = (x1:x0)
+ *   attempt a = 0..999: the list draws;  attempt 1000: the draw word of the corrupt_head fallback.
+ * tail_ptr [R+1] / tail_idx: the per-relation SORTED tail-type lists.
+ */
+typedef struct { uint32_t key[2], c0, hi16, c2, c3; } philox_pair;
+static uint64_t next_from_philox(void *state, int attempt) {
+    philox_pair *p = state;
+    uint32_t ctr[4] = { p->c0, (uint32_t)attempt | p->hi16, p->c2, p->c3 }, x[4];
+    orc_philox4x32_10(ctr, p->key, x);
+    return ((uint64_t)x[1] << 32) | x[0];
+}
+void orc_corrupt_typed_philox(const orc_index *ix, uint64_t seed, uint64_t step, uint32_t stream, const int64_t *tail_ptr,
+                              const int64_t *tail_idx, const int64_t *qh, const int64_t *qr, int64_t n, int64_t *out) {
+    philox_pair p = { { (uint32_t)seed, (uint32_t)(seed >> 32) }, 0, 0, (uint32_t)step,
+                      ((uint32_t)(step >> 32) & 0xffffu) | (stream << 16) };
+    for (int64_t i = 0; i < n; i++) {
+        p.c0 = (uint32_t)i; p.hi16 = (uint32_t)((uint64_t)i >> 32) << 16;
+        out[i] = corrupt_typed_core(ix, tail_ptr, tail_idx, qh[i], qr[i], next_from_philox, &p, NULL);
+    }
+}
+
 /* number of emitted negatives that are train triples (must be 0): property check helper */
 int64_t orc_count_train_leaks(const orc_index *ix, const int64_t *bh, const int64_t *bt, const int64_t *br,
                               int64_t from, int64_t to) {

@@ -59,6 +59,9 @@ def lib():
     _i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
     L.orc_sample_subgraph_philox.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, _i64p, _i64p, _i64p, C.c_int64,
                                              _i64p, C.c_int64, _i64p, C.c_int64, C.c_int64, C.c_int, C.c_int, _i32p, _i32p, _i32p]
+    L.orc_corrupt_typed_words.restype = C.c_int64
+    L.orc_corrupt_typed_words.argtypes = [C.c_void_p, _i64p, _i64p, _i64p, _i64p, C.c_int64, _i64p, C.c_int64, C.POINTER(C.c_uint64), _i64p]
+    L.orc_corrupt_typed_philox.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, _i64p, _i64p, _i64p, _i64p, C.c_int64, _i64p]
     L.orc_count_train_leaks.restype = C.c_int64
     L.orc_count_train_leaks.argtypes = [C.c_void_p, _i64p, _i64p, _i64p, C.c_int64, C.c_int64]
     L.orc_philox_selftest.restype = C.c_int
@@ -179,6 +182,23 @@ class OracleIndex:
                                          _i64(er), len(eh), _i64(nodes), len(nodes), _i64(l2g), len(l2g), neg, int(bern),
                                          int(filt), oh, ot, orl)
         return np.stack([oh, ot]), orl
+
+    def corrupt_typed_words(self, tail_ptr, tail_idx, h, r, words, lcg_state=0):
+        """corrupt(h, r) of Corrupt.h:179-195 fed the given random words in order (the reference's libc rand() values) and, for
+        the corrupt_head fallback, thread 0's LCG started at lcg_state -> (tails, words consumed, final LCG state)"""
+        out = np.zeros(len(h), np.int64)
+        st = C.c_uint64(int(lcg_state))
+        used = lib().orc_corrupt_typed_words(self._h, _i64(tail_ptr), _i64(tail_idx), _i64(h), _i64(r), len(h), _i64(words),
+                                             len(words), C.byref(st), out)
+        return out, int(used), st.value
+
+    def corrupt_typed_philox(self, seed, step, tail_ptr, tail_idx, h, r, stream=0):
+        """CPU replay of mre_corrupt_typed (corrupt(h, r), Corrupt.h:179-195) over the sorted per-relation tail-type lists"""
+        out = np.zeros(len(h), np.int64)
+        idx = _i64(tail_idx) if len(tail_idx) else np.zeros(1, np.int64)
+        lib().orc_corrupt_typed_philox(self._h, C.c_uint64(seed), C.c_uint64(step), C.c_uint32(stream), _i64(tail_ptr), idx,
+                                       _i64(h), _i64(r), len(h), out)
+        return out
 
     def count_train_leaks(self, bh, bt, br, start, stop):
         return lib().orc_count_train_leaks(self._h, _i64(bh), _i64(bt), _i64(br), start, stop)

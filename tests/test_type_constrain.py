@@ -163,3 +163,89 @@ def test_empty_type_lists_are_skipped(mre):
             h, t, r = int(th[k]), int(tt[k]), int(tr[k])
             raw, filt = ds.oracle.rank_from_scores_constrained(ko.transe_scores(ent, rel, 1, side, h, t, r), side, h, t, r, lists[r])
             assert (c[0][k], c[2][k]) == (raw, filt)
+
+
+# ------------------------------------------------------------------------------------------------ corrupt(h, r)
+def test_oracle_corrupt_matches_compiled_reference(fb15k237):
+    """oracle/kge_oracle.c's corrupt() fed the libc rand() values the compiled reference consumed (and thread 0's LCG for the
+    corrupt_head fallback) returns the reference's own tails: tests/golden/golden_corrupt.npz (make_golden_corrupt.py), 2 048
+    (h, r) pairs of FB15K237, 44 of them through the 1000-redraw fallback (Corrupt.h:179-195)"""
+    z, R, heads, tails = tc_lists()
+    g = gu.load("golden_corrupt.npz")
+    h, r = g["h"].astype(np.int64), g["r"].astype(np.int64)
+    got, used, _ = fb15k237.oracle.corrupt_typed_words(z["tail_ptr"], z["tail_idx"].astype(np.int64), h, r, g["words"].astype(np.int64), int(g["lcg0"]))
+    assert used == len(g["words"])
+    assert np.array_equal(got, g["tails"].astype(np.int64))
+
+
+def corrupt_cases(fb15k237):
+    """FB15K237 pairs of the reference fixture (fallbacks included) on the real tail-type lists"""
+    z, R, heads, tails = tc_lists()
+    g = gu.load("golden_corrupt.npz")
+    return z, tails, g["h"].astype(np.int64), g["r"].astype(np.int64)
+
+
+def check_corrupt_properties(orc, tails, h, r, out, all_known_falls_back=True):
+    for a, b, t in zip(h.tolist(), r.tolist(), out.tolist()):
+        assert not orc.find(a, t, b)                                       # never a known triple of any split ...
+        exhausted = all(orc.find(a, int(x), b) for x in tails[b])
+        assert exhausted or t in tails[b]                                  # ... from the type list unless it is exhausted
+
+
+def test_corrupt_philox_replay_properties(fb15k237):
+    z, tails, h, r = corrupt_cases(fb15k237)
+    out = fb15k237.oracle.corrupt_typed_philox(192, 3, z["tail_ptr"], z["tail_idx"].astype(np.int64), h, r)
+    check_corrupt_properties(fb15k237.oracle, tails, h, r, out)
+    again = fb15k237.oracle.corrupt_typed_philox(192, 3, z["tail_ptr"], z["tail_idx"].astype(np.int64), h, r)
+    other = fb15k237.oracle.corrupt_typed_philox(192, 4, z["tail_ptr"], z["tail_idx"].astype(np.int64), h, r)
+    assert np.array_equal(out, again) and not np.array_equal(out, other)
+    # uniform over the admissible part of the list: one pair, many steps
+    k = int(np.argmax([len(tails[b]) for b in r]))
+    adm = np.array([x for x in tails[r[k]] if not fb15k237.oracle.find(int(h[k]), int(x), int(r[k]))])
+    n = 4000
+    draws = np.concatenate([fb15k237.oracle.corrupt_typed_philox(5, s, z["tail_ptr"], z["tail_idx"].astype(np.int64), np.full(200, h[k]), np.full(200, r[k]))
+                            for s in range(n // 200)])
+    assert set(draws.tolist()) <= set(adm.tolist())
+    assert len(np.unique(draws)) > 0.6 * min(len(adm), n)
+
+
+@pytest.mark.gpu
+def test_corrupt_typed_gpu_bit_exact(env, fb15k237, mre):
+    """mre_corrupt_typed == the CPU replay of the same Philox stream, element for element (fallback pairs included)"""
+    eng, ix, rk = env
+    z, tails, h, r = corrupt_cases(fb15k237)
+    smp = eng.Sampler(ix, ctx=rk.ctx, seed=192)
+    for step in (0, 3, 1 << 33):
+        out = smp.corrupt_typed(step, dev(h), dev(r)).cpu().numpy()
+        want = fb15k237.oracle.corrupt_typed_philox(192, step, z["tail_ptr"], z["tail_idx"].astype(np.int64), h, r)
+        assert np.array_equal(out, want)
+    check_corrupt_properties(fb15k237.oracle, tails, h, r, out)
+    plain = eng.KGIndex.from_arrays(fb15k237.E, fb15k237.R, fb15k237.train).to_device(0)
+    with pytest.raises(mre.MreError, match="no type constraints"):
+        eng.Sampler(plain, ctx=rk.ctx).corrupt_typed(0, dev(h), dev(r))
+
+
+@pytest.mark.gpu
+def test_corrupt_typed_gpu_empty_and_exhausted_lists(mre):
+    """an empty list and a list whose every member is known both take the corrupt_head fallback; type lists installed AFTER
+    the index went to the device are uploaded too"""
+    eng = mre.engine
+    E, R = 50, 3
+    ds = helpers.synthetic_graph(9, E, R, 600, 30, 30)
+    ix = eng.KGIndex.from_arrays(E, R, ds.train, ds.valid, ds.test).to_device(0)
+    h0, r0 = int(ds.train[0][0]), 1
+    known = np.array(sorted({int(t) for hh, t, rr in zip(*ds.train) if hh == h0 and rr == r0} | {0}))
+    ds2 = helpers.synthetic_graph(9, E, R, 600, 30, 30)
+    lists = [np.zeros(0, np.int64), known[known != 0] if len(known) > 1 else np.zeros(0, np.int64), np.arange(E)]
+    ptr = np.concatenate([[0], np.cumsum([len(l) for l in lists])]).astype(np.int64)
+    idx = np.concatenate(lists).astype(np.int64)
+    ix.set_type_constrain(ptr, idx, ptr, idx)
+    rng = np.random.default_rng(1)
+    h = np.concatenate([[h0] * 8, rng.integers(0, E, 500)]).astype(np.int64)
+    r = np.concatenate([[r0] * 8, rng.integers(0, R, 500)]).astype(np.int64)
+    smp = eng.Sampler(ix, seed=7)
+    out = smp.corrupt_typed(2, dev(h), dev(r)).cpu().numpy()
+    want = ds2.oracle.corrupt_typed_philox(7, 2, ptr, idx, h, r)
+    assert np.array_equal(out, want)
+    for a, b, t in zip(h.tolist(), r.tolist(), out.tolist()):
+        assert not any((hh, tt, rr) == (a, t, b) for hh, tt, rr in zip(*ds.train))     # the fallback never emits a train triple
