@@ -78,7 +78,9 @@ class Workload:
     groups = None          # (query_counts, cand_lists)
     side = 1
     index_splits = None    # (train, valid, test) for MRE_FILTER_INDEX
-    filt_csr = None        # host (ptr, idx)
+    filt_csr = None        # host (ptr, idx): per-query known lists (what the parity checks read; the device path of --filter csr)
+    filter = "index"       # how the known-true triples reach the library: "index" = an mre_index over them (MRE_FILTER_INDEX, the
+                           # reference's _find over tripleList), "csr" = per-query lists (MRE_FILTER_CSR, the paper's e1rel_e2 lists)
     known = None           # (h, t, r) triples whose tails are "known" besides the test triples themselves (synthetic train split)
     flush_l2 = True
 
@@ -157,6 +159,7 @@ def config_of(w, world):
     Q = len(w.q_h) if w.index_splits is None else 2 * len(w.index_splits[2][0])
     return {"workload": w.name, "desc": w.desc, "E": w.E, "R": w.R, "D": w.D, "queries_per_step": int(Q), "scorer": w.scorer,
             "rank_mode": w.rank_mode,
+            "filter": "known-true triples held by an mre_index (MRE_FILTER_INDEX)" if (w.filter == "index" or w.index_splits is not None) else "per-query known lists (MRE_FILTER_CSR)",
             "l2": "256 MiB buffer written between timed steps (L2 flush)" if w.flush_l2 else "inputs (2 GB of tables) exceed the 126 MB L2; no flush",
             "sharding": "one global query set per step, contiguous blocks per rank (strong scaling), tables replicated, "
                         "ONE int64 all-reduce of the metric sums per step inside the timed region"}
@@ -455,7 +458,11 @@ class Runner:
             side_host = side_d = w.side
         if w.groups is not None:
             kw["groups"] = eng.CandidateGroups.from_lists(w.groups[0], w.groups[1], dev)
-        if w.filt_csr is not None:
+        if index is None and w.filt_csr is not None and w.filter == "index":
+            # the known triples = the test tasks themselves (+ the synthetic train split): one index over them, replicated per rank
+            empty = (np.zeros(0, np.int64),) * 3
+            index = eng.KGIndex.from_arrays(w.E, w.R, w.known if w.known is not None else empty, None, (q_h, q_t, q_r)).to_device(self.local)
+        elif w.filt_csr is not None:
             ptr, idx = w.filt_csr
             kw["filt_csr"] = (torch.from_numpy(ptr[lo:hi + 1] - ptr[lo]).to(dev), torch.from_numpy(np.ascontiguousarray(idx[ptr[lo]:ptr[hi]])).to(dev))
         if index is not None:
@@ -505,12 +512,14 @@ class Runner:
         l0 = ctx.launches
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         out = None
+        t_host = time.perf_counter()
         for a, b in ev:
             if flush_l2:
                 self.flush.zero_()
             a.record()
             out = step()
             b.record()
+        self.host_ms_per_step = 1e3 * (time.perf_counter() - t_host) / steps    # launch-side cost: the host must stay ahead of the GPU
         self.barrier()
         ms = self.max_over_ranks(sum(a.elapsed_time(b) for a, b in ev))
         launches = ctx.launches - l0
@@ -577,7 +586,7 @@ class Runner:
                "config": config_of(w, self.world), "roofline": self.roofline(w, p["Q"], kern_ms, kern_n),
                "e2e": {"value": Qg * es / e2e_s, "unit": "queries/s", "steps": es, "h2d_bytes_per_step": p["h2d"], "d2h_bytes_per_step": p["d2h"],
                        "api": "mre_rank_host through Ranker.rank_host: pinned host query ids in, int32 rank counts out, metric sums (+ all-reduce)"},
-               "gpu_launches": int(launches), "result": {"tail": summ[1], "head": summ[0]}}
+               "gpu_launches": int(launches), "host_ms_per_step": self.host_ms_per_step, "result": {"tail": summ[1], "head": summ[0]}}
         if sampler:
             out["clocks"] = sampler.summary()
         return out, p
@@ -690,6 +699,7 @@ def main():
     ap.add_argument("--queries", type=int, default=None, help="synthetic2m: global queries per step (default 131072; the north_star's full size is 1000000)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--opt", action="append", default=[], help="mre_ctx_option key=value (e.g. bil_products=1); repeatable")
+    ap.add_argument("--filter", default="index", choices=["index", "csr"], help="developer: how the known-true triples reach the library (default: an index over them)")
     ap.add_argument("--no-flush", action="store_true", help="developer: skip the L2 flush between timed steps (the line then says so and is not a bench value)")
     ap.add_argument("--no-extra", action="store_true", help="skip the extra legs (other workloads, cpu_baseline, parity)")
     args = ap.parse_args()
@@ -709,6 +719,7 @@ def main():
         return bench_zsl.main(args, rank, world, local)
 
     w = load_workload(args.workload, args.queries)
+    w.filter = args.filter
     if args.no_flush:
         w.flush_l2 = False
         w.desc += " [developer run: NO L2 flush between steps]"
@@ -785,7 +796,7 @@ def main():
         out = {"metric": "filtered-rank eval queries/sec", "value": line["value"], "unit": "queries/s", "n_gpus": world, "steps": args.steps,
                "warmup": args.warmup, "ms_per_step": line["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                "dtype": "f32", "data": "synthetic", "config": line["config"], "roofline": line["roofline"], "cpu_baseline": cpu_base,
-               "e2e": line["e2e"], "gpu_launches": line["gpu_launches"], "clocks": line.get("clocks"), "parity": parity,
+               "e2e": line["e2e"], "gpu_launches": line["gpu_launches"], "host_ms_per_step": line.get("host_ms_per_step"), "clocks": line.get("clocks"), "parity": parity,
                "result": line["result"], "extra": extra}
         emit(out)
     if world > 1:

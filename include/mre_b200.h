@@ -139,9 +139,8 @@ int64_t mre_ctx_launch_count(const mre_ctx *ctx);
  * DistMult / ComplEx path (3: BF16 hi/lo split, hi*hi + lo*hi + hi*lo; 1: one FP16 product with a wider -- still rigorous --
  * near-tie guard and more exact re-scores; the COUNTS are those of the sequential FP32 scorer either way);
  * "bil_pair" [1] = CTA pairs (cta_group::2) on that path; "transe_ctas_per_sm" [0 = built-in]; "zsl_fp32" [0] = run the ZSL
- * pair contraction on the FP32 CUDA-core kernels instead of 3xTF32 tcgen05; "tf_fused" [0] = the known-true tile filter as
- * one cooperative launch instead of three plain ones (it then cannot overlap the other pre-pass kernels).  Unknown keys fail
- * with MRE_ERR_INVALID.
+ * pair contraction on the FP32 CUDA-core kernels instead of 3xTF32 tcgen05; "transe_lpt" [1] = cost-balanced (longest item
+ * first) work-item order of the TransE kernel on jobs of a few waves.  Unknown keys fail with MRE_ERR_INVALID.
  */
 int mre_ctx_option(mre_ctx *ctx, const char *key, int64_t value);
 /* Read-and-reset a device-side statistic (synchronises the device): "bil_rescored" = columns of the DistMult / ComplEx path that
@@ -178,12 +177,13 @@ typedef struct mre_rank_job {
     const int64_t *group_qptr;
     const int64_t *group_cptr;
     const int64_t *cand_idx;
-    /* MRE_FILTER_CSR: device int64 prefix [Q+1] and entity ids; entries outside the query's candidate
-     * group are ignored; the true entity is always excluded from the filtered counts. */
+    /* MRE_FILTER_CSR: device int64 prefix [Q+1] and entity ids, each query's slice SORTED ASCENDING (repeated ids
+     * count once); entries outside the query's candidate group are ignored; the true entity is always excluded
+     * from the filtered counts. */
     const int64_t *filt_ptr;
     const int64_t *filt_idx;
-    /* optional upper bound on the number of (query, known entity) pairs of this job (MRE_FILTER_CSR: filt_ptr[Q]);
-     * 0 = unknown, the library then reads the exact count back with one small stream synchronisation */
+    /* MRE_FILTER_CSR: filt_ptr[Q], the number of list entries (an upper bound will do; a smaller value drops entries).
+     * With it the known-true correction runs flattened over the entries; 0 = unknown: one warp walks each query's list. */
     int64_t filt_nnz;
     /* output, device int32 [4][Q]: raw_lt, raw_eq, filt_lt, filt_eq
      *   raw_lt  = #{j in S_q : s_j <  s_true}          raw_eq  = #{j in S_q : s_j == s_true}

@@ -14,7 +14,7 @@ BUILD_DIR = os.path.join(_HERE, "build")
 LIB_PATH = os.environ.get("MRE_B200_LIB") or os.path.join(BUILD_DIR, "libmre_b200.so")   # override: A/B timing of two builds
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include", "mre_b200.h")
 
-SOURCES = ["index.cpp", "tma_host.cpp", "abi.cu", "transe_rank.cu", "metrics.cu", "sampler.cu", "train_step.cu", "bilinear_rank.cu", "tile_filter.cu", "zsl_rank.cu"]
+SOURCES = ["index.cpp", "tma_host.cpp", "abi.cu", "transe_rank.cu", "metrics.cu", "sampler.cu", "train_step.cu", "bilinear_rank.cu", "zsl_rank.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
               "-Xcompiler", "-fPIC,-O2", "-shared"]
 

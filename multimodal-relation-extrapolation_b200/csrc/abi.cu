@@ -354,7 +354,7 @@ int mre_ctx_option(mre_ctx *ctx, const char *key, int64_t value) {
     } else if (k == "bil_pair") ctx->opt_bil_pair = value != 0;
     else if (k == "transe_ctas_per_sm") ctx->opt_transe_ctas = (int)std::max<int64_t>(0, value);
     else if (k == "zsl_fp32") ctx->opt_zsl_fp32 = value != 0;
-    else if (k == "tf_fused") ctx->opt_tf_fused = value != 0;
+    else if (k == "transe_lpt") ctx->opt_transe_lpt = value != 0;
     else {
         set_error("unknown option '%s'", key);
         return MRE_ERR_INVALID;

@@ -12,9 +12,10 @@
 //                      head v = [t_re r_re + t_im r_im | t_im r_re - t_re r_im]
 // the one true dense contraction of the hot path, so it runs as a tcgen05 GEMM whose epilogue never writes scores:
 // accumulator tiles (128 queries x 256 entities, FP32) live in TMEM, double-buffered; four epilogue warps read them
-// back with tcgen05.ld (one query row per thread), compare against the query's true score and count, taking the
-// known-true columns routed to the tile by tile_filter.cu back out of the filtered count; columns closer to the true
-// score than an error guard are re-scored in scalar FP32, which makes the COUNTS those of the sequential FP32 scorer.
+// back with tcgen05.ld (one query row per thread), compare against the query's true score and count (raw and filtered
+// counters alike; bil_known_kernel scores each query's few known-true entities exactly and takes them back out of the
+// filtered ones); columns closer to the true score than an error guard are re-scored in scalar FP32, which makes the COUNTS
+// those of the sequential FP32 scorer.
 // Precision: the reference is FP32, and the COUNTS must be those of the FP32 scorer.  The tensor cores only have to decide
 // every column that is not a near-tie, so every operand is split x ~= hi + lo into two BF16 values (hi = rn(x),
 // lo = rn(x - hi): 16 significant bits) and each product is issued as THREE kind::f16 BF16 MMAs  hi*hi + lo*hi + hi*lo
@@ -75,8 +76,7 @@ constexpr int RESCORE_WARPS = 4;             // one per epilogue warp of the fir
 constexpr int BIL_THREADS = (2 + EPI_WARPS + RESCORE_WARPS) * 32;
 constexpr int EPI_WARP0 = 2;
 constexpr int PEND_CAP = 512;                // per epilogue warp: ring of near-ties handed to its re-score warp through shared memory
-constexpr int MASK_STRIDE = 9;               // words per row of the per-warp known-true mask (8 + 1 pad: conflict-free)
-constexpr size_t BIL_SMEM = 1024 + (size_t)2 * (64 / BK) * (2 * A_BYTES + 2 * B_BYTES) + 48 * sizeof(uint64_t) + EPI_WARPS * 32 * MASK_STRIDE * 4 + RESCORE_WARPS * (PEND_CAP * sizeof(uint2) + 16) + 64;   // both configurations: 192 KiB of stages
+constexpr size_t BIL_SMEM = 1024 + (size_t)2 * (64 / BK) * (2 * A_BYTES + 2 * B_BYTES) + 48 * sizeof(uint64_t) + RESCORE_WARPS * (PEND_CAP * sizeof(uint2) + 16) + 64;   // both configurations: 192 KiB of stages
 constexpr uint32_t TMEM_COLS = 512;     // two 256-column accumulator buffers
 
 struct BilParams {
@@ -303,6 +303,61 @@ __device__ __forceinline__ float bil_dot(const float *__restrict__ v, const floa
     return acc;
 }
 
+// The filtered counts' correction (rank_common.cuh: known_correction) with the bilinear element: term = v_d * e_d (its own
+// rounding), fold acc + term -- bil_dot's steps exactly, the arithmetic the tile kernel's decisions are guaranteed to agree with
+// (sign outside the guard, exact re-score inside).  p.qvec / p.ent are the full-precision [.., Kp] tables, p.D = Kp.
+struct BilKnownOp {
+    const float *ent;
+    const float *qvec, *v;
+    const float2 *thr;
+    int64_t D;
+    float st;
+    __device__ __forceinline__ void query(int64_t q, int, int64_t, int64_t, int64_t) {
+        v = qvec + q * D;
+    }
+    __device__ __forceinline__ float vec(int d) const { return __ldg(v + d); }
+    static constexpr int VSTRIDE = 1;
+    __device__ __forceinline__ const float *flat_query(int64_t q, int64_t, int, int64_t, int64_t, int64_t) {
+        st = -thr[q].x;
+        return qvec + q * D;
+    }
+    __device__ __forceinline__ float direct(int64_t x) const { return bil_dot(v, ent + x * D, D); }
+    __device__ __forceinline__ void thresholds(int64_t q) { st = -thr[q].x; }
+    __device__ __forceinline__ bool truth_ties() const { return st == st; }
+    __device__ __forceinline__ float term(float a, float e) const { return a * e; }
+    __device__ __forceinline__ float fold(float acc, float t) const { return acc + t; }
+    __device__ __forceinline__ void classify(float acc, int &lt, int &eq) const {
+        if (acc > st) lt++;
+        else if (acc == st) eq++;
+    }
+};
+__global__ void __launch_bounds__(KNOWN_WARPS * 32) bil_known_kernel(const RankParams p) {
+    __shared__ float sT[KNOWN_WARPS][32][33];
+    __shared__ int64_t sX[KNOWN_WARPS][32];
+    BilKnownOp op{p.ent, p.qvec, nullptr, p.thr, p.D, 0.f};
+    known_correction(p, op, sT[threadIdx.x >> 5], sX[threadIdx.x >> 5]);
+}
+// (Building the query vector from the embedding rows instead, so that this kernel could run beside bil_query_kernel on the second
+// stream, was measured SLOWER: four row loads per element and a scalar direct path cost more than the overlap saves --
+// ComplEx step 0.61 -> 0.85 ms.)
+__global__ void __launch_bounds__(KNOWN_WARPS * 32) bil_known_score_kernel(const RankParams p, const KnownRuns kr) {
+    __shared__ float sT[KNOWN_WARPS][32][33];
+    __shared__ int64_t sX[KNOWN_WARPS][32];
+    BilKnownOp op{p.ent, p.qvec, nullptr, p.thr, p.D, 0.f};
+    known_score_runs(p, kr, op, sT[threadIdx.x >> 5], sX[threadIdx.x >> 5]);
+}
+__global__ void __launch_bounds__(KNOWN_WARPS * 32) bil_known_compare_kernel(const RankParams p, const KnownRuns kr) {
+    BilKnownOp op{p.ent, p.qvec, nullptr, p.thr, p.D, 0.f};
+    known_compare_runs(p, kr, op);
+}
+__global__ void __launch_bounds__(KNOWN_WARPS * 32) bil_known_flat_kernel(const RankParams p) {
+    __shared__ float sT[KNOWN_WARPS][32][33];
+    __shared__ int64_t sX[KNOWN_WARPS][32];
+    __shared__ const float *sV[KNOWN_WARPS][32];
+    BilKnownOp op{p.ent, p.qvec, nullptr, p.thr, p.D, 0.f};
+    known_correction_flat(p, op, sT[threadIdx.x >> 5], sX[threadIdx.x >> 5], sV[threadIdx.x >> 5]);
+}
+
 __global__ void bil_predict_kernel(const float *__restrict__ ent, int64_t E, int64_t K, const float *__restrict__ qv,
                                    float *__restrict__ out) {
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -340,8 +395,7 @@ bilinear_rank_kernel(const BilParams bp, const __grid_constant__ CUtensorMap tm_
     const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + MAX_STAGES), tfull0 = smem_u32(bars + 2 * MAX_STAGES),
                    tempty0 = smem_u32(bars + 2 * MAX_STAGES + 2);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * MAX_STAGES + 4);
-    uint32_t *mask_all = reinterpret_cast<uint32_t *>(bars + 48);      // per epilogue warp: [32 rows][MASK_STRIDE] known-true bits
-    uint2 *pend_all = reinterpret_cast<uint2 *>(mask_all + EPI_WARPS * 32 * MASK_STRIDE);   // per epilogue warp: [PEND_CAP] ring of near-ties
+    uint2 *pend_all = reinterpret_cast<uint2 *>(bars + 48);   // per epilogue warp: [PEND_CAP] ring of near-ties
     volatile uint32_t *pend_ctl = reinterpret_cast<volatile uint32_t *>(pend_all + RESCORE_WARPS * PEND_CAP);   // per ring: published, consumed, done
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_kb = (int)((bp.k8 + BK - 1) / BK);
@@ -461,7 +515,7 @@ bilinear_rank_kernel(const BilParams bp, const __grid_constant__ CUtensorMap tm_
         const int quarter = warp & 3;                   // TMEM lanes [32 * quarter, 32 * quarter + 32)
         const int chalf = (warp - EPI_WARP0) >> 2;      // which column slice of the accumulator tile this warp compares
         const int row = quarter * 32 + lane;            // query row of the tile owned by this thread
-        // Near-ties (columns within the guard of s_true) are handed, as (query, entity | known << 31), to this warp's RE-SCORE
+        // Near-ties (columns within the guard of s_true) are handed, as (query, entity), to this warp's RE-SCORE
         // warp through a small shared-memory ring; the exact scalar re-score (two row gathers per entry: pure latency) thus
         // never sits on the epilogue's critical path.  published / consumed are monotonic counters.
         static_assert(EPI_WARPS == RESCORE_WARPS, "one re-score warp per epilogue warp");
@@ -471,22 +525,19 @@ bilinear_rank_kernel(const BilParams bp, const __grid_constant__ CUtensorMap tm_
         volatile uint32_t *ctl = pend_ctl + ring_id * 4;
         uint32_t n_pub = 0;                             // warp-uniform copy of ctl[0]
         auto rescore = [&](uint2 it2) {
-            const int64_t q2 = it2.x, ent_id = it2.y & 0x7fffffffu;
-            const bool kn = (it2.y >> 31) != 0u;
+            const int64_t q2 = it2.x, ent_id = it2.y;
             const float s2 = bil_dot(p.qvec + q2 * p.D, p.ent + ent_id * p.D, p.D);
             const float st = -__ldg(&p.thr[q2].x);
-            if (s2 > st) { atomicAdd(p.counts + q2, 1); if (!kn) atomicAdd(p.counts + 2 * p.Q + q2, 1); }
-            if (s2 == st) { atomicAdd(p.counts + p.Q + q2, 1); if (!kn) atomicAdd(p.counts + 3 * p.Q + q2, 1); }
+            if (s2 > st) { atomicAdd(p.counts + q2, 1); atomicAdd(p.counts + 2 * p.Q + q2, 1); }
+            if (s2 == st) { atomicAdd(p.counts + p.Q + q2, 1); atomicAdd(p.counts + 3 * p.Q + q2, 1); }
         };
-        uint32_t *mask = mask_all + (warp - EPI_WARP0) * 32 * MASK_STRIDE;
-        // Per-tile metadata (tile geometry, this row's true score and guard, the tile's known-true pair range) is
+        // Per-tile metadata (tile geometry, this row's true score and guard) is
         // fetched ONE TILE AHEAD: a lone epilogue warp per SM sub-partition cannot hide dependent global-load latency,
         // and the epilogue of tile t must finish before the MMA warp may start tile t + 2.
         struct TileMeta {
             int64_t qbase, crow0;
             int nq, ne;
             float sim_true, guard;
-            uint32_t pf0, pf1;
         };
         const GroupDesc gd0 = p.groups[0];
         auto load_meta = [&](int64_t item) {
@@ -520,12 +571,6 @@ bilinear_rank_kernel(const BilParams bp, const __grid_constant__ CUtensorMap tm_
                 m.sim_true = -__ldg(&p.thr[m.qbase + row].x);
                 m.guard = __ldg(bp.delta + m.qbase + row);
             }
-            m.pf0 = m.pf1 = 0;
-            if (qt < gd.n_qt) {                    // the known-true pairs were routed per (query tile, candidate tile)
-                const int64_t fitem = PAIR ? gd.item0 + (int64_t)et * gd.n_qt + qt : item;
-                m.pf0 = __ldg(p.tf_ptr + fitem);
-                m.pf1 = __ldg(p.tf_ptr + fitem + 1);
-            }
             return m;
         };
         uint32_t tile = 0;
@@ -538,28 +583,16 @@ bilinear_rank_kernel(const BilParams bp, const __grid_constant__ CUtensorMap tm_
             const int nq = cur.nq, ne = cur.ne;
             const bool q_ok = row < nq;
             const float sim_true = cur.sim_true, guard = cur.guard;
-            // known-true mask of this warp's 32 rows: the pairs tile_filter.cu routed to this item (the truth included)
-            const uint32_t pf0 = cur.pf0, pf1 = cur.pf1;
-            const bool has_mask = pf1 > pf0;
-            if (has_mask) {
-                for (int k = lane; k < 32 * MASK_STRIDE; k += 32) mask[k] = 0u;
-                __syncwarp();
-                for (uint32_t k = pf0 + lane; k < pf1; k += 32) {
-                    const uint32_t pr = __ldg(p.tf_pairs + k);
-                    const int prow = (int)(pr >> 16), pcol = (int)(pr & 0xffffu);
-                    if ((prow >> 5) == quarter) atomicOr(&mask[(prow & 31) * MASK_STRIDE + (pcol >> 5)], 1u << (pcol & 31));
-                }
-                __syncwarp();
-            }
             const uint32_t buf = tile & 1;
             mbar_wait(tfull0 + 8 * buf, (tile >> 1) & 1);
             tc_fence_after();
-            int r_lt = 0, f_lt = 0, r_eq = 0, f_eq = 0;      // raw / filtered counts of this thread's query row
+            int r_lt = 0;      // columns of this thread's query row that beat the true entity (raw and filtered counters alike:
+                               // bil_known_kernel takes the known-true entities back out of the filtered ones)
             const uint32_t taddr = tmem_base + buf * BN + ((uint32_t)(quarter * 32) << 16);
             // better <=> larger similarity (predict = -sim).  s > thr_hi: counted; s < thr_lo: not; in between: near-tie
             const float thr_hi = sim_true + guard, thr_lo = sim_true - guard;
             // One chunk = 32 accumulator columns of this thread's row.  The two comparisons are collected as BIT MASKS, so
-            // the counts, the known-true subtraction and the near-tie set are a handful of popc / and instructions and the
+            // the counts and the near-tie set are a handful of popc / and instructions and the
             // cold paths below are rolled loops: the kernel stays a few thousand instructions (it was 22 K when every cold
             // path was unrolled 32x, which thrashed the instruction cache under the MMA-issuing warp).
             auto process = [&](const uint32_t (&v)[32], int c0) {
@@ -589,9 +622,7 @@ bilinear_rank_kernel(const BilParams bp, const __grid_constant__ CUtensorMap tm_
                 const uint32_t valid = left >= 32 ? 0xffffffffu : ((1u << left) - 1u);   // padding of the last candidate tile
                 const uint32_t gtm = (g4[0] | (g4[1] << 8) | (g4[2] << 16) | (g4[3] << 24)) & valid;
                 const uint32_t gem = ~(l4[0] | (l4[1] << 8) | (l4[2] << 16) | (l4[3] << 24)) & valid;
-                const uint32_t mw = has_mask ? mask[lane * MASK_STRIDE + (c0 >> 5)] : 0u;   // known-true columns of this chunk
                 r_lt += __popc(gtm);
-                f_lt += __popc(gtm & ~mw);
                 uint32_t near = gem & ~gtm;                     // rare: park the near-ties for the exact re-score
                 if (__any_sync(0xffffffffu, near != 0u)) {
                     // slots by a warp prefix sum of the per-lane counts: no atomics
@@ -609,10 +640,9 @@ bilinear_rank_kernel(const BilParams bp, const __grid_constant__ CUtensorMap tm_
                         while (near) {
                             const int c = __ffs(near) - 1;
                             near &= near - 1;
-                            const uint32_t kn = (mw >> c) & 1u;
                             const int64_t crow = cur.crow0 + c0 + c;
                             const int64_t ent_id = p.all_entities ? crow : __ldg(p.cand_idx + crow);
-                            pend[(slot++) & (PEND_CAP - 1)] = make_uint2((uint32_t)(qbase + row), (uint32_t)ent_id | (kn << 31));
+                            pend[(slot++) & (PEND_CAP - 1)] = make_uint2((uint32_t)(qbase + row), (uint32_t)ent_id);
                         }
                         n_pub += total;
                         __syncwarp();
@@ -622,10 +652,9 @@ bilinear_rank_kernel(const BilParams bp, const __grid_constant__ CUtensorMap tm_
                         while (near) {
                             const int c = __ffs(near) - 1;
                             near &= near - 1;
-                            const uint32_t kn = (mw >> c) & 1u;
                             const int64_t crow = cur.crow0 + c0 + c;
                             const int64_t ent_id = p.all_entities ? crow : __ldg(p.cand_idx + crow);
-                            rescore(make_uint2((uint32_t)(qbase + row), (uint32_t)ent_id | (kn << 31)));
+                            rescore(make_uint2((uint32_t)(qbase + row), (uint32_t)ent_id));
                         }
                     }
                     __syncwarp();
@@ -667,10 +696,7 @@ bilinear_rank_kernel(const BilParams bp, const __grid_constant__ CUtensorMap tm_
             }
             if (q_ok) {
                 const int64_t q = qbase + row;
-                if (r_lt) atomicAdd(p.counts + q, r_lt);
-                if (r_eq) atomicAdd(p.counts + p.Q + q, r_eq);
-                if (f_lt) atomicAdd(p.counts + 2 * p.Q + q, f_lt);
-                if (f_eq) atomicAdd(p.counts + 3 * p.Q + q, f_eq);
+                if (r_lt) { atomicAdd(p.counts + q, r_lt); atomicAdd(p.counts + 2 * p.Q + q, r_lt); }
             }
         }
         __syncwarp();
@@ -700,24 +726,23 @@ bilinear_rank_kernel(const BilParams bp, const __grid_constant__ CUtensorMap tm_
             if (NPROD == 3) {
                 for (uint32_t k = lane; k < n_new; k += 32) {
                     const uint2 it2 = pend[(cons + k) & (PEND_CAP - 1)];
-                    const int64_t q2 = it2.x, ent_id = it2.y & 0x7fffffffu;
-                    const bool kn = (it2.y >> 31) != 0u;
+                    const int64_t q2 = it2.x, ent_id = it2.y;
                     const float s2 = bil_dot(p.qvec + q2 * p.D, p.ent + ent_id * p.D, p.D);
                     const float st = -__ldg(&p.thr[q2].x);
-                    if (s2 > st) { atomicAdd(p.counts + q2, 1); if (!kn) atomicAdd(p.counts + 2 * p.Q + q2, 1); }
-                    if (s2 == st) { atomicAdd(p.counts + p.Q + q2, 1); if (!kn) atomicAdd(p.counts + 3 * p.Q + q2, 1); }
+                    if (s2 > st) { atomicAdd(p.counts + q2, 1); atomicAdd(p.counts + 2 * p.Q + q2, 1); }
+                    if (s2 == st) { atomicAdd(p.counts + p.Q + q2, 1); atomicAdd(p.counts + 3 * p.Q + q2, 1); }
                 }
             } else
             for (uint32_t k0 = 0; k0 < n_new; k0 += 128) {
                 int64_t q2[4], ent_id[4];
-                bool kn[4], live[4];
+                bool live[4];
                 const float4 *v4[4], *e4[4];
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
                     const uint32_t k = k0 + 32 * u + lane;
                     live[u] = k < n_new;
                     const uint2 it2 = live[u] ? pend[(cons + k) & (PEND_CAP - 1)] : make_uint2(0u, 0u);
-                    q2[u] = it2.x; ent_id[u] = it2.y & 0x7fffffffu; kn[u] = (it2.y >> 31) != 0u;
+                    q2[u] = it2.x; ent_id[u] = it2.y;
                     v4[u] = reinterpret_cast<const float4 *>(p.qvec + q2[u] * p.D);
                     e4[u] = reinterpret_cast<const float4 *>(p.ent + ent_id[u] * p.D);
                 }
@@ -740,8 +765,8 @@ bilinear_rank_kernel(const BilParams bp, const __grid_constant__ CUtensorMap tm_
                 for (int u = 0; u < 4; u++) {
                     if (!live[u]) continue;
                     const float st = -__ldg(&p.thr[q2[u]].x);
-                    if (acc[u] > st) { atomicAdd(p.counts + q2[u], 1); if (!kn[u]) atomicAdd(p.counts + 2 * p.Q + q2[u], 1); }
-                    if (acc[u] == st) { atomicAdd(p.counts + p.Q + q2[u], 1); if (!kn[u]) atomicAdd(p.counts + 3 * p.Q + q2[u], 1); }
+                    if (acc[u] > st) { atomicAdd(p.counts + q2[u], 1); atomicAdd(p.counts + 2 * p.Q + q2[u], 1); }
+                    if (acc[u] == st) { atomicAdd(p.counts + p.Q + q2[u], 1); atomicAdd(p.counts + 3 * p.Q + q2[u], 1); }
                 }
             }
             __syncwarp();
@@ -919,13 +944,8 @@ static int run_bilinear(mre_ctx *ctx, const mre_index *ix, const mre_rank_job *j
     RankParams &p = bp.r;
     const int nprod = ctx->opt_bil_products == 1 ? 1 : 3;
     MRE_TRY(fill_rank_params(ctx, ix, job, BM, BN, st, p));
-    // the known-true tile filter needs only the job's descriptors: it runs on the context's second stream beside the table
-    // and query pre-pass kernels, joined before the rank kernel
-    if (job->Q > 0) {
-        cudaStream_t aux = nullptr;
-        MRE_TRY(ctx->fork_aux(st, &aux));
-        MRE_TRY(build_tile_filter(ctx, job, p, BM, BN, aux));
-    }
+    const bool shared_runs = !store && job->Q > 0 && p.filter == MRE_FILTER_INDEX;
+    const unsigned qgrid = (unsigned)((std::max<int64_t>(p.Q, 1) + KNOWN_WARPS - 1) / KNOWN_WARPS);
     MRE_TRY(bil_prepass(ctx, job, nprod, job->counts, st, sc));
     p.ent = sc.ent_full;
     p.D = sc.Kp;
@@ -934,6 +954,20 @@ static int run_bilinear(mre_ctx *ctx, const mre_index *ix, const mre_rank_job *j
     if (job->Q == 0) return MRE_OK;
     p.thr = sc.thr;
     bp.delta = sc.delta;
+    if (!store) {   // known-true correction of the filtered counters (needs the query vectors, thresholds and zeroed counters)
+        if (shared_runs) {                       // every run the job touches scored once, then every query's thresholds against them
+            KnownRuns kr{};
+            MRE_TRY(known_runs_scratch(ctx, p, kr));
+            bil_known_score_kernel<<<qgrid, KNOWN_WARPS * 32, 0, st>>>(p, kr);
+            bil_known_compare_kernel<<<qgrid, KNOWN_WARPS * 32, 0, st>>>(p, kr);
+            ctx->launches += 1;
+        } else if (known_is_flat(p))
+            bil_known_flat_kernel<<<(unsigned)((p.filt_nnz + p.Q + KNOWN_WARPS * 32 - 1) / (KNOWN_WARPS * 32)), KNOWN_WARPS * 32, 0, st>>>(p);
+        else
+            bil_known_kernel<<<(unsigned)((p.Q + KNOWN_WARPS - 1) / KNOWN_WARPS), KNOWN_WARPS * 32, 0, st>>>(p);
+        ctx->launches += 1;
+        MRE_CUDA(cudaGetLastError());
+    }
     // candidate tables the B tiles stream from
     const uint16_t *b_hi = sc.ent_hi, *b_lo = sc.ent_lo;
     int64_t cand_rows = job->E;
@@ -970,7 +1004,6 @@ static int run_bilinear(mre_ctx *ctx, const mre_index *ix, const mre_rank_job *j
     bp.store = store;
     bp.store_ld = cand_rows;
     bp.rescored = ctx->stats.as<unsigned long long>();
-    MRE_TRY(ctx->join_aux(st));
     MRE_TRY(ctx->time_begin(st));
     int rc;
     if (nprod == 3) {

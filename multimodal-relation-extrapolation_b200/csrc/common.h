@@ -103,6 +103,10 @@ struct mre_ctx {
     mre::DevBuf qvec, qvec2;         // per-query vectors (hi/lo for bilinear)
     mre::DevBuf thr;                 // per-query thresholds (2 floats) + true scores
     mre::DevBuf tiles;               // tile descriptors
+    mre::DevBuf sched;               // cost-balanced work-item order of the TransE kernel (candidate groups)
+    mre::DevBuf known_score, known_stamp, known_range;   // shared-run known-true pass (MRE_FILTER_INDEX): see rank_common.cuh KnownRuns
+    unsigned int known_epoch = 0;
+    size_t known_n = 0;
     mre::DevBuf counters;            // raw/corr counters, work counters
     mre::DevBuf misc;                // loss partials etc.
     mre::DevBuf misc2;               // known-true pair list of the tile filter
@@ -116,10 +120,8 @@ struct mre_ctx {
     int allow_smem(const void *func, size_t bytes);
     // tunables (mre_ctx_option): BF16/FP16 MMAs per product of the bilinear path, CTA pairs on/off, persistent CTAs per SM of the
     // TransE kernel, FP32 fallback of the ZSL scorer -- developer A/B switches, read from the context, never from the environment
-    int opt_bil_products = 3, opt_bil_pair = 1, opt_transe_ctas = 0, opt_zsl_fp32 = 0, opt_tf_fused = 0;
-    int tf_fused_blocks_per_sm = 0;  // occupancy of the cooperative tile-filter kernel on this device (queried once)
+    int opt_bil_products = 3, opt_bil_pair = 1, opt_transe_ctas = 0, opt_zsl_fp32 = 0, opt_transe_lpt = 1;
     unsigned int bil_epoch = 0;      // generation tag of the bilinear path's max-row-norm slot (no reset launch per call)
-    int64_t counters_armed = 0;      // leading uint32 counters of `counters` known to be zero (tf_fill runs them back down)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // optional per-launch timing of the dominant (rank) kernel: event pairs recorded on the launching stream
     bool timing = false;

@@ -25,12 +25,13 @@
 // half the issue slots of the scalar form, which leaves the FP32 pipe -- not instruction issue -- as the bound, with the
 // LDS / barrier / address instructions issuing in the shadow of the two-cycle packed instructions.  Per (q, e) pair the
 // accumulation is still sequential over d with the same roundings, so counts stay bit-identical to the oracle.  The
-// epilogue compares the 64 accumulators against the per-query thresholds, masks the known-true slots routed to this
-// tile by tile_filter.cu (raw and filtered counts come from the SAME registers), reduces the counts with warp
-// shuffles and adds them to the per-query counters.  The kernel is bound by the FP32 pipe: 2 lane-ops per (q, e, d).
+// epilogue compares the 64 accumulators against the per-query thresholds, reduces the counts with warp shuffles and adds them
+// to the raw AND the filtered counters of the query; the known-true entities of each query (a handful) are scored by
+// transe_known_kernel with the same accumulation order and taken back out of the filtered counters.  The kernel is bound by the FP32 pipe: 2 lane-ops per (q, e, d).
 #include <math.h>
 #include <stdlib.h>
 
+#include <algorithm>
 #include <type_traits>
 #include <vector>
 
@@ -61,10 +62,9 @@ constexpr int CONSUMER_WARPS = MRE_RANK_WARPS;
 constexpr int RANK_THREADS = CONSUMER_WARPS * 32;
 constexpr int NTQ = RANK_THREADS / 16;              // threads along the query dimension of the tile
 constexpr int NI = (TQ / 2) / NTQ;              // query PAIR-rows per thread (4 with 8 warps: an 8-query x 8-entity register tile)
-constexpr int KW = (NI * 16 + 63) / 64;             // 64-bit words of one thread's known-true mask
 constexpr uint32_t QBOX_BYTES = (TQ / 2) * 128;             // 64 query pair-rows x 128 B (16 d-values of two queries)
 constexpr uint32_t STAGE_BYTES = (TQ + TILE_E) * CHUNK * 4;  // two 8 KiB query-pair boxes + one 16 KiB candidate box
-constexpr size_t RANK_SMEM = 1024 + (size_t)STAGES * STAGE_BYTES + STAGES * sizeof(uint64_t) + 4 * sizeof(int) + CONSUMER_WARPS * 32 * KW * sizeof(unsigned long long) + (size_t)TQ * sizeof(float2) + 64;
+constexpr size_t RANK_SMEM = 1024 + (size_t)STAGES * STAGE_BYTES + STAGES * sizeof(uint64_t) + 4 * sizeof(int) + (size_t)TQ * sizeof(float2) + 64;
 
 // ------------------------------------------------------------------------------------------ scalar scorer
 // The one definition of a TransE accumulator: sequential over d, acc = acc + |v - e| (p = 1) or fma(u, u, acc) (p = 2), with
@@ -247,6 +247,67 @@ __global__ void transe_predict_kernel(const float *__restrict__ ent, const float
 }
 
 // ------------------------------------------------------------------------------------------ main kernel
+// The filtered counts' correction (rank_common.cuh: known_correction) with the TransE element: v_d = h_d + r_d (tail query) or
+// -(r_d - t_d) (head query), term u = v_d - e_d (one rounding), fold acc + |u| (p = 1) or fma(u, u, acc) (p = 2) -- transe_acc's
+// steps exactly -- and the tile kernel's threshold compare.
+template <int P>
+struct TranseKnownOp {
+    const float *ent, *rel, *a, *r;
+    const float2 *thr;
+    int64_t D;
+    int side;
+    float2 th;
+    __device__ __forceinline__ void query(int64_t q, int s, int64_t h, int64_t t, int64_t rr) {
+        side = s;
+        a = ent + (s ? h : t) * D;
+        r = rel + rr * D;
+    }
+    __device__ __forceinline__ float vec(int d) const { return side ? __ldg(a + d) + __ldg(r + d) : -(__ldg(r + d) - __ldg(a + d)); }
+    // flattened form: the query vector as transe_query_kernel wrote it (the same v), pair-interleaved by slot
+    static constexpr int VSTRIDE = 2;
+    const float *qvec;
+    __device__ __forceinline__ const float *flat_query(int64_t q, int64_t slot, int, int64_t, int64_t, int64_t) {
+        th = thr[q];
+        return qvec + (slot >> 1) * (2 * D) + (slot & 1);
+    }
+    __device__ __forceinline__ float direct(int64_t x) const { return transe_acc<P>(a, r, side, ent + x * D, D); }
+    __device__ __forceinline__ void thresholds(int64_t q) { th = thr[q]; }
+    __device__ __forceinline__ bool truth_ties() const { return th.x < th.y; }       // what the tile kernel decides for acc_true
+    __device__ __forceinline__ float term(float v, float e) const { return v - e; }
+    __device__ __forceinline__ float fold(float acc, float u) const { return P == 1 ? acc + fabsf(u) : fmaf(u, u, acc); }
+    __device__ __forceinline__ void classify(float acc, int &lt, int &eq) const {
+        if (acc < th.x) lt++;
+        else if (acc < th.y) eq++;
+    }
+};
+template <int P>
+__global__ void __launch_bounds__(KNOWN_WARPS * 32) transe_known_kernel(const RankParams p, const float *__restrict__ rel) {
+    __shared__ float sT[KNOWN_WARPS][32][33];
+    __shared__ int64_t sX[KNOWN_WARPS][32];
+    TranseKnownOp<P> op{p.ent, rel, nullptr, nullptr, p.thr, p.D, 0, make_float2(0.f, 0.f), p.qvec};
+    known_correction(p, op, sT[threadIdx.x >> 5], sX[threadIdx.x >> 5]);
+}
+template <int P>
+__global__ void __launch_bounds__(KNOWN_WARPS * 32) transe_known_score_kernel(const RankParams p, const float *__restrict__ rel, const KnownRuns kr) {
+    __shared__ float sT[KNOWN_WARPS][32][33];
+    __shared__ int64_t sX[KNOWN_WARPS][32];
+    TranseKnownOp<P> op{p.ent, rel, nullptr, nullptr, p.thr, p.D, 0, make_float2(0.f, 0.f), p.qvec};
+    known_score_runs(p, kr, op, sT[threadIdx.x >> 5], sX[threadIdx.x >> 5]);
+}
+template <int P>
+__global__ void __launch_bounds__(KNOWN_WARPS * 32) transe_known_compare_kernel(const RankParams p, const KnownRuns kr) {
+    TranseKnownOp<P> op{p.ent, nullptr, nullptr, nullptr, p.thr, p.D, 0, make_float2(0.f, 0.f), p.qvec};
+    known_compare_runs(p, kr, op);
+}
+template <int P>
+__global__ void __launch_bounds__(KNOWN_WARPS * 32) transe_known_flat_kernel(const RankParams p) {
+    __shared__ float sT[KNOWN_WARPS][32][33];
+    __shared__ int64_t sX[KNOWN_WARPS][32];
+    __shared__ const float *sV[KNOWN_WARPS][32];
+    TranseKnownOp<P> op{p.ent, nullptr, nullptr, nullptr, p.thr, p.D, 0, make_float2(0.f, 0.f), p.qvec};
+    known_correction_flat(p, op, sT[threadIdx.x >> 5], sX[threadIdx.x >> 5], sV[threadIdx.x >> 5]);
+}
+
 // acc (two queries' accumulators against one entity) <- one more element d: u = q - e ; acc + |u|  (p = 1) | fma(u, u, acc)
 // ptxas turns the {e, e} pair into a scalar-broadcast operand and folds the |.| into the add: FADD2 R, R.F32x2, -R.F32 ;
 // FADD2 R, R.F32x2, |R|.F32x2  (FFMA2 for p = 2): two instructions for four lane-ops.
@@ -295,8 +356,8 @@ constexpr int K4_UNROLL = MRE_K4_UNROLL;
 // written into shared memory with the hardware 128-byte swizzle.  Issued by ONE thread.
 __device__ __forceinline__ void issue_chunk(const RankParams &p, const CUtensorMap *tm_q, const CUtensorMap *tm_e, int64_t flat,
                                             int n_chunks, uint32_t ring_u32, uint32_t full0) {
-    const int64_t item = blockIdx.x + (flat / n_chunks) * (int64_t)gridDim.x;
-    if (item >= p.total_items) return;
+    const int64_t item = cta_item(p, flat / n_chunks);
+    if (item < 0) return;
     const int c = (int)(flat % n_chunks);
     int g, qt, et;
     decode_item(p, item, g, qt, et);
@@ -321,9 +382,7 @@ transe_rank_kernel(const RankParams p, const __grid_constant__ CUtensorMap tm_q,
     unsigned char *ring = smem_raw + (ring_u32 - smem_u32(smem_raw));
     uint64_t *bars = reinterpret_cast<uint64_t *>(ring + (size_t)STAGES * STAGE_BYTES);
     int *done = reinterpret_cast<int *>(bars + STAGES);  // per-stage count of warps that finished reading the stage
-    // per-warp known-true masks: bit (row slot * 8 + j) of lane l's word marks one accumulator of that thread
-    unsigned long long *wmask = reinterpret_cast<unsigned long long *>(done + 4) + (threadIdx.x >> 5) * 32 * KW;   // [lane][KW]
-    float2 *thr_s = reinterpret_cast<float2 *>(reinterpret_cast<unsigned long long *>(done + 4) + CONSUMER_WARPS * 32 * KW);   // [warps][4 NI rows]
+    float2 *thr_s = reinterpret_cast<float2 *>(done + 4);   // [warps][4 NI rows]
     const uint32_t full0 = smem_u32(bars);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_chunks = (int)((p.D + CHUNK - 1) / CHUNK);
@@ -347,7 +406,9 @@ transe_rank_kernel(const RankParams p, const __grid_constant__ CUtensorMap tm_q,
     const int te = threadIdx.x & 15, tq = threadIdx.x >> 4;
     const int xe = te & 7, xq = tq & 7;
     int64_t it = 0;
-    for (int64_t item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+    for (int64_t k_item = 0;; k_item++) {
+        const int64_t item = cta_item(p, k_item);
+        if (item < 0) break;
         int g, qt, et;
         decode_item(p, item, g, qt, et);
         const GroupDesc gd = p.groups[g];
@@ -355,9 +416,6 @@ transe_rank_kernel(const RankParams p, const __grid_constant__ CUtensorMap tm_q,
         const int nq = (int)min((int64_t)TQ, gd.q0 + gd.nq - qbase);
         const int ne = (int)min((int64_t)TILE_E, gd.nc - (int64_t)et * TILE_E);
         const int ni_act = (nq + 2 * NTQ - 1) / (2 * NTQ);    // slabs of NTQ pair-rows (2 NTQ queries) holding at least one query
-        // this item's known-true pairs; the first 32 are fetched now so the epilogue does not wait on them
-        const uint32_t pf0 = __ldg(p.tf_ptr + item), pf1 = __ldg(p.tf_ptr + item + 1);
-        const uint32_t pair0 = pf0 + lane < pf1 ? __ldg(p.tf_pairs + pf0 + lane) : 0xffffffffu;
         // thresholds of this warp's 16 query rows -> shared memory (asynchronous copy: nobody waits for it before the epilogue);
         // slot k of the warp = row 2 ((2 warp + k / 2NI) + NTQ ((k % 2NI) / 2)) + k % 2; rows past the group's end get -inf (never counted)
         if (lane < 4 * NI) {
@@ -454,40 +512,16 @@ transe_rank_kernel(const RankParams p, const __grid_constant__ CUtensorMap tm_q,
             continue;
         }
 #endif
-        // ---- known-true mask of this warp's 32 threads: every pair routed to this item by tile_filter.cu
         cp_async_wait_all();
-        unsigned long long known[KW];
-#pragma unroll
-        for (int k = 0; k < KW; k++) known[k] = 0ull;
-        if (pf1 > pf0) {
-#pragma unroll
-            for (int k = 0; k < KW; k++) wmask[lane * KW + k] = 0ull;
-            __syncwarp();
-            for (uint32_t k = pf0 + lane; k < pf1; k += 32) {
-                const uint32_t pr = k < pf0 + 32 ? pair0 : __ldg(p.tf_pairs + k);
-                const int row = (int)(pr >> 16), col = (int)(pr & 0xffffu);
-                const int prw = row >> 1;                    // pair-row; owner thread: tq = prw % NTQ, te = col % 16
-                const int otq = prw % NTQ;
-                if ((otq >> 1) == warp) {
-                    const int bit = ((((prw / NTQ) << 1) | (row & 1)) << 3) | (col >> 4);   // (2 i + half) * 8 + j
-                    atomicOr(&wmask[(((otq & 1) << 4) | (col & 15)) * KW + (bit >> 6)], 1ull << (bit & 63));
-                }
-            }
-            __syncwarp();
-#pragma unroll
-            for (int k = 0; k < KW; k++) known[k] = wmask[lane * KW + k];
-        }
         // ---- epilogue: compare against the per-query thresholds, count, reduce over the 16 lanes sharing a query row.
         // lt <=> s < th.x ; eq <=> th.x <= s < th.y, so eq = #(s < th.y) - #(s < th.x): two independent compare-and-count
         // chains per accumulator.  The thresholds of the warp's 16 rows were staged in shared memory at item start.
-        unsigned long long known_or = 0ull;
-#pragma unroll
-        for (int k = 0; k < KW; k++) known_or |= known[k];
-        const bool any_known = __any_sync(0xffffffffu, known_or != 0ull);   // warp-uniform: most warps of most tiles hold none
+        // Known-true entities are NOT looked at here: transe_known_kernel scores each of them with the same arithmetic and takes
+        // them out of the filtered counters, so raw and filtered counts receive the same additions from this kernel.
         __syncwarp();
         const float2 *th_w = thr_s + warp * (4 * NI) + (tq & 1) * (2 * NI);
-        if (!any_known && ne == TILE_E) {
-            // fast path (nearly every tile): no known-true slot in this warp, no candidate padding.  Two rows share one
+        if (ne == TILE_E) {
+            // fast path (every tile but a group's last): no candidate padding.  Two rows share one
             // word (four 8-bit counters, each at most 128 after the reduction), so 4 shuffles serve 2 rows.
 #pragma unroll
             for (int i = 0; i < NI; i++) {
@@ -513,7 +547,7 @@ transe_rank_kernel(const RankParams p, const __grid_constant__ CUtensorMap tm_q,
                 }
             }
         } else {
-            // general path: candidate padding of a group's last tile and / or known-true slots to take out of the filtered counts
+            // candidate padding of a group's last tile: columns past the group's end never count
 #pragma unroll
             for (int i2 = 0; i2 < 2 * NI; i2++) {             // i2 = 2 i + half (unrolled: register arrays need static indices)
                 const int ql = 2 * (tq + NTQ * (i2 >> 1)) + (i2 & 1);
@@ -526,18 +560,15 @@ transe_rank_kernel(const RankParams p, const __grid_constant__ CUtensorMap tm_q,
                     const bool ok = (te + 16 * j) < ne;
                     const bool lt = ok && sc < th.x;
                     const bool eq = NEED_EQ && ok && !lt && sc < th.y;
-                    const bool kn = (known[(i2 * 8) >> 6] >> ((i2 * 8 + j) & 63)) & 1ull;
-                    packed += (lt ? 1u : 0u) + (eq ? 0x100u : 0u) + ((lt && kn) ? 0x10000u : 0u) + ((eq && kn) ? 0x1000000u : 0u);
+                    packed += (lt ? 1u : 0u) + (eq ? 0x100u : 0u);
                 }
 #pragma unroll
                 for (int m = 1; m < 16; m <<= 1) packed += __shfl_xor_sync(0xffffffffu, packed, m);
                 if (te == 0 && packed) {
                     const int64_t q = qbase + ql;
-                    const int n_lt = packed & 0xff, n_eq = (packed >> 8) & 0xff, k_lt = (packed >> 16) & 0xff, k_eq = packed >> 24;
-                    if (n_lt) atomicAdd(p.counts + q, n_lt);
-                    if (n_eq) atomicAdd(p.counts + p.Q + q, n_eq);
-                    if (n_lt - k_lt) atomicAdd(p.counts + 2 * p.Q + q, n_lt - k_lt);
-                    if (n_eq - k_eq) atomicAdd(p.counts + 3 * p.Q + q, n_eq - k_eq);
+                    const int n_lt = packed & 0xff, n_eq = (packed >> 8) & 0xff;
+                    if (n_lt) { atomicAdd(p.counts + q, n_lt); atomicAdd(p.counts + 2 * p.Q + q, n_lt); }
+                    if (NEED_EQ && n_eq) { atomicAdd(p.counts + p.Q + q, n_eq); atomicAdd(p.counts + 3 * p.Q + q, n_eq); }
                 }
             }
         }
@@ -590,7 +621,7 @@ static int build_groups(mre_ctx *ctx, const mre_rank_job *job, int tile_q, int t
 }
 
 int fill_rank_params(mre_ctx *ctx, const mre_index *ix, const mre_rank_job *job, int tile_q, int tile_e, cudaStream_t st,
-                     RankParams &p) {
+                     RankParams &p, std::vector<GroupDesc> *groups_out) {
     std::vector<GroupDesc> groups;
     int64_t items = 0, slots = 0, pitems = 0;
     MRE_TRY(build_groups(ctx, job, tile_q, tile_e, groups, &items, &slots, &pitems));
@@ -621,7 +652,78 @@ int fill_rank_params(mre_ctx *ctx, const mre_index *ix, const mre_rank_job *job,
         MRE_CHECK_ARG(job->filt_ptr && job->filt_idx, "MRE_FILTER_CSR needs filt_ptr and filt_idx");
     }
     p.filt_ptr = job->filt_ptr; p.filt_idx = job->filt_idx;
+    p.filt_nnz = job->filter == MRE_FILTER_CSR ? std::max<int64_t>(job->filt_nnz, 0) : 0;
+    if (job->filter == MRE_FILTER_NONE) p.filt_ptr = p.filt_idx = nullptr;
     p.counts = job->counts;
+    if (groups_out) groups_out->swap(groups);
+    return MRE_OK;
+}
+
+// scratch of the shared-run known-true pass (MRE_FILTER_INDEX): score + stamp columns parallel to the index's payload columns,
+// the per-query run ranges, and the job's epoch (stamps of earlier jobs are simply stale: no clearing between jobs)
+int known_runs_scratch(mre_ctx *ctx, const RankParams &p, KnownRuns &kr) {
+    const size_t n = (size_t)std::max<int64_t>(p.n_all, 1);
+    const size_t need = 2 * n * sizeof(unsigned int);
+    if (ctx->known_stamp.cap < need || ctx->known_n != n || ctx->known_epoch >= 0xfffffffeu) {
+        // first use, another index on this context (the second column moves), or the epochs ran out: start from clean stamps
+        MRE_TRY(ctx->known_stamp.reserve(need));
+        MRE_CUDA(cudaMemset(ctx->known_stamp.p, 0, ctx->known_stamp.cap));
+        ctx->known_epoch = 0;
+        ctx->known_n = n;
+    }
+    ctx->known_epoch += 1;
+    MRE_TRY(ctx->known_score.reserve(2 * n * sizeof(float)));
+    MRE_TRY(ctx->known_range.reserve((size_t)std::max<int64_t>(p.Q, 1) * 2 * sizeof(int64_t)));
+    kr.score0 = ctx->known_score.as<float>(); kr.score1 = kr.score0 + n;
+    kr.stamp0 = ctx->known_stamp.as<unsigned int>(); kr.stamp1 = kr.stamp0 + n;
+    kr.range = ctx->known_range.as<int64_t>();
+    kr.epoch = ctx->known_epoch;
+    return MRE_OK;
+}
+
+// Candidate groups give work items of UNEQUAL cost: the last query tile of a group holds 1 .. TQ queries and the kernel skips its
+// empty 64-query slabs, and a job is only a few waves of items (FB15K-237-ZS: 680 items over 148 CTAs), so the round-robin order
+// leaves whole CTAs idle through the last wave.  Longest-processing-time-first: items sorted by cost (stable), each dealt to the
+// least-loaded CTA; a CTA walks its list in that order (expensive items first, the cheap partial tiles fill the tail).
+static int build_item_schedule(mre_ctx *ctx, const std::vector<GroupDesc> &groups, int64_t total_items, int grid, cudaStream_t st,
+                               RankParams &p) {
+    struct Item { int32_t id; float cost; };
+    std::vector<Item> items;
+    items.reserve((size_t)total_items);
+    for (const GroupDesc &g : groups) {
+        for (int et = 0; et < g.n_et; et++)
+            for (int qt = 0; qt < g.n_qt; qt++) {
+                const int64_t nq = std::min<int64_t>(TQ, g.nq - (int64_t)qt * TQ);
+                const int slabs = (int)((nq + 2 * NTQ - 1) / (2 * NTQ));
+                // full tile: NI slabs at full speed; partial tile: the guarded loop, ~1.2x per slab; + the epilogue / ring turn-around
+                const float cost = (slabs == NI ? (float)NI : 1.2f * (float)slabs) + 0.3f;
+                items.push_back({(int32_t)(g.item0 + (int64_t)et * g.n_qt + qt), cost});
+            }
+    }
+    std::stable_sort(items.begin(), items.end(), [](const Item &a, const Item &b) { return a.cost > b.cost; });
+    std::vector<std::vector<int32_t>> lists((size_t)grid);
+    std::vector<std::pair<float, int>> heap;      // (load, cta) min-heap
+    heap.reserve((size_t)grid);
+    for (int c = 0; c < grid; c++) heap.push_back({0.f, c});
+    auto cmp = [](const std::pair<float, int> &a, const std::pair<float, int> &b) { return a.first > b.first || (a.first == b.first && a.second > b.second); };
+    std::make_heap(heap.begin(), heap.end(), cmp);
+    for (const Item &it : items) {
+        std::pop_heap(heap.begin(), heap.end(), cmp);
+        auto &top = heap.back();
+        lists[(size_t)top.second].push_back(it.id);
+        top.first += it.cost;
+        std::push_heap(heap.begin(), heap.end(), cmp);
+    }
+    size_t rounds = 0;
+    for (auto &l : lists) rounds = std::max(rounds, l.size());
+    std::vector<int32_t> sched(rounds * (size_t)grid, -1);
+    for (int c = 0; c < grid; c++)
+        for (size_t k = 0; k < lists[(size_t)c].size(); k++) sched[k * (size_t)grid + (size_t)c] = lists[(size_t)c][k];
+    MRE_TRY(ctx->sched.reserve(std::max<size_t>(sched.size(), 1) * sizeof(int32_t)));
+    // pageable source: staged by the runtime before cudaMemcpyAsync returns
+    MRE_CUDA(cudaMemcpyAsync(ctx->sched.p, sched.data(), sched.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    p.sched = ctx->sched.as<int32_t>();
+    p.sched_rounds = (int32_t)rounds;
     return MRE_OK;
 }
 
@@ -660,12 +762,16 @@ static int transe_queries(mre_ctx *ctx, const RankParams &p, const float *rel, c
     return MRE_OK;
 }
 
+static int transe_grid(const mre_ctx *ctx, int64_t total_items) {
+    const int per_sm = ctx->opt_transe_ctas > 0 ? ctx->opt_transe_ctas : CTAS_PER_SM;
+    return (int)std::max<int64_t>(1, std::min<int64_t>(total_items, (int64_t)ctx->sm_count * per_sm));
+}
+
 template <int P, bool NEED_EQ>
 static int launch_rank(mre_ctx *ctx, const RankParams &p, const CUtensorMap &tm_q, const CUtensorMap &tm_e, cudaStream_t st) {
     auto kern = transe_rank_kernel<P, NEED_EQ>;
     MRE_TRY(ctx->allow_smem(reinterpret_cast<const void *>(kern), RANK_SMEM));     // per device: function attributes are
-    const int per_sm = ctx->opt_transe_ctas > 0 ? ctx->opt_transe_ctas : CTAS_PER_SM;
-    int grid = (int)std::max<int64_t>(1, std::min<int64_t>(p.total_items, (int64_t)ctx->sm_count * per_sm));
+    const int grid = transe_grid(ctx, p.total_items);
     kern<<<grid, RANK_THREADS, RANK_SMEM, st>>>(p, tm_q, tm_e);
     ctx->launches += 1;
     MRE_CUDA(cudaGetLastError());
@@ -678,17 +784,29 @@ int rank_transe(mre_ctx *ctx, const mre_index *ix, const mre_rank_job *job, cuda
     int64_t Dp = 0;
     MRE_TRY(transe_tables(ctx, job, st, &ent, &rel, &Dp));
     RankParams p{};
-    MRE_TRY(fill_rank_params(ctx, ix, job, TQ, TILE_E, st, p));
+    std::vector<GroupDesc> groups;
+    MRE_TRY(fill_rank_params(ctx, ix, job, TQ, TILE_E, st, p, &groups));
     p.ent = ent;
     p.D = Dp;
     if (job->Q == 0) return MRE_OK;
-    // the known-true tile filter (count / scan / fill) needs only the job's descriptors: it runs on the context's second
-    // stream beside the query-vector and threshold kernels, joined before the rank kernel
-    cudaStream_t aux = nullptr;
-    MRE_TRY(ctx->fork_aux(st, &aux));
-    MRE_TRY(build_tile_filter(ctx, job, p, TQ, TILE_E, aux));
-    // the table the candidate tiles stream from: the entity table itself, or the gathered candidate rows (gathered on the second
-    // stream too: it depends on the tables and the candidate lists only)
+    const int rank_grid = transe_grid(ctx, p.total_items);
+    // (jobs of many waves lose nothing to the last one and would need a long list: round-robin there)
+    if (ctx->opt_transe_lpt && p.total_items > rank_grid && p.total_items <= 64LL * rank_grid)
+        MRE_TRY(build_item_schedule(ctx, groups, p.total_items, rank_grid, st, p));
+    // Known-true correction, part 1 (MRE_FILTER_INDEX): every run the job touches is scored once.  It needs the tables and the
+    // index only, so it runs on the context's second stream beside the gather / query kernels and is joined before part 2.
+    KnownRuns kr{};
+    const unsigned qgrid = (unsigned)((p.Q + KNOWN_WARPS - 1) / KNOWN_WARPS);
+    if (p.filter == MRE_FILTER_INDEX) {
+        MRE_TRY(known_runs_scratch(ctx, p, kr));
+        cudaStream_t aux = nullptr;
+        MRE_TRY(ctx->fork_aux(st, &aux));
+        if (job->p_norm == 1) transe_known_score_kernel<1><<<qgrid, KNOWN_WARPS * 32, 0, aux>>>(p, rel, kr);
+        else transe_known_score_kernel<2><<<qgrid, KNOWN_WARPS * 32, 0, aux>>>(p, rel, kr);
+        ctx->launches += 1;
+        MRE_CUDA(cudaGetLastError());
+    }
+    // the table the candidate tiles stream from: the entity table itself, or the gathered candidate rows
     const float *cand_table = ent;
     int64_t cand_rows = job->E;
     if (!p.all_entities) {
@@ -696,8 +814,8 @@ int rank_transe(mre_ctx *ctx, const mre_index *ix, const mre_rank_job *job, cuda
         MRE_CHECK_ARG(cand_rows < (1LL << 31), "too many candidate rows");
         MRE_TRY(ctx->ent_aux.reserve((size_t)std::max<int64_t>(cand_rows, 1) * Dp * sizeof(float)));
         if (cand_rows > 0) {
-            gather_rows_kernel<<<grid_for(cand_rows * (Dp >> 2), 256), 256, 0, aux>>>(ent, Dp, job->cand_idx, cand_rows,
-                                                                                      ctx->ent_aux.as<float>());
+            gather_rows_kernel<<<grid_for(cand_rows * (Dp >> 2), 256), 256, 0, st>>>(ent, Dp, job->cand_idx, cand_rows,
+                                                                                     ctx->ent_aux.as<float>());
             ctx->launches += 1;
         }
         cand_table = ctx->ent_aux.as<float>();
@@ -706,11 +824,25 @@ int rank_transe(mre_ctx *ctx, const mre_index *ix, const mre_rank_job *job, cuda
     else MRE_TRY(transe_queries<2>(ctx, p, rel, st));
     p.qvec = ctx->qvec.as<float>();
     p.thr = ctx->thr.as<float2>();
+    // part 2: take the known-true entities out of the filtered counters (needs the thresholds and the zeroed counters)
+    if (p.filter == MRE_FILTER_INDEX) {       // compare every query's thresholds against its run's stored scores
+        MRE_TRY(ctx->join_aux(st));
+        if (job->p_norm == 1) transe_known_compare_kernel<1><<<qgrid, KNOWN_WARPS * 32, 0, st>>>(p, kr);
+        else transe_known_compare_kernel<2><<<qgrid, KNOWN_WARPS * 32, 0, st>>>(p, kr);
+    } else if (known_is_flat(p)) {            // list prefix known on the host: one (query, entry) pair per lane
+        const unsigned kgrid = (unsigned)((p.filt_nnz + p.Q + KNOWN_WARPS * 32 - 1) / (KNOWN_WARPS * 32));
+        if (job->p_norm == 1) transe_known_flat_kernel<1><<<kgrid, KNOWN_WARPS * 32, 0, st>>>(p);
+        else transe_known_flat_kernel<2><<<kgrid, KNOWN_WARPS * 32, 0, st>>>(p);
+    } else {                                  // one warp walks each query's list
+        if (job->p_norm == 1) transe_known_kernel<1><<<qgrid, KNOWN_WARPS * 32, 0, st>>>(p, rel);
+        else transe_known_kernel<2><<<qgrid, KNOWN_WARPS * 32, 0, st>>>(p, rel);
+    }
+    ctx->launches += 1;
+    MRE_CUDA(cudaGetLastError());
     CUtensorMap tm_q, tm_e;
     // query vectors: [slots / 2 pair-rows][2 Dp floats], box = 64 pair-rows x 32 floats (16 d-values of two queries)
     MRE_TRY(make_tmap_f32_2d(&tm_q, p.qvec, std::max<int64_t>(p.total_slots / 2, 1), 2 * Dp, 2 * Dp, TQ / 2, CHUNK));
     MRE_TRY(make_tmap_f32_2d(&tm_e, cand_table, std::max<int64_t>(cand_rows, 1), Dp, Dp, TILE_E, CHUNK));
-    MRE_TRY(ctx->join_aux(st));
     MRE_TRY(ctx->time_begin(st));
     // the tie count is always on: one extra compare per score, in the epilogue only
     if (job->p_norm == 1) MRE_TRY((launch_rank<1, true>(ctx, p, tm_q, tm_e, st)));

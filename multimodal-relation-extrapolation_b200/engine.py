@@ -247,7 +247,8 @@ class Ranker:
             job.cand_idx = _ptr(groups.cand)
         if filt_csr is not None:
             job.filt_ptr, job.filt_idx = _ptr(filt_csr[0]), _ptr(filt_csr[1])
-            job.filt_nnz = int(filt_csr[1].numel()) if hasattr(filt_csr[1], "numel") else len(filt_csr[1])
+            # (ptr, idx) or (ptr, idx, nnz): nnz = filt_ptr[Q] (an upper bound will do; 0 = unknown to the caller)
+            job.filt_nnz = int(filt_csr[2]) if len(filt_csr) > 2 else int(filt_csr[1].numel())
         return job, keep
 
     def rank(self, scorer, tables, q_h, q_t, q_r, side, *, p_norm=1, normalize=False, index=None, filter=None,

@@ -60,17 +60,25 @@ class TrainDataLoader(object):
             self.batch_size = self.tripleTotal // self.nbatches
         if self.nbatches is None:
             self.nbatches = self.tripleTotal // self.batch_size
-        self.batch_seq_size = self.batch_size * (1 + self.negative_ent + self.negative_rel)
         self.step = 0
-        if not device_batches:
-            self.batch_h = np.zeros(self.batch_seq_size, dtype=np.int64)
-            self.batch_t = np.zeros(self.batch_seq_size, dtype=np.int64)
-            self.batch_r = np.zeros(self.batch_seq_size, dtype=np.int64)
-            self.batch_y = np.zeros(self.batch_seq_size, dtype=np.float32)
+        self.batch_seq_size = 0
+        self._size_buffers()
+
+    def _size_buffers(self):
+        """host batch arrays of B (1 + neg_ent + neg_rel) rows; re-made whenever a setter changed the sizes (the library
+        writes exactly that many elements into them)"""
+        n = self.batch_size * (1 + self.negative_ent + self.negative_rel)
+        if n != self.batch_seq_size and not self.device_batches:
+            self.batch_h = np.zeros(n, dtype=np.int64)
+            self.batch_t = np.zeros(n, dtype=np.int64)
+            self.batch_r = np.zeros(n, dtype=np.int64)
+            self.batch_y = np.zeros(n, dtype=np.float32)
+        self.batch_seq_size = n
 
     def _draw(self, mode):
         step = self.step
         self.step += 1
+        self._size_buffers()
         if self.device_batches:
             return self.sampler.sample(step, self.batch_size, self.negative_ent, mode=mode, bern=self.bern)
         return self.sampler.sample_host(step, self.batch_size, self.negative_ent, mode=mode, bern=self.bern,

@@ -24,9 +24,10 @@ def runner(mre):
     return bench, bench.Runner(0, 1, 0)
 
 
-def run_counts(runner, name):
+def run_counts(runner, name, filt="index"):
     bench, R = runner
     w = bench.load_workload(name)
+    w.filter = filt                 # "index": the known triples held by an mre_index (bench default); "csr": per-query lists
     p = R.prepare(w)
     p["step_dev"]()
     torch.cuda.synchronize()
@@ -42,9 +43,10 @@ def oracle_scores(w, h, t, r):
     return ko.complex_scores_contracted(tabs[0], tabs[1], tabs[2], tabs[3], 1, h, t, r)
 
 
+@pytest.mark.parametrize("filt", ["index", "csr"])
 @pytest.mark.parametrize("name", ["db15k_zs", "distmult", "complex"])
-def test_all_entity_workloads_bit_exact_vs_sequential_oracle(runner, name):
-    w, p, c = run_counts(runner, name)
+def test_all_entity_workloads_bit_exact_vs_sequential_oracle(runner, name, filt):
+    w, p, c = run_counts(runner, name, filt)
     ptr, idx = w.filt_csr
     sel = np.unique(np.linspace(0, len(w.q_h) - 1, 520).astype(np.int64))
     assert len(sel) >= 500
@@ -87,10 +89,11 @@ def test_all_entity_workloads_vs_reference_golden(runner, name):
     assert par["checked"] == len(i) and par["mismatches"] == 0
 
 
-def test_candidate_workload_vs_reference_main_evaluate(runner):
+@pytest.mark.parametrize("filt", ["index", "csr"])
+def test_candidate_workload_vs_reference_main_evaluate(runner, filt):
     """configs[0]: rel2candidates + ties//2 -- the reference class's evaluate + main.evaluate on the same candidate lists"""
     bench, R = runner
-    w, p, c = run_counts(runner, "fb15k237_zs")
+    w, p, c = run_counts(runner, "fb15k237_zs", filt)
     g = gu.load("golden_bench.npz")
     pos = {}
     for i, key in enumerate(zip(w.q_h.tolist(), w.q_r.tolist(), w.q_t.tolist())):

@@ -113,6 +113,12 @@ def test_cross_sampling_modes(mre, kg):
             assert len(d["batch_h"]) == 64 * 4 and len(d["batch_t"]) == 64 and len(d["batch_r"]) == 64
         else:
             assert len(d["batch_t"]) == 64 * 4 and len(d["batch_h"]) == 64 and len(d["batch_r"]) == 64
+    # the setters re-size the host batch arrays (the library writes B (1 + neg) elements into them)
+    loader.set_ent_neg_rate(9)
+    loader.set_batch_size(128)
+    c = loader.cross_sampling()
+    big = c["batch_h"] if c["mode"] == "head_batch" else c["batch_t"]
+    assert len(big) == 128 * 10 and loader.batch_seq_size == 128 * 10
     torch.manual_seed(0)
     m = ok.module.model.TransE(kg.E, kg.R, dim=16).cuda()
     s = m(a)

@@ -217,3 +217,41 @@ def test_metrics_histogram(mre):
     assert np.array_equal(hist, np.bincount(c[2] + 1, minlength=400))
     raw = rk.metrics(dev(c), dev(side), "strict", raw=True)["sums"].cpu().numpy()
     assert raw[0][1] + raw[1][1] == (c[0] + 1).sum()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("scorer", ["transe", "distmult"])
+def test_known_true_correction_paths_agree(mre, scorer):
+    """the filtered counts do not depend on how the known-true lists reach the library: MRE_FILTER_CSR with the exact entry
+    count (flattened correction pass), an over-estimate, an unknown count (one warp per query) and the same lists held by
+    the index (MRE_FILTER_INDEX); repeated ids in a list count once; all equal the oracle's counts"""
+    eng = mre.engine
+    E, R, D = 700, 5, 72
+    ds = helpers.synthetic_graph(3, E, R, 6000, 300, 500)
+    rng = np.random.default_rng(4)
+    ent = rng.standard_normal((E, D)).astype(np.float32)
+    rel = rng.standard_normal((R, D)).astype(np.float32)
+    th, tt, tr = ds.oracle.test_triples()
+    side = (np.arange(len(th)) % 2).astype(np.uint8)
+    ix = eng.KGIndex.from_arrays(E, R, ds.train, ds.valid, ds.test).to_device(0)
+    rk = eng.Ranker(device=0)
+    tabs = (dev(ent), dev(rel))
+    q = (dev(th), dev(tt), dev(tr), dev(side))
+    want = rk.rank(scorer, tabs, *q, index=ix).cpu().numpy()
+    score = (lambda s, h, t, r: ko.transe_scores(ent, rel, 1, s, h, t, r)) if scorer == "transe" else \
+            (lambda s, h, t, r: ko.distmult_scores(ent, rel, s, h, t, r))
+    raw, filt = helpers.oracle_counts(ds, score, th[:60], tt[:60], tr[:60], side[:60])
+    assert np.array_equal(want[0][:60], raw) and np.array_equal(want[2][:60], filt)
+    # the index's lists as CSR slices (sorted; every third list carries a repeated id)
+    allh, allt, allr = (np.concatenate([s[k] for s in (ds.train, ds.valid, ds.test)]) for k in range(3))
+    lists = []
+    for k, (h, t, r, s) in enumerate(zip(th, tt, tr, side)):
+        l = np.unique(allt[(allh == h) & (allr == r)]) if s else np.unique(allh[(allt == t) & (allr == r)])
+        lists.append(np.sort(np.concatenate([l, l[:1]])) if k % 3 == 0 else l)
+    ptr = np.concatenate([[0], np.cumsum([len(l) for l in lists])]).astype(np.int64)
+    idx = np.concatenate(lists).astype(np.int64)
+    for nnz in (len(idx), len(idx) + 777, 0):
+        got = rk.rank(scorer, tabs, *q, filt_csr=(dev(ptr), dev(idx), nnz)).cpu().numpy()
+        assert np.array_equal(got, want), nnz
+    none = rk.rank(scorer, tabs, *q).cpu().numpy()          # no lists: only the true entity leaves the filtered counts
+    assert np.array_equal(none[0], want[0]) and np.array_equal(none[2], none[0]) and np.array_equal(none[3], none[1] - 1)
