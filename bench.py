@@ -686,7 +686,7 @@ def sub_bench(module, rank, world, local, steps, warmup, gpus):
     box = {}
     ns = argparse.Namespace(steps=steps, warmup=warmup, impl="ours", no_extra=False, gpus=gpus, emit=lambda o: box.update(o), nested=True)
     module.main(ns, rank, world, local)
-    keep = ("metric", "value", "unit", "ms_per_step", "steps", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks", "result", "scaling")
+    keep = ("metric", "value", "unit", "ms_per_step", "steps", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks", "result", "scaling", "gradient_exchange", "replicas_identical")
     return {k: box[k] for k in keep if k in box}
 
 

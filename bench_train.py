@@ -76,10 +76,31 @@ def main(args, rank, world, local):
     ctx = eng.Context(local)
     ix = eng.KGIndex.from_arrays(E, R, *splits).to_device(local)
     smp = eng.Sampler(ix, ctx=ctx, seed=192, stream_id=rank)
-    # both tables (and both gradient tables) live back to back in ONE buffer: a data-parallel step is one flat all-reduce
-    # and one SGD kernel with 1/world folded into the learning rate
-    tab = torch.empty((E + R) * D, dtype=torch.float32, device=dev)
-    grad = torch.zeros_like(tab)
+    # both tables (and both gradient tables) live back to back in ONE buffer.  N > 1: the buffers sit in NVLink peer memory and
+    # the gradient sum is FUSED into the SGD kernel (mre_dp_sgd_step: reduce-scatter + update + all-gather over P2P loads / stores,
+    # 1/world folded into the learning rate); --opt train_allreduce=nccl (or a box without CUDA IPC) falls back to one NCCL
+    # all-reduce of the flat buffer + the plain SGD kernel, and the line says which
+    n_par = (E + R) * D
+    pg, exchange = None, "none (1 GPU)"
+    want_nccl = any(o == "train_allreduce=nccl" for o in getattr(args, "opt", []) or [])
+    if world > 1 and not want_nccl:
+        ok = torch.ones(1, device=dev)
+        try:
+            pg = mre_b200.dist.PeerGroup(ctx, n_par)
+        except Exception as e:  # noqa: BLE001
+            sys.stderr.write(f"[rank {rank}] peer memory unavailable ({e}); falling back to NCCL\n")
+            ok.zero_()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if ok.item() == 0:
+            pg = None
+    if pg is not None:
+        tab, grad = pg.weights, pg.grads
+        exchange = "fused: gradient reduce-scatter + SGD + weight all-gather in ONE kernel over NVLink peer memory (mre_dp_sgd_step)"
+    else:
+        tab = torch.empty(n_par, dtype=torch.float32, device=dev)
+        grad = torch.zeros_like(tab)
+        if world > 1:
+            exchange = "NCCL all-reduce of the flat gradient buffer + SGD kernel"
     ent_d, rel_d = tab[:E * D].view(E, D), tab[E * D:].view(R, D)
     g_ent, g_rel = grad[:E * D].view(E, D), grad[E * D:].view(R, D)
     ent_d.copy_(torch.from_numpy(ent)); rel_d.copy_(torch.from_numpy(rel))
@@ -90,10 +111,16 @@ def main(args, rank, world, local):
         h, t, r, y = smp.sample(state["step"], B, neg)
         state["step"] += 1
         loss, _, _, _ = eng.transe_margin_step(ctx, ent_d, rel_d, h, t, r, B, neg, 5.0, 1, True, grad_ent=g_ent, grad_rel=g_rel)
+        update()
+        return loss
+
+    def update():
+        if pg is not None:
+            pg.sgd_step(lr / world)
+            return
         if dctx is not None:
             dctx.all_reduce_flat(grad)
         eng.sgd_update(ctx, tab, grad, lr / world)
-        return loss
 
     host = [np.empty(n, np.int64) for _ in range(3)] + [np.empty(n, np.float32)]
     pinned = [torch.empty(n, dtype=torch.int64).pin_memory() for _ in range(3)]
@@ -106,9 +133,7 @@ def main(args, rank, world, local):
             p.copy_(torch.from_numpy(a))
         h, t, r = (p.to(dev, non_blocking=True) for p in pinned)
         loss, _, _, _ = eng.transe_margin_step(ctx, ent_d, rel_d, h, t, r, B, neg, 5.0, 1, True, grad_ent=g_ent, grad_rel=g_rel)
-        if dctx is not None:
-            dctx.all_reduce_flat(grad)
-        eng.sgd_update(ctx, tab, grad, lr / world)
+        update()
         return float(loss.item())
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -118,6 +143,7 @@ def main(args, rank, world, local):
             dist.barrier()
         torch.cuda.synchronize()
 
+    barrier()                     # every rank's buffers hold the initial tables before anyone's first exchange
     for _ in range(args.warmup):
         step_dev()
     barrier()
@@ -165,6 +191,13 @@ def main(args, rank, world, local):
             s, kind = cpu_reference_step(w, threads, 3)
         cpu_base = {"value": n / s, "unit": "triples/s", "cores": threads, "kind": kind,
                     "sample": "3 full steps: Base.so sampling on all host threads + torch-CPU forward/backward of the reference expressions"}
+    xinfo = {"gradient_exchange": exchange}
+    if pg is not None:
+        pg.check()
+        wsum = tab.double().sum().reshape(1)                     # the replicas must hold identical weights
+        ws = [torch.zeros_like(wsum) for _ in range(world)]
+        dist.all_gather(ws, wsum)
+        xinfo["replicas_identical"] = bool(all(torch.equal(x, ws[0]) for x in ws))
     if rank == 0:
         args.emit({
             "metric": "train triples/sec", "value": value, "unit": "triples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -177,6 +210,6 @@ def main(args, rank, world, local):
             "cpu_baseline": cpu_base,
             "e2e": {"value": world * n * args.steps / e2e_s, "unit": "triples/s", "h2d_bytes_per_step": 3 * n * 8, "d2h_bytes_per_step": 3 * n * 8 + n * 4 + 4,
                     "api": "sample_host (reference loader contract: numpy batch on the host) -> pinned H2D -> margin step -> loss.item()"},
-            "gpu_launches": int(launches), "clocks": clocks.summary(), "result": {"last_loss": float(loss.item())}})
+            "gpu_launches": int(launches), "clocks": clocks.summary(), "result": {"last_loss": float(loss.item())}, **xinfo})
     if world > 1 and not getattr(args, "nested", False):
         dist.destroy_process_group()

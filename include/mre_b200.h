@@ -381,6 +381,41 @@ int mre_ns_train_step(mre_ctx *ctx, int32_t scorer, const float *ent, const floa
 /* w -= lr * g (torch.optim.SGD as Trainer.py:73-78 configures it), then g = 0; device arrays of n floats */
 int mre_sgd_update(mre_ctx *ctx, float *w, float *g, int64_t n, float lr, void *stream);
 
+/* ------------------------------------------------------------------------------- multi-GPU (one process per GPU) */
+/*
+ * The reference is one process on one GPU (Trainer.py:43-78; Test.h:232-277 sums the metrics in one address space).  The two
+ * exchanges of the data-parallel path -- the gradient sum of a training step and the integer metric sums of a sharded
+ * evaluation -- run here over NVLink PEER MEMORY, without any collective library:
+ *   mre_peer_group_create   cudaMalloc of this rank's region [weights n | gradients n | exchange area | flags] + its CUDA IPC
+ *                           handle (MRE_PEER_HANDLE_BYTES bytes).  The caller ships the handles between the processes by any
+ *                           means (dist.py: torch.distributed.all_gather_object) and hands all of them, in rank order, to
+ *   mre_peer_group_connect  which maps every other rank's region (cudaIpcOpenMemHandle).
+ *   mre_peer_weights / mre_peer_grads   this rank's flat parameter and gradient buffers inside the region (n floats each):
+ *                           the embedding tables and gradient tables of the training step live there back to back.
+ *   mre_dp_sgd_step         ONE kernel per rank and step = reduce-scatter + SGD + all-gather: rank r sums slice r of every rank's
+ *                           gradient buffer (P2P loads, rank order), applies w -= lr * sum, stores the new slice into every rank's
+ *                           weight buffer (P2P stores), and zeroes its own gradient buffer once every rank is done with it.  Pass
+ *                           lr / world for the mean of the ranks' mean losses.  All ranks must call it once per step, in step;
+ *                           weights stay bit-identical on all ranks.  max_blocks: 0 = one block per SM (tests pass a small number).
+ *   mre_peer_allreduce_i64  in-place sum over the ranks of a device int64 vector of at most 64 words (mre_metrics' sums_out).
+ *   mre_peer_group_error    MRE_ERR_CUDA if an exchange ever timed out (a rank did not arrive within ~20 s; nothing hangs).
+ * Flags carry the exchange number, which only grows: no resets, no host synchronisation between steps.
+ */
+typedef struct mre_peer_group mre_peer_group;
+#define MRE_PEER_HANDLE_BYTES 64
+#define MRE_PEER_MAX_RANKS 16
+int mre_peer_group_create(mre_ctx *ctx, int32_t rank, int32_t world, int64_t n_floats, mre_peer_group **out,
+                          unsigned char *handle_out /* [MRE_PEER_HANDLE_BYTES] */);
+int mre_peer_group_connect(mre_peer_group *g, const unsigned char *handles /* [world][MRE_PEER_HANDLE_BYTES], rank order */);
+/* the same for "ranks" that are all groups of THIS process on one device (tests): all[p] = rank p's group */
+int mre_peer_group_connect_local(mre_peer_group *g, mre_peer_group *const *all);
+void mre_peer_group_destroy(mre_peer_group *g);
+float *mre_peer_weights(mre_peer_group *g);
+float *mre_peer_grads(mre_peer_group *g);
+int mre_dp_sgd_step(mre_ctx *ctx, mre_peer_group *g, float lr, int32_t max_blocks, void *stream);
+int mre_peer_allreduce_i64(mre_ctx *ctx, mre_peer_group *g, int64_t *vec, int32_t count, void *stream);
+int mre_peer_group_error(mre_peer_group *g);
+
 /* ------------------------------------------------------------------------------------------- probes */
 /* FP32 add-rate microbenchmark (the better of a scalar FADD and a packed FADD2 stream): lane-ops per second in *lane_ops_per_s (the TransE roofline
  * denominator) and the SM clock-independent instruction count used. Synchronous. */

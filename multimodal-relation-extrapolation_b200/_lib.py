@@ -14,7 +14,7 @@ BUILD_DIR = os.path.join(_HERE, "build")
 LIB_PATH = os.environ.get("MRE_B200_LIB") or os.path.join(BUILD_DIR, "libmre_b200.so")   # override: A/B timing of two builds
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include", "mre_b200.h")
 
-SOURCES = ["index.cpp", "tma_host.cpp", "abi.cu", "transe_rank.cu", "metrics.cu", "sampler.cu", "train_step.cu", "bilinear_rank.cu", "zsl_rank.cu"]
+SOURCES = ["index.cpp", "tma_host.cpp", "abi.cu", "transe_rank.cu", "metrics.cu", "sampler.cu", "train_step.cu", "bilinear_rank.cu", "zsl_rank.cu", "peer.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
               "-Xcompiler", "-fPIC,-O2", "-shared"]
 
@@ -26,6 +26,7 @@ RANK_STRICT, RANK_TIES_HALF, RANK_PESSIMISTIC = 0, 1, 2
 TOTAL_ENTITY, TOTAL_RELATION, TOTAL_TRAIN, TOTAL_VALID, TOTAL_TEST, TOTAL_TRIPLE = range(6)
 SPLIT_TRAIN, SPLIT_VALID, SPLIT_TEST = 0, 1, 2
 LOSS_MARGIN, LOSS_SIGMOID, LOSS_SOFTPLUS = 0, 1, 2
+PEER_HANDLE_BYTES = 64
 
 
 class MreError(RuntimeError):
@@ -138,6 +139,18 @@ def lib():
     L.mre_bilinear_backward.argtypes = [vp, i32, vp, vp, vp, vp, i64, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp]
     L.mre_ns_loss.argtypes = [vp, i32, vp, i64, i64, f32, i32, f32, vp, vp, vp]
     L.mre_ns_train_step.argtypes = [vp, i32, vp, vp, vp, vp, i64, vp, vp, vp, i64, i64, i32, f32, i32, f32, i32, i32, vp, vp, vp, vp, vp, vp, vp]
+    L.mre_peer_group_create.argtypes = [vp, i32, i32, i64, P(vp), C.c_char_p]
+    L.mre_peer_group_connect.argtypes = [vp, C.c_char_p]
+    L.mre_peer_group_connect_local.argtypes = [vp, P(vp)]
+    L.mre_peer_group_destroy.argtypes = [vp]
+    L.mre_peer_group_destroy.restype = None
+    L.mre_peer_weights.argtypes = [vp]
+    L.mre_peer_weights.restype = vp
+    L.mre_peer_grads.argtypes = [vp]
+    L.mre_peer_grads.restype = vp
+    L.mre_dp_sgd_step.argtypes = [vp, vp, f32, i32, vp]
+    L.mre_peer_allreduce_i64.argtypes = [vp, vp, vp, i32, vp]
+    L.mre_peer_group_error.argtypes = [vp]
     L.mre_probe_fp32_peak.argtypes = [vp, P(C.c_double)]
     L.mre_probe_tf32_peak.argtypes = [vp, P(C.c_double)]
     L.mre_probe_bf16_peak.argtypes = [vp, P(C.c_double)]

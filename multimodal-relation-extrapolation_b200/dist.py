@@ -69,6 +69,84 @@ class DistContext:
         dist.barrier()
 
 
+class _DevArray:
+    """a raw device pointer dressed as a CUDA array (zero-copy torch.as_tensor view of library-owned peer memory)"""
+
+    def __init__(self, ptr, n, typestr="<f4"):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+class PeerGroup:
+    """mre_peer_group: the flat parameter + gradient buffers of a data-parallel trainer in NVLink peer memory, with the gradient
+    reduction fused into the SGD kernel (mre_dp_sgd_step) and the int64 metric all-reduce (mre_peer_allreduce_i64) -- no
+    collective library on the data path; torch.distributed only carries the 64-byte IPC handles once, at construction.
+
+        pg = PeerGroup(ctx, n_floats)          # collective over the default process group (or world = 1 without one)
+        pg.weights, pg.grads                   # float32 [n_floats] views of this rank's region
+        pg.sgd_step(lr / pg.world)             # every rank, once per step
+
+    `peers` (test hook): a list of PeerGroup-s of THIS process standing in for the ranks (connect_local)."""
+
+    def __init__(self, ctx, n_floats, rank=None, world=None, local=False):
+        from . import _lib as L
+        import ctypes as C
+        self.ctx, self.L = ctx, L
+        if rank is None:
+            rank = dist.get_rank() if dist.is_initialized() else 0
+            world = dist.get_world_size() if dist.is_initialized() else 1
+        self.rank, self.world, self.n = int(rank), int(world), int(n_floats)
+        handle = C.create_string_buffer(L.PEER_HANDLE_BYTES)
+        out = C.c_void_p()
+        L.check(L.lib().mre_peer_group_create(ctx._h, self.rank, self.world, self.n, C.byref(out), handle))
+        self._h = out.value
+        self.handle = handle.raw
+        if not local:
+            if self.world > 1:
+                handles = [None] * self.world
+                dist.all_gather_object(handles, self.handle)
+            else:
+                handles = [self.handle]
+            L.check(L.lib().mre_peer_group_connect(self._h, b"".join(handles)))
+            self._views()
+
+    @staticmethod
+    def connect_local(groups):
+        import ctypes as C
+        arr = (C.c_void_p * len(groups))(*[g._h for g in groups])
+        for g in groups:
+            g.L.check(g.L.lib().mre_peer_group_connect_local(g._h, arr))
+            g._views()
+
+    def _views(self):
+        lib = self.L.lib()
+        dev = torch.device("cuda", self.ctx.device)
+        self.weights = torch.as_tensor(_DevArray(lib.mre_peer_weights(self._h), self.n), device=dev)
+        self.grads = torch.as_tensor(_DevArray(lib.mre_peer_grads(self._h), self.n), device=dev)
+
+    def sgd_step(self, lr, max_blocks=0):
+        self.L.check(self.L.lib().mre_dp_sgd_step(self.ctx._h, self._h, float(lr), int(max_blocks), torch.cuda.current_stream().cuda_stream))
+
+    def all_reduce_i64(self, vec):
+        assert vec.is_cuda and vec.dtype == torch.int64 and vec.is_contiguous() and vec.numel() <= 64
+        self.L.check(self.L.lib().mre_peer_allreduce_i64(self.ctx._h, self._h, vec.data_ptr(), vec.numel(), torch.cuda.current_stream().cuda_stream))
+        return vec
+
+    def check(self):
+        self.L.check(self.L.lib().mre_peer_group_error(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.weights = self.grads = None
+            self.L.lib().mre_peer_group_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+
 def metrics_from_hist(hist):
     """rank histogram (hist[k] = #queries with rank k) -> dict(n, mr, mrr, hits1/3/5/10); float64 from integers only"""
     h = np.asarray(hist.cpu() if isinstance(hist, torch.Tensor) else hist, dtype=np.int64)

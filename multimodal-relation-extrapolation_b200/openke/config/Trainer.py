@@ -1,8 +1,10 @@
 """Trainer (OpenKE/openke/config/Trainer.py:18-99): same constructor, same epoch/batch loop, same optimiser choices.
-With a fusable strategy (TransE + MarginLoss) and opt_method "sgd" one step is: Philox sample on the device ->
-mre_transe_margin_step (forward + backward) -> [NCCL all-reduce of the two gradient tables when data-parallel] ->
-mre_sgd_update; nothing crosses PCIe.  Any other combination runs the strategy's autograd forward and the torch
-optimiser on the same kernels' scores."""
+With a fusable strategy (any library scorer + library loss, no regulariser) and opt_method "sgd" one step is: Philox sample on
+the device -> mre_ns_train_step (forward + loss + backward) -> mre_sgd_update; nothing crosses PCIe.  Data-parallel
+(`dist=DistContext()`): the embedding tables and their gradients are moved into NVLink peer memory once (PeerGroup) and the
+update becomes mre_dp_sgd_step -- gradient reduce-scatter + SGD + weight all-gather in ONE kernel per rank, no collective
+library on the step; if peer memory cannot be set up the step falls back to NCCL all-reduces of the gradient tables.  Any
+other combination runs the strategy's autograd forward and the torch optimiser on the same kernels' scores."""
 import os
 
 import torch
@@ -28,6 +30,42 @@ class Trainer(object):
         self.checkpoint_dir = checkpoint_dir
         self.dist = dist
         self.losses = []
+        self.peer = None              # PeerGroup holding the tables + gradients when data-parallel and fused
+        self._peer_tried = False
+
+    def _adopt_peer_memory(self):
+        """data-parallel + fused: re-home the embedding tables and their gradient tables, back to back, in one peer-memory region
+        (parameters keep their identity: only .data / .grad are re-pointed), so that the update is mre_dp_sgd_step"""
+        if self._peer_tried or self.dist is None or self.dist.world == 1:
+            return
+        self._peer_tried = True
+        import torch.distributed as td
+        from ... import dist as mdist
+        tabs = self.model.model.tables()
+        sizes = [t.numel() for t in tabs]
+        n = (sum(sizes) + 3) & ~3
+        ok = torch.ones(1, device=tabs[0].device)
+        pg = None
+        try:
+            assert all(s % 4 == 0 for s in sizes)          # every table starts 16-byte aligned inside the flat buffer
+            pg = mdist.PeerGroup(self.model.model.ctx(), n)
+        except Exception as e:  # noqa: BLE001
+            print(f"peer memory unavailable ({e}); data-parallel steps use NCCL all-reduces")
+            ok.zero_()
+        td.all_reduce(ok, op=td.ReduceOp.MIN)
+        if ok.item() == 0:
+            return
+        off = 0
+        for t, s in zip(tabs, sizes):
+            w, g = pg.weights[off:off + s].view_as(t), pg.grads[off:off + s].view_as(t)
+            w.copy_(t.data)
+            if t.grad is not None:
+                g.copy_(t.grad)
+            t.data, t.grad = w, g
+            off += s
+        td.barrier()
+        torch.cuda.synchronize()
+        self.peer = pg
 
     def _fused(self):
         return (self.use_gpu and hasattr(self.model, "can_fuse") and self.model.can_fuse()
@@ -44,7 +82,11 @@ class Trainer(object):
                  "batch_r": self.to_var(data["batch_r"], self.use_gpu), "batch_y": self.to_var(data["batch_y"], self.use_gpu),
                  "mode": data["mode"]}
         if self._fused():
+            self._adopt_peer_memory()
             loss = self.model.fused_step(batch)
+            if self.peer is not None:
+                self.peer.sgd_step(self.alpha / self.dist.world)      # mean over ranks of the per-rank mean losses
+                return loss
             tabs = self.model.model.tables()
             if self.dist is not None:
                 self.dist.all_reduce_grads([t.grad for t in tabs])
