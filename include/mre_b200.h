@@ -231,6 +231,21 @@ int mre_metrics(mre_ctx *ctx, const int32_t *counts, const uint8_t *q_side, int3
                 int32_t rank_mode, int32_t raw, int64_t *sums_out, double *rr_out,
                 int64_t *hist, int64_t hist_len, void *stream);
 
+/* ------------------------------------------------------------------------------ projected translation models */
+/*
+ * TransH / TransD rank through the TransE kernel over PER-RELATION entity tables: the projection the reference applies to the
+ * E rows of every 1-vs-all query (TransH._transfer, TransH.py:66-74: e - (e . w^) w^ with w^ = F.normalize(norm_vector[r]);
+ * TransD._transfer, TransD.py:92-109: F.normalize(e + (e . e_p) r_p), dim_e == dim_r) depends on the relation only, so
+ * mre_relation_project writes out[slot * E + e, :] once for the slot-th relation of `rels` (renormalize != 0 applies _calc's
+ * F.normalize again, TransH.py:51-55).  A job then ranks with one candidate group per relation over this table.
+ * ent [E, D]; ent_aux [E, D] = ent_transfer (TransD) or NULL; rel_aux [R, D] = norm_vector (TransH) / rel_transfer (TransD);
+ * rels: device int64 [n_rel]; out: device float32 [n_rel * E, D]; D <= 512.
+ */
+#define MRE_PROJECT_TRANSH 0
+#define MRE_PROJECT_TRANSD 1
+int mre_relation_project(mre_ctx *ctx, int32_t kind, const float *ent, const float *ent_aux, const float *rel_aux,
+                         const int64_t *rels, int64_t n_rel, int64_t E, int64_t D, int32_t renormalize, float *out, void *stream);
+
 /* ------------------------------------------------------------------------------------------ sampling */
 /*
  * One training batch of B positives + B*neg Bernoulli-corrupted negatives, layout [B pos | neg blocks of B]

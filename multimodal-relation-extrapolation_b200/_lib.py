@@ -14,7 +14,7 @@ BUILD_DIR = os.path.join(_HERE, "build")
 LIB_PATH = os.environ.get("MRE_B200_LIB") or os.path.join(BUILD_DIR, "libmre_b200.so")   # override: A/B timing of two builds
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include", "mre_b200.h")
 
-SOURCES = ["index.cpp", "tma_host.cpp", "abi.cu", "transe_rank.cu", "metrics.cu", "sampler.cu", "train_step.cu", "bilinear_rank.cu", "zsl_rank.cu", "peer.cu"]
+SOURCES = ["index.cpp", "tma_host.cpp", "abi.cu", "transe_rank.cu", "metrics.cu", "sampler.cu", "train_step.cu", "bilinear_rank.cu", "zsl_rank.cu", "peer.cu", "project.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
               "-Xcompiler", "-fPIC,-O2", "-shared"]
 
@@ -27,6 +27,7 @@ TOTAL_ENTITY, TOTAL_RELATION, TOTAL_TRAIN, TOTAL_VALID, TOTAL_TEST, TOTAL_TRIPLE
 SPLIT_TRAIN, SPLIT_VALID, SPLIT_TEST = 0, 1, 2
 LOSS_MARGIN, LOSS_SIGMOID, LOSS_SOFTPLUS = 0, 1, 2
 PEER_HANDLE_BYTES = 64
+PROJECT_TRANSH, PROJECT_TRANSD = 0, 1
 
 
 class MreError(RuntimeError):
@@ -139,6 +140,7 @@ def lib():
     L.mre_bilinear_backward.argtypes = [vp, i32, vp, vp, vp, vp, i64, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp]
     L.mre_ns_loss.argtypes = [vp, i32, vp, i64, i64, f32, i32, f32, vp, vp, vp]
     L.mre_ns_train_step.argtypes = [vp, i32, vp, vp, vp, vp, i64, vp, vp, vp, i64, i64, i32, f32, i32, f32, i32, i32, vp, vp, vp, vp, vp, vp, vp]
+    L.mre_relation_project.argtypes = [vp, i32, vp, vp, vp, vp, i64, i64, i64, i32, vp, vp]
     L.mre_peer_group_create.argtypes = [vp, i32, i32, i64, P(vp), C.c_char_p]
     L.mre_peer_group_connect.argtypes = [vp, C.c_char_p]
     L.mre_peer_group_connect_local.argtypes = [vp, P(vp)]

@@ -53,6 +53,8 @@ class Tester(object):
             q_h, q_t, q_r, side = q_h[lo:hi], q_t[lo:hi], q_r[lo:hi], side[lo:hi]
         to = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
         side_d = to(side)
+        if hasattr(m, "rank_queries"):          # per-relation projected tables (TransH, TransD): model/_projected.py
+            return m.rank_queries(q_h, q_t, q_r, side, dl.index), side_d
         tabs = tuple(t.detach().contiguous() for t in m.tables())
         counts = m.ranker().rank(m.scorer, tabs, to(q_h), to(q_t), to(q_r), side_d, index=dl.index, **m.rank_kwargs())
         return counts, side_d

@@ -45,7 +45,8 @@ class NegativeSampling(nn.Module):
         from ..loss._ns_loss import NegativeSamplingLoss
         from ..model.SimplE import SimplE
         return (isinstance(self.loss, NegativeSamplingLoss) and getattr(self.model, "scorer", None) in engine.SCORERS
-                and not isinstance(self.model, SimplE) and not getattr(self.model, "margin_flag", False)
+                and not isinstance(self.model, SimplE) and getattr(self.model, "fusable", True)
+                and not getattr(self.model, "margin_flag", False)
                 and self.regul_rate == 0 and self.l3_regul_rate == 0)
 
     def fused_step(self, data):
