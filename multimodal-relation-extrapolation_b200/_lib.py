@@ -16,7 +16,7 @@ INCLUDE = os.path.join(os.path.dirname(_HERE), "include", "mre_b200.h")
 
 SOURCES = ["index.cpp", "tma_host.cpp", "abi.cu", "transe_rank.cu", "metrics.cu", "sampler.cu", "train_step.cu", "bilinear_rank.cu", "zsl_rank.cu", "peer.cu", "project.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
-              "-Xcompiler", "-fPIC,-O2", "-shared"]
+              "-Xcompiler", "-fPIC,-O2,-pthread", "-shared"]
 
 # constants mirrored from include/mre_b200.h
 OK = 0

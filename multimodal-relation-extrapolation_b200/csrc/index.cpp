@@ -14,6 +14,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <thread>
 #include <numeric>
 #include <string>
 
@@ -98,23 +99,64 @@ static int pack(const int64_t *h, const int64_t *t, const int64_t *r, int64_t n,
     return MRE_OK;
 }
 
+// std::sort over `threads` chunks on as many host threads, then pairwise std::inplace_merge rounds (the chunks of a round merge
+// in parallel too).  The reference sorts its five lists one after the other on one thread (Reader.h:107-109,201-227).
+template <class Less>
+static void parallel_sort(std::vector<Triple> &v, Less less, int threads) {
+    const size_t n = v.size();
+    if (threads <= 1 || n < 65536) {
+        std::sort(v.begin(), v.end(), less);
+        return;
+    }
+    std::vector<size_t> cut((size_t)threads + 1);
+    for (int i = 0; i <= threads; i++) cut[(size_t)i] = n * (size_t)i / (size_t)threads;
+    {
+        std::vector<std::thread> pool;
+        for (int i = 0; i < threads; i++)
+            pool.emplace_back([&, i] { std::sort(v.begin() + (ptrdiff_t)cut[(size_t)i], v.begin() + (ptrdiff_t)cut[(size_t)i + 1], less); });
+        for (auto &t : pool) t.join();
+    }
+    for (int width = 1; width < threads; width *= 2) {
+        std::vector<std::thread> pool;
+        for (int i = 0; i + width < threads; i += 2 * width) {
+            const size_t lo = cut[(size_t)i], mid = cut[(size_t)(i + width)], hi = cut[(size_t)std::min(i + 2 * width, threads)];
+            pool.emplace_back([&, lo, mid, hi] { std::inplace_merge(v.begin() + (ptrdiff_t)lo, v.begin() + (ptrdiff_t)mid, v.begin() + (ptrdiff_t)hi, less); });
+        }
+        for (auto &t : pool) t.join();
+    }
+}
+
+static int host_threads() {
+    const unsigned hc = std::thread::hardware_concurrency();
+    return (int)std::max(1u, std::min(hc ? hc : 1u, 16u));
+}
+
 static int build(mre_index *ix, std::vector<Triple> &train_raw, std::vector<Triple> &valid, std::vector<Triple> &test) {
     const int64_t R = ix->R;
     ix->n_train_raw = (int64_t)train_raw.size();
+    // the three independent chains -- membership list, the two train orders, the test / valid orders -- run side by side, each
+    // sort itself split over a share of the host threads
+    const int per = std::max(1, host_threads() / 3);
 
     // membership list: test + RAW train + valid, (h,r,t) order, duplicates kept (Reader.h:201-226)
     ix->all_head.reserve(test.size() + train_raw.size() + valid.size());
     ix->all_head.insert(ix->all_head.end(), test.begin(), test.end());
     ix->all_head.insert(ix->all_head.end(), train_raw.begin(), train_raw.end());
     ix->all_head.insert(ix->all_head.end(), valid.begin(), valid.end());
-    std::sort(ix->all_head.begin(), ix->all_head.end(), less_hrt);
+    std::thread chain_all([&] { parallel_sort(ix->all_head, less_hrt, per); });
+    std::thread chain_test([&] {
+        parallel_sort(test, less_rht, std::max(1, per / 2));
+        parallel_sort(valid, less_rht, std::max(1, per / 2));
+    });
 
     // train: sort, drop duplicates (Reader.h:91-105), second order (Reader.h:107-109)
-    std::sort(train_raw.begin(), train_raw.end(), less_hrt);
+    parallel_sort(train_raw, less_hrt, per);
     train_raw.erase(std::unique(train_raw.begin(), train_raw.end(), same), train_raw.end());
     ix->train_head.swap(train_raw);
     ix->train_tail = ix->train_head;
-    std::sort(ix->train_tail.begin(), ix->train_tail.end(), less_trh);
+    parallel_sort(ix->train_tail, less_trh, per);
+    chain_all.join();
+    chain_test.join();
 
     // tph / hpt in float32 exactly as Reader.h:142-159: float counters of distinct (h,r) / (t,r) pairs,
     // then (integer frequency) / (float count)
@@ -139,8 +181,6 @@ static int build(mre_index *ix, std::vector<Triple> &train_raw, std::vector<Trip
         ix->bern_prob[(size_t)r] = num / den;
     }
 
-    std::sort(test.begin(), test.end(), less_rht);
-    std::sort(valid.begin(), valid.end(), less_rht);
     ix->test.swap(test);
     ix->valid.swap(valid);
     return MRE_OK;
