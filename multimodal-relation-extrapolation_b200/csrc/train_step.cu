@@ -66,6 +66,53 @@ __global__ void __launch_bounds__(256) transe_fwd_kernel(const float *__restrict
     }
 }
 
+// The same forward for D % 4 == 0 and D <= 128 * MAXV: a lane owns float4 groups, the three rows are fetched once with 128-bit
+// loads and stay in registers through the norm and score phases (the kernel above reads them twice).
+template <int P, int MAXV>
+__global__ void __launch_bounds__(256) transe_fwd_vec_kernel(const float *__restrict__ ent, const float *__restrict__ rel, int D,
+                                                             const int64_t *__restrict__ bh, const int64_t *__restrict__ bt,
+                                                             const int64_t *__restrict__ br, int64_t n, int normalize,
+                                                             float *__restrict__ score) {
+    const int lane = threadIdx.x & 31;
+    const int nv = D >> 2;
+    const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n; i += warps) {
+        const float4 *vh = reinterpret_cast<const float4 *>(ent + bh[i] * D), *vt = reinterpret_cast<const float4 *>(ent + bt[i] * D),
+                     *vr = reinterpret_cast<const float4 *>(rel + br[i] * D);
+        float xh[MAXV][4], xr[MAXV][4], xt[MAXV][4];
+        float sh = 0.f, sr = 0.f, st = 0.f;
+#pragma unroll
+        for (int k = 0; k < MAXV; k++) {
+            const int v = lane + 32 * k;
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 a = v < nv ? vh[v] : z, b = v < nv ? vr[v] : z, e = v < nv ? vt[v] : z;
+            xh[k][0] = a.x; xh[k][1] = a.y; xh[k][2] = a.z; xh[k][3] = a.w;
+            xr[k][0] = b.x; xr[k][1] = b.y; xr[k][2] = b.z; xr[k][3] = b.w;
+            xt[k][0] = e.x; xt[k][1] = e.y; xt[k][2] = e.z; xt[k][3] = e.w;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                sh = fmaf(xh[k][j], xh[k][j], sh); sr = fmaf(xr[k][j], xr[k][j], sr); st = fmaf(xt[k][j], xt[k][j], st);
+            }
+        }
+        float nh = 1.f, nr = 1.f, nt = 1.f;
+        if (normalize) {
+            nh = fmaxf(sqrtf(warp_sum(sh)), NORM_EPS);
+            nr = fmaxf(sqrtf(warp_sum(sr)), NORM_EPS);
+            nt = fmaxf(sqrtf(warp_sum(st)), NORM_EPS);
+        }
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < MAXV; k++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const float u = normalize ? (xh[k][j] / nh + xr[k][j] / nr) - xt[k][j] / nt : (xh[k][j] + xr[k][j]) - xt[k][j];
+                acc = P == 1 ? acc + fabsf(u) : fmaf(u, u, acc);
+            }
+        acc = warp_sum(acc);
+        if (lane == 0) score[i] = P == 1 ? acc : sqrtf(acc);
+    }
+}
+
 // Negative-sampling losses on the strategy's score layout (p_b = score[b], n_bk = score[B + k*B + b],
 // strategy/NegativeSampling.py:13-21), forward value and dLoss/dscore in ONE launch -- one thread per positive row b:
 //   MARGIN    mean_b sum_k w_bk max(p_b - n_bk, -m) + m                     MarginLoss.py:24-28 (module/loss.py:20-24)
@@ -199,6 +246,97 @@ __global__ void __launch_bounds__(256) transe_bwd_kernel(const float *__restrict
     }
 }
 
+// The same backward for D % 4 == 0 and D <= 128 * MAXV, the shape every config of the reference trains at (D = 200): a lane
+// owns float4 groups, the three rows are fetched ONCE with 128-bit loads and stay in registers through the norm, dot and
+// gradient phases (the kernel above re-reads and re-normalises them in each: nine divisions per element, three of them here),
+// and the gradients leave as 128-bit vector reductions (RED.ADD.F32x4: a quarter of the atomic instructions).  The kernel
+// above was issue-bound (72 % of issue slots, 1 290 warp instructions per triple); this one executes about a third of them.
+template <int P, int MAXV>
+__global__ void __launch_bounds__(256) transe_bwd_vec_kernel(const float *__restrict__ ent, const float *__restrict__ rel, int D,
+                                                             const int64_t *__restrict__ bh, const int64_t *__restrict__ bt,
+                                                             const int64_t *__restrict__ br, int64_t n, int normalize,
+                                                             const float *__restrict__ score, const float *__restrict__ dscore,
+                                                             float *__restrict__ grad_ent, float *__restrict__ grad_rel) {
+    const int lane = threadIdx.x & 31;
+    const int nv = D >> 2;
+    const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n; i += warps) {
+        const float c = dscore[i];
+        if (c == 0.f) continue;
+        const int64_t ih = bh[i], it = bt[i], ir = br[i];
+        const float4 *vh = reinterpret_cast<const float4 *>(ent + ih * D), *vt = reinterpret_cast<const float4 *>(ent + it * D),
+                     *vr = reinterpret_cast<const float4 *>(rel + ir * D);
+        float xh[MAXV][4], xr[MAXV][4], xt[MAXV][4];
+        float sh = 0.f, sr = 0.f, st = 0.f;
+#pragma unroll
+        for (int k = 0; k < MAXV; k++) {
+            const int v = lane + 32 * k;
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 a = v < nv ? vh[v] : z, b = v < nv ? vr[v] : z, e = v < nv ? vt[v] : z;
+            xh[k][0] = a.x; xh[k][1] = a.y; xh[k][2] = a.z; xh[k][3] = a.w;
+            xr[k][0] = b.x; xr[k][1] = b.y; xr[k][2] = b.z; xr[k][3] = b.w;
+            xt[k][0] = e.x; xt[k][1] = e.y; xt[k][2] = e.z; xt[k][3] = e.w;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                sh = fmaf(xh[k][j], xh[k][j], sh); sr = fmaf(xr[k][j], xr[k][j], sr); st = fmaf(xt[k][j], xt[k][j], st);
+            }
+        }
+        float nh = 1.f, nr = 1.f, nt = 1.f;
+        if (normalize) {
+            nh = fmaxf(sqrtf(warp_sum(sh)), NORM_EPS);
+            nr = fmaxf(sqrtf(warp_sum(sr)), NORM_EPS);
+            nt = fmaxf(sqrtf(warp_sum(st)), NORM_EPS);
+#pragma unroll
+            for (int k = 0; k < MAXV; k++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) { xh[k][j] = xh[k][j] / nh; xr[k][j] = xr[k][j] / nr; xt[k][j] = xt[k][j] / nt; }
+        }
+        float un = 1.f;
+        if (P == 2) {
+            const float s = score[i];
+            un = s > 0.f ? 1.f / s : 0.f;
+        }
+        float g[MAXV][4];
+        float dh = 0.f, dr = 0.f, dt = 0.f;
+#pragma unroll
+        for (int k = 0; k < MAXV; k++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const float u = (xh[k][j] + xr[k][j]) - xt[k][j];
+                g[k][j] = P == 1 ? (u > 0.f ? c : (u < 0.f ? -c : 0.f)) : c * u * un;
+                dh = fmaf(xh[k][j], g[k][j], dh); dr = fmaf(xr[k][j], g[k][j], dr); dt = fmaf(xt[k][j], g[k][j], dt);
+            }
+        float ah = 1.f, ar = 1.f, at = 1.f;                 // d(x / max(||x||, eps))/dx: (g - x^ (x^ . g)) / ||x||; below eps the map is x / eps
+        if (normalize) {
+            dh = warp_sum(dh); dr = warp_sum(dr); dt = warp_sum(dt);
+            if (!(nh > NORM_EPS)) dh = 0.f;
+            if (!(nr > NORM_EPS)) dr = 0.f;
+            if (!(nt > NORM_EPS)) dt = 0.f;
+            ah = 1.f / nh; ar = 1.f / nr; at = 1.f / nt;
+        } else {
+            dh = dr = dt = 0.f;
+        }
+        float4 *gh = reinterpret_cast<float4 *>(grad_ent + ih * D), *gt = reinterpret_cast<float4 *>(grad_ent + it * D),
+               *gr = reinterpret_cast<float4 *>(grad_rel + ir * D);
+#pragma unroll
+        for (int k = 0; k < MAXV; k++) {
+            const int v = lane + 32 * k;
+            if (v < nv) {
+                float oh[4], orr[4], ot[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    oh[j] = (g[k][j] - xh[k][j] * dh) * ah;
+                    orr[j] = (g[k][j] - xr[k][j] * dr) * ar;
+                    ot[j] = (-g[k][j] + xt[k][j] * dt) * at;
+                }
+                atomicAdd(gh + v, make_float4(oh[0], oh[1], oh[2], oh[3]));
+                atomicAdd(gr + v, make_float4(orr[0], orr[1], orr[2], orr[3]));
+                atomicAdd(gt + v, make_float4(ot[0], ot[1], ot[2], ot[3]));
+            }
+        }
+    }
+}
+
 // forward scores of the similarity models for explicit triples (Model.forward, DistMult.py:46-57, ComplEx.py:29-40):
 // one warp per triple; the value is the raw similarity (predict negates it)
 __global__ void __launch_bounds__(256) bilinear_fwd_kernel(int scorer, const float *__restrict__ ent, const float *__restrict__ ent_im,
@@ -274,8 +412,13 @@ int score_triples(mre_ctx *ctx, int scorer, const float *ent, const float *ent_i
     const int grid = launch_grid(ctx, n);
     if (scorer == MRE_TRANSE) {
         MRE_CHECK_ARG(p_norm == 1 || p_norm == 2, "p_norm must be 1 or 2");
-        if (p_norm == 1) transe_fwd_kernel<1><<<grid, 256, 0, st>>>(ent, rel, (int)D, h, t, r, n, normalize, score);
-        else transe_fwd_kernel<2><<<grid, 256, 0, st>>>(ent, rel, (int)D, h, t, r, n, normalize, score);
+        const bool vec = D % 4 == 0 && D <= 512 && ((uintptr_t)ent % 16 == 0) && ((uintptr_t)rel % 16 == 0);
+#define MRE_FWD(KERN) KERN<<<grid, 256, 0, st>>>(ent, rel, (int)D, h, t, r, n, normalize, score)
+        if (vec && D <= 256) { if (p_norm == 1) MRE_FWD((transe_fwd_vec_kernel<1, 2>)); else MRE_FWD((transe_fwd_vec_kernel<2, 2>)); }
+        else if (vec) { if (p_norm == 1) MRE_FWD((transe_fwd_vec_kernel<1, 4>)); else MRE_FWD((transe_fwd_vec_kernel<2, 4>)); }
+        else if (p_norm == 1) MRE_FWD(transe_fwd_kernel<1>);
+        else MRE_FWD(transe_fwd_kernel<2>);
+#undef MRE_FWD
     } else {
         MRE_CHECK_ARG(scorer == MRE_DISTMULT || (scorer == MRE_COMPLEX && ent_im && rel_im), "bad scorer / missing ComplEx tables");
         bilinear_fwd_kernel<<<grid, 256, 0, st>>>(scorer, ent, ent_im, rel, rel_im, (int)D, h, t, r, n, score);
@@ -292,8 +435,16 @@ int transe_backward(mre_ctx *ctx, const float *ent, const float *rel, int64_t D,
     MRE_CHECK_ARG(p_norm == 1 || p_norm == 2, "p_norm must be 1 or 2");
     if (n == 0) return MRE_OK;
     const int grid = launch_grid(ctx, n);
-    if (p_norm == 1) transe_bwd_kernel<1><<<grid, 256, 0, st>>>(ent, rel, (int)D, h, t, r, n, normalize, score, dscore, grad_ent, grad_rel);
-    else transe_bwd_kernel<2><<<grid, 256, 0, st>>>(ent, rel, (int)D, h, t, r, n, normalize, score, dscore, grad_ent, grad_rel);
+    // rows and gradient rows 16-byte aligned (D % 4 == 0 on cudaMalloc'ed tables) and short enough to live in registers: the
+    // vector form; anything else: the scalar form
+    const bool vec = D % 4 == 0 && D <= 512 && ((uintptr_t)ent % 16 == 0) && ((uintptr_t)rel % 16 == 0) && ((uintptr_t)grad_ent % 16 == 0) &&
+                     ((uintptr_t)grad_rel % 16 == 0);
+#define MRE_BWD(P, KERN) KERN<<<grid, 256, 0, st>>>(ent, rel, (int)D, h, t, r, n, normalize, score, dscore, grad_ent, grad_rel)
+    if (vec && D <= 256) { if (p_norm == 1) MRE_BWD(1, (transe_bwd_vec_kernel<1, 2>)); else MRE_BWD(2, (transe_bwd_vec_kernel<2, 2>)); }
+    else if (vec) { if (p_norm == 1) MRE_BWD(1, (transe_bwd_vec_kernel<1, 4>)); else MRE_BWD(2, (transe_bwd_vec_kernel<2, 4>)); }
+    else if (p_norm == 1) MRE_BWD(1, transe_bwd_kernel<1>);
+    else MRE_BWD(2, transe_bwd_kernel<2>);
+#undef MRE_BWD
     ctx->launches += 1;
     MRE_CUDA(cudaGetLastError());
     return MRE_OK;

@@ -12,10 +12,29 @@ from oracle import openke_torch as ot
 pytestmark = pytest.mark.gpu
 
 
+def l1_kinks(ent, rel, bh, bt, br, normalize, tol=1e-6):
+    """(mask over ent gradients, mask over rel gradients) of the elements that receive a contribution from a triple whose residual
+    u_d = (h^ + r^ - t^)_d is within `tol` of zero: d|u|/du jumps from -1 to +1 there, so an implementation whose row norm differs
+    in the last bit may take the other one-sided derivative (each such triple moves the element by 2 / (B neg)).  Those
+    elements are compared with that allowance; everything else at the stated tolerance."""
+    e, r = torch.from_numpy(ent), torch.from_numpy(rel)
+    h, t, rr = e[bh], e[bt], r[br]
+    if normalize:
+        h, t, rr = (torch.nn.functional.normalize(x, 2, -1) for x in (h, t, rr))
+    near = ((h + rr) - t).abs() < tol
+    me, mr = np.zeros(ent.shape, bool), np.zeros(rel.shape, bool)
+    i, d = np.nonzero(near.numpy())
+    me[bh[i], d] = True
+    me[bt[i], d] = True
+    mr[br[i], d] = True
+    return me, mr
+
+
+@pytest.mark.parametrize("D", [200, 300, 50])     # register-resident float4 kernels (2 and 4 groups per lane) and the scalar kernels
 @pytest.mark.parametrize("p_norm,normalize,margin", [(1, True, 5.0), (2, True, 5.0), (1, False, 3.0), (2, False, 1.0)])
-def test_margin_step_matches_torch_autograd(mre, fb15k237, p_norm, normalize, margin):
+def test_margin_step_matches_torch_autograd(mre, fb15k237, p_norm, normalize, margin, D):
     eng = mre.engine
-    E, R, D = fb15k237.E, fb15k237.R, 200
+    E, R = fb15k237.E, fb15k237.R
     B, neg = 512, 25
     ent, rel = gu.xavier_tables(gu.SEED, [(E, D), (R, D)])
     if not normalize:
@@ -29,11 +48,14 @@ def test_margin_step_matches_torch_autograd(mre, fb15k237, p_norm, normalize, ma
                                               want_scores=True)
     assert np.allclose(sc.cpu().numpy(), score_o.numpy(), rtol=1e-5, atol=1e-6)
     assert np.isclose(loss.item(), loss_o.item(), rtol=1e-5)
-    for mine, ref in ((ge, ge_o), (gr, gr_o)):
+    kinks = l1_kinks(ent, rel, bh, bt, br, normalize) if p_norm == 1 else (np.zeros(ent.shape, bool), np.zeros(rel.shape, bool))
+    for mine, ref, kink in ((ge, ge_o, kinks[0]), (gr, gr_o, kinks[1])):
         ref = ref.numpy()
         scale = np.abs(ref).max()
         assert scale > 0
-        assert np.abs(mine.cpu().numpy() - ref).max() <= 5e-5 * scale
+        err = np.abs(mine.cpu().numpy() - ref)
+        assert err[~kink].max() <= 5e-5 * scale
+        assert kink.sum() <= 64 and (err[kink].max() if kink.any() else 0.0) <= 64 * 2.0 / (B * neg)
     # SGD update (Trainer.py:73-78 with opt_method sgd): w -= lr * g, gradient buffer zeroed
     w = d(ent).clone()
     eng.sgd_update(ctx, w, ge, 0.5)
@@ -70,9 +92,12 @@ def test_margin_step_config4_full_batch(mre, fb15k237):
     loss, ge, gr, sc = eng.transe_margin_step(ctx, d(ent), d(rel), d(bh), d(bt), d(br), B, neg, margin, 1, True, want_scores=True)
     assert np.allclose(sc.cpu().numpy(), score_o.numpy(), rtol=1e-5, atol=1e-6)
     assert np.isclose(loss.item(), loss_o.item(), rtol=1e-5)
-    for mine, ref in ((ge, ge_o), (gr, gr_o)):
+    kinks = l1_kinks(ent, rel, bh, bt, br, True)
+    for mine, ref, kink in ((ge, ge_o, kinks[0]), (gr, gr_o, kinks[1])):
         ref = ref.numpy()
-        assert np.abs(mine.cpu().numpy() - ref).max() <= 5e-5 * np.abs(ref).max()
+        err = np.abs(mine.cpu().numpy() - ref)
+        assert err[~kink].max() <= 5e-5 * np.abs(ref).max()
+        assert kink.sum() <= 64 and (err[kink].max() if kink.any() else 0.0) <= 64 * 2.0 / (B * neg)
 
 
 def _ref_scores(kind, tabs, bh, bt, br):
