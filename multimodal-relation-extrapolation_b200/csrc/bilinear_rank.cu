@@ -338,8 +338,8 @@ __global__ void __launch_bounds__(KNOWN_WARPS * 32) bil_known_kernel(const RankP
     known_correction(p, op, sT[threadIdx.x >> 5], sX[threadIdx.x >> 5]);
 }
 // (Building the query vector from the embedding rows instead, so that this kernel could run beside bil_query_kernel on the second
-// stream, was measured SLOWER: four row loads per element and a scalar direct path cost more than the overlap saves --
-// ComplEx step 0.61 -> 0.85 ms.)
+// stream, was measured twice and does not pay: with a scalar short-run path the ComplEx step went 0.61 -> 0.85 ms, with the
+// vector staged in shared memory 0.607 -> 0.616 ms -- the two kernels compete for the same SMs and L2 misses.)
 __global__ void __launch_bounds__(KNOWN_WARPS * 32) bil_known_score_kernel(const RankParams p, const KnownRuns kr) {
     __shared__ float sT[KNOWN_WARPS][32][33];
     __shared__ int64_t sX[KNOWN_WARPS][32];
