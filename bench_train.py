@@ -107,10 +107,28 @@ def main(args, rank, world, local):
     state = {"step": 0}
     lr = 1.0
 
-    def step_dev():
-        h, t, r, y = smp.sample(state["step"], B, neg)
+    # The next batch does not depend on the weights: its Philox sampling runs on a side stream BESIDE this step's gradient
+    # exchange / update kernel (which leaves most of every SM free) and is joined by an event before the next forward.
+    side = torch.cuda.Stream(device=dev)
+
+    def draw():
+        main = torch.cuda.current_stream()
+        with torch.cuda.stream(side):
+            batch = smp.sample(state["step"], B, neg)
+            ev = torch.cuda.Event()
+            ev.record(side)
+        for x in batch:
+            x.record_stream(main)
         state["step"] += 1
+        return batch, ev
+
+    def step_dev():
+        if state.get("next") is None:
+            state["next"] = draw()
+        (h, t, r, y), ev = state["next"]
+        torch.cuda.current_stream().wait_event(ev)
         loss, _, _, _ = eng.transe_margin_step(ctx, ent_d, rel_d, h, t, r, B, neg, 5.0, 1, True, grad_ent=g_ent, grad_rel=g_rel)
+        state["next"] = draw()
         update()
         return loss
 
