@@ -110,24 +110,29 @@ def main(args, rank, world, local):
     # The next batch does not depend on the weights: its Philox sampling runs on a side stream BESIDE this step's gradient
     # exchange / update kernel (which leaves most of every SM free) and is joined by an event before the next forward.
     side = torch.cuda.Stream(device=dev)
+    bufs = [tuple([torch.empty(n, dtype=torch.int64, device=dev) for _ in range(3)] + [torch.empty(n, dtype=torch.float32, device=dev)])
+            for _ in range(2)]                       # two batches in flight: the one being trained on and the one being drawn
+    free_ev = [None, None]                           # recorded on the main stream when a buffer's batch has been consumed
 
     def draw():
-        main = torch.cuda.current_stream()
+        k = state["step"] & 1
         with torch.cuda.stream(side):
-            batch = smp.sample(state["step"], B, neg)
+            if free_ev[k] is not None:
+                side.wait_event(free_ev[k])
+            batch = smp.sample(state["step"], B, neg, out=bufs[k])
             ev = torch.cuda.Event()
             ev.record(side)
-        for x in batch:
-            x.record_stream(main)
         state["step"] += 1
-        return batch, ev
+        return batch, ev, k
 
     def step_dev():
         if state.get("next") is None:
             state["next"] = draw()
-        (h, t, r, y), ev = state["next"]
+        (h, t, r, y), ev, k = state["next"]
         torch.cuda.current_stream().wait_event(ev)
         loss, _, _, _ = eng.transe_margin_step(ctx, ent_d, rel_d, h, t, r, B, neg, 5.0, 1, True, grad_ent=g_ent, grad_rel=g_rel)
+        free_ev[k] = torch.cuda.Event()
+        free_ev[k].record()
         state["next"] = draw()
         update()
         return loss

