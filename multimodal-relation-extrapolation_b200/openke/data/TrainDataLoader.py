@@ -75,10 +75,48 @@ class TrainDataLoader(object):
             self.batch_y = np.zeros(n, dtype=np.float32)
         self.batch_seq_size = n
 
+    def _draw_prefetched(self):
+        """device batches in "normal" mode: batch k was drawn on a side stream while the consumer worked on batch k - 1 (its
+        Philox stream depends on (seed, step) only), into one of two buffer sets; the consumer's stream waits for the draw, the
+        next draw waits until the consumer's work on the buffer it overwrites has been enqueued and finished"""
+        import torch
+        n = self.batch_seq_size
+        dev = self.sampler.device
+        st = getattr(self, "_pf", None)
+        if st is None or st["n"] != n or st["key"] != (self.batch_size, self.negative_ent, self.bern):
+            st = {"n": n, "key": (self.batch_size, self.negative_ent, self.bern), "side": torch.cuda.Stream(device=dev), "next": None,
+                  "bufs": [tuple([torch.empty(n, dtype=torch.int64, device=dev) for _ in range(3)] + [torch.empty(n, dtype=torch.float32, device=dev)])
+                           for _ in range(2)], "free": [None, None]}
+            self._pf = st
+
+        def launch():
+            k = self.step & 1
+            with torch.cuda.stream(st["side"]):
+                if st["free"][k] is not None:
+                    st["side"].wait_event(st["free"][k])
+                batch = self.sampler.sample(self.step, self.batch_size, self.negative_ent, mode=0, bern=self.bern, out=st["bufs"][k])
+                ev = torch.cuda.Event()
+                ev.record(st["side"])
+            self.step += 1
+            return batch, ev, k
+
+        if st["next"] is None:
+            st["next"] = launch()
+        batch, ev, k = st["next"]
+        cur = torch.cuda.current_stream(dev)
+        cur.wait_event(ev)
+        # the PREVIOUS batch's buffer (the other set) is free once everything enqueued so far on the consumer's stream is done
+        st["free"][1 - k] = torch.cuda.Event()
+        st["free"][1 - k].record(cur)
+        st["next"] = launch()
+        return batch
+
     def _draw(self, mode):
+        self._size_buffers()
+        if self.device_batches and mode == 0:
+            return self._draw_prefetched()
         step = self.step
         self.step += 1
-        self._size_buffers()
         if self.device_batches:
             return self.sampler.sample(step, self.batch_size, self.negative_ent, mode=mode, bern=self.bern)
         return self.sampler.sample_host(step, self.batch_size, self.negative_ent, mode=mode, bern=self.bern,
