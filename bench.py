@@ -782,7 +782,7 @@ def main():
                     extra[name] = {"error": f"{type(e).__name__}: {e}"}
             try:
                 import bench_train
-                extra["train"] = sub_bench(bench_train, rank, world, local, 20, 3, args.gpus)
+                extra["train"] = sub_bench(bench_train, rank, world, local, 60, 6, args.gpus)
             except Exception as e:  # noqa: BLE001
                 extra["train"] = {"error": f"{type(e).__name__}: {e}"}
             if world == 1:
