@@ -50,6 +50,8 @@ extern "C" {
 #define MRE_TRANSE   0   /* OpenKE/openke/module/model/TransE.py:46-60, module/NegativeSampling.py:142-157 */
 #define MRE_DISTMULT 1   /* OpenKE/openke/module/model/DistMult.py:34-44 */
 #define MRE_COMPLEX  2   /* OpenKE/openke/module/model/ComplEx.py:20-27 */
+#define MRE_ROTATE   3   /* OpenKE/openke/module/model/RotatE.py:44-78: ent rows [re | im] (D = 2 dim), rel rows = phases (dim);
+                            mre_rank only (forward on explicit triples stays with the host mirror) */
 
 /* filter sources */
 #define MRE_FILTER_NONE  0   /* raw ranks only */
@@ -161,7 +163,7 @@ typedef struct mre_rank_job {
     const float *ent_im;     /* [E, D]   ComplEx only (ent_im_embeddings) */
     const float *rel_im;     /* [R, D]   ComplEx only */
     int64_t E, R, D;
-    int32_t scorer;          /* MRE_TRANSE | MRE_DISTMULT | MRE_COMPLEX */
+    int32_t scorer;          /* MRE_TRANSE | MRE_DISTMULT | MRE_COMPLEX | MRE_ROTATE */
     int32_t p_norm;          /* TransE: 1 or 2 (TransE.py:10,59) */
     int32_t normalize;       /* TransE norm_flag (TransE.py:47-50): L2-normalise h, r, t rows first */
     int32_t filter;          /* MRE_FILTER_* */
@@ -190,6 +192,8 @@ typedef struct mre_rank_job {
      *   filt_*  = the same over S_q minus known-true entities minus the true entity itself
      * OpenKE's l_s / l_filter_s (Test.h:80-87) are raw_lt / filt_lt. */
     int32_t *counts;
+    /* MRE_ROTATE: rel_embedding_range / pi in float32 (RotatE.py:49: phase = r / (rel_embedding_range / pi)); 0 otherwise */
+    float rotate_phase_div;
 } mre_rank_job;
 
 /* asynchronous on `stream`; `ix` may be NULL unless filter == MRE_FILTER_INDEX */

@@ -14,13 +14,13 @@ BUILD_DIR = os.path.join(_HERE, "build")
 LIB_PATH = os.environ.get("MRE_B200_LIB") or os.path.join(BUILD_DIR, "libmre_b200.so")   # override: A/B timing of two builds
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include", "mre_b200.h")
 
-SOURCES = ["index.cpp", "tma_host.cpp", "abi.cu", "transe_rank.cu", "metrics.cu", "sampler.cu", "train_step.cu", "bilinear_rank.cu", "zsl_rank.cu", "peer.cu", "project.cu"]
+SOURCES = ["index.cpp", "tma_host.cpp", "abi.cu", "transe_rank.cu", "metrics.cu", "sampler.cu", "train_step.cu", "bilinear_rank.cu", "zsl_rank.cu", "peer.cu", "project.cu", "rotate_rank.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
               "-Xcompiler", "-fPIC,-O2,-pthread", "-shared"]
 
 # constants mirrored from include/mre_b200.h
 OK = 0
-TRANSE, DISTMULT, COMPLEX = 0, 1, 2
+TRANSE, DISTMULT, COMPLEX, ROTATE = 0, 1, 2, 3
 FILTER_NONE, FILTER_INDEX, FILTER_CSR = 0, 1, 2
 RANK_STRICT, RANK_TIES_HALF, RANK_PESSIMISTIC = 0, 1, 2
 TOTAL_ENTITY, TOTAL_RELATION, TOTAL_TRAIN, TOTAL_VALID, TOTAL_TEST, TOTAL_TRIPLE = range(6)
@@ -53,7 +53,7 @@ class RankJob(C.Structure):
         ("side", C.c_int32), ("n_groups", C.c_int32), ("Q", C.c_int64),
         ("group_qptr", C.c_void_p), ("group_cptr", C.c_void_p), ("cand_idx", C.c_void_p),
         ("filt_ptr", C.c_void_p), ("filt_idx", C.c_void_p), ("filt_nnz", C.c_int64),
-        ("counts", C.c_void_p),
+        ("counts", C.c_void_p), ("rotate_phase_div", C.c_float),
     ]
 
 

@@ -56,7 +56,7 @@ static int check_job(const mre_rank_job *job) {
     MRE_CHECK_ARG(job->Q >= 0, "Q must be non-negative");
     MRE_CHECK_ARG(job->E < (1LL << 31) && job->Q < (1LL << 31), "E and Q must fit int32 counts");
     MRE_CHECK_ARG(job->ent && job->rel, "ent / rel table is NULL");
-    MRE_CHECK_ARG(job->scorer >= MRE_TRANSE && job->scorer <= MRE_COMPLEX, "unknown scorer %d", job->scorer);
+    MRE_CHECK_ARG(job->scorer >= MRE_TRANSE && job->scorer <= MRE_ROTATE, "unknown scorer %d", job->scorer);
     MRE_CHECK_ARG(job->scorer != MRE_COMPLEX || (job->ent_im && job->rel_im), "ComplEx needs ent_im and rel_im");
     MRE_CHECK_ARG(job->filter >= MRE_FILTER_NONE && job->filter <= MRE_FILTER_CSR, "unknown filter %d", job->filter);
     MRE_CHECK_ARG(job->side == 0 || job->side == 1, "side must be 0 or 1");
@@ -68,6 +68,7 @@ static int check_job(const mre_rank_job *job) {
 
 static int dispatch_rank(mre_ctx *ctx, const mre_index *ix, const mre_rank_job *job, cudaStream_t st) {
     if (job->scorer == MRE_TRANSE) return rank_transe(ctx, ix, job, st);
+    if (job->scorer == MRE_ROTATE) return rank_rotate(ctx, ix, job, st);
     return rank_bilinear(ctx, ix, job, st);
 }
 

@@ -321,6 +321,7 @@ struct BilKnownOp {
         st = -thr[q].x;
         return qvec + q * D;
     }
+    static constexpr bool DIRECT_ONLY = false;
     __device__ __forceinline__ float direct(int64_t x) const { return bil_dot(v, ent + x * D, D); }
     __device__ __forceinline__ void thresholds(int64_t q) { st = -thr[q].x; }
     __device__ __forceinline__ bool truth_ties() const { return st == st; }

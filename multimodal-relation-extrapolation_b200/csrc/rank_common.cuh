@@ -319,7 +319,7 @@ __device__ __forceinline__ void known_score_runs(const RankParams &p, const Know
         if (__shfl_sync(0xffffffffu, old, 0) == kr.epoch) continue;      // another warp of this job scores the segment
         if (!ready) { op.query(q, side, h, t, r); ready = true; }
         const int64_t s1 = min(hi, s0 + KNOWN_SEG);
-        if (s1 - s0 <= KNOWN_DIRECT) {
+        if (Op::DIRECT_ONLY || s1 - s0 <= KNOWN_DIRECT) {
             // a handful of entries (the zero-shot test sets: 2-3 known tails per (h, r)): one entry per lane, scored by the scalar
             // scorer itself -- few lanes, so the row-per-lane access pattern costs nothing, and no instruction is spent on idle lanes
             const int64_t i = s0 + lane;

@@ -270,6 +270,7 @@ struct TranseKnownOp {
         th = thr[q];
         return qvec + (slot >> 1) * (2 * D) + (slot & 1);
     }
+    static constexpr bool DIRECT_ONLY = false;
     __device__ __forceinline__ float direct(int64_t x) const { return transe_acc<P>(a, r, side, ent + x * D, D); }
     __device__ __forceinline__ void thresholds(int64_t q) { th = thr[q]; }
     __device__ __forceinline__ bool truth_ties() const { return th.x < th.y; }       // what the tile kernel decides for acc_true

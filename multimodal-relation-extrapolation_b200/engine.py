@@ -184,7 +184,7 @@ class Context:
         return v.value
 
 
-SCORERS = {"transe": L.TRANSE, "distmult": L.DISTMULT, "complex": L.COMPLEX}
+SCORERS = {"transe": L.TRANSE, "distmult": L.DISTMULT, "complex": L.COMPLEX, "rotate": L.ROTATE}
 RANK_MODES = {"strict": L.RANK_STRICT, "ties_half": L.RANK_TIES_HALF, "pessimistic": L.RANK_PESSIMISTIC}
 
 
@@ -214,7 +214,7 @@ class Ranker:
         self.ctx = ctx or Context(device)
         self.device = torch.device("cuda", self.ctx.device)
 
-    def _job(self, scorer, tables, Q, side, p_norm, normalize, index, filt, groups, filt_csr):
+    def _job(self, scorer, tables, Q, side, p_norm, normalize, index, filt, groups, filt_csr, phase_div=0.0):
         job = L.RankJob()
         if scorer == "complex":
             ent, ent_im, rel, rel_im = tables
@@ -227,7 +227,11 @@ class Ranker:
         job.ent, job.rel = _ptr(ent), _ptr(rel)
         job.E, job.D = ent.shape
         job.R = rel.shape[0]
-        assert rel.shape[1] == ent.shape[1]
+        if scorer == "rotate":                  # ent rows [re | im], rel rows = phases (RotatE.py:13-14)
+            assert 2 * rel.shape[1] == ent.shape[1] and phase_div > 0
+            job.rotate_phase_div = float(phase_div)
+        else:
+            assert rel.shape[1] == ent.shape[1]
         job.scorer = SCORERS[scorer]
         job.p_norm, job.normalize = int(p_norm), int(bool(normalize))
         if filt is None:
@@ -252,10 +256,11 @@ class Ranker:
         return job, keep
 
     def rank(self, scorer, tables, q_h, q_t, q_r, side, *, p_norm=1, normalize=False, index=None, filter=None,
-             groups=None, filt_csr=None, out=None):
-        """Device queries -> device int32 counts [4, Q] = (raw_lt, raw_eq, filt_lt, filt_eq).  Asynchronous."""
+             groups=None, filt_csr=None, out=None, phase_div=0.0):
+        """Device queries -> device int32 counts [4, Q] = (raw_lt, raw_eq, filt_lt, filt_eq).  Asynchronous.
+        `phase_div`: RotatE only (rel_embedding_range / pi)."""
         Q = q_h.numel()
-        job, keep = self._job(scorer, tables, Q, side, p_norm, normalize, index, filter, groups, filt_csr)
+        job, keep = self._job(scorer, tables, Q, side, p_norm, normalize, index, filter, groups, filt_csr, phase_div)
         for t in (q_h, q_t, q_r):
             assert t.is_cuda and t.dtype == torch.int64 and t.is_contiguous() and t.numel() == Q
         if not isinstance(side, (int, np.integer)):
@@ -267,10 +272,10 @@ class Ranker:
         return counts
 
     def rank_host(self, scorer, tables, q_h, q_t, q_r, side, *, p_norm=1, normalize=False, index=None, filter=None,
-                  groups=None, filt_csr=None, out=None):
+                  groups=None, filt_csr=None, out=None, phase_div=0.0):
         """Host (numpy / pinned torch CPU) queries -> host int32 counts [4, Q]; copies included; synchronous."""
         Q = len(q_h)
-        job, keep = self._job(scorer, tables, Q, side, p_norm, normalize, index, filter, groups, filt_csr)
+        job, keep = self._job(scorer, tables, Q, side, p_norm, normalize, index, filter, groups, filt_csr, phase_div)
         arrs = []
         for a in (q_h, q_t, q_r):
             a = a if isinstance(a, torch.Tensor) else _i64(a)

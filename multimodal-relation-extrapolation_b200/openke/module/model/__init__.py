@@ -6,5 +6,6 @@ from .SimplE import SimplE
 from .TransH import TransH
 from .TransD import TransD
 from .Analogy import Analogy
+from .RotatE import RotatE
 
-__all__ = ["Model", "TransE", "DistMult", "ComplEx", "SimplE", "TransH", "TransD", "Analogy"]
+__all__ = ["Model", "TransE", "DistMult", "ComplEx", "SimplE", "TransH", "TransD", "Analogy", "RotatE"]

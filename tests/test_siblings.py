@@ -125,3 +125,81 @@ def test_projected_models_train_through_the_library_losses(mre):
         opt.step()
         with torch.no_grad():
             assert strat(data).item() < l0.item()
+
+
+# ------------------------------------------------------------------------------------------------ RotatE
+def build_rotate(mre, E, R, D, wname):
+    m = mre.openke.module.model.RotatE(E, R, dim=D, margin=6.0, epsilon=2.0)
+    ent, rel = gu.WEIGHT_SETS[wname](gu.SEED + 11, [(E, 2 * D), (R, D)])       # as tests/golden/make_golden_rotate.py
+    ent = ent / np.abs(ent).max() * m.ent_embedding_range.item()
+    rel = rel / np.abs(rel).max() * m.rel_embedding_range.item()
+    m.ent_embeddings.weight.data.copy_(torch.from_numpy(ent.astype(np.float32)))
+    m.rel_embeddings.weight.data.copy_(torch.from_numpy(rel.astype(np.float32)))
+    return m.cuda()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("wname", list(gu.WEIGHT_SETS))
+def test_rotate_ranks_vs_reference_golden(mre, fb15k237, wname):
+    """RotatE through its own tile kernel (csrc/rotate_rank.cu): filtered counts inside the 1e-5 relative tie band of the reference
+    module's own scores (tests/golden/golden_rotate.npz), equal where the band is empty; the same counts from a CSR filter and from
+    a candidate-group job over all entities; predict() within 2e-5 relative of the reference's probe scores"""
+    from mre_b200.openke.module.model._projected import known_lists
+    g = gu.load("golden_rotate.npz")
+    eng = mre.engine
+    E, R, D = fb15k237.E, fb15k237.R, int(g["D"])
+    model = build_rotate(mre, E, R, D, wname)
+    ix = eng.KGIndex.from_arrays(E, R, fb15k237.train, fb15k237.valid, fb15k237.test).to_device(0)
+    th, tt, tr = fb15k237.oracle.test_triples()
+    qidx = g["qidx"]
+    q_h, q_t, q_r = np.repeat(th[qidx], 2), np.repeat(tt[qidx], 2), np.repeat(tr[qidx], 2)
+    side = np.tile(np.array([0, 1], np.uint8), len(qidx))
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    tabs = tuple(t.detach().contiguous() for t in model.tables())
+    rk, kw = model.ranker(), model.rank_kwargs()
+    c = rk.rank("rotate", tabs, dev(q_h), dev(q_t), dev(q_r), dev(side), index=ix, **kw).cpu().numpy()
+    key = f"{wname}_rotate"
+    filt, raw = c[2].reshape(-1, 2), c[0].reshape(-1, 2)
+    lo, hi, ref = g[key + "_lo"], g[key + "_hi"], g[key + "_filt"]
+    outside = (filt < lo) | (filt > hi)
+    assert not outside.any(), (int(outside.sum()), filt[outside][:4], lo[outside][:4], hi[outside][:4])
+    exact = lo == hi
+    assert np.array_equal(filt[exact], ref[exact]) and int(exact.sum()) >= 20
+    assert np.all(np.abs(raw - g[key + "_raw"]) <= (hi - lo))
+    # the same job with the known lists handed over as a CSR filter, and as one candidate group holding every entity
+    fptr, fidx = known_lists(ix, q_h, q_t, q_r, side)
+    c2 = rk.rank("rotate", tabs, dev(q_h), dev(q_t), dev(q_r), dev(side), filt_csr=(dev(fptr), dev(fidx), len(fidx)), **kw).cpu().numpy()
+    assert np.array_equal(c, c2)
+    groups = eng.CandidateGroups.from_lists([len(q_h)], [np.arange(E)], "cuda")
+    c3 = rk.rank("rotate", tabs, dev(q_h), dev(q_t), dev(q_r), dev(side), index=ix, groups=groups, **kw).cpu().numpy()
+    assert np.array_equal(c, c3)
+    probe = g["probe"]
+    for k in (0, len(qidx) // 2, len(qidx) - 1):
+        i = int(qidx[k])
+        h, t, r = int(th[i]), int(tt[i]), int(tr[i])
+        for s in (0, 1):
+            ids = np.concatenate([[h if s == 0 else t], probe])
+            data = ({"batch_h": dev(ids), "batch_t": dev(np.array([t])), "batch_r": dev(np.array([r])), "mode": "head_batch"} if s == 0
+                    else {"batch_h": dev(np.array([h])), "batch_t": dev(ids), "batch_r": dev(np.array([r])), "mode": "tail_batch"})
+            assert np.allclose(model.predict(data), g[key + "_probe"][k, s], rtol=2e-5, atol=2e-6)
+
+
+@pytest.mark.gpu
+def test_rotate_trains_through_the_library_losses(mre):
+    """RotatE.forward() is differentiable to both tables: one strategy step with the self-adversarial sigmoid loss lowers the loss"""
+    ok = mre.openke
+    E, R, D, B, neg = 300, 7, 16, 64, 4
+    rng = np.random.default_rng(0)
+    h, t, r = rng.integers(0, E, B * (1 + neg)), rng.integers(0, E, B * (1 + neg)), np.tile(rng.integers(0, R, B), 1 + neg)
+    data = {"batch_h": torch.from_numpy(h).cuda(), "batch_t": torch.from_numpy(t).cuda(), "batch_r": torch.from_numpy(r).cuda(),
+            "batch_y": torch.ones(1).cuda(), "mode": "normal"}
+    torch.manual_seed(1)
+    m = ok.module.model.RotatE(E, R, dim=D).cuda()
+    strat = ok.module.strategy.NegativeSampling(model=m, loss=ok.module.loss.SigmoidLoss(adv_temperature=2), batch_size=B).cuda()
+    opt = torch.optim.SGD(m.parameters(), lr=0.5)
+    l0 = strat(data)
+    l0.backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() and p.grad.abs().sum() > 0 for p in m.parameters() if p.requires_grad)
+    opt.step()
+    with torch.no_grad():
+        assert strat(data).item() < l0.item()
