@@ -137,6 +137,11 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar, uint16_t mask) {
 __device__ __forceinline__ void cp_async_8(uint32_t dst, const void *src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
 }
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const void *src) {      // L2 -> shared memory, no L1 allocation
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
