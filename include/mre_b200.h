@@ -105,10 +105,30 @@ int mre_index_create(int64_t E, int64_t R,
  * (setInPath + importTrainFiles + importTestFiles, Setting.h:17-27, Reader.h:53-257).
  * valid2id.txt / test2id.txt may be absent (training-only use). */
 int mre_index_create_from_dir(const char *in_path, mre_index **out);
+/*
+ * mre_index_create + mre_index_to_device(device) with every sort of the build on the GPU (csrc/index_build.cu): the three
+ * std::sort calls of importTrainFiles / importTestFiles (Reader.h:91-109, 201-227), the de-duplication (Reader.h:91-105) and the
+ * freqRel / distinct-pair counters behind tph / hpt (Reader.h:142-159) run as LSD radix-sort passes, a flag / scan / compact and
+ * an atomic histogram over int32 id columns; the sorted lists are copied back so that every host getter answers as after
+ * mre_index_create, and the filter / sampler tables are written in place on `device`.  Same bits as the host build.
+ * Limits: E, R and the total number of triples below 2^31 (MRE_ERR_INVALID otherwise: use mre_index_create).
+ * build_ms (optional): device time of the build proper (first sort to last table written; the copy-back of the lists excluded).
+ */
+int mre_index_create_device(int device, int64_t E, int64_t R,
+                            const int64_t *train_h, const int64_t *train_t, const int64_t *train_r, int64_t n_train,
+                            const int64_t *valid_h, const int64_t *valid_t, const int64_t *valid_r, int64_t n_valid,
+                            const int64_t *test_h, const int64_t *test_t, const int64_t *test_r, int64_t n_test,
+                            mre_index **out, double *build_ms);
 void mre_index_destroy(mre_index *ix);
 /* upload the filter / sampler tables to `device` (idempotent) */
 int mre_index_to_device(mre_index *ix, int device);
 int64_t mre_index_total(const mre_index *ix, int which);
+/* One column of the device-resident tables, copied to host_out (NULL: only the length is returned; < 0 on error).  which:
+ * 0-3 the filter tables over all splits, de-duplicated -- key h R + r / payload t in (h,r,t) order, key t R + r / payload h in
+ * (t,r,h) order (what _find bisects, Corrupt.h:166-177); 4-9 the sampler tables over de-duplicated train -- h, r, t and key
+ * h R + r in (h,r,t) order, key t R + r / payload h in (t,r,h) order (trainHead / trainTail, Reader.h:107-140); int64 each;
+ * 10 the Bernoulli threshold per relation (float32, Base.cpp:113).  For tests and debugging. */
+int64_t mre_index_device_column(const mre_index *ix, int which, void *host_out);
 int mre_index_get_split(const mre_index *ix, int split, int64_t *h, int64_t *t, int64_t *r);
 /* left_mean = tph, right_mean = hpt per relation (Reader.h:142-159) */
 int mre_index_get_means(const mre_index *ix, float *tph, float *hpt);

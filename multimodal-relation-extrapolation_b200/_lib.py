@@ -14,7 +14,7 @@ BUILD_DIR = os.path.join(_HERE, "build")
 LIB_PATH = os.environ.get("MRE_B200_LIB") or os.path.join(BUILD_DIR, "libmre_b200.so")   # override: A/B timing of two builds
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include", "mre_b200.h")
 
-SOURCES = ["index.cpp", "tma_host.cpp", "abi.cu", "transe_rank.cu", "metrics.cu", "sampler.cu", "train_step.cu", "bilinear_rank.cu", "zsl_rank.cu", "peer.cu", "project.cu", "rotate_rank.cu"]
+SOURCES = ["index.cpp", "tma_host.cpp", "abi.cu", "transe_rank.cu", "metrics.cu", "sampler.cu", "train_step.cu", "bilinear_rank.cu", "zsl_rank.cu", "peer.cu", "project.cu", "rotate_rank.cu", "index_build.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
               "-Xcompiler", "-fPIC,-O2,-pthread", "-shared"]
 
@@ -100,6 +100,9 @@ def lib():
     L.mre_device_ok.argtypes = [i32]
     L.mre_index_create.argtypes = [i64, i64] + [vp, vp, vp, i64] * 3 + [P(vp)]
     L.mre_index_create_from_dir.argtypes = [C.c_char_p, P(vp)]
+    L.mre_index_create_device.argtypes = [i32, i64, i64] + [vp, vp, vp, i64] * 3 + [P(vp), P(C.c_double)]
+    L.mre_index_device_column.argtypes = [vp, i32, vp]
+    L.mre_index_device_column.restype = i64
     L.mre_index_destroy.argtypes = [vp]
     L.mre_index_destroy.restype = None
     L.mre_index_to_device.argtypes = [vp, i32]

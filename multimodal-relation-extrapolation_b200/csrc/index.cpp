@@ -480,6 +480,32 @@ int mre_index_to_device(mre_index *ix, int device) {
     return upload_type_lists(ix);
 }
 
+int64_t mre_index_device_column(const mre_index *ix, int which, void *host_out) {
+    if (!ix || ix->device < 0) {
+        set_error("the index has no device tables (call mre_index_to_device or build with mre_index_create_device)");
+        return -1;
+    }
+    const void *src[11] = {ix->d_all_hr_key, ix->d_all_hr_val, ix->d_all_tr_key, ix->d_all_tr_val, ix->d_tr_h, ix->d_tr_r, ix->d_tr_t,
+                           ix->d_tr_hr_key, ix->d_tr_tr_key, ix->d_tr_tr_val, ix->d_bern_prob};
+    if (which < 0 || which > 10) {
+        set_error("unknown device column %d", which);
+        return -1;
+    }
+    const int64_t n = which < 4 ? ix->n_all : which < 10 ? ix->n_train : ix->R;
+    if (host_out && n > 0) {
+        int cur = 0;
+        cudaGetDevice(&cur);
+        cudaSetDevice(ix->device);
+        const cudaError_t e = cudaMemcpy(host_out, src[which], (size_t)n * (which == 10 ? sizeof(float) : sizeof(int64_t)), cudaMemcpyDeviceToHost);
+        cudaSetDevice(cur);
+        if (e != cudaSuccess) {
+            set_error("mre_index_device_column: %s", cudaGetErrorString(e));
+            return -1;
+        }
+    }
+    return n;
+}
+
 int64_t mre_index_total(const mre_index *ix, int which) {
     if (!ix) return -1;
     switch (which) {

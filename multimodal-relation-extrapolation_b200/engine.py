@@ -59,6 +59,34 @@ class KGIndex:
         return cls(out.value)
 
     @classmethod
+    def from_arrays_device(cls, E, R, train, valid=None, test=None, device=0):
+        """from_arrays + to_device with the sorts, the de-duplication and the relation counters run on the GPU
+        (mre_index_create_device: LSD radix sort, csrc/index_build.cu); `build_ms` holds the device time of the build."""
+        empty = (np.zeros(0, np.int64),) * 3
+        cols, keep = [], []
+        for split in (train, valid or empty, test or empty):
+            h, t, r = (_i64(x) for x in split)
+            assert len(h) == len(t) == len(r)
+            keep += [h, t, r]
+            cols += [h.ctypes.data, t.ctypes.data, r.ctypes.data, len(h)]
+        out, ms = C.c_void_p(), C.c_double(0.0)
+        L.check(L.lib().mre_index_create_device(int(device), int(E), int(R), *cols, C.byref(out), C.byref(ms)))
+        ix = cls(out.value)
+        ix.device, ix.build_ms = int(device), ms.value
+        return ix
+
+    def device_column(self, which):
+        """one column of the device tables as a host array (mre_index_device_column)"""
+        lib = L.lib()
+        n = lib.mre_index_device_column(self._h, int(which), None)
+        if n < 0:
+            raise L.MreError(lib.mre_last_error().decode())
+        out = np.empty(n, np.float32 if which == 10 else np.int64)
+        if lib.mre_index_device_column(self._h, int(which), out.ctypes.data) < 0:
+            raise L.MreError(lib.mre_last_error().decode())
+        return out
+
+    @classmethod
     def from_dir(cls, in_path):
         """setInPath + importTrainFiles + importTestFiles (Setting.h:17-27, Reader.h:53-257)."""
         out = C.c_void_p()
