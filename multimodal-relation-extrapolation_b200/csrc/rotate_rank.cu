@@ -8,7 +8,7 @@
 //   OpenKE/openke/base/Test.h:65-192             testHead / testTail on the E-long score vector
 // The margin is a constant shift of every score of a query: the counts do not depend on it, so the kernel ranks the distance
 // itself.  Per (query, entity, complex dimension): two subtractions, m = fma(di, di, dr * dr), one square root (MUFU-bound: one
-// MUFU.SQRT per complex dimension against the FP32 pipe's 2 lane-ops per real dimension of TransE) and one add, sequential over
+// MUFU.SQRT -- 16 per clock per SM -- per complex dimension beside five FP32 instructions) and one add, sequential over
 // d per pair -- the same accumulation in the tile kernel, in the threshold of the true entity and in the known-true correction
 // pass (rotate_acc), so `s_j < s_true` is decided on identical bits.  A plain shared-memory tile kernel (64 queries x 64
 // candidates per CTA, 4 x 4 per thread), not the TMA / packed-FADD2 machinery of the TransE kernel.
@@ -28,9 +28,23 @@ constexpr int RT_CH = 16;         // complex dimensions per shared-memory chunk
 constexpr int RT_THREADS = 256;   // 16 x 16 threads, a 4 x 4 micro-tile each
 
 // the one definition of a RotatE accumulator: v = [v_re | v_im], e = [e_re | e_im] (Dc complex dimensions each)
+#ifndef MRE_ROTATE_SQRT_APPROX
+#define MRE_ROTATE_SQRT_APPROX 1
+#endif
 __device__ __forceinline__ float rotate_step(float acc, float vr, float vi, float er, float ei) {
     const float dr = vr - er, di = vi - ei;
-    return acc + sqrtf(fmaf(di, di, dr * dr));
+    const float m = fmaf(di, di, dr * dr);
+#if MRE_ROTATE_SQRT_APPROX
+    // one MUFU.SQRT (2 ulp) instead of MUFU.RSQ + the Newton / special-case sequence of the IEEE square root: the tile loop is then
+    // bound by the MUFU unit (16 per clock per SM) rather than by a dozen FP32 instructions per element.  Every decision of a job
+    // -- tile kernel, threshold, known-true pass -- goes through this one function, so the counts stay self-consistent; against the
+    // reference's torch.norm the difference (~1e-7 relative on a sum of dim terms) is far inside the 1e-5 tie band.
+    float s;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(m));
+    return acc + s;
+#else
+    return acc + sqrtf(m);
+#endif
 }
 __device__ __forceinline__ float rotate_acc(const float *__restrict__ v, const float *__restrict__ e, int Dc) {
     float acc = 0.f;
