@@ -121,6 +121,7 @@ struct mre_ctx {
     // tunables (mre_ctx_option): BF16/FP16 MMAs per product of the bilinear path, CTA pairs on/off, persistent CTAs per SM of the
     // TransE kernel, FP32 fallback of the ZSL scorer -- developer A/B switches, read from the context, never from the environment
     int opt_bil_products = 3, opt_bil_pair = 1, opt_transe_ctas = 0, opt_zsl_fp32 = 0, opt_transe_lpt = 1;
+    int zsl_const_slot = 0;          // this context's slot of the ZSL kernel's constant-bank vectors (zsl_rank.cu)
     unsigned int bil_epoch = 0;      // generation tag of the bilinear path's max-row-norm slot (no reset launch per call)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // optional per-launch timing of the dominant (rank) kernel: event pairs recorded on the launching stream

@@ -598,6 +598,8 @@ int mre_ctx_create(int device, mre_ctx **out) {
     MRE_CUDA(cudaSetDevice(device));
     mre_ctx *c = new mre_ctx();
     c->device = device;
+    static std::atomic<int> next_slot{0};
+    c->zsl_const_slot = next_slot.fetch_add(1) % 16;      // ZT_CONST_SLOTS (zsl_rank.cu)
     cudaDeviceProp p;
     MRE_CUDA(cudaGetDeviceProperties(&p, device));
     c->sm_count = p.multiProcessorCount;

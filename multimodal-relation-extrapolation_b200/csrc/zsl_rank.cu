@@ -393,6 +393,17 @@ constexpr int ZT_THREADS = 32 * (ZT_PROD_WARPS + ZT_EPI_WARPS + 1);
 constexpr int ZT_XPITCH = 36;                                      // floats per staged residual row (32 + 4: conflict-free both ways)
 constexpr int ZT_A_BYTES = ZT_CTA_ROWS * ZT_BK * 4;                // one of the hi / lo operand tiles of a stage (this CTA's rows)
 
+// The epilogue's three per-column vectors (proj2 bias, LayerNorm gain and bias) are the same for every row of every tile.  Read from
+// shared memory they cost two L1TEX data-pipe wavefronts per warp-uniform LDS.128 (165 M per sweep on the pipe that bounds the
+// kernel, profiles/r2_zsl_gather_experiments.md); from the constant bank they are LDC reads through the constant cache and cost
+// the data pipe nothing.  One slot per context (contexts are not shared between concurrently running streams -- the same contract
+// as the context's scratch buffers), filled by a stream-ordered device-to-device copy before the launch.
+#ifndef MRE_ZT_CONST_VEC
+#define MRE_ZT_CONST_VEC 1
+#endif
+constexpr int ZT_CONST_SLOTS = 16, ZT_CONST_D = 224;
+__constant__ float c_zsl_vec[ZT_CONST_SLOTS][3][ZT_CONST_D];
+
 struct ZslTcParams {
     const float *A1, *B1, *A, *B, *sA, *sB;                         // sA / sB: row sums of A / B
     const int64_t *q_head, *q_rel, *cand;
@@ -400,7 +411,7 @@ struct ZslTcParams {
     const float *rsum, *bR;                                         // [n_rel, D]: sum_k r_k / ||r_k||;  [n_rel]: ln_b . rsum
     const float *b2, *ln_g, *ln_b;
     float ln_eps, inv_nvec;
-    int D, K, NP, nkb;
+    int D, K, NP, nkb, cslot;
     uint32_t idesc;
     int64_t P, tiles;
     float *score;
@@ -696,9 +707,15 @@ __global__ void __launch_bounds__(ZT_THREADS, 1) zsl_tc_kernel(const __grid_cons
                                 const int c = c0 + 8 * k + 4 * h;
                                 const float4 a = (MRE_ZT_DIAG & 1) ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldg(xa + c / 4);
                                 const float4 b = *reinterpret_cast<const float4 *>(&stg[lane][8 * k + 4 * h]), rr4 = __ldg(rs + c / 4);
+#if MRE_ZT_CONST_VEC
+                                const float4 b2 = *reinterpret_cast<const float4 *>(&c_zsl_vec[p.cslot][0][c]);
+                                const float4 gg = *reinterpret_cast<const float4 *>(&c_zsl_vec[p.cslot][1][c]);
+                                const float4 be = *reinterpret_cast<const float4 *>(&c_zsl_vec[p.cslot][2][c]);
+#else
                                 const float4 b2 = *reinterpret_cast<const float4 *>(&s_vec[0][c]);
                                 const float4 gg = *reinterpret_cast<const float4 *>(&s_vec[1][c]);
                                 const float4 be = *reinterpret_cast<const float4 *>(&s_vec[2][c]);
+#endif
                                 const float xs[4] = {a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w};
                                 const float b2s[4] = {b2.x, b2.y, b2.z, b2.w}, gs[4] = {gg.x, gg.y, gg.z, gg.w};
                                 const float bes[4] = {be.x, be.y, be.z, be.w}, rrs[4] = {rr4.x, rr4.y, rr4.z, rr4.w};
@@ -851,6 +868,15 @@ int zsl_rank(mre_ctx *ctx, const mre_zsl_model *m, const float *A, const float *
         tp.rsum = rel_aux; tp.bR = rel_aux + n_rel * D; tp.b2 = m->proj2_b; tp.ln_g = m->ln_g; tp.ln_b = m->ln_b;
         tp.ln_eps = m->ln_eps; tp.inv_nvec = 1.f / (float)n_vec;
         tp.D = D; tp.K = K; tp.NP = NP; tp.nkb = K / ZT_BK;
+        tp.cslot = ctx->zsl_const_slot;
+#if MRE_ZT_CONST_VEC
+        {   // stream-ordered: the previous launch of this context has read its slot before these copies run
+            const size_t row = (size_t)ZT_CONST_D * sizeof(float), base_off = (size_t)tp.cslot * 3 * row;
+            MRE_CUDA(cudaMemcpyToSymbolAsync(c_zsl_vec, m->proj2_b, (size_t)D * sizeof(float), base_off, cudaMemcpyDeviceToDevice, st));
+            MRE_CUDA(cudaMemcpyToSymbolAsync(c_zsl_vec, m->ln_g, (size_t)D * sizeof(float), base_off + row, cudaMemcpyDeviceToDevice, st));
+            MRE_CUDA(cudaMemcpyToSymbolAsync(c_zsl_vec, m->ln_b, (size_t)D * sizeof(float), base_off + 2 * row, cudaMemcpyDeviceToDevice, st));
+        }
+#endif
         tp.idesc = umma_idesc_tf32(256, NP);
         tp.P = P; tp.tiles = (P + ZT_ROWS - 1) / ZT_ROWS;
         tp.score = sc;
