@@ -162,3 +162,38 @@ def test_paper_evaluate_matches_paper_oracle(mre):
     got = sc.evaluate(hrow, rrow, trow).cpu().numpy()
     assert np.allclose(got, np.abs(ent[:50] + rel[:50] - ent[100:150]).sum(-1), rtol=1e-5)
     assert paper.zsl_rank_metrics([np.array([0.9, 0.1, 0.5]), np.array([0.1, 0.9, 0.5])])[2] == (1 + 1 / 3) / 2
+
+
+def test_tester_runs_rotate_through_its_own_kernel(mre, kg):
+    """Tester.run_link_prediction with a RotatE model (scorer "rotate", csrc/rotate_rank.cu): the metric tuple against a numpy
+    float32 restatement of RotatE._calc (OpenKE/openke/module/model/RotatE.py:44-78) ranked by the oracle's Test.h loop"""
+    ok = mre.openke
+    torch.manual_seed(5)
+    Dc = 24
+    model = ok.module.model.RotatE(kg.E, kg.R, dim=Dc, margin=6.0, epsilon=2.0)
+    loader = ok.data.TestDataLoader(kg.path, "link")
+    tester = ok.config.Tester(model=model, data_loader=loader, use_gpu=True)
+    mrr, mr, hit10, hit3, hit1 = tester.run_link_prediction(type_constrain=False)
+    ent, rel = (t.detach().cpu().numpy() for t in model.tables())
+    phase = rel / np.float32(model.phase_div())
+    re_r, im_r = np.cos(phase), np.sin(phase)
+    re_e, im_e = ent[:, :Dc], ent[:, Dc:]
+    acc = ko.MetricAccumulator()
+    th, tt, tr = kg.oracle.test_triples()
+    for i in range(len(th)):
+        h, t, r = int(th[i]), int(tt[i]), int(tr[i])
+        for side in (0, 1):
+            if side == 0:        # head_batch: conj(r) o t - h
+                re_s = (re_r[r] * re_e[t] + im_r[r] * im_e[t]) - re_e
+                im_s = (re_r[r] * im_e[t] - im_r[r] * re_e[t]) - im_e
+            else:                # tail_batch: h o r - t
+                re_s = (re_e[h] * re_r[r] - im_e[h] * im_r[r]) - re_e
+                im_s = (re_e[h] * im_r[r] + im_e[h] * re_r[r]) - im_e
+            s = np.sqrt(re_s * re_s + im_s * im_s).sum(-1, dtype=np.float32) - np.float32(6.0)
+            acc.add(side, *kg.oracle.rank_from_scores(np.ascontiguousarray(s, np.float32), side, h, t, r))
+    want = acc.final(kg.oracle.test_total)
+    assert np.allclose([mrr, hit10, hit3, hit1], [want[0], want[2], want[3], want[4]], atol=1e-3)
+    assert np.isclose(mr, want[1], rtol=1e-3)
+    head, tail = next(iter(loader))
+    s = tester.test_one_step(tail)
+    assert s.dtype == np.float32 and s.shape == (kg.E,)
