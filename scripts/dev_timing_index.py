@@ -6,7 +6,8 @@ import numpy as np
 import mre_b200
 eng = mre_b200.engine
 out = []
-for n, E, R in ((310_116, 14_541, 237), (5_200_000, 2_000_000, 1_000), (50_000_000, 20_000_000, 10_000)):
+SIZES = ((310_116, 14_541, 237), (5_200_000, 2_000_000, 1_000), (50_000_000, 20_000_000, 10_000))
+for n, E, R in SIZES[int(os.environ.get("MRE_IB_FIRST", "0")):]:
     rng = np.random.default_rng(1)
     tr = tuple(rng.integers(0, m, n) for m in (E, E, R))
     va = tuple(rng.integers(0, m, n // 20) for m in (E, E, R))
