@@ -791,6 +791,11 @@ def main():
                     extra["zsl"] = sub_bench(bench_zsl, rank, world, local, 10, 3, args.gpus)
                 except Exception as e:  # noqa: BLE001
                     extra["zsl"] = {"error": f"{type(e).__name__}: {e}"}
+                for name, fn in (("rotate", extra_rotate), ("index_build", extra_index_build)):
+                    try:
+                        extra[name] = fn(R)
+                    except Exception as e:  # noqa: BLE001
+                        extra[name] = {"error": f"{type(e).__name__}: {e}"}
 
     if rank == 0:
         out = {"metric": "filtered-rank eval queries/sec", "value": line["value"], "unit": "queries/s", "n_gpus": world, "steps": args.steps,
@@ -801,6 +806,54 @@ def main():
         emit(out)
     if world > 1:
         R.torch.distributed.destroy_process_group()
+
+
+def extra_rotate(R):
+    """RotatE all-entity ranking through its own tile kernel (csrc/rotate_rank.cu): kernel time by CUDA events on the
+    launching stream, against the MUFU rate (one square root per query x entity x complex dimension)"""
+    import mre_b200
+    torch = R.torch
+    E, Rn, Dc, Q = 14541, 237, 100, 8192
+    rng = np.random.default_rng(SEED)
+    ent = torch.from_numpy((rng.random((E, 2 * Dc), dtype=np.float32) - 0.5) * 0.16).to(R.dev)
+    rel = torch.from_numpy((rng.random((Rn, Dc), dtype=np.float32) - 0.5) * 0.16).to(R.dev)
+    q_h, q_t, q_r = (torch.from_numpy(rng.integers(0, n, Q)).to(R.dev) for n in (E, E, Rn))
+    rk = mre_b200.engine.Ranker(device=R.dev.index or 0)
+    kw = dict(filter="none", phase_div=0.08 / np.pi)
+    for _ in range(3):
+        rk.rank("rotate", (ent, rel), q_h, q_t, q_r, 1, **kw)
+    torch.cuda.synchronize()
+    rk.ctx.timing(True)
+    rk.ctx.timing_read()
+    for _ in range(10):
+        rk.rank("rotate", (ent, rel), q_h, q_t, q_r, 1, **kw)
+    torch.cuda.synchronize()
+    ms, n = rk.ctx.timing_read()
+    rk.ctx.timing(False)
+    ms /= n
+    peak = rk.ctx.probe_mufu_peak()
+    return {"value": Q / ms * 1e3, "unit": "queries/s", "kernel_ms": ms, "config": {"E": E, "complex_dim": Dc, "queries": Q, "filter": "none"},
+            "roofline": {"bound": "mufu", "achieved": Q * E * Dc / ms * 1e3, "peak": peak, "unit": "sqrt/s", "frac": Q * E * Dc / ms * 1e3 / peak,
+                         "peak_source": "MUFU.SQRT microbenchmark run in this process (mre_probe_mufu_peak); nominal 148 SM x 16 / clk x 1.965 GHz = 4.65e12"}}
+
+
+def extra_index_build(R):
+    """Reader.h's index (sorts, de-duplication, tph / hpt) built on the GPU (mre_index_create_device) beside the host build"""
+    import mre_b200
+    eng = mre_b200.engine
+    n, E, Rn = 5_200_000, 2_000_000, 1_000
+    rng = np.random.default_rng(SEED)
+    tr, va, te = (tuple(rng.integers(0, m, k) for m in (E, E, Rn)) for k in (n, n // 20, n // 20))
+    dev_id = R.dev.index or 0
+    eng.KGIndex.from_arrays_device(E, Rn, tuple(x[:1000] for x in tr), device=dev_id)       # first-call costs stay out of the timing
+    t0 = time.perf_counter()
+    dev = eng.KGIndex.from_arrays_device(E, Rn, tr, va, te, device=dev_id)
+    t1 = time.perf_counter()
+    host = eng.KGIndex.from_arrays(E, Rn, tr, va, te).to_device(dev_id)
+    t2 = time.perf_counter()
+    same = all(np.array_equal(host.device_column(c), dev.device_column(c), equal_nan=True) for c in range(11))
+    return {"triples": n + 2 * (n // 20), "E": E, "R": Rn, "gpu_build_device_ms": dev.build_ms, "gpu_build_wall_s": t1 - t0,
+            "host_build_wall_s": t2 - t1, "host_threads": os.cpu_count(), "same_bits_as_host_build": bool(same)}
 
 
 if __name__ == "__main__":

@@ -459,6 +459,9 @@ int mre_peer_group_error(mre_peer_group *g);
 /* FP32 add-rate microbenchmark (the better of a scalar FADD and a packed FADD2 stream): lane-ops per second in *lane_ops_per_s (the TransE roofline
  * denominator) and the SM clock-independent instruction count used. Synchronous. */
 int mre_probe_fp32_peak(mre_ctx *ctx, double *lane_ops_per_s);
+/* MUFU.SQRT (sqrt.approx.ftz) rate microbenchmark: square roots per second in *ops_per_s -- the roofline denominator of the RotatE tile
+ * kernel (RotatE.py:74-76: one complex modulus per query x entity x dimension). Synchronous. */
+int mre_probe_mufu_peak(mre_ctx *ctx, double *ops_per_s);
 /* tcgen05 dense MMA microbenchmarks, flops per second: kind::f16 with BF16 operands (what the DistMult / ComplEx kernel
  * issues -- its roofline denominator when MEASURED_PEAKS.json is absent) and kind::tf32 (for reference) */
 int mre_probe_bf16_peak(mre_ctx *ctx, double *flops_per_s);

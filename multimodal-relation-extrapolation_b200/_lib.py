@@ -157,6 +157,7 @@ def lib():
     L.mre_peer_allreduce_i64.argtypes = [vp, vp, vp, i32, vp]
     L.mre_peer_group_error.argtypes = [vp]
     L.mre_probe_fp32_peak.argtypes = [vp, P(C.c_double)]
+    L.mre_probe_mufu_peak.argtypes = [vp, P(C.c_double)]
     L.mre_probe_tf32_peak.argtypes = [vp, P(C.c_double)]
     L.mre_probe_bf16_peak.argtypes = [vp, P(C.c_double)]
     L.mre_ctx_timing.argtypes = [vp, i32]

@@ -110,6 +110,44 @@ __global__ void __launch_bounds__(256) fadd2_probe_kernel(float *out, int iters,
     if (s == 12345ull) out[0] = 1.f;  // never true in practice; keeps the chain live
 }
 
+// MUFU.SQRT stream (sqrt.approx.ftz): sixteen independent chains per thread, nothing else on the way -- the RotatE tile loop's bound
+__global__ void __launch_bounds__(256) mufu_probe_kernel(float *out, int iters, float c) {
+    float a[PROBE_ACC];
+#pragma unroll
+    for (int i = 0; i < PROBE_ACC; i++) a[i] = c + (float)(threadIdx.x + i);
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+#pragma unroll
+            for (int i = 0; i < PROBE_ACC; i++) asm volatile("sqrt.approx.ftz.f32 %0, %0;" : "+f"(a[i]));
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < PROBE_ACC; i++) s += a[i];
+    if (s == 12345.678f) out[0] = s;  // never true in practice; keeps the chain live
+}
+
+int probe_mufu_peak(mre_ctx *ctx, double *ops_per_s) {
+    MRE_CHECK_ARG(ops_per_s != nullptr, "NULL output");
+    MRE_TRY(ctx->misc.reserve(256));
+    const int iters = 1024, blocks = ctx->sm_count * 8, threads = 256;
+    double best = 0;
+    for (int rep = 0; rep < 5; rep++) {
+        MRE_CUDA(cudaEventRecord(ctx->ev0, 0));
+        mufu_probe_kernel<<<blocks, threads>>>(ctx->misc.as<float>(), iters, 1.5f);
+        MRE_CUDA(cudaEventRecord(ctx->ev1, 0));
+        MRE_CUDA(cudaEventSynchronize(ctx->ev1));
+        float ms = 0;
+        MRE_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        const double ops = (double)blocks * threads * iters * 8.0 * PROBE_ACC;
+        if (rep > 0) best = std::max(best, ops / (ms * 1e-3));
+    }
+    ctx->launches += 5;
+    *ops_per_s = best;
+    return MRE_OK;
+}
+
 int probe_fp32_peak(mre_ctx *ctx, double *lane_ops_per_s) {
     MRE_CHECK_ARG(lane_ops_per_s != nullptr, "NULL output");
     MRE_TRY(ctx->misc.reserve(256));
@@ -332,6 +370,12 @@ int mre_probe_fp32_peak(mre_ctx *ctx, double *lane_ops_per_s) {
     MRE_CHECK_ARG(ctx != nullptr, "ctx is NULL");
     MRE_CUDA(cudaSetDevice(ctx->device));
     return probe_fp32_peak(ctx, lane_ops_per_s);
+}
+
+int mre_probe_mufu_peak(mre_ctx *ctx, double *ops_per_s) {
+    MRE_CHECK_ARG(ctx != nullptr, "ctx is NULL");
+    MRE_CUDA(cudaSetDevice(ctx->device));
+    return probe_mufu_peak(ctx, ops_per_s);
 }
 
 int mre_probe_tf32_peak(mre_ctx *ctx, double *flops_per_s) {

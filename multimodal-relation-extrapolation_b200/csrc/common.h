@@ -182,6 +182,7 @@ int zsl_rank(mre_ctx *ctx, const mre_zsl_model *m, const float *A, const float *
              const int64_t *q_rel, const int64_t *cand_ptr, const int64_t *cand_idx, int64_t T, int64_t P, const float *rel_vecs,
              int64_t n_rel, int32_t n_vec, float *scores, int32_t *counts, cudaStream_t st);
 int probe_fp32_peak(mre_ctx *ctx, double *lane_ops_per_s);
+int probe_mufu_peak(mre_ctx *ctx, double *ops_per_s);
 int probe_tf32_peak(mre_ctx *ctx, double *flops_per_s);
 int probe_bf16_peak(mre_ctx *ctx, double *flops_per_s);
 }  // namespace mre

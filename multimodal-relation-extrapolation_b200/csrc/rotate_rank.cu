@@ -46,6 +46,29 @@ __device__ __forceinline__ float rotate_step(float acc, float vr, float vi, floa
     return acc + sqrtf(m);
 #endif
 }
+// two candidates at once, packed (sub / mul / fma / add .f32x2: the same IEEE roundings per lane, half the FP32 instructions --
+// at the MUFU bound the scalar form keeps 82 % of the issue slots busy)
+__device__ __forceinline__ float rotate_sqrt(float m) {
+    float s;
+#if MRE_ROTATE_SQRT_APPROX
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(m));
+#else
+    s = sqrtf(m);
+#endif
+    return s;
+}
+__device__ __forceinline__ void rotate_step2(uint64_t &acc, float vr, float vi, uint64_t er, uint64_t ei) {
+    uint64_t dr, di, m, sq;
+    asm("{\n\t.reg .b64 t;\n\tmov.b64 t, {%1, %1};\n\tsub.rn.f32x2 %0, t, %2;\n\t}" : "=l"(dr) : "f"(vr), "l"(er));
+    asm("{\n\t.reg .b64 t;\n\tmov.b64 t, {%1, %1};\n\tsub.rn.f32x2 %0, t, %2;\n\t}" : "=l"(di) : "f"(vi), "l"(ei));
+    asm("mul.rn.f32x2 %0, %1, %1;" : "=l"(m) : "l"(dr));
+    asm("fma.rn.f32x2 %0, %1, %1, %0;" : "+l"(m) : "l"(di));
+    float m0, m1;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(m0), "=f"(m1) : "l"(m));
+    const float s0 = rotate_sqrt(m0), s1 = rotate_sqrt(m1);
+    asm("mov.b64 %0, {%1, %2};" : "=l"(sq) : "f"(s0), "f"(s1));
+    asm("add.rn.f32x2 %0, %0, %1;" : "+l"(acc) : "l"(sq));
+}
 __device__ __forceinline__ float rotate_acc(const float *__restrict__ v, const float *__restrict__ e, int Dc) {
     float acc = 0.f;
     for (int d = 0; d < Dc; d++) acc = rotate_step(acc, v[d], v[Dc + d], __ldg(e + d), __ldg(e + Dc + d));
@@ -92,11 +115,9 @@ __global__ void __launch_bounds__(RT_THREADS) rotate_rank_kernel(const RankParam
         const GroupDesc gd = p.groups[g];
         const int64_t qbase = gd.q0 + (int64_t)qt * RT_T, cbase = gd.c0 + (int64_t)et * RT_T;
         const int nq = (int)min((int64_t)RT_T, gd.q0 + gd.nq - qbase), ne = (int)min((int64_t)RT_T, gd.nc - (int64_t)et * RT_T);
-        float acc[4][4];
+        uint64_t acc2[4][2];                                       // [query][candidate pair]: two FP32 accumulators per register pair
 #pragma unroll
-        for (int i = 0; i < 4; i++)
-#pragma unroll
-            for (int j = 0; j < 4; j++) acc[i][j] = 0.f;
+        for (int i = 0; i < 4; i++) acc2[i][0] = acc2[i][1] = 0ull;
         // this thread stages row (threadIdx.x / 4) of both operands, dimensions 4 (threadIdx.x % 4) .. + 3 of every chunk
         const int lrow = threadIdx.x >> 2, ld4 = (threadIdx.x & 3) * 4;
         const float *qrow = lrow < nq ? p.qvec + (qbase + lrow) * p.D : nullptr;
@@ -117,15 +138,21 @@ __global__ void __launch_bounds__(RT_THREADS) rotate_rank_kernel(const RankParam
             const int nd = min(RT_CH, Dc - c0);
             for (int d = 0; d < nd; d++) {
                 const float4 qr = *reinterpret_cast<const float4 *>(&sQ[0][d][ty * 4]), qi = *reinterpret_cast<const float4 *>(&sQ[1][d][ty * 4]);
-                const float4 er = *reinterpret_cast<const float4 *>(&sE[0][d][tx * 4]), ei = *reinterpret_cast<const float4 *>(&sE[1][d][tx * 4]);
+                const ulonglong2 er = *reinterpret_cast<const ulonglong2 *>(&sE[0][d][tx * 4]), ei = *reinterpret_cast<const ulonglong2 *>(&sE[1][d][tx * 4]);
                 const float vr[4] = {qr.x, qr.y, qr.z, qr.w}, vi[4] = {qi.x, qi.y, qi.z, qi.w};
-                const float xr[4] = {er.x, er.y, er.z, er.w}, xi[4] = {ei.x, ei.y, ei.z, ei.w};
 #pragma unroll
-                for (int i = 0; i < 4; i++)
-#pragma unroll
-                    for (int j = 0; j < 4; j++) acc[i][j] = rotate_step(acc[i][j], vr[i], vi[i], xr[j], xi[j]);
+                for (int i = 0; i < 4; i++) {
+                    rotate_step2(acc2[i][0], vr[i], vi[i], er.x, ei.x);
+                    rotate_step2(acc2[i][1], vr[i], vi[i], er.y, ei.y);
+                }
             }
         }
+        float acc[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int jp = 0; jp < 2; jp++)
+                asm("mov.b64 {%0, %1}, %2;" : "=f"(acc[i][2 * jp]), "=f"(acc[i][2 * jp + 1]) : "l"(acc2[i][jp]));
         // ---- compare + count: raw and filtered counters alike (the known-true correction pass takes the known entities back out)
 #pragma unroll
         for (int i = 0; i < 4; i++) {

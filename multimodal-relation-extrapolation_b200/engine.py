@@ -201,6 +201,11 @@ class Context:
         L.check(L.lib().mre_probe_fp32_peak(self._h, C.byref(v)))
         return v.value
 
+    def probe_mufu_peak(self):
+        v = C.c_double()
+        L.check(L.lib().mre_probe_mufu_peak(self._h, C.byref(v)))
+        return v.value
+
     def probe_bf16_peak(self):
         v = C.c_double()
         L.check(L.lib().mre_probe_bf16_peak(self._h, C.byref(v)))

@@ -22,5 +22,6 @@ torch.cuda.synchronize()
 ms, n = rk.ctx.timing_read()
 ms /= n
 elems = Q * E * Dc
+peak = rk.ctx.probe_mufu_peak()
 print(f"{os.environ.get('MRE_B200_LIB', 'default')}: rotate kernel {ms:.3f} ms, {elems / ms / 1e9:.2f} T complex-dim elements/s "
-      f"(MUFU bound 148 x 16 x 1.965 GHz = 4.65 T/s -> {elems / ms / 1e9 / 4.65:.2f})")
+      f"(MUFU.SQRT probe {peak / 1e12:.2f} T/s -> {elems / ms * 1e3 / peak:.2f}; nominal 148 x 16 x 1.965 GHz = 4.65 T/s -> {elems / ms / 1e9 / 4.65:.2f})")
