@@ -384,7 +384,12 @@ __global__ void __launch_bounds__(256, 2) zsl_layer2_kernel(const mre_zsl_model 
 #ifndef MRE_ZT_STAGES
 #define MRE_ZT_STAGES 4
 #endif
-constexpr int ZT_ROWS = 256, ZT_CTA_ROWS = 128, ZT_BK = 16, ZT_STAGES = MRE_ZT_STAGES, ZT_PROD_WARPS = 8, ZT_EPI_WARPS = 8;
+#ifndef MRE_ZT_EPI_WARPS
+#define MRE_ZT_EPI_WARPS 4      // 4: one epilogue warp per TMEM lane quarter, all columns (13 warps: 128 registers per thread); 8: two, splitting the columns
+#endif
+constexpr int ZT_ROWS = 256, ZT_CTA_ROWS = 128, ZT_BK = 16, ZT_STAGES = MRE_ZT_STAGES, ZT_PROD_WARPS = 8, ZT_EPI_WARPS = MRE_ZT_EPI_WARPS;
+constexpr int ZT_HALVES = ZT_EPI_WARPS / 4;
+static_assert(ZT_EPI_WARPS == 4 || ZT_EPI_WARPS == 8, "one or two epilogue warps per TMEM lane quarter");
 constexpr int ZT_PASSES = ZT_CTA_ROWS / (ZT_PROD_WARPS * 8);      // a producer warp covers its rows 8 at a time
 constexpr int ZT_THREADS = 32 * (ZT_PROD_WARPS + ZT_EPI_WARPS + 1);
 #ifndef MRE_ZT_DIAG
@@ -485,7 +490,8 @@ __device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_d, uint64_t desc_a,
         : "memory");
 }
 
-__global__ void __launch_bounds__(ZT_THREADS, 1) zsl_tc_kernel(const __grid_constant__ CUtensorMap tm_hi,
+// (launch bound 512 with 13 warps: 4 warps at most share a scheduler's 512 registers per lane -> 128 per thread; 17 warps: 96)
+__global__ void __launch_bounds__(ZT_THREADS > 512 ? ZT_THREADS : 512, 1) zsl_tc_kernel(const __grid_constant__ CUtensorMap tm_hi,
                                                                const __grid_constant__ CUtensorMap tm_lo, const ZslTcParams p) {
     extern __shared__ uint8_t zt_smem[];
     __shared__ __align__(8) uint64_t bars[2 * ZT_STAGES + 4];
@@ -647,7 +653,7 @@ __global__ void __launch_bounds__(ZT_THREADS, 1) zsl_tc_kernel(const __grid_cons
         // from the CTA's own pool, and the gather warps have nothing to give back)
         const int ew = warp - ZT_PROD_WARPS, q = warp & 3, half = ew >> 2, r = q * 32 + lane;
         const int nch = p.D / 8, c_split = ((nch + 1) / 2) * 8;
-        const int c_lo = half ? c_split : 0, c_hi = half ? p.D : c_split;
+        const int c_lo = half ? c_split : 0, c_hi = (half || ZT_HALVES == 1) ? p.D : c_split;
         const int ngrp = (c_hi - c_lo + 31) / 32;
         const uint32_t t_lane = tmem + ((uint32_t)(q * 32) << 16);
         const float inv_d = 1.f / (float)p.D;
@@ -739,11 +745,13 @@ __global__ void __launch_bounds__(ZT_THREADS, 1) zsl_tc_kernel(const __grid_cons
             if (lane == 0) mbar_arrive_cluster_relaxed(acc_empty_leader0 + 8 * buf);   // this warp is done with the accumulator buffer
             // the upper column half hands its partial sums to the lower one (buffers alternate with the tile parity: the
             // writer can be at most one tile ahead of the reader)
-            if (half) s_part[n & 1][q][lane] = make_float4(var, q2, sgb, dotp);
-            asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+            if (ZT_HALVES == 2 && half) s_part[n & 1][q][lane] = make_float4(var, q2, sgb, dotp);
+            if (ZT_HALVES == 2) asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
             if (!half && pr0 < p.P) {
-                const float4 o = s_part[n & 1][q][lane];
-                var += o.x; q2 += o.y; sgb += o.z; dotp += o.w;
+                if (ZT_HALVES == 2) {
+                    const float4 o = s_part[n & 1][q][lane];
+                    var += o.x; q2 += o.y; sgb += o.z; dotp += o.w;
+                }
                 const float rstd = rsqrtf(var * inv_d + p.ln_eps);
                 const float dot = fmaf(rstd, dotp, b_r);
                 const float nn = fmaf(rstd * rstd, q2, fmaf(2.f * rstd, sgb, s_scal[1]));
