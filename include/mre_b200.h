@@ -119,6 +119,8 @@ int mre_index_create_device(int device, int64_t E, int64_t R,
                             const int64_t *valid_h, const int64_t *valid_t, const int64_t *valid_r, int64_t n_valid,
                             const int64_t *test_h, const int64_t *test_t, const int64_t *test_r, int64_t n_test,
                             mre_index **out, double *build_ms);
+/* mre_index_create_from_dir with the build on the GPU: the files are parsed on the host, then as mre_index_create_device */
+int mre_index_create_from_dir_device(const char *in_path, int device, mre_index **out, double *build_ms);
 void mre_index_destroy(mre_index *ix);
 /* upload the filter / sampler tables to `device` (idempotent) */
 int mre_index_to_device(mre_index *ix, int device);

@@ -101,6 +101,7 @@ def lib():
     L.mre_index_create.argtypes = [i64, i64] + [vp, vp, vp, i64] * 3 + [P(vp)]
     L.mre_index_create_from_dir.argtypes = [C.c_char_p, P(vp)]
     L.mre_index_create_device.argtypes = [i32, i64, i64] + [vp, vp, vp, i64] * 3 + [P(vp), P(C.c_double)]
+    L.mre_index_create_from_dir_device.argtypes = [C.c_char_p, i32, P(vp), P(C.c_double)]
     L.mre_index_device_column.argtypes = [vp, i32, vp]
     L.mre_index_device_column.restype = i64
     L.mre_index_destroy.argtypes = [vp]

@@ -139,6 +139,7 @@ struct mre_ctx {
 };
 
 namespace mre {
+int read_benchmark_dir(const std::string &dir, int64_t *E, int64_t *R, std::vector<Triple> &tr, std::vector<Triple> &va, std::vector<Triple> &te);   // index.cpp
 // implemented in the .cu files
 int rank_transe(mre_ctx *ctx, const mre_index *ix, const mre_rank_job *job, cudaStream_t st);
 int rank_bilinear(mre_ctx *ctx, const mre_index *ix, const mre_rank_job *job, cudaStream_t st);

@@ -322,6 +322,17 @@ static int read_type_constrain(const std::string &path, mre_index *ix) {
     return MRE_OK;
 }
 
+// entity2id.txt / relation2id.txt counts + the three *2id.txt splits of a benchmark directory (`dir` ends with '/')
+int read_benchmark_dir(const std::string &dir, int64_t *E, int64_t *R, std::vector<Triple> &tr, std::vector<Triple> &va, std::vector<Triple> &te) {
+    MRE_TRY(read_count(dir + "entity2id.txt", E));
+    MRE_TRY(read_count(dir + "relation2id.txt", R));
+    MRE_CHECK_ARG(*E > 0 && *R > 0, "%s: E and R must be positive", dir.c_str());
+    MRE_TRY(read_triples(dir + "train2id.txt", false, *E, *R, tr));
+    MRE_TRY(read_triples(dir + "valid2id.txt", true, *E, *R, va));
+    MRE_TRY(read_triples(dir + "test2id.txt", true, *E, *R, te));
+    return MRE_OK;
+}
+
 template <class T>
 static int upload(const std::vector<T> &v, T **dst) {
     size_t bytes = std::max<size_t>(v.size(), 1) * sizeof(T);
@@ -384,17 +395,12 @@ int mre_index_create_from_dir(const char *in_path, mre_index **out) {
     std::string dir(in_path);
     if (!dir.empty() && dir.back() != '/') dir += '/';
     int64_t E = 0, R = 0;
-    MRE_TRY(read_count(dir + "entity2id.txt", &E));
-    MRE_TRY(read_count(dir + "relation2id.txt", &R));
-    MRE_CHECK_ARG(E > 0 && R > 0, "%s: E and R must be positive", in_path);
+    std::vector<Triple> tr, va, te;
+    MRE_TRY(read_benchmark_dir(dir, &E, &R, tr, va, te));
     mre_index *ix = new mre_index();
     ix->E = E;
     ix->R = R;
-    std::vector<Triple> tr, va, te;
-    int rc = read_triples(dir + "train2id.txt", false, E, R, tr);
-    if (rc == MRE_OK) rc = read_triples(dir + "valid2id.txt", true, E, R, va);
-    if (rc == MRE_OK) rc = read_triples(dir + "test2id.txt", true, E, R, te);
-    if (rc == MRE_OK) rc = build(ix, tr, va, te);
+    int rc = build(ix, tr, va, te);
     if (rc == MRE_OK) {   // importTypeFiles (Reader.h:267-317); the file is optional here, the reference crashes without it
         FILE *f = fopen((dir + "type_constrain.txt").c_str(), "r");
         if (f) {

@@ -17,7 +17,10 @@
 // 2 048-triple tiles wrote isolated 32-byte sectors and ran 2.4x slower once the lists outgrew L2), warp w owning the contiguous
 // keys [512 w, 512 w + 512) in sixteen coalesced rounds:
 // rank inside a warp round by match.any + popc, across rounds and warps by per-warp running bases in shared memory.
+#include <stdio.h>
+
 #include <algorithm>
+#include <string>
 #include <thread>
 #include <vector>
 
@@ -519,6 +522,37 @@ extern "C" int mre_index_create_device(int device, int64_t E, int64_t R, const i
     if (rc != MRE_OK) {
         mre_index_destroy(ix);
         return rc;
+    }
+    *out = ix;
+    return MRE_OK;
+}
+
+// mre_index_create_from_dir with the build on the GPU: the files are parsed on the host, everything after that as above
+extern "C" int mre_index_create_from_dir_device(const char *in_path, int device, mre_index **out, double *build_ms) {
+    MRE_CHECK_ARG(in_path && out, "NULL argument");
+    std::string dir(in_path);
+    if (!dir.empty() && dir.back() != '/') dir += '/';
+    int64_t E = 0, R = 0;
+    std::vector<Triple> sp[3];
+    MRE_TRY(read_benchmark_dir(dir, &E, &R, sp[0], sp[1], sp[2]));
+    std::vector<int64_t> col[3][3];
+    for (int k = 0; k < 3; k++) {
+        for (auto &c : col[k]) c.resize(sp[k].size());
+        for (size_t i = 0; i < sp[k].size(); i++) { col[k][0][i] = sp[k][i].h; col[k][1][i] = sp[k][i].t; col[k][2][i] = sp[k][i].r; }
+        std::vector<Triple>().swap(sp[k]);
+    }
+    mre_index *ix = nullptr;
+    MRE_TRY(mre_index_create_device(device, E, R, col[0][0].data(), col[0][1].data(), col[0][2].data(), (int64_t)col[0][0].size(), col[1][0].data(),
+                                    col[1][1].data(), col[1][2].data(), (int64_t)col[1][0].size(), col[2][0].data(), col[2][1].data(), col[2][2].data(),
+                                    (int64_t)col[2][0].size(), &ix, build_ms));
+    FILE *f = fopen((dir + "type_constrain.txt").c_str(), "r");      // importTypeFiles (Reader.h:267-317); optional here
+    if (f) {
+        fclose(f);
+        const int rc = mre_index_load_type_constrain(ix, (dir + "type_constrain.txt").c_str());
+        if (rc != MRE_OK) {
+            mre_index_destroy(ix);
+            return rc;
+        }
     }
     *out = ix;
     return MRE_OK;

@@ -87,11 +87,18 @@ class KGIndex:
         return out
 
     @classmethod
-    def from_dir(cls, in_path):
-        """setInPath + importTrainFiles + importTestFiles (Setting.h:17-27, Reader.h:53-257)."""
+    def from_dir(cls, in_path, device=None):
+        """setInPath + importTrainFiles + importTestFiles (Setting.h:17-27, Reader.h:53-257).  `device`: build the tables on
+        that GPU (mre_index_create_from_dir_device: radix sorts instead of the host sorts; the index then lives on it)."""
         out = C.c_void_p()
-        L.check(L.lib().mre_index_create_from_dir(str(in_path).encode(), C.byref(out)))
-        return cls(out.value)
+        if device is None:
+            L.check(L.lib().mre_index_create_from_dir(str(in_path).encode(), C.byref(out)))
+            return cls(out.value)
+        ms = C.c_double(0.0)
+        L.check(L.lib().mre_index_create_from_dir_device(str(in_path).encode(), int(device), C.byref(out), C.byref(ms)))
+        ix = cls(out.value)
+        ix.device, ix.build_ms = int(device), ms.value
+        return ix
 
     def __del__(self):
         try:

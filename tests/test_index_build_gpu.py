@@ -85,3 +85,30 @@ def test_device_build_rejects_out_of_range_ids(mre):
     train = (np.array([0, 1, 7]), np.array([1, 2, 0]), np.array([0, 0, 0]))
     with pytest.raises(mre._lib.MreError, match="train triple 2"):
         eng.KGIndex.from_arrays_device(5, 2, train, device=0)
+
+
+@pytest.mark.gpu
+def test_from_dir_on_device_matches_host(mre, tmp_path):
+    """KGIndex.from_dir(path, device=0) (mre_index_create_from_dir_device: host parse, GPU build, type_constrain.txt loaded when
+    present) against KGIndex.from_dir(path).to_device(0); a TestDataLoader built on it serves the Tester"""
+    import helpers
+    from oracle import ref_driver as rd
+    eng = mre.engine
+    ds = helpers.synthetic_graph(21, 500, 9, 8000, 300, 300)
+    d = rd.write_benchmark_dir(str(tmp_path / "kg"), ds.E, ds.R, ds.train, ds.valid, ds.test)
+    rng = np.random.default_rng(2)
+    with open(d + "/type_constrain.txt", "w") as f:            # importTypeFiles' format: per relation a head line, then a tail line
+        f.write(f"{ds.R}\n")
+        for r in range(ds.R):
+            for _ in range(2):
+                ids = np.unique(rng.integers(0, ds.E, 40))
+                f.write(f"{r}\t{len(ids)}\t" + "\t".join(map(str, ids.tolist())) + "\n")
+    host = eng.KGIndex.from_dir(d).to_device(0)
+    dev = eng.KGIndex.from_dir(d, device=0)
+    assert_same_index(host, dev)
+    assert dev.has_type_constrain
+    for side in (0, 1):
+        for x, y in zip(host.type_constrain(side), dev.type_constrain(side)):
+            assert np.array_equal(x, y)
+    loader = mre.openke.data.TestDataLoader(d, "link", index=dev)
+    assert loader.get_triple_tot() == host.test_tot
