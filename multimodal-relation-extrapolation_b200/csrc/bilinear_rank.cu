@@ -341,7 +341,10 @@ __global__ void __launch_bounds__(KNOWN_WARPS * 32) bil_known_kernel(const RankP
 // (Building the query vector from the embedding rows instead, so that this kernel could run beside bil_query_kernel on the second
 // stream, was measured twice and does not pay: with a scalar short-run path the ComplEx step went 0.61 -> 0.85 ms, with the
 // vector staged in shared memory 0.607 -> 0.616 ms -- the two kernels compete for the same SMs and L2 misses.)
-__global__ void __launch_bounds__(KNOWN_WARPS * 32) bil_known_score_kernel(const RankParams p, const KnownRuns kr) {
+#ifndef MRE_BIL_KNOWN_MINB
+#define MRE_BIL_KNOWN_MINB 3
+#endif
+__global__ void __launch_bounds__(KNOWN_WARPS * 32, MRE_BIL_KNOWN_MINB) bil_known_score_kernel(const RankParams p, const KnownRuns kr) {
     __shared__ float sT[KNOWN_WARPS][32][33];
     __shared__ int64_t sX[KNOWN_WARPS][32];
     BilKnownOp op{p.ent, p.qvec, nullptr, p.thr, p.D, 0.f};

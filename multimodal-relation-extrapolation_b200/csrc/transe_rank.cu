@@ -289,7 +289,7 @@ __global__ void __launch_bounds__(KNOWN_WARPS * 32) transe_known_kernel(const Ra
     known_correction(p, op, sT[threadIdx.x >> 5], sX[threadIdx.x >> 5]);
 }
 template <int P>
-__global__ void __launch_bounds__(KNOWN_WARPS * 32) transe_known_score_kernel(const RankParams p, const float *__restrict__ rel, const KnownRuns kr) {
+__global__ void __launch_bounds__(KNOWN_WARPS * 32, 3) transe_known_score_kernel(const RankParams p, const float *__restrict__ rel, const KnownRuns kr) {
     __shared__ float sT[KNOWN_WARPS][32][33];
     __shared__ int64_t sX[KNOWN_WARPS][32];
     TranseKnownOp<P> op{p.ent, rel, nullptr, nullptr, p.thr, p.D, 0, make_float2(0.f, 0.f), p.qvec};
