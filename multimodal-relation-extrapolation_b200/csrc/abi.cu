@@ -227,6 +227,7 @@ int mre_predict(mre_ctx *ctx, const mre_rank_job *job, int64_t query, float *sco
     if (!j.counts) j.counts = &dummy;  // unused by predict; keeps check_job happy
     MRE_TRY(check_job(&j));
     MRE_CHECK_ARG(query >= 0 && query < job->Q, "query %lld out of range", (long long)query);
+    MRE_CHECK_ARG(job->scorer != MRE_ROTATE, "MRE_ROTATE is served by mre_rank only (RotatE.predict on explicit batches stays with the host mirror)");
     MRE_CUDA(cudaSetDevice(ctx->device));
     if (job->scorer == MRE_TRANSE) return predict_transe(ctx, job, query, scores_out, (cudaStream_t)stream);
     return predict_bilinear(ctx, job, query, scores_out, (cudaStream_t)stream);
@@ -238,7 +239,7 @@ int mre_bilinear_scores(mre_ctx *ctx, const mre_rank_job *job, float *scores_out
     int32_t dummy = 0;
     if (!j.counts) j.counts = &dummy;
     MRE_TRY(check_job(&j));
-    MRE_CHECK_ARG(job->scorer != MRE_TRANSE, "mre_bilinear_scores is for the DistMult / ComplEx (tensor-core) path");
+    MRE_CHECK_ARG(job->scorer == MRE_DISTMULT || job->scorer == MRE_COMPLEX, "mre_bilinear_scores is for the DistMult / ComplEx (tensor-core) path");
     MRE_CUDA(cudaSetDevice(ctx->device));
     return bilinear_scores(ctx, job, scores_out, (cudaStream_t)stream);
 }

@@ -332,6 +332,8 @@ class Ranker:
 
     def predict(self, scorer, tables, q_h, q_t, q_r, side, query=0, *, p_norm=1, normalize=False):
         """Model.predict's float32[E] vector for one query (device tensor)."""
+        if scorer == "rotate":
+            raise L.MreError("RotatE is served by rank() only: use the model's own predict() for explicit batches")
         Q = q_h.numel()
         job, keep = self._job(scorer, tables, Q, side, p_norm, normalize, None, "none", None, None)
         job.q_h, job.q_t, job.q_r = _ptr(q_h), _ptr(q_t), _ptr(q_r)

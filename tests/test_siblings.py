@@ -182,6 +182,9 @@ def test_rotate_ranks_vs_reference_golden(mre, fb15k237, wname):
             data = ({"batch_h": dev(ids), "batch_t": dev(np.array([t])), "batch_r": dev(np.array([r])), "mode": "head_batch"} if s == 0
                     else {"batch_h": dev(np.array([h])), "batch_t": dev(ids), "batch_r": dev(np.array([r])), "mode": "tail_batch"})
             assert np.allclose(model.predict(data), g[key + "_probe"][k, s], rtol=2e-5, atol=2e-6)
+    # the library's per-query score vector and tensor-core score matrix are not RotatE's: refused, not mis-dispatched
+    with pytest.raises(mre._lib.MreError):
+        rk.predict("rotate", tabs, dev(q_h), dev(q_t), dev(q_r), dev(side))
 
 
 @pytest.mark.gpu
