@@ -402,7 +402,8 @@ constexpr int ZT_A_BYTES = ZT_CTA_ROWS * ZT_BK * 4;                // one of the
 // shared memory they cost two L1TEX data-pipe wavefronts per warp-uniform LDS.128 (165 M per sweep on the pipe that bounds the
 // kernel, profiles/r2_zsl_gather_experiments.md); from the constant bank they are LDC reads through the constant cache and cost
 // the data pipe nothing.  One slot per context (contexts are not shared between concurrently running streams -- the same contract
-// as the context's scratch buffers), filled by a stream-ordered device-to-device copy before the launch.
+// as the context's scratch buffers), filled by a stream-ordered device-to-device copy before the launch.  Sixteen slots, handed out
+// round-robin at mre_ctx_create: seventeen or more contexts scoring DIFFERENT models at the same time on one device would share one.
 #ifndef MRE_ZT_CONST_VEC
 #define MRE_ZT_CONST_VEC 1
 #endif
