@@ -206,3 +206,59 @@ def test_rotate_trains_through_the_library_losses(mre):
     opt.step()
     with torch.no_grad():
         assert strat(data).item() < l0.item()
+
+
+def _rotate_scores64(ent, rel, phase_div, side, h, t, r):
+    """RotatE._calc (RotatE.py:44-78) for one 1-vs-all query in float64 (the margin shift is irrelevant to the counts)"""
+    Dc = rel.shape[1]
+    e64, ph = ent.astype(np.float64), rel[r].astype(np.float64) / float(phase_div)
+    re_r, im_r, re_e, im_e = np.cos(ph), np.sin(ph), e64[:, :Dc], e64[:, Dc:]
+    if side == 0:
+        re_s, im_s = (re_r * re_e[t] + im_r * im_e[t]) - re_e, (re_r * im_e[t] - im_r * re_e[t]) - im_e
+    else:
+        re_s, im_s = (re_e[h] * re_r - im_e[h] * im_r) - re_e, (re_e[h] * im_r + im_e[h] * re_r) - im_e
+    return np.sqrt(re_s * re_s + im_s * im_s).sum(-1)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("Dc", [1, 7, 16, 33])
+def test_rotate_edge_shapes(mre, Dc):
+    """RotatE tile kernel on ragged shapes -- a complex dimension that is not a multiple of the 16-wide chunk (or of 4), entity and
+    query counts off the 64-wide tiles, ragged candidate groups with a CSR filter, an empty job: every count inside the 1e-5 relative
+    band of a float64 restatement"""
+    eng = mre.engine
+    rng = np.random.default_rng(40 + Dc)
+    E, R, Q = 211, 5, 75
+    ent = ((rng.random((E, 2 * Dc), dtype=np.float32) - 0.5) * 0.2).astype(np.float32)
+    rel = ((rng.random((R, Dc), dtype=np.float32) - 0.5) * 0.2).astype(np.float32)
+    div = np.float32(0.1 / np.pi)
+    q_r = np.sort(rng.integers(0, R, Q))
+    q_h, q_t = rng.integers(0, E, Q), rng.integers(0, E, Q)
+    side = (np.arange(Q) % 2).astype(np.uint8)
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    rk = eng.Ranker(device=0)
+    tabs = (dev(ent), dev(rel))
+    # per-query known lists (sorted), handed over as a CSR filter
+    known = [np.unique(rng.integers(0, E, rng.integers(0, 6))) for _ in range(Q)]
+    fptr = np.concatenate([[0], np.cumsum([len(k) for k in known])]).astype(np.int64)
+    fidx = np.concatenate(known).astype(np.int64) if fptr[-1] else np.zeros(0, np.int64)
+    # ragged candidate groups: one per relation present, 1 .. E candidates each
+    rels, counts = np.unique(q_r, return_counts=True)
+    cand = [np.sort(rng.choice(E, int(rng.integers(1, E + 1)), replace=False)) for _ in rels]
+    groups = eng.CandidateGroups.from_lists(counts, cand, "cuda")
+    for use_groups in (False, True):
+        c = rk.rank("rotate", tabs, dev(q_h), dev(q_t), dev(q_r), dev(side), filt_csr=(dev(fptr), dev(fidx), len(fidx)),
+                    groups=groups if use_groups else None, phase_div=float(div)).cpu().numpy()
+        for q in range(Q):
+            s = _rotate_scores64(ent, rel, div, int(side[q]), int(q_h[q]), int(q_t[q]), int(q_r[q]))
+            truth = int(q_h[q]) if side[q] == 0 else int(q_t[q])
+            S = np.arange(E) if not use_groups else cand[int(np.searchsorted(rels, q_r[q]))]
+            band = 1e-5 * max(abs(s[truth]), float(np.abs(s).mean()))
+            others = S[S != truth]
+            raw_lo, raw_hi = int((s[others] < s[truth] - band).sum()), int((s[others] <= s[truth] + band).sum())
+            assert raw_lo <= c[0][q] + 0 <= raw_hi and c[0][q] + c[1][q] >= raw_lo, (use_groups, q, c[:, q], raw_lo, raw_hi)
+            unf = others[~np.isin(others, known[q])]
+            f_lo, f_hi = int((s[unf] < s[truth] - band).sum()), int((s[unf] <= s[truth] + band).sum())
+            assert f_lo <= c[2][q] <= f_hi, (use_groups, q, c[:, q], f_lo, f_hi)
+    empty = torch.zeros(0, dtype=torch.int64, device="cuda")
+    assert rk.rank("rotate", tabs, empty, empty, empty, 1, filter="none", phase_div=float(div)).shape == (4, 0)
