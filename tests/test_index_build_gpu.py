@@ -50,7 +50,7 @@ def test_device_build_matches_host_build_on_fb15k237(mre, fb15k237):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("case", ["wide_ids", "heavy_duplicates", "train_only", "tiny", "one_relation"])
+@pytest.mark.parametrize("case", ["wide_ids", "heavy_duplicates", "train_only", "tiny", "one_relation", "empty"])
 def test_device_build_matches_host_build_on_synthetic_graphs(mre, case):
     eng = mre.engine
     rng = np.random.default_rng(11)
@@ -71,6 +71,10 @@ def test_device_build_matches_host_build_on_synthetic_graphs(mre, case):
         E, R = 5, 2
         train = (np.array([4, 0, 4]), np.array([1, 2, 1]), np.array([1, 0, 1]))
         valid, test = (np.array([3]), np.array([3]), np.array([0])), (np.array([0]), np.array([2]), np.array([0]))
+    elif case == "empty":                # no triple at all: every table empty, tph / hpt = 0 / 0
+        E, R = 4, 3
+        train = valid = test = None
+        train = (np.zeros(0, np.int64),) * 3
     else:                                # R = 1: a relation column of one bit
         E, R = 70_000, 1
         train, valid, test = draw(100_000, E, R), draw(1_000, E, R), draw(1_000, E, R)
