@@ -212,11 +212,21 @@ __global__ void keys_kernel(const Cols a, int64_t n, int64_t R, int which, int64
 // freqRel, and the number of distinct (fixed entity, r) pairs per relation (Reader.h:142-159), over a list sorted with r inside
 // the fixed entity: which = 0 -> the (h,r,t) order counts distinct (h,r); 1 -> the (t,r,h) order counts distinct (t,r)
 __global__ void rel_count_kernel(const Cols a, int64_t n, int which, unsigned long long *__restrict__ freq, unsigned long long *__restrict__ distinct) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const int32_t r = a.r[i];
-        if (freq) atomicAdd(freq + r, 1ull);
+    const int lane = threadIdx.x & 31;
+    // warp-aggregated: the lanes that hold the same relation elect one to add their total (a few hundred relations take millions of
+    // increments: one atomic per (warp, relation) instead of one per triple)
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x, n_round = (n + stride - 1) / stride * stride;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
+        const bool ok = i < n;
+        const int32_t r = ok ? a.r[i] : -1 - lane;
         const int32_t *f = which ? a.t : a.h;
-        if (i == 0 || f[i] != f[i - 1] || r != a.r[i - 1]) atomicAdd(distinct + r, 1ull);
+        const bool first = ok && (i == 0 || f[i] != f[i - 1] || r != a.r[i - 1]);
+        const unsigned peers = __match_any_sync(0xffffffffu, r);
+        const unsigned firsts = __ballot_sync(0xffffffffu, first) & peers;
+        if (ok && (peers & ((1u << lane) - 1u)) == 0) {          // lowest lane of its relation
+            if (freq) atomicAdd(freq + r, (unsigned long long)__popc(peers));
+            if (firsts) atomicAdd(distinct + r, (unsigned long long)__popc(firsts));
+        }
     }
 }
 
